@@ -1,0 +1,330 @@
+"""ctypes binding for the CPU ORACLE (oracle/libjpeg_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Product code under
+jpeg_b200/ never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libjpeg_oracle.so")
+
+INTERVAL_NONE = (1 << 63) - 1
+
+ERRORS = {
+    0: "ok", -1: "truncatedEntropyCodedSegment", -2: "invalidCompositeValue", -3: "invalidCompositeBlockRun",
+    -4: "undefinedScanHuffmanDCReference", -5: "undefinedScanHuffmanACReference",
+    -6: "undefinedScanQuantizationReference", -7: "precondition", -10: "lexing", -11: "parsing",
+    -12: "decoding", -13: "unsupported",
+}
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code):
+        super().__init__(f"oracle error {code} ({ERRORS.get(code, '?')})")
+        self.code = code
+
+
+class HuffSpec(C.Structure):
+    _fields_ = [("present", C.c_int), ("counts", C.c_uint8 * 16), ("values", C.c_uint8 * 256)]
+
+    @classmethod
+    def make(cls, counts, values):
+        t = cls()
+        t.present = 1
+        for i, c in enumerate(counts):
+            t.counts[i] = c
+        for i, v in enumerate(values):
+            t.values[i] = v
+        return t
+
+    def as_tuple(self):
+        n = sum(self.counts)
+        return bytes(self.counts), bytes(self.values[:n])
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("jpeg_oracle.c", "jpeg_oracle.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_SO)
+    u8p, u16p, i16p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_int16), C.POINTER(C.c_int)
+    L.orc_zigzag.argtypes = [C.c_int, C.c_int]
+    L.orc_extend.argtypes = [C.c_int, C.c_uint]
+    L.orc_compact.argtypes = [C.c_int, ip, C.POINTER(C.c_uint)]
+    L.orc_huff_lookup.argtypes = [C.POINTER(HuffSpec), C.c_uint, ip, ip]
+    L.orc_huff_from_frequencies.argtypes = [C.POINTER(C.c_int64), C.POINTER(HuffSpec)]
+    L.orc_huff_encoder.argtypes = [C.POINTER(HuffSpec), u16p, u8p]
+    L.orc_quanta.argtypes = [C.c_double, C.c_int, u16p]
+    L.orc_decompress.restype = C.c_void_p
+    L.orc_decompress.argtypes = [C.c_char_p, C.c_size_t, ip]
+    L.orc_spectral_create.restype = C.c_void_p
+    L.orc_spectral_create.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int]
+    L.orc_spectral_free.argtypes = [C.c_void_p]
+    L.orc_spectral_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
+    L.orc_spectral_plane_info.argtypes = [C.c_void_p, C.c_int, ip, ip, ip]
+    L.orc_spectral_coefficients.restype = i16p
+    L.orc_spectral_coefficients.argtypes = [C.c_void_p, C.c_int]
+    L.orc_spectral_quanta.restype = u16p
+    L.orc_spectral_quanta.argtypes = [C.c_void_p, C.c_int]
+    L.orc_spectral_set_quanta.argtypes = [C.c_void_p, C.c_int, u16p]
+    L.orc_decode_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip,
+                                  C.POINTER(HuffSpec), C.POINTER(HuffSpec), C.c_void_p, C.POINTER(C.c_uint64),
+                                  C.c_int, C.c_int64, C.c_int]
+    L.orc_idct_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_interleave.argtypes = [C.POINTER(C.c_void_p), ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_unpack_rgb.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    L.orc_unpack_ycc.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    L.orc_pack_rgb.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    L.orc_decompose_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p]
+    L.orc_fdct_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_encode_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int64,
+                                  C.POINTER(HuffSpec), C.POINTER(HuffSpec), C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_size_t)]
+    L.orc_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ints(xs):
+    return (C.c_int * len(xs))(*xs)
+
+
+def units(size, stride):
+    return size // stride + (1 if size % stride else 0)
+
+
+def zigzag_table():
+    L = lib()
+    return np.array([[L.orc_zigzag(k, h) for k in range(8)] for h in range(8)], dtype=np.int32)
+
+
+def quanta(level, chrominance):
+    out = np.zeros(64, dtype=np.uint16)
+    lib().orc_quanta(float(level), int(bool(chrominance)), out.ctypes.data_as(C.POINTER(C.c_uint16)))
+    return out
+
+
+def huff_from_frequencies(freq):
+    f = (C.c_int64 * 256)(*[int(x) for x in freq])
+    t = HuffSpec()
+    lib().orc_huff_from_frequencies(f, C.byref(t))
+    return t
+
+
+def huff_encoder(spec):
+    code = np.zeros(256, dtype=np.uint16)
+    ln = np.zeros(256, dtype=np.uint8)
+    lib().orc_huff_encoder(C.byref(spec), code.ctypes.data_as(C.POINTER(C.c_uint16)),
+                           ln.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return code, ln
+
+
+def huff_lookup(spec, codeword):
+    s, l = C.c_int(), C.c_int()
+    e = lib().orc_huff_lookup(C.byref(spec), codeword, C.byref(s), C.byref(l))
+    if e:
+        raise OracleError(e)
+    return s.value, l.value
+
+
+class Spectral:
+    """Mirror of JPEG.Data.Spectral<JPEG.Common> held by the oracle."""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = lib()
+        sz, bl, sc = _ints([0, 0]), _ints([0, 0]), _ints([0, 0])
+        nc, pr = C.c_int(), C.c_int()
+        L.orc_spectral_info(handle, sz, bl, C.byref(nc), sc, C.byref(pr))
+        self.size = (sz[0], sz[1])
+        self.blocks = (bl[0], bl[1])
+        self.scale = (sc[0], sc[1])
+        self.ncomp = nc.value
+        self.process = pr.value
+
+    @classmethod
+    def decompress(cls, data: bytes):
+        err = C.c_int()
+        h = lib().orc_decompress(data, len(data), C.byref(err))
+        if not h:
+            raise OracleError(err.value)
+        return cls(h)
+
+    @classmethod
+    def create(cls, size, factors, progressive=False):
+        flat = [v for f in factors for v in f]
+        h = lib().orc_spectral_create(size[0], size[1], len(factors), _ints(flat), int(progressive))
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_spectral_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def plane_info(self, p):
+        u, f = _ints([0, 0]), _ints([0, 0])
+        cid = C.c_int()
+        lib().orc_spectral_plane_info(self._h, p, u, f, C.byref(cid))
+        return (u[0], u[1]), (f[0], f[1]), cid.value
+
+    def units(self, p):
+        return self.plane_info(p)[0]
+
+    def factor(self, p):
+        return self.plane_info(p)[1]
+
+    def coefficients(self, p):
+        """numpy view (no copy) of the plane's Int16 buffer, shape (uy, ux, 64)."""
+        (ux, uy), _, _ = self.plane_info(p)
+        ptr = lib().orc_spectral_coefficients(self._h, p)
+        n = 64 * ux * uy
+        if n == 0:
+            return np.zeros((uy, ux, 64), dtype=np.int16)
+        arr = np.ctypeslib.as_array(ptr, shape=(n,))
+        return arr.reshape(uy, ux, 64)
+
+    def quanta(self, p):
+        ptr = lib().orc_spectral_quanta(self._h, p)
+        return np.ctypeslib.as_array(ptr, shape=(64,)).copy()
+
+    def set_quanta(self, p, q):
+        q = np.ascontiguousarray(q, dtype=np.uint16)
+        lib().orc_spectral_set_quanta(self._h, p, q.ctypes.data_as(C.POINTER(C.c_uint16)))
+
+    def decode_scan(self, band, bits, comps, dcsel, acsel, dc, ac, ecss, interval=INTERVAL_NONE, extend=False):
+        """Spectral.decode(ecss:interval:scan:tables:extend:). ecss = list of unstuffed bytes."""
+        cat = b"".join(ecss)
+        offs = [0]
+        for e in ecss:
+            offs.append(offs[-1] + len(e))
+        dcs = (HuffSpec * 4)(*dc)
+        acs = (HuffSpec * 4)(*ac)
+        buf = C.create_string_buffer(cat, len(cat) + 1)
+        e = lib().orc_decode_scan(self._h, band[0], band[1], bits[0], -1 if bits[1] is None else bits[1],
+                                  len(comps), _ints(comps), _ints(dcsel), _ints(acsel), dcs, acs,
+                                  C.cast(buf, C.c_void_p), (C.c_uint64 * len(offs))(*offs), len(ecss),
+                                  interval, int(extend))
+        if e:
+            raise OracleError(e)
+
+    def encode_scan(self, band, bits, comps, dcsel, acsel, interval_mcus=0):
+        """Returns (stuffed ECS bytes incl. RSTn, dc tables[4], ac tables[4])."""
+        dcs, acs = (HuffSpec * 4)(), (HuffSpec * 4)()
+        out, n = C.c_void_p(), C.c_size_t()
+        e = lib().orc_encode_scan(self._h, band[0], band[1], bits[0], -1 if bits[1] is None else bits[1],
+                                  len(comps), _ints(comps), _ints(dcsel), _ints(acsel), interval_mcus, dcs, acs,
+                                  C.byref(out), C.byref(n))
+        if e:
+            raise OracleError(e)
+        data = C.string_at(out, n.value)
+        lib().orc_free(out)
+        return data, list(dcs), list(acs)
+
+    # --- transform stages -------------------------------------------------
+    def idct(self):
+        """Spectral.idct() -> list of uint16 planes, each (8uy, 8ux)."""
+        planes = []
+        for p in range(self.ncomp):
+            (ux, uy), _, _ = self.plane_info(p)
+            planes.append(idct_plane(self.coefficients(p), self.quanta(p)))
+        return planes
+
+    def to_rectangular(self, cosited=False):
+        planes = self.idct()
+        return interleave(planes, [self.units(p) for p in range(self.ncomp)],
+                          [self.factor(p) for p in range(self.ncomp)], self.size, cosited)
+
+
+def idct_plane(coef, q, precision=8):
+    coef = np.ascontiguousarray(coef, dtype=np.int16)
+    uy, ux = coef.shape[0], coef.shape[1]
+    q = np.ascontiguousarray(q, dtype=np.uint16)
+    out = np.zeros((8 * uy, 8 * ux), dtype=np.uint16)
+    lib().orc_idct_plane(coef.ctypes.data, ux, uy, q.ctypes.data, precision, out.ctypes.data)
+    return out
+
+
+def interleave(planes, units_list, factors, size, cosited=False):
+    n = len(planes)
+    planes = [np.ascontiguousarray(p, dtype=np.uint16) for p in planes]
+    ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in planes])
+    out = np.zeros((size[1], size[0], n), dtype=np.uint16)
+    lib().orc_interleave(ptrs, _ints([v for u in units_list for v in u]), _ints([v for f in factors for v in f]),
+                         n, size[0], size[1], int(cosited), out.ctypes.data)
+    return out
+
+
+def unpack_rgb(interleaved):
+    il = np.ascontiguousarray(interleaved, dtype=np.uint16)
+    h, w, n = il.shape
+    out = np.zeros((h, w, 3), dtype=np.uint8)
+    lib().orc_unpack_rgb(il.ctypes.data, h * w, n, out.ctypes.data)
+    return out
+
+
+def unpack_ycc(interleaved):
+    il = np.ascontiguousarray(interleaved, dtype=np.uint16)
+    h, w, n = il.shape
+    out = np.zeros((h, w, 3), dtype=np.uint8)
+    lib().orc_unpack_ycc(il.ctypes.data, h * w, n, out.ctypes.data)
+    return out
+
+
+def pack_rgb(rgb, ncomp=3):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w, _ = rgb.shape
+    out = np.zeros((h, w, ncomp), dtype=np.uint16)
+    lib().orc_pack_rgb(rgb.ctypes.data, h * w, ncomp, out.ctypes.data)
+    return out
+
+
+def decompose(interleaved, factors):
+    il = np.ascontiguousarray(interleaved, dtype=np.uint16)
+    h, w, n = il.shape
+    scx = max(f[0] for f in factors)
+    scy = max(f[1] for f in factors)
+    planes = []
+    for p, (fx, fy) in enumerate(factors):
+        ux, uy = units(w * fx, 8 * scx), units(h * fy, 8 * scy)
+        out = np.zeros((8 * uy, 8 * ux), dtype=np.uint16)
+        lib().orc_decompose_plane(il.ctypes.data, w, h, n, p, fx, fy, scx, scy, out.ctypes.data)
+        planes.append(out)
+    return planes
+
+
+def fdct_plane(samples, q, precision=8):
+    s = np.ascontiguousarray(samples, dtype=np.uint16)
+    uy, ux = s.shape[0] // 8, s.shape[1] // 8
+    q = np.ascontiguousarray(q, dtype=np.uint16)
+    out = np.zeros((uy, ux, 64), dtype=np.int16)
+    lib().orc_fdct_plane(s.ctypes.data, ux, uy, q.ctypes.data, precision, out.ctypes.data)
+    return out
+
+
+def decode_rgb(data: bytes):
+    """Rectangular<Common>.decompress + unpack(as: RGB) and unpack(as: YCbCr)."""
+    s = Spectral.decompress(data)
+    rect = s.to_rectangular()
+    return unpack_rgb(rect), unpack_ycc(rect), s

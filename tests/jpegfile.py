@@ -1,0 +1,89 @@
+"""Minimal JPEG container splitter for the tests (markers + raw entropy-coded bytes; nothing is decoded)."""
+from __future__ import annotations
+
+
+def split(data: bytes):
+    """Returns a list of (marker, body, ecs) where ecs is the raw (still stuffed, incl. RSTn) bytes that follow
+    an SOS segment, b'' otherwise."""
+    out = []
+    i, n = 0, len(data)
+    while i < n:
+        assert data[i] == 0xFF, (i, data[i])
+        while data[i] == 0xFF:
+            i += 1
+        m = data[i]
+        i += 1
+        if m in (0xD8, 0xD9):
+            out.append((m, b"", b""))
+            if m == 0xD9:
+                break
+            continue
+        ln = (data[i] << 8) | data[i + 1]
+        body = data[i + 2:i + ln]
+        i += ln
+        ecs = b""
+        if m == 0xDA:
+            j = i
+            while True:
+                k = data.index(b"\xff", j)
+                nxt = data[k + 1]
+                if nxt == 0x00 or 0xD0 <= nxt <= 0xD7:
+                    j = k + 2
+                    continue
+                if nxt == 0xFF:
+                    j = k + 1
+                    continue
+                break
+            ecs = data[i:k]
+            i = k
+        out.append((m, body, ecs))
+    return out
+
+
+def unstuff_split(ecs: bytes):
+    """Raw scan bytes -> list of unstuffed per-interval ECS (what the reference lexer hands to the decoder,
+    decode.swift:130-190)."""
+    parts, cur = [], bytearray()
+    i, n = 0, len(ecs)
+    while i < n:
+        b = ecs[i]
+        if b != 0xFF:
+            cur.append(b)
+            i += 1
+            continue
+        nxt = ecs[i + 1]
+        if nxt == 0x00:
+            cur.append(0xFF)
+            i += 2
+        elif 0xD0 <= nxt <= 0xD7:
+            parts.append(bytes(cur))
+            cur = bytearray()
+            i += 2
+        elif nxt == 0xFF:
+            i += 1
+        else:
+            raise ValueError("marker inside scan")
+    parts.append(bytes(cur))
+    return parts
+
+
+def parse_dht(body: bytes):
+    """-> list of (class, target, counts(16 bytes), values)."""
+    out, i = [], 0
+    while i < len(body):
+        cls, tgt = body[i] >> 4, body[i] & 15
+        counts = body[i + 1:i + 17]
+        n = sum(counts)
+        out.append((cls, tgt, bytes(counts), bytes(body[i + 17:i + 17 + n])))
+        i += 17 + n
+    return out
+
+
+def parse_dqt(body: bytes):
+    out, i = [], 0
+    while i < len(body):
+        prec, tgt = body[i] >> 4, body[i] & 15
+        assert prec == 0
+        out.append((tgt, list(body[i + 1:i + 65])))
+        i += 65
+    return out
