@@ -1,0 +1,598 @@
+// api.cu -- the C-ABI of libjpeg_sm100.so (include/jpeg_sm100.h): lifecycle, layer B (device pointers) and
+// layer A (host buffers; what the Swift shim binds).  There is no CPU fallback anywhere in this library.
+#include "common.cuh"
+
+// kernels' launchers (idct.cu, color.cu, huffman_decode.cu, fdct.cu, encode.cu)
+int jpeg_idct_launch_u8(jpeg_sm100_ctx *, const int16_t *, uint32_t, uint32_t, uint32_t, const float[64], uint8_t *, uint64_t);
+int jpeg_idct_launch_u16(jpeg_sm100_ctx *, const int16_t *, uint32_t, uint32_t, uint32_t, const float[64], int, uint16_t *, uint64_t);
+int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *, const jpeg_sm100_dev_planar *, uint32_t, uint32_t, int, uint8_t *);
+int jpeg_color_interleave(jpeg_sm100_ctx *, const jpeg_sm100_dev_planar *, uint32_t, uint32_t, int, uint16_t *);
+int jpeg_color_unpack(jpeg_sm100_ctx *, const uint16_t *, uint64_t, int, uint8_t *, bool);
+int jpeg_color_pack_rgb(jpeg_sm100_ctx *, const uint8_t *, uint64_t, int, uint16_t *);
+int jpeg_color_decompose(jpeg_sm100_ctx *, const void *, bool, uint32_t, uint32_t, const jpeg_sm100_dev_planar *);
+int jpeg_huffman_decode_scan(jpeg_sm100_ctx *, const jpeg_sm100_scan_desc *, const uint8_t *, const uint64_t *, uint32_t,
+                             uint64_t, int, const jpeg_sm100_huff_table *, int, const jpeg_sm100_dev_spectral *, int32_t *);
+int jpeg_fdct_launch(jpeg_sm100_ctx *, const void *, int, uint64_t, uint32_t, uint32_t, uint32_t, const float[64], int,
+                     int16_t *, uint64_t);
+int jpeg_huffman_encode_scan(jpeg_sm100_ctx *, const jpeg_sm100_scan_desc *, const jpeg_sm100_dev_spectral *, uint64_t,
+                             jpeg_sm100_huff_table *, uint8_t *, uint64_t, uint64_t *, uint64_t *h_needed);
+
+// =====================================================================================================================
+// lifecycle
+// =====================================================================================================================
+JPEG_API int jpeg_sm100_abi_version(void) { return JPEG_SM100_ABI_VERSION; }
+
+static int create_common(int device, cudaStream_t borrowed, bool borrow, jpeg_sm100_ctx **out)
+{
+    if (!out) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return JPEG_SM100_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JPEG_SM100_ERR_CUDA;
+    if (prop.major != 10) return JPEG_SM100_ERR_CUDA;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return JPEG_SM100_ERR_CUDA;
+    jpeg_sm100_ctx *ctx = new jpeg_sm100_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (borrow) {
+        ctx->stream = borrowed;
+        ctx->owns_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return JPEG_SM100_ERR_CUDA;
+        }
+        ctx->owns_stream = true;
+    }
+    *out = ctx;
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_create(int device, jpeg_sm100_ctx **out) { return create_common(device, nullptr, false, out); }
+JPEG_API int jpeg_sm100_create_on_stream(int device, void *stream, jpeg_sm100_ctx **out)
+{
+    return create_common(device, reinterpret_cast<cudaStream_t>(stream), true, out);
+}
+JPEG_API void jpeg_sm100_destroy(jpeg_sm100_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->scratch)
+        if (b.ptr) cudaFree(b.ptr);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+JPEG_API int jpeg_sm100_sync(jpeg_sm100_ctx *ctx)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+JPEG_API const char *jpeg_sm100_error_string(int code)
+{
+    switch (code) {
+    case JPEG_SM100_OK: return "ok";
+    case JPEG_SM100_ERR_TRUNCATED_ECS: return "truncatedEntropyCodedSegment";
+    case JPEG_SM100_ERR_INVALID_COMPOSITE_VALUE: return "invalidCompositeValue";
+    case JPEG_SM100_ERR_INVALID_BLOCK_RUN: return "invalidCompositeBlockRun";
+    case JPEG_SM100_ERR_UNDEFINED_DC: return "undefinedScanHuffmanDCReference";
+    case JPEG_SM100_ERR_UNDEFINED_AC: return "undefinedScanHuffmanACReference";
+    case JPEG_SM100_ERR_PRECONDITION: return "precondition failure in the reference";
+    case JPEG_SM100_ERR_INVALID_HUFFMAN: return "invalidHuffmanTable";
+    case JPEG_SM100_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case JPEG_SM100_ERR_UNSUPPORTED: return "unsupported";
+    case JPEG_SM100_ERR_NO_MEMORY: return "out of memory / buffer too small";
+    case JPEG_SM100_ERR_CUDA: return "CUDA error (no sm_100 device, or a runtime failure)";
+    default: return "unknown";
+    }
+}
+JPEG_API const char *jpeg_sm100_last_cuda_error(jpeg_sm100_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+JPEG_API uint64_t    jpeg_sm100_launch_count(jpeg_sm100_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+JPEG_API int jpeg_sm100_malloc(jpeg_sm100_ctx *ctx, size_t bytes, void **p)
+{
+    if (!ctx || !p) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMalloc(p, bytes ? bytes : 1));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_free(jpeg_sm100_ctx *ctx, void *p)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaFree(p));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_malloc_host(jpeg_sm100_ctx *ctx, size_t bytes, void **p)
+{
+    if (!ctx || !p) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMallocHost(p, bytes ? bytes : 1));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_free_host(jpeg_sm100_ctx *ctx, void *p)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    CU_TRY(ctx, cudaFreeHost(p));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_upload(jpeg_sm100_ctx *ctx, void *d, const void *h, size_t n)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ctx->stream));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_download(jpeg_sm100_ctx *ctx, void *h, const void *d, size_t n)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_memset(jpeg_sm100_ctx *ctx, void *d, int v, size_t n)
+{
+    if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n) CU_TRY(ctx, cudaMemsetAsync(d, v, n, ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+// =====================================================================================================================
+// layer B
+// =====================================================================================================================
+#define REQUIRE_CTX(ctx)                                                                                             \
+    do {                                                                                                             \
+        if (!(ctx)) return JPEG_SM100_ERR_INVALID_ARGUMENT;                                                          \
+        CU_TRY((ctx), cudaSetDevice((ctx)->device));                                                                 \
+    } while (0)
+
+JPEG_API int jpeg_sm100_dev_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
+                                        const uint64_t *d_ecs_offsets, uint32_t n_ecs, uint64_t interval, int extend,
+                                        const jpeg_sm100_huff_table *tables, int tables_shared,
+                                        const jpeg_sm100_dev_spectral *spectral, int32_t *d_status)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_huffman_decode_scan(ctx, scan, d_ecs, d_ecs_offsets, n_ecs, interval, extend, tables, tables_shared,
+                                    spectral, d_status);
+}
+
+JPEG_API int jpeg_sm100_dev_idct(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *sp, const uint16_t *quanta,
+                                 int precision, const jpeg_sm100_dev_planar *pl)
+{
+    REQUIRE_CTX(ctx);
+    if (!sp || !pl || !quanta || sp->n_planes != pl->n_planes || sp->n_images != pl->n_images || sp->n_planes > 4)
+        return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (precision < 1 || precision > 16 || (pl->sample_bytes == 1 && precision != 8)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < sp->n_planes; ++p) {
+        const auto &s = sp->plane[p];
+        const auto &d = pl->plane[p];
+        if (s.units_x != d.units_x || s.units_y != d.units_y || s.units_x < 0 || s.units_y < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        float q[64];
+        modulate_quanta(quanta + 64 * p, 0.125f, q);
+        const uint64_t blocks = (uint64_t) s.units_x * s.units_y;
+        // images contiguous in both buffers => one launch for the whole batch; otherwise one launch per image
+        const bool contiguous = sp->n_images == 1 || s.image_stride == blocks * 64;
+        const uint32_t launches = contiguous ? 1 : sp->n_images;
+        for (uint32_t i = 0; i < launches; ++i) {
+            const int16_t *src = s.coef + (size_t) i * s.image_stride;
+            const uint32_t n = contiguous ? sp->n_images : 1;
+            if (pl->sample_bytes == 1)
+                J_TRY(jpeg_idct_launch_u8(ctx, src, n, s.units_x, s.units_y, q,
+                                          reinterpret_cast<uint8_t *>(d.samples) + (size_t) i * d.image_stride, d.image_stride));
+            else
+                J_TRY(jpeg_idct_launch_u16(ctx, src, n, s.units_x, s.units_y, q, precision,
+                                           reinterpret_cast<uint16_t *>(d.samples) + (size_t) i * d.image_stride, d.image_stride));
+        }
+    }
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_dev_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy,
+                                           int cosited, uint8_t *d_rgb)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_planar_to_rgb8(ctx, pl, sx, sy, cosited, d_rgb);
+}
+JPEG_API int jpeg_sm100_dev_interleave(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy,
+                                       int cosited, uint16_t *d_out)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_interleave(ctx, pl, sx, sy, cosited, d_out);
+}
+JPEG_API int jpeg_sm100_dev_unpack_rgb8(jpeg_sm100_ctx *ctx, const uint16_t *d_il, uint64_t n, int arity, uint8_t *d_rgb)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_unpack(ctx, d_il, n, arity, d_rgb, true);
+}
+JPEG_API int jpeg_sm100_dev_unpack_ycc8(jpeg_sm100_ctx *ctx, const uint16_t *d_il, uint64_t n, int arity, uint8_t *d_ycc)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_unpack(ctx, d_il, n, arity, d_ycc, false);
+}
+JPEG_API int jpeg_sm100_dev_rgb8_to_planar(jpeg_sm100_ctx *ctx, const uint8_t *d_rgb, uint32_t sx, uint32_t sy,
+                                           const jpeg_sm100_dev_planar *pl)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_decompose(ctx, d_rgb, true, sx, sy, pl);
+}
+JPEG_API int jpeg_sm100_dev_pack_rgb8(jpeg_sm100_ctx *ctx, const uint8_t *d_rgb, uint64_t n, int arity, uint16_t *d_il)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_pack_rgb(ctx, d_rgb, n, arity, d_il);
+}
+JPEG_API int jpeg_sm100_dev_decompose(jpeg_sm100_ctx *ctx, const uint16_t *d_il, uint32_t sx, uint32_t sy,
+                                      const jpeg_sm100_dev_planar *pl)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_color_decompose(ctx, d_il, false, sx, sy, pl);
+}
+JPEG_API int jpeg_sm100_dev_fdct(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *pl, const uint16_t *quanta, int precision,
+                                 const jpeg_sm100_dev_spectral *sp)
+{
+    REQUIRE_CTX(ctx);
+    if (!sp || !pl || !quanta || sp->n_planes != pl->n_planes || sp->n_images != pl->n_images || sp->n_planes > 4)
+        return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (precision < 1 || precision > 16 || (pl->sample_bytes == 1 && precision > 8)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < sp->n_planes; ++p) {
+        const auto &d = sp->plane[p];
+        const auto &s = pl->plane[p];
+        if (s.units_x != d.units_x || s.units_y != d.units_y) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        float q[64];
+        modulate_quanta(quanta + 64 * p, 8.0f, q);
+        J_TRY(jpeg_fdct_launch(ctx, s.samples, pl->sample_bytes, s.image_stride, sp->n_images, s.units_x, s.units_y, q,
+                               precision, d.coef, d.image_stride));
+    }
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_dev_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan,
+                                        const jpeg_sm100_dev_spectral *sp, uint64_t interval_mcus,
+                                        jpeg_sm100_huff_table *tables_out, uint8_t *d_ecs, uint64_t ecs_image_stride,
+                                        uint64_t *d_ecs_len)
+{
+    REQUIRE_CTX(ctx);
+    return jpeg_huffman_encode_scan(ctx, scan, sp, interval_mcus, tables_out, d_ecs, ecs_image_stride, d_ecs_len, nullptr);
+}
+
+// =====================================================================================================================
+// layer A: host buffers, synchronous.  scratch slots 0..7 belong to this file.
+// =====================================================================================================================
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct PlaneSet {
+    jpeg_sm100_dev_spectral sp;
+    size_t                  bytes[4];
+};
+
+// uploads n planes of coefficients into one scratch allocation
+int upload_spectral(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_plane_i16 *planes, uint32_t n, const int32_t *factors,
+                    PlaneSet &out)
+{
+    if (n < 1 || n > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    memset(&out, 0, sizeof out);
+    size_t total = 0, off[4];
+    for (uint32_t p = 0; p < n; ++p) {
+        if (planes[p].units_x < 0 || planes[p].units_y < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        out.bytes[p] = (size_t) 128 * planes[p].units_x * planes[p].units_y;
+        off[p] = total;
+        total += align_up(out.bytes[p], 1024);
+    }
+    void *base = nullptr;
+    J_TRY(scratch_reserve(ctx, slot, total + 1024, &base));
+    out.sp.n_images = 1;
+    out.sp.n_planes = n;
+    for (uint32_t p = 0; p < n; ++p) {
+        out.sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(base) + off[p]);
+        out.sp.plane[p].image_stride = out.bytes[p] / 2;
+        out.sp.plane[p].units_x = planes[p].units_x;
+        out.sp.plane[p].units_y = planes[p].units_y;
+        out.sp.plane[p].factor_x = factors ? factors[2 * p] : 1;
+        out.sp.plane[p].factor_y = factors ? factors[2 * p + 1] : 1;
+        if (out.bytes[p]) {
+            if (!planes[p].coef) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+            CU_TRY(ctx, cudaMemcpyAsync(out.sp.plane[p].coef, planes[p].coef, out.bytes[p], cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    return JPEG_SM100_OK;
+}
+
+int alloc_planar(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_dev_spectral &sp, int sample_bytes,
+                 jpeg_sm100_dev_planar &pl)
+{
+    memset(&pl, 0, sizeof pl);
+    pl.n_images = sp.n_images;
+    pl.n_planes = sp.n_planes;
+    pl.sample_bytes = sample_bytes;
+    size_t total = 0, off[4];
+    for (uint32_t p = 0; p < sp.n_planes; ++p) {
+        off[p] = total;
+        total += align_up((size_t) 64 * sp.plane[p].units_x * sp.plane[p].units_y * sample_bytes * sp.n_images, 1024);
+    }
+    void *base = nullptr;
+    J_TRY(scratch_reserve(ctx, slot, total + 1024, &base));
+    for (uint32_t p = 0; p < sp.n_planes; ++p) {
+        pl.plane[p].samples = reinterpret_cast<uint8_t *>(base) + off[p];
+        pl.plane[p].image_stride = (uint64_t) 64 * sp.plane[p].units_x * sp.plane[p].units_y;
+        pl.plane[p].units_x = sp.plane[p].units_x;
+        pl.plane[p].units_y = sp.plane[p].units_y;
+        pl.plane[p].factor_x = sp.plane[p].factor_x;
+        pl.plane[p].factor_y = sp.plane[p].factor_y;
+    }
+    return JPEG_SM100_OK;
+}
+
+}  // namespace
+
+JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *ecs_concat,
+                                    const uint64_t *ecs_offsets, uint32_t n_ecs, uint64_t interval, int extend,
+                                    const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4],
+                                    jpeg_sm100_plane_i16 *planes, uint32_t n_planes)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !planes || !dc || !ac || (n_ecs && (!ecs_offsets))) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n_ecs == 0) return JPEG_SM100_OK;
+    // without DRI the reference's stride yields one element: only the first ECS is consumed (decode.swift:3500)
+    if (interval == JPEG_SM100_INTERVAL_NONE) n_ecs = 1;
+    PlaneSet ps;
+    J_TRY(upload_spectral(ctx, 0, planes, n_planes, nullptr, ps));
+    const uint64_t total = ecs_offsets[n_ecs];
+    void          *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr;
+    J_TRY(scratch_reserve(ctx, 1, total + 64, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 2, sizeof(uint64_t) * ((size_t) n_ecs + 1), &d_off));
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_status));
+    if (total) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, ecs_concat, total, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_off, ecs_offsets, sizeof(uint64_t) * ((size_t) n_ecs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    jpeg_sm100_huff_table tables[8];
+    memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
+    memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
+    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off),
+                                   n_ecs, interval, extend, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+    int32_t status = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+    for (uint32_t p = 0; p < n_planes; ++p)
+        if (ps.bytes[p])
+            CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return status;
+}
+
+static int idct_host(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t ux, uint32_t uy, const uint16_t quanta[64],
+                     int precision, void *samples, int sample_bytes)
+{
+    REQUIRE_CTX(ctx);
+    if (!quanta || ((uint64_t) ux * uy && (!coef || !samples))) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_plane_i16 hp = {const_cast<int16_t *>(coef), (int32_t) ux, (int32_t) uy};
+    PlaneSet             ps;
+    J_TRY(upload_spectral(ctx, 0, &hp, 1, nullptr, ps));
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, ps.sp, sample_bytes, pl));
+    J_TRY(jpeg_sm100_dev_idct(ctx, &ps.sp, quanta, precision, &pl));
+    const size_t bytes = (size_t) 64 * ux * uy * sample_bytes;
+    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(samples, pl.plane[0].samples, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_idct(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t ux, uint32_t uy, const uint16_t quanta[64],
+                             int precision, uint16_t *samples)
+{
+    return idct_host(ctx, coef, ux, uy, quanta, precision, samples, 2);
+}
+JPEG_API int jpeg_sm100_idct_u8(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t ux, uint32_t uy,
+                                const uint16_t quanta[64], uint8_t *samples)
+{
+    return idct_host(ctx, coef, ux, uy, quanta, 8, samples, 1);
+}
+
+// uploads host uint16 planes; returns a device planar view
+static int upload_planar_u16(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_plane_u16 *planes, uint32_t n, bool copy,
+                             jpeg_sm100_dev_planar &pl)
+{
+    if (n < 1 || n > 4 || !planes) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_dev_spectral geo;
+    memset(&geo, 0, sizeof geo);
+    geo.n_images = 1;
+    geo.n_planes = n;
+    for (uint32_t p = 0; p < n; ++p) {
+        if (planes[p].units_x < 0 || planes[p].units_y < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        geo.plane[p].units_x = planes[p].units_x;
+        geo.plane[p].units_y = planes[p].units_y;
+        geo.plane[p].factor_x = planes[p].factor_x;
+        geo.plane[p].factor_y = planes[p].factor_y;
+    }
+    J_TRY(alloc_planar(ctx, slot, geo, 2, pl));
+    if (copy)
+        for (uint32_t p = 0; p < n; ++p) {
+            const size_t bytes = (size_t) 128 * planes[p].units_x * planes[p].units_y;
+            if (bytes) CU_TRY(ctx, cudaMemcpyAsync(pl.plane[p].samples, planes[p].samples, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_interleave(jpeg_sm100_ctx *ctx, const jpeg_sm100_plane_u16 *planes, uint32_t n, uint32_t sx,
+                                   uint32_t sy, int cosited, uint16_t *out)
+{
+    REQUIRE_CTX(ctx);
+    jpeg_sm100_dev_planar pl;
+    J_TRY(upload_planar_u16(ctx, 4, planes, n, true, pl));
+    const size_t bytes = (size_t) sx * sy * n * 2;
+    void        *d_out = nullptr;
+    J_TRY(scratch_reserve(ctx, 5, bytes + 64, &d_out));
+    J_TRY(jpeg_color_interleave(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint16_t *>(d_out)));
+    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+static int unpack_host(jpeg_sm100_ctx *ctx, const uint16_t *il, uint64_t n_px, int arity, uint8_t *out, bool to_rgb)
+{
+    REQUIRE_CTX(ctx);
+    if (arity != 1 && arity != 3) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    void *d_il = nullptr, *d_out = nullptr;
+    J_TRY(scratch_reserve(ctx, 5, n_px * arity * 2 + 64, &d_il));
+    J_TRY(scratch_reserve(ctx, 6, n_px * 3 + 64, &d_out));
+    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(d_il, il, n_px * arity * 2, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(jpeg_color_unpack(ctx, reinterpret_cast<uint16_t *>(d_il), n_px, arity, reinterpret_cast<uint8_t *>(d_out), to_rgb));
+    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n_px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+JPEG_API int jpeg_sm100_unpack_rgb8(jpeg_sm100_ctx *ctx, const uint16_t *il, uint64_t n, int arity, uint8_t *rgb)
+{
+    return unpack_host(ctx, il, n, arity, rgb, true);
+}
+JPEG_API int jpeg_sm100_unpack_ycc8(jpeg_sm100_ctx *ctx, const uint16_t *il, uint64_t n, int arity, uint8_t *ycc)
+{
+    return unpack_host(ctx, il, n, arity, ycc, false);
+}
+
+JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_plane_i16 *planes, uint32_t n,
+                                         const uint16_t *quanta, const int32_t *factors, uint32_t sx, uint32_t sy,
+                                         int cosited, uint8_t *rgb)
+{
+    REQUIRE_CTX(ctx);
+    if (!planes || !quanta || !factors || (n != 1 && n != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    PlaneSet ps;
+    J_TRY(upload_spectral(ctx, 0, planes, n, factors, ps));
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, ps.sp, 1, pl));
+    J_TRY(jpeg_sm100_dev_idct(ctx, &ps.sp, quanta, 8, &pl));
+    const size_t bytes = (size_t) sx * sy * 3;
+    void        *d_rgb = nullptr;
+    J_TRY(scratch_reserve(ctx, 6, bytes + 64, &d_rgb));
+    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
+    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+// ---- encode ----
+JPEG_API int jpeg_sm100_pack_rgb8(jpeg_sm100_ctx *ctx, const uint8_t *rgb, uint64_t n_px, int arity, uint16_t *il)
+{
+    REQUIRE_CTX(ctx);
+    if (arity != 1 && arity != 3) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    void *d_rgb = nullptr, *d_il = nullptr;
+    J_TRY(scratch_reserve(ctx, 6, n_px * 3 + 64, &d_rgb));
+    J_TRY(scratch_reserve(ctx, 5, n_px * arity * 2 + 64, &d_il));
+    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, n_px * 3, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(jpeg_color_pack_rgb(ctx, reinterpret_cast<uint8_t *>(d_rgb), n_px, arity, reinterpret_cast<uint16_t *>(d_il)));
+    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(il, d_il, n_px * arity * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_decompose(jpeg_sm100_ctx *ctx, const uint16_t *il, uint32_t sx, uint32_t sy,
+                                  jpeg_sm100_plane_u16 *planes, uint32_t n)
+{
+    REQUIRE_CTX(ctx);
+    jpeg_sm100_dev_planar pl;
+    J_TRY(upload_planar_u16(ctx, 4, planes, n, false, pl));
+    const size_t bytes = (size_t) sx * sy * n * 2;
+    void        *d_il = nullptr;
+    J_TRY(scratch_reserve(ctx, 5, bytes + 64, &d_il));
+    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(d_il, il, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(jpeg_color_decompose(ctx, d_il, false, sx, sy, &pl));
+    for (uint32_t p = 0; p < n; ++p) {
+        const size_t pb = (size_t) 128 * planes[p].units_x * planes[p].units_y;
+        if (pb) CU_TRY(ctx, cudaMemcpyAsync(planes[p].samples, pl.plane[p].samples, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_fdct(jpeg_sm100_ctx *ctx, const uint16_t *samples, uint32_t ux, uint32_t uy,
+                             const uint16_t quanta[64], int precision, int16_t *coef)
+{
+    REQUIRE_CTX(ctx);
+    if (!quanta || ((uint64_t) ux * uy && (!samples || !coef))) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_plane_u16  hp = {const_cast<uint16_t *>(samples), (int32_t) ux, (int32_t) uy, 1, 1};
+    jpeg_sm100_dev_planar pl;
+    J_TRY(upload_planar_u16(ctx, 4, &hp, 1, true, pl));
+    jpeg_sm100_plane_i16 geo = {nullptr, (int32_t) ux, (int32_t) uy};
+    PlaneSet             ps;
+    // reuse upload_spectral for the allocation only (no source pointer => nothing copied when empty)
+    memset(&ps, 0, sizeof ps);
+    {
+        void *base = nullptr;
+        ps.bytes[0] = (size_t) 128 * ux * uy;
+        J_TRY(scratch_reserve(ctx, 0, ps.bytes[0] + 1024, &base));
+        ps.sp.n_images = 1;
+        ps.sp.n_planes = 1;
+        ps.sp.plane[0].coef = reinterpret_cast<int16_t *>(base);
+        ps.sp.plane[0].image_stride = ps.bytes[0] / 2;
+        ps.sp.plane[0].units_x = geo.units_x;
+        ps.sp.plane[0].units_y = geo.units_y;
+        ps.sp.plane[0].factor_x = ps.sp.plane[0].factor_y = 1;
+    }
+    J_TRY(jpeg_sm100_dev_fdct(ctx, &pl, quanta, precision, &ps.sp));
+    if (ps.bytes[0]) CU_TRY(ctx, cudaMemcpyAsync(coef, ps.sp.plane[0].coef, ps.bytes[0], cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_rgb8_to_spectral(jpeg_sm100_ctx *ctx, const uint8_t *rgb, uint32_t sx, uint32_t sy,
+                                         jpeg_sm100_plane_i16 *planes, uint32_t n, const uint16_t *quanta,
+                                         const int32_t *factors)
+{
+    REQUIRE_CTX(ctx);
+    if (!planes || !quanta || !factors || (n != 1 && n != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    // device coefficient planes (no upload), 8-bit sample planes, RGB input
+    PlaneSet ps;
+    memset(&ps, 0, sizeof ps);
+    size_t total = 0, off[4];
+    for (uint32_t p = 0; p < n; ++p) {
+        ps.bytes[p] = (size_t) 128 * planes[p].units_x * planes[p].units_y;
+        off[p] = total;
+        total += align_up(ps.bytes[p], 1024);
+    }
+    void *base = nullptr;
+    J_TRY(scratch_reserve(ctx, 0, total + 1024, &base));
+    ps.sp.n_images = 1;
+    ps.sp.n_planes = n;
+    for (uint32_t p = 0; p < n; ++p) {
+        ps.sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(base) + off[p]);
+        ps.sp.plane[p].image_stride = ps.bytes[p] / 2;
+        ps.sp.plane[p].units_x = planes[p].units_x;
+        ps.sp.plane[p].units_y = planes[p].units_y;
+        ps.sp.plane[p].factor_x = factors[2 * p];
+        ps.sp.plane[p].factor_y = factors[2 * p + 1];
+    }
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, ps.sp, 1, pl));
+    const size_t rgb_bytes = (size_t) sx * sy * 3;
+    void        *d_rgb = nullptr;
+    J_TRY(scratch_reserve(ctx, 6, rgb_bytes + 64, &d_rgb));
+    if (rgb_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, rgb_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(jpeg_color_decompose(ctx, d_rgb, true, sx, sy, &pl));
+    J_TRY(jpeg_sm100_dev_fdct(ctx, &pl, quanta, 8, &ps.sp));
+    for (uint32_t p = 0; p < n; ++p)
+        if (ps.bytes[p]) CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const jpeg_sm100_plane_i16 *planes,
+                                    uint32_t n_planes, uint64_t interval_mcus, jpeg_sm100_huff_table dc_out[4],
+                                    jpeg_sm100_huff_table ac_out[4], uint8_t *ecs, uint64_t ecs_capacity, uint64_t *ecs_len)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !planes || !dc_out || !ac_out || !ecs_len) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    PlaneSet ps;
+    J_TRY(upload_spectral(ctx, 0, planes, n_planes, nullptr, ps));
+    // worst case: every coefficient costs 16 + 16 bits, doubled by stuffing, plus RST markers
+    uint64_t blocks = 0;
+    for (uint32_t p = 0; p < n_planes; ++p) blocks += (uint64_t) (planes[p].units_x + 4) * (planes[p].units_y + 4);
+    const uint64_t cap = blocks * 64 * 8 + 4096;
+    void          *d_ecs = nullptr, *d_len = nullptr;
+    J_TRY(scratch_reserve(ctx, 1, cap, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_len));
+    jpeg_sm100_huff_table tables[8];
+    uint64_t              needed = 0;
+    J_TRY(jpeg_huffman_encode_scan(ctx, scan, &ps.sp, interval_mcus, tables, reinterpret_cast<uint8_t *>(d_ecs), cap,
+                                   reinterpret_cast<uint64_t *>(d_len), &needed));
+    memcpy(dc_out, tables, sizeof(jpeg_sm100_huff_table) * 4);
+    memcpy(ac_out, tables + 4, sizeof(jpeg_sm100_huff_table) * 4);
+    *ecs_len = needed;
+    if (needed > ecs_capacity) return JPEG_SM100_ERR_NO_MEMORY;
+    if (needed) CU_TRY(ctx, cudaMemcpyAsync(ecs, d_ecs, needed, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}

@@ -1,0 +1,417 @@
+// color.cu -- K2 (upsample + interleave + YCbCr->RGB + pack) and K4 (RGB->YCbCr + box downsample).
+//
+// Replaces Planar.interleaved(cosite:) (decode.swift:4182-4276), Color.unpack for RGB / YCbCr
+// (jpeg.swift:441-453, 493-572), RGB.pack (jpeg.swift:463-478, 584-599) and Rectangular.decomposed()
+// (encode.swift:389-425).  All arithmetic is the reference's binary32 sequence, never contracted.
+#include "common.cuh"
+
+namespace {
+
+struct PlanarView {
+    const void *samples[4];
+    uint64_t    image_stride[4];  // samples
+    int32_t     width[4];         // 8 * units_x
+    int32_t     height[4];        // 8 * units_y
+    int32_t     fx[4], fy[4];
+    int32_t     n_planes;
+    int32_t     scale_x, scale_y;
+    int32_t     size_x, size_y;
+    int32_t     cosited;
+    uint32_t    n_images;
+};
+
+template <typename T>
+__device__ __forceinline__ float sample_at(const T *pl, int w, int x, int y)
+{
+    return (float) pl[(size_t) w * y + x];
+}
+
+// decode.swift:4236-4265: one output sample of plane p at pixel (x, y), as the UInt16 the reference stores
+template <typename T>
+__device__ __forceinline__ uint32_t upsampled(const PlanarView &V, int p, uint32_t img, int x, int y)
+{
+    const T *pl = reinterpret_cast<const T *>(V.samples[p]) + (size_t) img * V.image_stride[p];
+    const int w = V.width[p];
+    if (V.n_planes == 1 || (V.fx[p] == V.scale_x && V.fy[p] == V.scale_y)) return (uint32_t) pl[(size_t) w * y + x];
+    int ax, ay, bx, by, cx, cy;
+    if (V.cosited) {
+        ax = ay = 0;
+        bx = V.fx[p], by = V.fy[p];
+        cx = V.scale_x, cy = V.scale_y;
+    } else {
+        ax = V.fx[p] - V.scale_x, ay = V.fy[p] - V.scale_y;
+        bx = 2 * V.fx[p], by = 2 * V.fy[p];
+        cx = 2 * V.scale_x, cy = 2 * V.scale_y;
+    }
+    const int dx = w - 1, dy = V.height[p] - 1;
+    const int nx = ax + bx * x, ny = ay + by * y;
+    const int ix = nx / cx, rx = nx - ix * cx;  // truncating, like quotientAndRemainder
+    const int iy = ny / cy, ry = ny - iy * cy;
+    const int jx = min(ix + 1, dx), jy = min(iy + 1, dy);
+    const float tx = fmaxf(0.0f, fminf(__fdiv_rn((float) rx, (float) cx), 1.0f));
+    const float ty = fmaxf(0.0f, fminf(__fdiv_rn((float) ry, (float) cy), 1.0f));
+    const float u00 = sample_at(pl, w, ix, iy), u01 = sample_at(pl, w, jx, iy);
+    const float u10 = sample_at(pl, w, ix, jy), u11 = sample_at(pl, w, jx, jy);
+    const float v0 = fadd(fmul(u00, fsub(1.0f, tx)), fmul(u01, tx));
+    const float v1 = fadd(fmul(u10, fsub(1.0f, tx)), fmul(u11, tx));
+    const float r = fadd(fmul(v0, fsub(1.0f, ty)), fmul(v1, ty));
+    return (uint32_t) __float2int_rz(roundf(r));  // .rounded(): to nearest, ties away from zero
+}
+
+// jpeg.swift:441-453  YCbCr.rgb
+__device__ __forceinline__ void ycc_to_rgb(uint32_t y8, uint32_t cb8, uint32_t cr8, float &r, float &g, float &b)
+{
+    const float Y = (float) (y8 & 0xffu), db = fsub((float) (cb8 & 0xffu), 128.0f),
+                dr = fsub((float) (cr8 & 0xffu), 128.0f);
+    r = fadd(fadd(Y, fmul(0.00000f, db)), fmul(1.40200f, dr));
+    g = fadd(fadd(Y, fmul(-0.34414f, db)), fmul(-0.71414f, dr));
+    b = fadd(fadd(Y, fmul(1.77200f, db)), fmul(0.00000f, dr));
+}
+__device__ __forceinline__ uint32_t clamp_u8(float v) { return (uint32_t) __float2int_rz(fmaxf(0.0f, fminf(v, 255.0f))); }
+
+// ---- generic planes -> RGB8: any sampling factors, centred or co-sited; 4 pixels per thread -------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_planar_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
+{
+    const uint32_t groups_x = (uint32_t) (V.size_x + 3) / 4;
+    const uint64_t per_image = (uint64_t) groups_x * V.size_y;
+    const uint64_t total = per_image * V.n_images;
+    const bool     word_rows = (V.size_x & 3) == 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      y = (int) (rem / groups_x);
+        const int      x0 = (int) (rem - (uint32_t) y * groups_x) * 4;
+        uint8_t       *dst = rgb + ((size_t) img * V.size_y + y) * (size_t) V.size_x * 3 + (size_t) x0 * 3;
+        uint32_t       out[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = min(x0 + j, V.size_x - 1);
+            uint32_t  Y = upsampled<T>(V, 0, img, x, y), cb = 128, cr = 128;
+            if (V.n_planes == 3) {
+                cb = upsampled<T>(V, 1, img, x, y);
+                cr = upsampled<T>(V, 2, img, x, y);
+            }
+            float r, g, b;
+            ycc_to_rgb(Y, cb, cr, r, g, b);
+            out[3 * j] = clamp_u8(r);
+            out[3 * j + 1] = clamp_u8(g);
+            out[3 * j + 2] = clamp_u8(b);
+        }
+        if (word_rows) {
+            uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+            d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+            d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24);
+            d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | (out[11] << 24);
+        } else {
+            const int n = min(4, V.size_x - x0) * 3;
+            for (int k = 0; k < n; ++k) dst[k] = (uint8_t) out[k];
+        }
+    }
+}
+
+// ---- fast path: 4:2:0, centred, 8-bit planes -> RGB8 -------------------------------------------------------------
+// Thread = 8 x 2 pixels (columns 8t..8t+7 of rows 2r+1, 2r+2; row 0 handled by r = -1).  For these factors every
+// interpolation weight is a multiple of 1/4, every float product/sum in decode.swift:4258-4264 is exact, and
+// `.rounded()` of the exact value equals (9a + 3b + 3c + d + 8) >> 4 -- integer arithmetic, bit-identical.
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+__global__ void __launch_bounds__(128)
+k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
+{
+    const int      W = V.size_x, H = V.size_y;
+    const int      groups_x = (W + 7) / 8;
+    const int      row_pairs = H / 2 + 1;  // r = -1 .. ceil((H-1)/2)-1
+    const uint64_t per_image = (uint64_t) groups_x * row_pairs;
+    const uint64_t total = per_image * V.n_images;
+    const int      yw = V.width[0], cw = V.width[1], ch = V.height[1];
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      rp = (int) (rem / groups_x);
+        const int      gx = (int) (rem - (uint32_t) rp * groups_x);
+        const int      r = rp - 1;         // chroma row pair (r, r+1) feeds luma rows 2r+1, 2r+2
+        const int      x0 = 8 * gx, c0 = 4 * gx;
+        const uint8_t *Yp = reinterpret_cast<const uint8_t *>(V.samples[0]) + (size_t) img * V.image_stride[0];
+        const uint8_t *Cp[2] = {reinterpret_cast<const uint8_t *>(V.samples[1]) + (size_t) img * V.image_stride[1],
+                                reinterpret_cast<const uint8_t *>(V.samples[2]) + (size_t) img * V.image_stride[2]};
+        const int ra = max(r, 0), rb = min(r + 1, ch - 1);
+        // horizontally interpolated chroma, scaled by 4, for the 8 columns, rows ra and rb
+        int hc[2][2][8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint8_t *row = Cp[c] + (size_t) cw * (rr ? rb : ra);
+                const uint32_t mid = *reinterpret_cast<const uint32_t *>(row + c0);  // chroma c0..c0+3 (planes are padded to 8)
+                const int      left = row[max(c0 - 1, 0)];
+                const int      right = row[min(c0 + 4, cw - 1)];
+                int            s[6] = {left, (int) byte_of(mid, 0), (int) byte_of(mid, 1), (int) byte_of(mid, 2),
+                                       (int) byte_of(mid, 3), right};
+                // pixel x = 8g + j: even x = 2m uses (c[m-1], c[m]) weights (1, 3); odd x = 2m+1 uses (c[m], c[m+1]) weights (3, 1)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = j >> 1;  // chroma index relative to c0
+                    hc[c][rr][j] = (j & 1) ? 3 * s[m + 1] + s[m + 2] : s[m] + 3 * s[m + 1];
+                }
+                if (x0 == 0) hc[c][rr][0] = 4 * s[1];  // x = 0: t clamps to 0 -> u[0] alone (decode.swift:4250)
+            }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int y = 2 * r + 1 + k;
+            if (y < 0 || y >= H) continue;
+            // vertical weights: row 2r+1 -> (3, 1), row 2r+2 -> (1, 3); for y = 0 (r = -1) both rows are c[0],
+            // which reproduces the reference's t = 0 clamp; at the bottom rb clamps to the padded plane edge
+            const int wa = (k == 0) ? 3 : 1, wb = 4 - wa;
+            const uint2 yy = *reinterpret_cast<const uint2 *>(Yp + (size_t) yw * y + x0);
+            uint32_t    out[24];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t Y = byte_of(j < 4 ? yy.x : yy.y, j & 3);
+                const uint32_t cb = (uint32_t) (wa * hc[0][0][j] + wb * hc[0][1][j] + 8) >> 4;
+                const uint32_t cr = (uint32_t) (wa * hc[1][0][j] + wb * hc[1][1][j] + 8) >> 4;
+                float rr_, gg_, bb_;
+                ycc_to_rgb(Y, cb, cr, rr_, gg_, bb_);
+                out[3 * j] = clamp_u8(rr_);
+                out[3 * j + 1] = clamp_u8(gg_);
+                out[3 * j + 2] = clamp_u8(bb_);
+            }
+            uint8_t *dst = rgb + ((size_t) img * H + y) * (size_t) W * 3 + (size_t) x0 * 3;
+            if ((W & 7) == 0) {
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                    d32[q] = out[4 * q] | (out[4 * q + 1] << 8) | (out[4 * q + 2] << 16) | (out[4 * q + 3] << 24);
+            } else {
+                const int n = min(8, W - x0) * 3;
+                for (int q = 0; q < n; ++q) dst[q] = (uint8_t) out[q];
+            }
+        }
+    }
+}
+
+// ---- planes -> interleaved uint16 (Rectangular.values) ------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_interleave(const __grid_constant__ PlanarView V, uint16_t *__restrict__ out)
+{
+    const uint64_t per_image = (uint64_t) V.size_x * V.size_y;
+    const uint64_t total = per_image * V.n_images;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      y = (int) (rem / (uint32_t) V.size_x), x = (int) (rem - (uint32_t) y * V.size_x);
+        for (int p = 0; p < V.n_planes; ++p) out[i * V.n_planes + p] = (uint16_t) upsampled<T>(V, p, img, x, y);
+    }
+}
+
+// jpeg.swift:551-572 RGB.unpack / 493-513 YCbCr.unpack
+template <bool TO_RGB>
+__global__ void __launch_bounds__(256)
+k_unpack(const uint16_t *__restrict__ il, uint64_t n_px, int arity, uint8_t *__restrict__ out)
+{
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (uint64_t) gridDim.x * blockDim.x) {
+        uint32_t Y, cb = 128, cr = 128;
+        if (arity == 1) Y = il[i];
+        else {
+            Y = il[3 * i];
+            cb = il[3 * i + 1];
+            cr = il[3 * i + 2];
+        }
+        if (TO_RGB) {
+            float r, g, b;
+            ycc_to_rgb(Y, cb, cr, r, g, b);
+            out[3 * i] = (uint8_t) clamp_u8(r);
+            out[3 * i + 1] = (uint8_t) clamp_u8(g);
+            out[3 * i + 2] = (uint8_t) clamp_u8(b);
+        } else {
+            out[3 * i] = (uint8_t) Y;
+            out[3 * i + 1] = (uint8_t) cb;
+            out[3 * i + 2] = (uint8_t) cr;
+        }
+    }
+}
+
+// ---- encode side ---------------------------------------------------------------------------------------------------
+// jpeg.swift:463-478 RGB.ycc
+__device__ __forceinline__ void rgb_to_ycc(uint32_t R8, uint32_t G8, uint32_t B8, uint32_t &y, uint32_t &cb, uint32_t &cr)
+{
+    const float R = (float) R8, G = (float) G8, B = (float) B8;
+    const float fy = fadd(fadd(fadd(0.0f, fmul(0.2990f, R)), fmul(0.5870f, G)), fmul(0.1140f, B));
+    const float fb = fadd(fadd(fadd(128.0f, fmul(-0.1687f, R)), fmul(-0.3313f, G)), fmul(0.5000f, B));
+    const float fr = fadd(fadd(fadd(128.0f, fmul(0.5000f, R)), fmul(-0.4187f, G)), fmul(-0.0813f, B));
+    y = clamp_u8(fy);
+    cb = clamp_u8(fb);
+    cr = clamp_u8(fr);
+}
+
+// jpeg.swift:584-599 RGB.pack
+__global__ void __launch_bounds__(256)
+k_pack_rgb(const uint8_t *__restrict__ rgb, uint64_t n_px, int arity, uint16_t *__restrict__ il)
+{
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (uint64_t) gridDim.x * blockDim.x) {
+        uint32_t y, cb, cr;
+        rgb_to_ycc(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], y, cb, cr);
+        if (arity == 1) il[i] = (uint16_t) y;
+        else {
+            il[3 * i] = (uint16_t) y;
+            il[3 * i + 1] = (uint16_t) cb;
+            il[3 * i + 2] = (uint16_t) cr;
+        }
+    }
+}
+
+// encode.swift:389-425 Rectangular.decomposed(): box filter with edge clamp, truncating mean, over the padded plane.
+// SRC_RGB8: the source is RGB8 and the colour conversion is fused (pack + decomposed in one pass: K4).
+template <typename T, bool SRC_RGB8>
+__global__ void __launch_bounds__(256)
+k_decompose(const void *__restrict__ src, const __grid_constant__ PlanarView V, int p)
+{
+    const int      w = V.width[p], h = V.height[p];
+    const uint64_t per_image = (uint64_t) w * h;
+    const uint64_t total = per_image * V.n_images;
+    const int      rx = V.scale_x / V.fx[p], ry = V.scale_y / V.fy[p];
+    const float    magnitude = (float) (rx * ry);
+    T             *out = reinterpret_cast<T *>(const_cast<void *>(V.samples[p]));
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      y = (int) (rem / (uint32_t) w), x = (int) (rem - (uint32_t) y * w);
+        const int      bx = x * V.scale_x / V.fx[p], by = y * V.scale_y / V.fy[p];
+        int            sum = 0;
+        for (int yy = by; yy < by + ry; ++yy)
+            for (int xx = bx; xx < bx + rx; ++xx) {
+                const int    ix = min(xx, V.size_x - 1), iy = min(yy, V.size_y - 1);
+                const size_t px = ((size_t) img * V.size_y + iy) * V.size_x + ix;
+                if (SRC_RGB8) {
+                    const uint8_t *s = reinterpret_cast<const uint8_t *>(src) + 3 * px;
+                    uint32_t       c[3];
+                    rgb_to_ycc(s[0], s[1], s[2], c[0], c[1], c[2]);
+                    sum += (int) c[V.n_planes == 1 ? 0 : p];
+                } else
+                    sum += reinterpret_cast<const uint16_t *>(src)[px * V.n_planes + p];
+            }
+        out[(size_t) img * V.image_stride[p] + (size_t) w * y + x] = (T) __float2int_rz(__fdiv_rn((float) sum, magnitude));
+    }
+}
+
+int fill_view(const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy, int cosited, PlanarView &V)
+{
+    if (!pl || pl->n_planes < 1 || pl->n_planes > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (pl->sample_bytes != 1 && pl->sample_bytes != 2) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    memset(&V, 0, sizeof V);
+    V.n_planes = (int) pl->n_planes;
+    V.n_images = pl->n_images;
+    V.size_x = (int) sx;
+    V.size_y = (int) sy;
+    V.cosited = cosited ? 1 : 0;
+    for (uint32_t p = 0; p < pl->n_planes; ++p) {
+        V.samples[p] = pl->plane[p].samples;
+        V.image_stride[p] = pl->plane[p].image_stride;
+        V.width[p] = 8 * pl->plane[p].units_x;
+        V.height[p] = 8 * pl->plane[p].units_y;
+        V.fx[p] = pl->plane[p].factor_x;
+        V.fy[p] = pl->plane[p].factor_y;
+        if (V.fx[p] < 1 || V.fy[p] < 1) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        V.scale_x = V.fx[p] > V.scale_x ? V.fx[p] : V.scale_x;
+        V.scale_y = V.fy[p] > V.scale_y ? V.fy[p] : V.scale_y;
+    }
+    return JPEG_SM100_OK;
+}
+
+inline uint32_t grid_for(jpeg_sm100_ctx *ctx, uint64_t work, int block, int per_sm)
+{
+    uint64_t g = (work + block - 1) / block;
+    uint64_t cap = (uint64_t) ctx->sm_count * per_sm;
+    if (g > cap) g = cap;
+    return g ? (uint32_t) g : 1u;
+}
+
+}  // namespace
+
+int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy,
+                              int cosited, uint8_t *d_rgb)
+{
+    PlanarView V;
+    J_TRY(fill_view(pl, sx, sy, cosited, V));
+    if (V.n_planes != 1 && V.n_planes != 3) return JPEG_SM100_ERR_UNSUPPORTED;
+    if ((uint64_t) sx * sy * pl->n_images == 0) return JPEG_SM100_OK;
+    static const bool no_fast = [] {
+        const char *e = getenv("JPEG_SM100_COLOR");
+        return e && strcmp(e, "generic") == 0;
+    }();
+    const bool is420 = V.n_planes == 3 && pl->sample_bytes == 1 && !cosited && V.fx[0] == 2 && V.fy[0] == 2 &&
+                       V.fx[1] == 1 && V.fy[1] == 1 && V.fx[2] == 1 && V.fy[2] == 1 &&
+                       V.width[1] == V.width[2] && V.height[1] == V.height[2] &&
+                       (reinterpret_cast<uintptr_t>(V.samples[0]) & 7) == 0 && (V.image_stride[0] & 7) == 0 &&
+                       (reinterpret_cast<uintptr_t>(V.samples[1]) & 3) == 0 && (V.image_stride[1] & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(V.samples[2]) & 3) == 0 && (V.image_stride[2] & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0;
+    if (is420 && !no_fast) {
+        const uint64_t work = (uint64_t) ((sx + 7) / 8) * (sy / 2 + 1) * pl->n_images;
+        k_ycc420_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
+        LAUNCH_CHECK(ctx);
+        return JPEG_SM100_OK;
+    }
+    const uint64_t work = (uint64_t) ((sx + 3) / 4) * sy * pl->n_images;
+    if (pl->sample_bytes == 1) k_planar_to_rgb8<uint8_t><<<grid_for(ctx, work, 256, 8), 256, 0, ctx->stream>>>(V, d_rgb);
+    else k_planar_to_rgb8<uint16_t><<<grid_for(ctx, work, 256, 8), 256, 0, ctx->stream>>>(V, d_rgb);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}
+
+int jpeg_color_interleave(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy, int cosited,
+                          uint16_t *d_out)
+{
+    PlanarView V;
+    J_TRY(fill_view(pl, sx, sy, cosited, V));
+    const uint64_t work = (uint64_t) sx * sy * pl->n_images;
+    if (work == 0) return JPEG_SM100_OK;
+    if (pl->sample_bytes == 1) k_interleave<uint8_t><<<grid_for(ctx, work, 256, 8), 256, 0, ctx->stream>>>(V, d_out);
+    else k_interleave<uint16_t><<<grid_for(ctx, work, 256, 8), 256, 0, ctx->stream>>>(V, d_out);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}
+
+int jpeg_color_unpack(jpeg_sm100_ctx *ctx, const uint16_t *d_il, uint64_t n_px, int arity, uint8_t *d_out, bool to_rgb)
+{
+    if (arity != 1 && arity != 3) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n_px == 0) return JPEG_SM100_OK;
+    if (to_rgb) k_unpack<true><<<grid_for(ctx, n_px, 256, 8), 256, 0, ctx->stream>>>(d_il, n_px, arity, d_out);
+    else k_unpack<false><<<grid_for(ctx, n_px, 256, 8), 256, 0, ctx->stream>>>(d_il, n_px, arity, d_out);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}
+
+int jpeg_color_pack_rgb(jpeg_sm100_ctx *ctx, const uint8_t *d_rgb, uint64_t n_px, int arity, uint16_t *d_il)
+{
+    if (arity != 1 && arity != 3) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n_px == 0) return JPEG_SM100_OK;
+    k_pack_rgb<<<grid_for(ctx, n_px, 256, 8), 256, 0, ctx->stream>>>(d_rgb, n_px, arity, d_il);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}
+
+// src_is_rgb8: fused colour conversion (K4) else uint16 interleaved source (plain decomposed())
+int jpeg_color_decompose(jpeg_sm100_ctx *ctx, const void *d_src, bool src_is_rgb8, uint32_t sx, uint32_t sy,
+                         const jpeg_sm100_dev_planar *pl)
+{
+    PlanarView V;
+    J_TRY(fill_view(pl, sx, sy, 0, V));
+    if (src_is_rgb8 && V.n_planes != 1 && V.n_planes != 3) return JPEG_SM100_ERR_UNSUPPORTED;
+    for (int p = 0; p < V.n_planes; ++p) {
+        if (V.scale_x % V.fx[p] || V.scale_y % V.fy[p]) return JPEG_SM100_ERR_UNSUPPORTED;
+        const uint64_t work = (uint64_t) V.width[p] * V.height[p] * V.n_images;
+        if (work == 0) continue;
+        const uint32_t g = grid_for(ctx, work, 256, 8);
+        if (pl->sample_bytes == 1) {
+            if (src_is_rgb8) k_decompose<uint8_t, true><<<g, 256, 0, ctx->stream>>>(d_src, V, p);
+            else k_decompose<uint8_t, false><<<g, 256, 0, ctx->stream>>>(d_src, V, p);
+        } else {
+            if (src_is_rgb8) k_decompose<uint16_t, true><<<g, 256, 0, ctx->stream>>>(d_src, V, p);
+            else k_decompose<uint16_t, false><<<g, 256, 0, ctx->stream>>>(d_src, V, p);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    return JPEG_SM100_OK;
+}

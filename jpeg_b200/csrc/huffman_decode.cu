@@ -1,0 +1,675 @@
+// huffman_decode.cu -- K3: restart-interval-parallel entropy decode, all five scan kinds.
+//
+// Replaces Spectral.decode(ecss:interval:scan:tables:extend:) (reference decode.swift:3476-3551) and everything
+// below it: the ten per-kind decoders (decode.swift:2880-3445), composites (2773-2872), EXTEND (2742-2754), the
+// two-level Huffman LUT (310-351, 1037-1265) and the 1-padded bitstream (jpeg.swift:1873-1916).
+//
+// B200 design
+//   * The only parallel axis the format offers is the restart interval (the reference decoder itself walks them in
+//     a serial loop, decode.swift:3500): one THREAD decodes one interval; a warp holds 32 intervals of one image.
+//   * Entropy decoding is a serial dependency chain per thread, so the kernel is latency- not bandwidth-bound.
+//     Each warp is its own CTA so that the ~n_images x n_intervals / 32 warps spread over all 148 x 4 schedulers.
+//   * The sequential / DC-first decoders are written as a flat per-symbol state machine: every loop trip decodes
+//     exactly one Huffman symbol whatever block the lane is in, so lanes never wait for each other at block or MCU
+//     boundaries (trip count = max over lanes of the interval's symbol count, not the sum of per-block maxima).
+//   * The reference's two-level (8 + 8 bit) LUT is reproduced entry for entry and staged in shared memory
+//     (a few KB for real tables); oversized tables fall back to global memory.
+//   * Coefficients go straight to their final zig-zag slot in the Spectral.Plane layout, 64 * (units_x * y + x) + z.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARP = 32;
+constexpr int MAX_LUT_SMEM = 40 * 1024;
+
+// ---- host: LUT construction (decode.swift:310-351 size, 1037-1240 decoder) ----------------------------------
+struct LutHeader {  // per image: 8 tables (dc0..3, ac0..3)
+    int32_t  n[8];
+    int32_t  zeta[8];
+    uint32_t offset[8];  // entry offset into the image's entry array
+    int32_t  present[8];
+    uint32_t total_entries;
+    uint32_t pad[3];
+};
+static_assert(sizeof(LutHeader) % 16 == 0, "header must keep 16-byte alignment");
+
+bool huff_size(const uint8_t counts[16], int &n, int &z)
+{
+    int interior = 1;
+    for (int l = 0; l < 8; ++l) {
+        if (!(interior > 0)) return false;
+        interior = 2 * interior - counts[l];
+    }
+    n = 256 - interior;
+    z = n;
+    for (int i = 0; i < 8; ++i) {
+        if (!(interior > 0)) return false;
+        z += (int) counts[8 + i] << (7 - i);
+        interior = 2 * interior - counts[8 + i];
+    }
+    return interior > 0;
+}
+
+// appends the table's entries (symbol | length << 8) to `entries`
+int build_lut(const jpeg_sm100_huff_table &t, std::vector<uint16_t> &entries, int &n, int &zeta)
+{
+    int z;
+    if (!huff_size(t.counts, n, z)) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+    int total = 0;
+    for (int l = 0; l < 16; ++l) total += t.counts[l];
+    if (total > 256) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+    zeta = z + n * 255;
+    const size_t start = entries.size();
+    int          base = 0;
+    for (int l = 0; l < 16; ++l) {
+        if (!((int) (entries.size() - start) < z)) break;
+        const int clones = (0x8080 >> l) & 0xff;
+        for (int s = 0; s < t.counts[l]; ++s)
+            for (int c = 0; c < clones && (int) (entries.size() - start) < z; ++c)
+                entries.push_back((uint16_t) (t.values[base + s] | ((l + 1) << 8)));
+        base += t.counts[l];
+    }
+    while ((int) (entries.size() - start) < z) entries.push_back(0x1000);  // unreachable for valid trees
+    return JPEG_SM100_OK;
+}
+
+// ---- device side ---------------------------------------------------------------------------------------------
+struct ScanParams {
+    int32_t  kind;  // 0 sequential, 1 dc first, 2 dc refine, 3 ac first, 4 ac refine
+    int32_t  band_lo, band_hi, al;
+    int32_t  n_comp;
+    int32_t  W, H;  // iteration grid: MCUs (interleaved) or the plane's units (single component)
+    int32_t  extend;
+    uint32_t n_ecs;
+    uint64_t interval;  // MCUs per interval; UINT64_MAX = none
+    int16_t *plane[4];
+    uint64_t image_stride[4];
+    int32_t  ux[4], uy[4], fx[4], fy[4];
+    int32_t  dc[4], ac[4];  // LUT indices: dc slot, 4 + ac slot
+    int32_t  mcu_blocks;
+    uint8_t  blk_comp[12], blk_dx[12], blk_dy[12];
+    const uint8_t  *ecs;
+    const uint64_t *offsets;
+    const uint8_t  *luts;        // per image: LutHeader + entries
+    uint64_t        lut_stride;  // bytes per image (0 = shared)
+    uint32_t        lut_smem;    // 1: stage entries in shared memory
+    int32_t        *status;      // n_images * n_ecs
+};
+
+struct BitReader {
+    const uint32_t *wp;      // next aligned word to load
+    uint64_t        acc;     // MSB-aligned bit buffer
+    int32_t         navail;  // bits in acc
+    int64_t         loaded;  // bytes of this interval already moved into acc (may be negative before start)
+    int64_t         nbytes;
+    int64_t         pos;     // bits consumed
+    int64_t         count;   // 8 * nbytes
+
+    __device__ __forceinline__ void load_word()
+    {
+        uint32_t be = 0xffffffffu;
+        if (loaded < nbytes) {
+            be = __byte_perm(__ldg(wp), 0, 0x0123);
+            const int64_t valid = nbytes - loaded;  // bytes of this word that belong to the interval
+            if (valid < 4) be |= 0xffffffffu >> (8 * (int) valid);  // jpeg.swift:1881-1887: pad with 1-bits
+        }
+        wp += 1;
+        loaded += 4;
+        acc |= (uint64_t) be << (32 - navail);
+        navail += 32;
+    }
+    __device__ __forceinline__ void init(const uint8_t *base, int64_t n)
+    {
+        nbytes = n;
+        count = 8 * n;
+        pos = 0;
+        const int lead = (int) (reinterpret_cast<uintptr_t>(base) & 3);
+        wp = reinterpret_cast<const uint32_t *>(base - lead);
+        acc = 0;
+        navail = 0;
+        loaded = -lead;
+        // first word: drop the `lead` bytes that precede the interval
+        uint32_t be = 0xffffffffu;
+        if (n > 0) {
+            be = __byte_perm(__ldg(wp), 0, 0x0123);
+            const int64_t valid = n + lead;  // bytes of the word up to the interval end
+            if (valid < 4) be |= 0xffffffffu >> (8 * (int) valid);
+        }
+        wp += 1;
+        loaded += 4;
+        acc = (uint64_t) be << (32 + 8 * lead);
+        navail = 32 - 8 * lead;
+        if (navail <= 32) load_word();
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (navail <= 32) load_word();
+    }
+    __device__ __forceinline__ uint32_t peek16() const { return (uint32_t) (acc >> 48); }
+    __device__ __forceinline__ void     consume(int n)
+    {
+        acc <<= n;
+        navail -= n;
+        pos += n;
+    }
+    // consume an arbitrary (possibly > 32) number of bits -- only reachable with corrupt DC symbols
+    __device__ void consume_long(int n)
+    {
+        while (n > 0) {
+            refill();
+            const int k = n < 16 ? n : 16;
+            consume(k);
+            n -= k;
+        }
+    }
+};
+
+// decode.swift:2742-2754 EXTEND with the reference's masking shifts
+__device__ __forceinline__ int extend16(int binade, uint32_t tail)
+{
+    const uint32_t t = tail & 0xffffu;
+    const uint32_t sign = t >> ((binade - 1) & 15);
+    const uint32_t high = ((0xffffu + sign) << (binade & 15)) & 0xffffu;
+    const uint32_t low = (t + (sign ^ 1u)) & 0xffffu;
+    return (int) (short) (high | low);
+}
+
+struct Lut {
+    const uint16_t *entries;  // shared or global
+    int32_t         n[8], zeta[8];
+    uint32_t        offset[8];
+};
+
+// decode.swift:1246-1265 Decoder[codeword] -> symbol | length << 8
+__device__ __forceinline__ uint32_t lut_lookup(const uint16_t *entries, int n, int zeta, uint32_t off, uint32_t cw)
+{
+    const int  i = (int) (cw >> 8);
+    const bool direct = i < n;
+    const bool valid = direct || ((int) cw < zeta);
+    const int  idx = direct ? i : (int) cw - 255 * n;
+    uint32_t   e = 0x1000u;  // (symbol 0, length 16)
+    if (valid) e = entries[off + idx];
+    return e;
+}
+
+#define FAIL_LANE(code)                                                                                              \
+    do {                                                                                                             \
+        err = (code);                                                                                                \
+        goto finished;                                                                                               \
+    } while (0)
+
+// ---- flat per-symbol state machine: sequential (kind 0) and DC-first (kind 1) scans --------------------------------
+template <bool LUT_SMEM>
+__global__ void __launch_bounds__(WARP) k_decode_flat(const __grid_constant__ ScanParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t img = blockIdx.y;
+    const uint32_t e = blockIdx.x * WARP + threadIdx.x;
+    const uint8_t *lut_img = P.luts + (size_t) img * P.lut_stride;
+    // the table header always lives in shared memory; the entries too when they fit
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
+    {
+        const uint32_t total = reinterpret_cast<const LutHeader *>(lut_img)->total_entries;
+        const uint32_t words = (uint32_t) sizeof(LutHeader) / 4 + (LUT_SMEM ? (total + 1) / 2 : 0);
+        uint32_t      *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = threadIdx.x; i < words; i += WARP) dst[i] = src[i];
+        __syncwarp();
+        if (LUT_SMEM) entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader));
+    }
+    if (e >= P.n_ecs) return;
+
+    int err = 0;
+    // rows of this interval: decode.swift:3205-3207 / 2897-2899 (integer division, clamped; we never grow planes)
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);  // interval < 2^32 (checked on the host)
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    BitReader br;
+    {
+        const uint64_t o0 = P.offsets[(size_t) img * P.n_ecs + e], o1 = P.offsets[(size_t) img * P.n_ecs + e + 1];
+        br.init(P.ecs + o0, (int64_t) (o1 - o0));
+    }
+    const bool dc_only = P.kind == 1;
+    const int  al = P.al;
+
+    int     pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;
+    int     mx = 0, blk = 0, z = 0;
+    int64_t my = r0;
+    bool    row_start = true;
+
+    // per-block state
+    int      comp = 0, dci = 0, aci = 0;
+    int16_t *bptr = nullptr;
+    bool     bvalid = false;
+
+    if (my >= r1) goto finished;
+    while (true) {
+        if (z == 0) {
+            if (row_start && blk == 0 && mx == 0) {
+                row_start = false;
+                if (P.extend) {  // decode.swift:3214-3220: stop silently at the end of the data
+                    br.refill();
+                    if (!(br.pos < br.count) || br.peek16() == 0xffffu) goto finished;
+                }
+            }
+            // locate the block
+            comp = P.blk_comp[blk];
+            const int bx = mx * P.fx[comp] + P.blk_dx[blk];
+            const int by = (int) my * P.fy[comp] + P.blk_dy[blk];
+            bvalid = P.plane[comp] != nullptr && bx < P.ux[comp] && by < P.uy[comp];
+            bptr = P.plane[comp] + (size_t) img * P.image_stride[comp] + 64 * ((size_t) P.ux[comp] * by + bx);
+            dci = P.dc[comp];
+            aci = P.ac[comp];
+        }
+        br.refill();
+        if (!(br.pos < br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+        const int      ti = (z == 0) ? dci : aci;
+        const uint32_t ent = lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], br.peek16());
+        const int      sym = (int) (ent & 0xffu);
+        br.consume((int) (ent >> 8));
+        bool block_done = false;
+        if (z == 0) {
+            // decode.swift:2788-2820 DC composite; 3248-3254 prediction
+            int diff = 0;
+            if (sym > 0) {
+                if (!(br.pos + sym <= br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                const uint32_t tail = br.peek16() >> ((16 - sym) & 15);
+                diff = extend16(sym, tail);
+                if (sym <= 16) br.consume(sym);
+                else br.consume_long(sym);
+            }
+            int pr = comp == 0 ? pred0 : comp == 1 ? pred1 : comp == 2 ? pred2 : pred3;
+            if (P.plane[comp] != nullptr) pr = (int) (short) (pr + diff);  // wrapping Int16, &+=
+            if (comp == 0) pred0 = pr;
+            else if (comp == 1) pred1 = pr;
+            else if (comp == 2) pred2 = pr;
+            else pred3 = pr;
+            if (bvalid) bptr[0] = (int16_t) ((uint32_t) pr << al);
+            z = 1;
+            block_done = dc_only;
+        } else {
+            // decode.swift:2822-2872 AC composite; 3258-3286 block loop
+            const int zeroes = sym >> 4, binade = sym & 15;
+            if (binade == 0) {
+                if (zeroes == 0) {
+                    block_done = true;  // .eob(1)
+                } else if (zeroes <= 14) {
+                    if (!(br.pos + zeroes <= br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                    FAIL_LANE(JPEG_SM100_ERR_INVALID_BLOCK_RUN);  // .eob(n > 1) in a sequential scan
+                } else {
+                    z += 15;  // .run(15, value: 0)
+                    if (z < 64) {
+                        if (bvalid) bptr[z] = 0;
+                        z += 1;
+                    }
+                    block_done = !(z < 64);
+                }
+            } else {
+                if (!(br.pos + binade <= br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                const uint32_t tail = br.peek16() >> (16 - binade);
+                const int      v = extend16(binade, tail);
+                br.consume(binade);
+                z += zeroes;
+                if (z < 64) {
+                    if (bvalid) bptr[z] = (int16_t) v;
+                    z += 1;
+                }
+                block_done = !(z < 64);
+            }
+        }
+        if (block_done) {
+            z = 0;
+            if (++blk == P.mcu_blocks) {
+                blk = 0;
+                if (++mx == P.W) {
+                    mx = 0;
+                    row_start = true;
+                    if (++my >= r1) break;
+                }
+            }
+        }
+    }
+finished:
+    if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
+}
+
+// ---- straightforward per-thread decoders for the refinement / AC progressive scans ---------------------------------
+__device__ __forceinline__ int16_t coef_get(const int16_t *pl, int ux, int uy, int x, int y, int z)
+{
+    if (!(x >= 0 && x < ux && y >= 0 && y < uy)) return 0;  // decode.swift:1459-1464
+    return pl[64 * ((size_t) ux * y + x) + z];
+}
+__device__ __forceinline__ void coef_set(int16_t *pl, int ux, int uy, int x, int y, int z, int16_t v)
+{
+    if (!(x >= 0 && x < ux && y >= 0 && y < uy)) return;  // decode.swift:1470-1475
+    pl[64 * ((size_t) ux * y + x) + z] = v;
+}
+
+template <bool LUT_SMEM>
+__global__ void __launch_bounds__(WARP) k_decode_progressive(const __grid_constant__ ScanParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t img = blockIdx.y;
+    const uint32_t e = blockIdx.x * WARP + threadIdx.x;
+    const uint8_t *lut_img = P.luts + (size_t) img * P.lut_stride;
+    // the table header always lives in shared memory; the entries too when they fit
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
+    {
+        const uint32_t total = reinterpret_cast<const LutHeader *>(lut_img)->total_entries;
+        const uint32_t words = (uint32_t) sizeof(LutHeader) / 4 + (LUT_SMEM ? (total + 1) / 2 : 0);
+        uint32_t      *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = threadIdx.x; i < words; i += WARP) dst[i] = src[i];
+        __syncwarp();
+        if (LUT_SMEM) entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader));
+    }
+    if (e >= P.n_ecs) return;
+    int err = 0;
+
+    // rows: lo / w ..< min(hi / w, limit), iterated through General.Range2 (common.swift:383-409): an empty y range
+    // still yields ONE row, lower > upper traps in the reference (decode.swift:3009-3013, 3031-3036, 3421-3425)
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r1 > P.H) r1 = P.H;
+    }
+    int64_t nrows = r1 - r0;
+    BitReader br;
+    const int al = P.al;
+    if (r0 > r1) FAIL_LANE(JPEG_SM100_ERR_PRECONDITION);
+    if (nrows == 0) nrows = 1;
+    {
+        const uint64_t o0 = P.offsets[(size_t) img * P.n_ecs + e], o1 = P.offsets[(size_t) img * P.n_ecs + e + 1];
+        br.init(P.ecs + o0, (int64_t) (o1 - o0));
+    }
+    if (P.kind == 2) {
+        // decode.swift:3007-3018, 3395-3445 DC refinement: one bit per block
+        for (int64_t my = r0; my < r0 + nrows; ++my)
+            for (int mx = 0; mx < P.W; ++mx)
+                for (int b = 0; b < P.mcu_blocks; ++b) {
+                    const int c = P.blk_comp[b];
+                    br.refill();
+                    if (!(br.pos < br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                    const int bit = (int) (br.peek16() >> 15);
+                    br.consume(1);
+                    if (P.plane[c] == nullptr) continue;
+                    int16_t  *pl = P.plane[c] + (size_t) img * P.image_stride[c];
+                    const int x = mx * P.fx[c] + P.blk_dx[b], y = (int) my * P.fy[c] + P.blk_dy[b];
+                    coef_set(pl, P.ux[c], P.uy[c], x, y, 0,
+                             (int16_t) (coef_get(pl, P.ux[c], P.uy[c], x, y, 0) | (int16_t) ((uint32_t) bit << al)));
+                }
+    } else {
+        int16_t  *pl = P.plane[0] + (size_t) img * P.image_stride[0];
+        const int ux = P.ux[0], uy = P.uy[0];
+        const int ti = P.ac[0];
+        const int tn = hdr->n[ti], tz = hdr->zeta[ti];
+        const uint32_t toff = hdr->offset[ti];
+        int       skip = 0;
+        for (int64_t y64 = r0; y64 < r0 + nrows; ++y64)
+            for (int x = 0; x < P.W; ++x) {
+                const int y = (int) y64;
+                int       z = P.band_lo;
+                while (z < P.band_hi) {
+                    int     zeroes = 0, kind, run = 0, v = 0;
+                    int16_t delta = 0;
+                    if (P.kind == 3) {
+                        // decode.swift:3038-3067 AC first scan
+                        if (skip != 0) {
+                            skip -= 1;
+                            break;
+                        }
+                    }
+                    if (P.kind == 4 && skip > 0) {
+                        zeroes = 64;
+                        delta = 0;
+                        skip -= 1;
+                        kind = 2;
+                    } else {
+                        // decode.swift:2822-2872 AC composite
+                        br.refill();
+                        if (!(br.pos < br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                        const uint32_t ent = lut_lookup(entries, tn, tz, toff, br.peek16());
+                        const int      sym = (int) (ent & 0xffu);
+                        br.consume((int) (ent >> 8));
+                        const int sz = sym >> 4, binade = sym & 15;
+                        if (binade == 0) {
+                            if (sz == 0) {
+                                kind = 1;
+                                run = 1;
+                            } else if (sz <= 14) {
+                                br.refill();
+                                if (!(br.pos + sz <= br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                                kind = 1;
+                                run = (1 << sz) | (int) (br.peek16() >> (16 - sz));
+                                br.consume(sz);
+                            } else {
+                                kind = 0;
+                                run = 15;
+                                v = 0;
+                            }
+                        } else {
+                            br.refill();
+                            if (!(br.pos + binade <= br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                            kind = 0;
+                            run = sz;
+                            v = extend16(binade, br.peek16() >> (16 - binade));
+                            br.consume(binade);
+                        }
+                    }
+                    if (P.kind == 3) {
+                        if (kind == 0) {
+                            z += run;
+                            if (!(z < P.band_hi)) break;
+                            coef_set(pl, ux, uy, x, y, z, (int16_t) ((uint32_t) v << al));
+                            z += 1;
+                        } else {
+                            skip = run - 1;
+                            break;
+                        }
+                        continue;
+                    }
+                    // decode.swift:3093-3149 AC refinement
+                    if (kind == 0) {
+                        if (!(v >= -1 && v <= 1)) FAIL_LANE(JPEG_SM100_ERR_INVALID_COMPOSITE_VALUE);
+                        zeroes = run;
+                        delta = (int16_t) v;
+                    } else if (kind == 1) {
+                        zeroes = 64;
+                        delta = 0;
+                        skip = run - 1;
+                    }
+                    int  skipped = 0;
+                    bool placed = false;
+                    do {
+                        const int16_t unrefined = coef_get(pl, ux, uy, x, y, z);
+                        if (unrefined == 0) {
+                            if (!(skipped < zeroes)) {
+                                coef_set(pl, ux, uy, x, y, z, (int16_t) ((uint32_t) (int) delta << al));
+                                z += 1;
+                                placed = true;
+                                break;
+                            }
+                            skipped += 1;
+                        } else {
+                            br.refill();
+                            if (!(br.pos < br.count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                            const int bit = (int) (br.peek16() >> 15);
+                            br.consume(1);
+                            const int d = (unrefined < 0 ? -1 : 1) * bit;
+                            coef_set(pl, ux, uy, x, y, z, (int16_t) (unrefined + (int16_t) ((uint32_t) d << al)));
+                        }
+                        z += 1;
+                    } while (z < P.band_hi);
+                    if (!placed) break;
+                }
+            }
+    }
+finished:
+    if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
+}
+
+// per image: first non-zero status in interval order (the reference throws at the first failing interval)
+__global__ void k_reduce_status(const int32_t *__restrict__ per_ecs, uint32_t n_ecs, int32_t *__restrict__ per_image)
+{
+    const uint32_t img = blockIdx.x;
+    __shared__ uint32_t first;
+    if (threadIdx.x == 0) first = 0xffffffffu;
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < n_ecs; e += blockDim.x)
+        if (per_ecs[(size_t) img * n_ecs + e] != 0) atomicMin(&first, e);
+    __syncthreads();
+    if (threadIdx.x == 0) per_image[img] = first == 0xffffffffu ? 0 : per_ecs[(size_t) img * n_ecs + first];
+}
+
+}  // namespace
+
+// Layer-B implementation.  scratch slots 8 (LUTs) and 9 (per-ECS status) belong to this file.
+int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
+                             const uint64_t *d_offsets, uint32_t n_ecs, uint64_t interval, int extend,
+                             const jpeg_sm100_huff_table *tables, int tables_shared,
+                             const jpeg_sm100_dev_spectral *sp, int32_t *d_status)
+{
+    if (!scan || !sp || !tables) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (scan->n_comp < 1 || scan->n_comp > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (!(scan->band_lo >= 0 && scan->band_lo < scan->band_hi && scan->band_hi <= 64)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    const bool initial = scan->bit_hi < 0;
+    ScanParams P;
+    memset(&P, 0, sizeof P);
+    if (scan->band_lo == 0 && scan->band_hi == 64) {
+        if (!initial) return JPEG_SM100_ERR_PRECONDITION;  // fatalError("unreachable") decode.swift:3512
+        P.kind = 0;
+    } else if (scan->band_lo == 0 && scan->band_hi == 1)
+        P.kind = initial ? 1 : 2;
+    else
+        P.kind = initial ? 3 : 4;
+    if (P.kind >= 3 && scan->n_comp != 1) return JPEG_SM100_ERR_PRECONDITION;
+    if (scan->bit_lo < 0 || scan->bit_lo > 15) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    const uint32_t n_images = sp->n_images;
+    if (n_images == 0 || n_ecs == 0) {
+        if (d_status && n_images) CU_TRY(ctx, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_images, ctx->stream));
+        return JPEG_SM100_OK;
+    }
+    if (interval == 0 || (interval != JPEG_SM100_INTERVAL_NONE && interval > 0xffffffffull))
+        return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    // stride(from: 0, to: .max, by: .max) yields a single element: without DRI only the first ECS is decoded
+    if (interval == JPEG_SM100_INTERVAL_NONE && n_ecs > 1) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+
+    P.band_lo = scan->band_lo;
+    P.band_hi = scan->band_hi;
+    P.al = scan->bit_lo;
+    P.n_comp = scan->n_comp;
+    P.extend = (extend && P.kind <= 1) ? 1 : 0;
+    P.n_ecs = n_ecs;
+    P.interval = interval;
+    P.ecs = d_ecs;
+    P.offsets = d_offsets;
+    const bool interleaved = scan->n_comp > 1;
+    int        volume = 0;
+    for (int c = 0; c < scan->n_comp; ++c) {
+        const int p = scan->comp[c].plane;
+        if (p >= (int) sp->n_planes) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        if (p < 0 && !interleaved) {  // decode.swift:3169-3173: nothing to do
+            if (d_status) CU_TRY(ctx, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_images, ctx->stream));
+            return JPEG_SM100_OK;
+        }
+        if (scan->comp[c].dc < 0 || scan->comp[c].dc > 3 || scan->comp[c].ac < 0 || scan->comp[c].ac > 3)
+            return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        P.dc[c] = scan->comp[c].dc;
+        P.ac[c] = 4 + scan->comp[c].ac;
+        if (p >= 0) {
+            P.plane[c] = sp->plane[p].coef;
+            P.image_stride[c] = sp->plane[p].image_stride;
+            P.ux[c] = sp->plane[p].units_x;
+            P.uy[c] = sp->plane[p].units_y;
+        }
+        P.fx[c] = interleaved ? scan->comp[c].factor_x : 1;
+        P.fy[c] = interleaved ? scan->comp[c].factor_y : 1;
+        if (P.fx[c] < 1 || P.fy[c] < 1 || P.fx[c] > 4 || P.fy[c] > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        for (int dy = 0; dy < P.fy[c]; ++dy)
+            for (int dx = 0; dx < P.fx[c]; ++dx) {
+                if (volume >= 12) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+                P.blk_comp[volume] = (uint8_t) c;
+                P.blk_dx[volume] = (uint8_t) dx;
+                P.blk_dy[volume] = (uint8_t) dy;
+                ++volume;
+            }
+    }
+    P.mcu_blocks = volume;
+    P.W = interleaved ? scan->blocks_x : P.ux[0];
+    P.H = interleaved ? scan->blocks_y : P.uy[0];
+    if (P.W <= 0 || P.H < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+
+    // LUTs (host) -> device.  decode.swift:2884-2895, 3186-3203: a missing table is an error of the scan
+    const uint32_t          n_sets = tables_shared ? 1 : n_images;
+    std::vector<uint8_t>    blob;
+    std::vector<LutHeader>  headers(n_sets);
+    std::vector<std::vector<uint16_t>> all(n_sets);
+    size_t                  max_entries = 0;
+    const bool need_dc = P.kind == 0 || P.kind == 1, need_ac = P.kind == 0 || P.kind == 3 || P.kind == 4;
+    for (uint32_t s = 0; s < n_sets; ++s) {
+        LutHeader &h = headers[s];
+        memset(&h, 0, sizeof h);
+        for (int c = 0; c < scan->n_comp; ++c) {
+            const int slots[2] = {need_dc ? P.dc[c] : -1, need_ac ? P.ac[c] : -1};
+            for (int k = 0; k < 2; ++k) {
+                const int ti = slots[k];
+                if (ti < 0 || h.present[ti]) continue;
+                const jpeg_sm100_huff_table &t = tables[(size_t) s * 8 + ti];
+                if (!t.present) return k == 0 ? JPEG_SM100_ERR_UNDEFINED_DC : JPEG_SM100_ERR_UNDEFINED_AC;
+                h.offset[ti] = (uint32_t) all[s].size();
+                J_TRY(build_lut(t, all[s], h.n[ti], h.zeta[ti]));
+                h.present[ti] = 1;
+            }
+        }
+        h.total_entries = (uint32_t) all[s].size();
+        if (all[s].size() > max_entries) max_entries = all[s].size();
+    }
+    const size_t entry_bytes = (max_entries * 2 + 15) & ~size_t(15);
+    const size_t stride = sizeof(LutHeader) + entry_bytes + 16;
+    blob.assign(stride * n_sets, 0);
+    for (uint32_t s = 0; s < n_sets; ++s) {
+        memcpy(blob.data() + stride * s, &headers[s], sizeof(LutHeader));
+        if (!all[s].empty()) memcpy(blob.data() + stride * s + sizeof(LutHeader), all[s].data(), all[s].size() * 2);
+    }
+    void *d_luts = nullptr;
+    J_TRY(scratch_reserve(ctx, 8, blob.size(), &d_luts));
+    // the blob is tiny (KBs); a synchronous-with-respect-to-host staged copy keeps `blob` reusable
+    CU_TRY(ctx, cudaMemcpyAsync(d_luts, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    P.luts = reinterpret_cast<const uint8_t *>(d_luts);
+    P.lut_stride = tables_shared ? 0 : stride;
+    P.lut_smem = entry_bytes <= (size_t) MAX_LUT_SMEM ? 1 : 0;
+
+    void *d_per_ecs = nullptr;
+    J_TRY(scratch_reserve(ctx, 9, sizeof(int32_t) * (size_t) n_images * n_ecs, &d_per_ecs));
+    P.status = reinterpret_cast<int32_t *>(d_per_ecs);
+
+    const dim3   grid((n_ecs + WARP - 1) / WARP, n_images);
+    const size_t smem = sizeof(LutHeader) + (P.lut_smem ? entry_bytes : 0);
+    if (P.kind <= 1) {
+        if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
+        else k_decode_flat<false><<<grid, WARP, smem, ctx->stream>>>(P);
+    } else {
+        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P);
+        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P);
+    }
+    LAUNCH_CHECK(ctx);
+    if (d_status) {
+        k_reduce_status<<<n_images, 128, 0, ctx->stream>>>(P.status, n_ecs, d_status);
+        LAUNCH_CHECK(ctx);
+    }
+    return JPEG_SM100_OK;
+}

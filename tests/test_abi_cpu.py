@@ -1,0 +1,56 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports exactly the symbols include/jpeg_sm100.h
+declares, and fails loudly (no fallback) when there is no B200."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "jpeg_sm100.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(jpeg_sm100_[a-z0-9_]+)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol():
+    from jpeg_b200 import lib
+    declared = _declared()
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    L = lib.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.jpeg_sm100_abi_version() == 1
+    assert L.jpeg_sm100_error_string(-1) == b"truncatedEntropyCodedSegment"
+
+
+def test_struct_layouts_match_header():
+    from jpeg_b200 import lib
+    assert C.sizeof(lib.HuffTable) == 4 + 16 + 256
+    assert C.sizeof(lib.ScanDesc) == 4 * 5 + 4 * 20 + 8
+    assert C.sizeof(lib.PlaneI16) == 16 and C.sizeof(lib.PlaneU16) == 24
+    assert C.sizeof(lib.DevSpectral) == 8 + 4 * 32 and C.sizeof(lib.DevPlanar) == 16 + 4 * 32
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail; nothing silently runs on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from jpeg_b200 import host, lib
+    h = C.c_void_p()
+    assert lib.load().jpeg_sm100_create(0, C.byref(h)) == lib.ERR_CUDA
+    with pytest.raises(lib.JpegSm100Error):
+        host.default_context()
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, smoke() and bench.py's baseline legs may touch oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "jpeg_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(base, f)).read()
+                code = "\n".join(l for l in text.splitlines() if "oracle" in l and not l.strip().startswith(("//", "#", "*", '"')))
+                assert "import oracle" not in code and "from oracle" not in code and "jpeg_oracle" not in code, f

@@ -1,0 +1,304 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C-ABI, against the CPU oracle (which is itself
+pinned bit-exactly to the reference's golden vectors by test_oracle_golden.py) and against the committed golden
+digests directly.  Bar: bit-exact everywhere -- the kernels evaluate the reference's binary32 arithmetic op for op
+(no FMA), so even the float stages are expected to match exactly, not merely within +-1.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import jpegfile as J
+from conftest import golden_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def H():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from jpeg_b200 import host
+    host.default_context()  # raises if libjpeg_sm100.so is missing or no sm_100 device is present
+    return host
+
+
+def _to_lib_tables(H, specs):
+    from jpeg_b200 import lib
+    return [lib.HuffTable.make(bytes(t.counts), bytes(t.values)) if t.present else None for t in specs]
+
+
+# ------------------------------------------------------------------------------------------------ whole files
+def test_golden_files_through_gpu(manifest, H, O):
+    """tests/regression/tests.swift:39-138 run through the CUDA path: coefficients, planes, YCbCr and RGB."""
+    for v in manifest["decode"]:
+        data = golden_bytes(v["jpeg"])
+        s = H.Spectral.decompress(data)
+        ref = O.Spectral.decompress(data)
+        assert s.size == ref.size and s.ncomp == ref.ncomp
+        for p in range(s.ncomp):
+            assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (v["jpeg"], "coefficients", p)
+            assert np.array_equal(s.quanta[s.planes[p].q], ref.quanta(p))
+        planar = s.idct()
+        for p, pl in enumerate(ref.idct()):
+            assert np.array_equal(planar.planes[p], pl), (v["jpeg"], "idct", p)
+        rect = planar.interleaved()
+        rgb, ycc = rect.unpack_rgb(), rect.unpack_ycc()
+        assert sha(rgb.tobytes()) == v["rgb_sha256"], v["jpeg"]
+        if "ycc_sha256" in v:
+            assert sha(ycc.tobytes()) == v["ycc_sha256"], v["jpeg"]
+        if "planes_sha256" in v:
+            for p, pl in enumerate(s.idct_u8()):
+                assert sha(pl.tobytes()) == v["planes_sha256"][p]
+        # fused coefficients -> RGB8 path
+        assert sha(s.to_rgb8().tobytes()) == v["rgb_sha256"], (v["jpeg"], "fused")
+
+
+def test_restart_files_through_gpu(manifest, H, O):
+    for rel in manifest["restart"]:
+        data = golden_bytes(rel)
+        s = H.Spectral.decompress(data)
+        ref = O.Spectral.decompress(data)
+        for p in range(s.ncomp):
+            assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), rel
+        rgb_ref = O.unpack_rgb(ref.to_rectangular())
+        assert np.array_equal(s.to_rgb8(), rgb_ref), rel
+
+
+def test_cosited_and_generic_upsampling(H, O, manifest):
+    """interleaved(cosite: true) and non-4:2:0 factors go through the generic kernel."""
+    eb = manifest["encode_basic"]
+    w, h = eb["size"]
+    rgb = np.frombuffer(golden_bytes(eb["rgb"]), dtype=np.uint8).reshape(h, w, 3)[:203, :187]
+    il = O.pack_rgb(rgb)
+    for factors in ([(2, 2), (1, 1), (1, 1)], [(2, 1), (1, 1), (1, 1)], [(1, 2), (1, 1), (1, 1)], [(4, 2), (1, 1), (2, 1)],
+                    [(1, 1), (1, 1), (1, 1)]):
+        planes = O.decompose(il, factors)
+        us = [(p.shape[1] // 8, p.shape[0] // 8) for p in planes]
+        for cosited in (False, True):
+            ref = O.interleave(planes, us, factors, (187, 203), cosited)
+            got = H.Planar((187, 203), us, factors, [p.copy() for p in planes]).interleaved(cosite=cosited)
+            assert np.array_equal(got.values, ref), (factors, cosited)
+            assert np.array_equal(got.unpack_rgb(), O.unpack_rgb(ref))
+
+
+# ------------------------------------------------------------------------------------------------ single stages
+@pytest.mark.parametrize("ux,uy", [(1, 1), (3, 2), (17, 5), (128, 1), (129, 3), (40, 40)])
+def test_idct_random_blocks(H, O, ux, uy):
+    """K1 on random coefficients incl. values that drive the output far outside 0..255 (clamp + trunc)."""
+    rng = np.random.default_rng(ux * 100 + uy)
+    coef = rng.integers(-64, 64, size=(uy, ux, 64)).astype(np.int16)
+    coef[..., 0] = rng.integers(-1024, 1024, size=(uy, ux))
+    coef[rng.random((uy, ux)) < 0.1] *= 30
+    q = rng.integers(1, 255, size=64).astype(np.uint16)
+    s = H.Spectral((8 * ux, 8 * uy), [(1, 1)])
+    s.planes[0].coef = coef
+    s.quanta.append(q)
+    s.planes[0].q = 1
+    ref = O.idct_plane(coef, q)
+    assert np.array_equal(s.idct().planes[0], ref)
+    assert np.array_equal(s.idct_u8()[0], ref.astype(np.uint8))
+
+
+def test_idct_empty_plane(H):
+    s = H.Spectral((8, 8), [(1, 1)])
+    s.planes[0].coef = np.zeros((0, 0, 64), np.int16)
+    s.planes[0].units = (0, 0)
+    assert s.idct().planes[0].size == 0
+
+
+def test_encode_front_end_stages(H, O, manifest):
+    """K4/K5: RGB.pack, decomposed() for four sampling modes, fdct at two compression levels -- bit-exact."""
+    eb = manifest["encode_basic"]
+    w, h = eb["size"]
+    rgb = np.frombuffer(golden_bytes(eb["rgb"]), dtype=np.uint8).reshape(h, w, 3)
+    il = O.pack_rgb(rgb)
+    for lum in ((1, 1), (1, 2), (2, 1), (2, 2)):
+        factors = [lum, (1, 1), (1, 1)]
+        rect = H.Rectangular.pack(rgb, factors)
+        assert np.array_equal(rect.values, il)
+        planar = rect.decomposed()
+        ref_planes = O.decompose(il, factors)
+        for p in range(3):
+            assert np.array_equal(planar.planes[p], ref_planes[p]), (lum, p)
+        for level in (0.0, 0.25, 2.0):
+            q = [O.quanta(level, 0), O.quanta(level, 1), O.quanta(level, 1)]
+            sp = planar.fdct(q)
+            for p in range(3):
+                assert np.array_equal(sp.planes[p].coef, O.fdct_plane(ref_planes[p], q[p])), (lum, level, p)
+
+
+# ------------------------------------------------------------------------------------------------ scan decode, all kinds
+def _oracle_scans(O, src, progression, rows):
+    """encode `src` (oracle Spectral) scan by scan with restart intervals of `rows` rows; returns per-scan inputs"""
+    out = []
+    for band, bits, comps in progression:
+        width = src.blocks[0] if len(comps) > 1 else src.units(comps[0])[0]
+        ival = rows * width if rows else 0
+        ecs, dct, act = src.encode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), ival)
+        out.append((band, bits, comps, dct, act, J.unstuff_split(ecs), ival or None))
+    return out
+
+
+PROGRESSIVE = [((0, 1), (1, None), [0, 1, 2]), ((1, 6), (1, None), [0]), ((1, 64), (1, None), [1]),
+               ((1, 64), (1, None), [2]), ((6, 64), (1, None), [0]), ((0, 1), (0, 1), [0, 1, 2]),
+               ((1, 64), (0, 1), [0]), ((1, 64), (0, 1), [1]), ((1, 64), (0, 1), [2])]
+BASELINE = [((0, 64), (0, None), [0, 1, 2])]
+BASELINE_SPLIT = [((0, 64), (0, None), [0]), ((0, 64), (0, None), [1, 2])]
+
+
+@pytest.mark.parametrize("name,progression", [("baseline", BASELINE), ("split", BASELINE_SPLIT),
+                                              ("progressive", PROGRESSIVE)])
+@pytest.mark.parametrize("rows", [0, 1, 2])
+def test_scan_decode_all_kinds(H, O, name, progression, rows):
+    """K3 against the oracle for the five scan kinds, interleaved and not, with and without restart intervals,
+    on an odd-sized 4:2:0 image (partial MCUs: out-of-plane blocks are decoded and dropped, decode.swift:1470)."""
+    src = O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))
+    fac = [src.factor(p) for p in range(3)]
+    dst = H.Spectral(src.size, fac, process=2)
+    for band, bits, comps, dct, act, parts, ival in _oracle_scans(O, src, progression, rows):
+        dst.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival)
+    for p in range(3):
+        assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (name, rows, p)
+
+
+def test_scan_decode_errors(H, O):
+    """Error parity: truncated data, undefined tables, EOB run in a sequential scan -- same code as the oracle."""
+    from jpeg_b200 import lib
+    src = O.Spectral.decompress(golden_bytes("gold/color-sequential-1.jpg"))
+    fac = [src.factor(p) for p in range(3)]
+    (band, bits, comps, dct, act, parts, ival), = _oracle_scans(O, src, BASELINE, 1)
+    dcl, acl = _to_lib_tables(H, dct), _to_lib_tables(H, act)
+    cc = [(c, 0, 0) for c in comps]
+
+    def run(parts_, dc_=dcl, ac_=acl, ival_=ival, H=H):
+        dst = H.Spectral(src.size, fac)
+        try:
+            dst.decode_scan(band, bits, cc, dc_, ac_, parts_, ival_)
+            return 0
+        except lib.JpegSm100Error as e:
+            return e.code
+
+    def run_oracle(parts_, dc_=dct, ac_=act):
+        dst = O.Spectral.create(src.size, fac)
+        try:
+            dst.decode_scan(band, bits, comps, [0] * 3, [0] * 3, dc_, ac_, parts_, interval=ival)
+            return 0
+        except O.OracleError as e:
+            return e.code
+
+    assert run(parts) == 0
+    cut = [p for p in parts]
+    cut[5] = cut[5][:len(cut[5]) // 2]
+    assert run(cut) == run_oracle(cut) == lib.ERR_TRUNCATED_ECS
+    empty = list(parts)
+    empty[0] = b""
+    assert run(empty) == run_oracle(empty) == lib.ERR_TRUNCATED_ECS
+    assert run(parts, dc_=[None] * 4) == lib.ERR_UNDEFINED_DC
+    assert run(parts, ac_=[None] * 4) == lib.ERR_UNDEFINED_AC
+    # garbage bytes: whatever the oracle says (error code or success), we say too
+    rng = np.random.default_rng(7)
+    for k in range(6):
+        junk = list(parts)
+        junk[k] = bytes(rng.integers(0, 256, len(parts[k]), dtype=np.uint8))
+        assert run(junk) == run_oracle(junk), k
+
+
+def test_scan_decode_extend_flag(H, O):
+    """extend = true (first scan): rows stop silently where the data ends (decode.swift:3214-3220)."""
+    src = O.Spectral.decompress(golden_bytes("gold/grayscale-sequential-1.jpg"))
+    (band, bits, comps, dct, act, parts, ival), = _oracle_scans(O, src, [((0, 64), (0, None), [0])], 0)
+    half = [parts[0][:len(parts[0]) // 2]]
+    from jpeg_b200 import lib
+    dst = H.Spectral(src.size, [(1, 1)])
+    with pytest.raises(lib.JpegSm100Error):
+        dst.decode_scan(band, bits, [(0, 0, 0)], _to_lib_tables(H, dct), _to_lib_tables(H, act), half, None, extend=False)
+
+
+# ------------------------------------------------------------------------------------------------ layer B: batches
+def test_batched_device_pipeline(H, O, manifest):
+    """Layer B on a small batch of different images with identical geometry and per-image tables:
+    dev_decode_scan -> dev_idct (8-bit) -> dev_planar_to_rgb8, all on device memory."""
+    import ctypes as C
+
+    import torch
+
+    from jpeg_b200 import lib
+    eb = manifest["encode_basic"]
+    w0, h0 = eb["size"]
+    full = np.frombuffer(golden_bytes(eb["rgb"]), dtype=np.uint8).reshape(h0, w0, 3)
+    W, Hh, N = 136, 104, 5
+    factors = [(2, 2), (1, 1), (1, 1)]
+    q = [O.quanta(0.25, 0), O.quanta(0.25, 1), O.quanta(0.25, 1)]
+    specs, all_parts, tables, want = [], [], [], []
+    for i in range(N):
+        rgb = np.ascontiguousarray(full[40 * i:40 * i + Hh, 30 * i:30 * i + W])
+        planes = O.decompose(O.pack_rgb(rgb), factors)
+        s = O.Spectral.create((W, Hh), factors)
+        for p in range(3):
+            s.coefficients(p)[...] = O.fdct_plane(planes[p], q[p])
+            s.set_quanta(p, q[p])
+        ecs, dct, act = s.encode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], s.blocks[0])
+        all_parts.append(J.unstuff_split(ecs))
+        tables += _to_lib_tables(H, dct) + _to_lib_tables(H, act)
+        specs.append(s)
+        want.append(O.unpack_rgb(s.to_rectangular()))
+    n_ecs = len(all_parts[0])
+    assert all(len(p) == n_ecs for p in all_parts)
+    cat = b"".join(b"".join(p) for p in all_parts)
+    offs = np.zeros(N * n_ecs + 1, dtype=np.uint64)
+    np.cumsum([len(e) for p in all_parts for e in p], out=offs[1:])
+    dev = torch.device("cuda:0")
+    d_ecs = torch.from_numpy(np.frombuffer(cat + b"\0" * 16, dtype=np.uint8).copy()).to(dev)
+    d_off = torch.from_numpy(offs.view(np.int64)).to(dev)
+    ctx = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    s0 = specs[0]
+    sp, pl = lib.DevSpectral(), lib.DevPlanar()
+    sp.n_images = pl.n_images = N
+    sp.n_planes = pl.n_planes = 3
+    pl.sample_bytes = 1
+    coefs, samples = [], []
+    for p in range(3):
+        ux, uy = s0.units(p)
+        c = torch.zeros((N, uy, ux, 64), dtype=torch.int16, device=dev)
+        sm = torch.zeros((N, 8 * uy, 8 * ux), dtype=torch.uint8, device=dev)
+        coefs.append(c)
+        samples.append(sm)
+        for dst, ptr, stride in ((sp.plane[p], c, 64 * ux * uy), (pl.plane[p], sm, 64 * ux * uy)):
+            dst.image_stride = stride
+            dst.units_x, dst.units_y = ux, uy
+            dst.factor_x, dst.factor_y = factors[p]
+        sp.plane[p].coef = c.data_ptr()
+        pl.plane[p].samples = sm.data_ptr()
+    desc = lib.ScanDesc()
+    desc.band_lo, desc.band_hi, desc.bit_lo, desc.bit_hi, desc.n_comp = 0, 64, 0, -1, 3
+    for i, (dcs, acs) in enumerate(((0, 0), (1, 1), (1, 1))):
+        desc.comp[i].plane = i
+        desc.comp[i].factor_x, desc.comp[i].factor_y = factors[i]
+        desc.comp[i].dc, desc.comp[i].ac = dcs, acs
+    desc.blocks_x, desc.blocks_y = s0.blocks
+    tabs = (lib.HuffTable * (8 * N))(*[t if t is not None else lib.HuffTable() for t in tables])
+    status = torch.zeros(N, dtype=torch.int32, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), n_ecs,
+                                               s0.blocks[0], 0, tabs, 0, C.byref(sp), status.data_ptr()))
+    qz = np.ascontiguousarray(np.stack(q), dtype=np.uint16)
+    ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(sp), qz.ctypes.data, 8, C.byref(pl)))
+    d_rgb = torch.zeros((N, Hh, W, 3), dtype=torch.uint8, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(pl), W, Hh, 0, d_rgb.data_ptr()))
+    torch.cuda.synchronize()
+    assert status.cpu().tolist() == [0] * N
+    for i in range(N):
+        for p in range(3):
+            assert np.array_equal(coefs[p][i].cpu().numpy(), specs[i].coefficients(p)), (i, p)
+        assert np.array_equal(d_rgb[i].cpu().numpy(), want[i]), i
+    assert ctx.launches >= 3 + 3 + 1
