@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpixels/s decode of 4K (3840x2160) baseline 4:2:0 JPEG, batch 64 synthetic frames per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path (libjpeg_sm100.so)
+    python bench.py --impl reference ...                      the reference's CPU path (restated oracle), host cores
+
+A "step" is one pass of the hot path over one batch: entropy decode (K3) -> dequantise + IDCT (K1) -> upsample +
+YCbCr->RGB + pack (K2).  `value` times it with every input already resident in HBM (CUDA events on the launching
+stream, max over ranks); `e2e` times the same work through the host-buffer C-ABI call
+jpeg_sm100_decode_batch_rgb8 with pinned host buffers, H2D and D2H copies inside the timed region.
+Inputs are produced by our own GPU encoder (K4-K7) from deterministic synthetic frames, DRI = one MCU row.
+Multi-GPU: independent images are sharded across ranks, no collective on the data path ("weak": 64 frames per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, BATCH = 3840, 2160, 64
+FACTORS = [(2, 2), (1, 1), (1, 1)]
+LEVEL = 0.25
+WORKLOAD = "3840x2160 baseline 4:2:0 decode, batch 64 synthetic frames per GPU, DRI = 240 MCUs (1 MCU row), level 0.25"
+METRIC = "Mpixels/s decode (4K 4:2:0 baseline)"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# CompressionLevel.quanta (encode.swift:286-333), restated for the product-side benchmark driver
+_LUM = [16, 11, 10, 16, 124, 140, 151, 161, 12, 12, 14, 19, 126, 158, 160, 155, 14, 13, 16, 24, 140, 157, 169, 156,
+        14, 17, 22, 29, 151, 187, 180, 162, 18, 22, 37, 56, 168, 109, 103, 177, 24, 35, 55, 64, 181, 104, 113, 192,
+        49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 199]
+_CHR = [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99,
+        47, 66, 99, 99, 99, 99, 99, 99] + [99] * 32
+
+
+def _zigzag(k, h):
+    p = 1 if k + h < 8 else 0
+    q = (k + h) & 1
+    a, b = 72 * (p ^ 1), 2 * p - 1
+    n = b * (k + h) - 14 * p + 15
+    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1
+
+
+def quanta(level, chroma):
+    key = _CHR if chroma else _LUM
+    out = np.zeros(64, dtype=np.uint16)
+    for h in range(8):
+        for k in range(8):
+            v = 1.0 * (1 - level) + key[8 * h + k] * level
+            v = float(int(v + 0.5)) if v >= 0 else -float(int(-v + 0.5))
+            out[_zigzag(k, h)] = int(max(1.0, min(v, 255.0)))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (restated C oracle; no Swift toolchain exists here)
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    from jpeg_b200 import synth
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    sample = max(1, min(cores, 32))
+    q = [O.quanta(LEVEL, 0), O.quanta(LEVEL, 1), O.quanta(LEVEL, 1)]
+
+    # inputs: the same synthetic frames, encoded by the oracle's reference-equivalent encoder (DRI = 240 MCUs)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import jpegfile as J
+
+    def make2(i):
+        rgb = synth.frame(i, W, H, "cpu").numpy()
+        planes = O.decompose(O.pack_rgb(rgb), FACTORS)
+        s = O.Spectral.create((W, H), FACTORS)
+        for p in range(3):
+            s.coefficients(p)[...] = O.fdct_plane(planes[p], q[p])
+        ecs, dct, act = s.encode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], 240)
+        return J.unstuff_split(ecs), dct, act
+
+    torch.set_num_threads(1)
+    with ThreadPoolExecutor(cores) as pool:
+        inputs = list(pool.map(make2, range(sample)))
+
+        def decode(inp):  # Spectral.decode(ecss:) -> idct -> interleaved -> unpack(as: RGB) on one core
+            parts, dct, act = inp
+            s = O.Spectral.create((W, H), FACTORS)
+            for p in range(3):
+                s.set_quanta(p, q[p])
+            s.decode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], dct, act, parts, interval=240)
+            return O.unpack_rgb(s.to_rectangular())[0, 0, 0]
+
+        for _ in range(args.warmup):
+            list(pool.map(decode, inputs))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(pool.map(decode, inputs))
+        dt = (time.perf_counter() - t0) / args.steps
+    value = sample * W * H / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "each step decodes a bounded sample of the workload on the host cores"},
+            "cpu_baseline": {"value": round(value, 2), "unit": "Mpixels/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} frames of the workload per step, one frame per thread, {cores} threads"},
+            "e2e": {"value": round(value, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from jpeg_b200 import batch, lib, synth
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: jpeg_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    ctx = lib.Context(local, stream=stream.cuda_stream)
+    geo = batch.Geometry((W, H), FACTORS)
+    q = np.stack([quanta(LEVEL, 0), quanta(LEVEL, 1), quanta(LEVEL, 1)])
+    n = args.batch
+
+    # ---- inputs: synthetic frames -> our GPU encoder -> (host) lexer ------------------------------------------------
+    ecs_all, tables_all = [], []
+    chunk = 8
+    for base in range(0, n, chunk):
+        frames = torch.stack([synth.frame(rank * n + i, W, H, dev) for i in range(base, min(n, base + chunk))])
+        ecs, tabs, _ = batch.encode_frames(ctx, frames, geo, q, geo.blocks[0])
+        ecs_all += [e.copy() for e in ecs]
+        tables_all += list(tabs)
+        del frames, _
+    torch.cuda.empty_cache()
+    inputs = batch.DecodeInputs(ecs_all, tables_all, n_ecs_expected=geo.blocks[1])
+    tables = (lib.HuffTable * (8 * n))(*tables_all)
+    desc = batch.sequential_scan(geo)
+    buf = batch.DeviceBuffers(geo, n, dev)
+    d_ecs = torch.from_numpy(inputs.ecs).to(dev)
+    d_off = torch.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    qz = np.ascontiguousarray(q, dtype=np.uint16)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ms = {"memset": [], "huffman": [], "idct": [], "color": []}
+
+    def step(record):
+        e = [ev() for _ in range(5)] if record else None
+        if record:
+            e[0].record(stream)
+        for c in buf.coef:
+            ctx.check(ctx.L.jpeg_sm100_memset(ctx.h, c.data_ptr(), 0, c.numel() * 2))
+        if record:
+            e[1].record(stream)
+        ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
+                                                   geo.blocks[0], 0, tables, 0, C.byref(buf.sp), d_status.data_ptr()))
+        if record:
+            e[2].record(stream)
+        ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), qz.ctypes.data, 8, C.byref(buf.pl)))
+        if record:
+            e[3].record(stream)
+        ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
+        if record:
+            e[4].record(stream)
+        return e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    assert d_status.cpu().abs().sum().item() == 0, "decode reported an error"
+    checksum = int(buf.rgb[0, ::97, ::89].to(torch.int64).sum().item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    t0, t1 = ev(), ev()
+    barrier()
+    t0.record(stream)
+    recs = [step(True) for _ in range(args.steps)]
+    t1.record(stream)
+    barrier()
+    launches = ctx.launches - launches0
+    total_ms = t0.elapsed_time(t1)
+    for e in recs:
+        for k, name in enumerate(("memset", "huffman", "idct", "color")):
+            stage_ms[name].append(e[k].elapsed_time(e[k + 1]))
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------------------
+    rgb_bytes = n * W * H * 3
+    h_ecs = torch.from_numpy(inputs.ecs).pin_memory()
+    h_off = torch.from_numpy(inputs.offsets.view(np.int64)).pin_memory()
+    h_rgb = torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory()
+    h_status = np.zeros(n, dtype=np.int32)
+
+    def e2e_step():
+        ctx.check(ctx.L.jpeg_sm100_decode_batch_rgb8(ctx.h, C.byref(desc), n, h_ecs.data_ptr(), h_off.data_ptr(), inputs.n_ecs,
+                                                     geo.blocks[0], tables, 0, qz.ctypes.data, W, H, 0, h_rgb.data_ptr(),
+                                                     h_status.ctypes.data))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - w0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(h_rgb.view(n, H, W, 3)[0, ::97, ::89].to(torch.int64).sum().item()) == checksum, "e2e result differs"
+
+    if world > 1:
+        t = torch.tensor([ms_per_step, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_s = t[0].item(), t[1].item()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        px_per_step = n * W * H * world
+        idct_ms = statistics.mean(stage_ms["idct"]) / 3.0  # three launches (Y, Cb, Cr) per step
+        idct_bytes = 192.0 * geo.total_blocks * n / 3.0    # algorithmic bytes of the average launch
+        achieved = idct_bytes / (idct_ms * 1e-3) / 1e9
+        shares = {k: round(statistics.mean(v) / (ms_per_step if world == 1 else sum(statistics.mean(x) for x in stage_ms.values())), 4)
+                  for k, v in stage_ms.items()}
+        huff_ms = statistics.mean(stage_ms["huffman"])
+        huff_bytes = inputs.ecs_bytes + 2.0 * 64 * geo.total_blocks * n
+        color_ms = statistics.mean(stage_ms["color"])
+        color_bytes = (64.0 * geo.total_blocks + 3.0 * W * H) * n
+        # CPU baseline on a bounded sample (single thread), same run
+        cpu = cpu_baseline_sample(ecs_all[:2], tables_all[:16], q)
+        line = {
+            "metric": METRIC, "value": round(px_per_step / (ms_per_step * 1e-3) / 1e6, 1), "unit": "Mpixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": n, "ecs_bytes_per_frame": inputs.ecs_bytes // n,
+                       "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective"},
+            "e2e": {"value": round(px_per_step / e2e_s / 1e6, 1), "unit": "Mpixels/s",
+                    "h2d_bytes_per_step": int(inputs.ecs_bytes + inputs.offsets.nbytes), "d2h_bytes_per_step": int(rgb_bytes + 4 * n)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",
+                         "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5)},
+            "stages": {"ms": {k: round(statistics.mean(v), 4) for k, v in stage_ms.items()}, "share_of_step": shares,
+                       "huffman_GBps": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1),
+                       "color_GBps": round(color_bytes / (color_ms * 1e-3) / 1e9, 1)},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(ecs_list, tables, q):
+    """the oracle (CPU restatement of the reference, 'port') on a bounded sample: 2 frames, one thread"""
+    try:
+        from jpeg_b200 import batch
+        from oracle import oracle as O
+        specs = []
+        for i, e in enumerate(ecs_list):
+            data, lens = batch.unstuff_split(e)
+            offs = np.concatenate([[0], np.cumsum(lens)])
+            parts = [data[offs[k]:offs[k + 1]].tobytes() for k in range(len(lens))]
+            dct = [O.HuffSpec.make(bytes(t.counts), bytes(t.values)) if t.present else O.HuffSpec() for t in tables[8 * i:8 * i + 4]]
+            act = [O.HuffSpec.make(bytes(t.counts), bytes(t.values)) if t.present else O.HuffSpec() for t in tables[8 * i + 4:8 * i + 8]]
+            specs.append((parts, dct, act))
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 8.0 and reps < 6:
+            for parts, dct, act in specs:
+                s = O.Spectral.create((W, H), FACTORS)
+                for p in range(3):
+                    s.set_quanta(p, q[p])
+                s.decode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], dct, act, parts, interval=240)
+                O.unpack_rgb(s.to_rectangular())
+            reps += 1
+        dt = time.perf_counter() - t0
+        return {"value": round(reps * len(specs) * W * H / dt / 1e6, 2), "unit": "Mpixels/s", "cores": 1, "kind": "port",
+                "sample": f"{len(specs)} frames of the workload x {reps} repetitions, single thread ({os.cpu_count()} cores present)"}
+    except Exception as e:  # the baseline is reported, never required
+        return {"value": None, "unit": "Mpixels/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

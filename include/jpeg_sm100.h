@@ -154,6 +154,21 @@ int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_plane_i16 
                                 const uint16_t *quanta_zigzag, const int32_t *factors_xy,
                                 uint32_t size_x, uint32_t size_y, int cosited, uint8_t *rgb);
 
+/* batch form of the above for N baseline (single sequential scan) images of identical geometry:
+ *   for each image:  Spectral.decode(ecss:...) -> idct() -> interleaved(cosite:) -> unpack(as: RGB.self)
+ * i.e. Rectangular.decompress(stream:) + unpack (decode.swift:4367, 4294) minus the container lexer.
+ * Host buffers in, host RGB8 out, one call, copies included; pass pinned memory (jpeg_sm100_malloc_host) for full
+ * PCIe rate.  Every plane of the image must be a component of `scan`.
+ *   ecs_offsets : n_images * n_ecs + 1 offsets into ecs_concat (image-major, unstuffed bytes)
+ *   tables      : n_images x 8 (dc[4], ac[4]) or 1 x 8 if tables_shared
+ *   quanta      : n_planes x 64 (zig-zag), shared by all images
+ *   rgb         : n_images * size_y * size_x * 3 bytes;  status: n_images codes (0 or the image's first error) */
+int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
+                                 const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs,
+                                 uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
+                                 const uint16_t *quanta_zigzag, uint32_t size_x, uint32_t size_y, int cosited,
+                                 uint8_t *rgb, int32_t *status);
+
 /* ---- encode ---- */
 
 /* replaces  JPEG.RGB.pack(_:as:)   jpeg.swift:584-599 (RGB.ycc 463-478) */

@@ -464,6 +464,71 @@ JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_p
     return JPEG_SM100_OK;
 }
 
+// batched host-buffer decode: H2D -> K3 -> K1 -> K2 -> D2H on the ctx stream
+JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
+                                          const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs,
+                                          uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
+                                          const uint16_t *quanta, uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb,
+                                          int32_t *status)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !ecs_offsets || !tables || !quanta || !rgb || n_images == 0 || n_ecs == 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (scan->band_lo != 0 || scan->band_hi != 64 || scan->bit_hi >= 0) return JPEG_SM100_ERR_UNSUPPORTED;
+    const uint32_t n_planes = (uint32_t) scan->n_comp;
+    if (n_planes != 1 && n_planes != 3) return JPEG_SM100_ERR_UNSUPPORTED;
+    int scx = 0, scy = 0;
+    for (uint32_t c = 0; c < n_planes; ++c) {
+        if (scan->comp[c].plane != (int) c) return JPEG_SM100_ERR_UNSUPPORTED;  // planes in scan order
+        scx = scan->comp[c].factor_x > scx ? scan->comp[c].factor_x : scx;
+        scy = scan->comp[c].factor_y > scy ? scan->comp[c].factor_y : scy;
+    }
+    if (scx < 1 || scy < 1) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_dev_spectral sp;
+    jpeg_sm100_dev_planar   pl;
+    memset(&sp, 0, sizeof sp);
+    sp.n_images = n_images;
+    sp.n_planes = n_planes;
+    size_t coef_total = 0, coef_off[4];
+    for (uint32_t p = 0; p < n_planes; ++p) {
+        const int fx = scan->comp[p].factor_x, fy = scan->comp[p].factor_y;
+        sp.plane[p].units_x = units_of((int) sx * fx, 8 * scx);
+        sp.plane[p].units_y = units_of((int) sy * fy, 8 * scy);
+        sp.plane[p].factor_x = fx;
+        sp.plane[p].factor_y = fy;
+        sp.plane[p].image_stride = (uint64_t) 64 * sp.plane[p].units_x * sp.plane[p].units_y;
+        coef_off[p] = coef_total;
+        coef_total += align_up((size_t) sp.plane[p].image_stride * 2 * n_images, 1024);
+    }
+    void *d_coef = nullptr, *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr, *d_rgb = nullptr;
+    J_TRY(scratch_reserve(ctx, 0, coef_total + 1024, &d_coef));
+    for (uint32_t p = 0; p < n_planes; ++p) sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(d_coef) + coef_off[p]);
+    J_TRY(alloc_planar(ctx, 4, sp, 1, pl));
+    const uint64_t n_off = (uint64_t) n_images * n_ecs + 1;
+    const uint64_t ecs_bytes = ecs_offsets[n_off - 1];
+    const size_t   rgb_bytes = (size_t) sx * sy * 3 * n_images;
+    J_TRY(scratch_reserve(ctx, 1, ecs_bytes + 64, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 2, n_off * 8, &d_off));
+    J_TRY(scratch_reserve(ctx, 3, sizeof(int32_t) * n_images + 64, &d_status));
+    J_TRY(scratch_reserve(ctx, 6, rgb_bytes + 64, &d_rgb));
+    if (ecs_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, ecs_concat, ecs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_off, ecs_offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_coef, 0, coef_total, ctx->stream));  // Spectral planes start zeroed (decode.swift:2241-2256)
+    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
+                                   interval, 0, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status)));
+    J_TRY(jpeg_sm100_dev_idct(ctx, &sp, quanta, 8, &pl));
+    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
+    if (rgb_bytes) CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> st(n_images, 0);
+    CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int first = 0;
+    for (uint32_t i = 0; i < n_images; ++i) {
+        if (status) status[i] = st[i];
+        if (st[i] && !first) first = st[i];
+    }
+    return first;
+}
+
 // ---- encode ----
 JPEG_API int jpeg_sm100_pack_rgb8(jpeg_sm100_ctx *ctx, const uint8_t *rgb, uint64_t n_px, int arity, uint16_t *il)
 {

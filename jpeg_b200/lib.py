@@ -113,6 +113,7 @@ SYMBOLS = {
     "jpeg_sm100_unpack_rgb8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_unpack_ycc8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_spectral_to_rgb8": (_i, [_vp, C.POINTER(PlaneI16), _u32, _vp, _vp, _u32, _u32, _i, _vp]),
+    "jpeg_sm100_decode_batch_rgb8": (_i, [_vp, _SD, _u32, _vp, _vp, _u32, _u64, _HT, _i, _vp, _u32, _u32, _i, _vp, _vp]),
     "jpeg_sm100_pack_rgb8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_decompose": (_i, [_vp, _vp, _u32, _u32, C.POINTER(PlaneU16), _u32]),
     "jpeg_sm100_fdct": (_i, [_vp, _vp, _u32, _u32, _vp, _i, _vp]),

@@ -301,4 +301,82 @@ def test_batched_device_pipeline(H, O, manifest):
         for p in range(3):
             assert np.array_equal(coefs[p][i].cpu().numpy(), specs[i].coefficients(p)), (i, p)
         assert np.array_equal(d_rgb[i].cpu().numpy(), want[i]), i
-    assert ctx.launches >= 3 + 3 + 1
+    assert ctx.launches >= 2 + 3 + 1  # decode + status reduce, one IDCT per plane, colour
+
+
+# ------------------------------------------------------------------------------------------------ entropy encode (K6/K7)
+@pytest.mark.parametrize("name,progression", [("baseline", BASELINE), ("split", BASELINE_SPLIT),
+                                              ("progressive", PROGRESSIVE)])
+@pytest.mark.parametrize("rows", [0, 1, 3])
+def test_scan_encode_all_kinds(H, O, name, progression, rows):
+    """GPU Spectral.encode(scan:) against the oracle: optimal tables and stuffed ECS bytes identical, for the five
+    scan kinds, with the reference's single-ECS form (rows = 0) and our RSTn extension."""
+    data = golden_bytes("gold/color-progressive-1.jpg")
+    src = O.Spectral.decompress(data)
+    dev = H.Spectral.decompress(data)
+    for band, bits, comps in progression:
+        width = src.blocks[0] if len(comps) > 1 else src.units(comps[0])[0]
+        sel = [0, 1, 1][:len(comps)] if len(comps) > 1 else [0]
+        want, dct, act = src.encode_scan(band, bits, comps, sel, sel, rows * width)
+        got, gdc, gac = dev.encode_scan(band, bits, [(c, d, d) for c, d in zip(comps, sel)], rows * width)
+        for k in range(4):
+            assert bool(gdc[k].present) == bool(dct[k].present) and bool(gac[k].present) == bool(act[k].present)
+            if dct[k].present:
+                assert gdc[k].as_tuple() == dct[k].as_tuple(), (name, band, bits, "dc", k)
+            if act[k].present:
+                assert gac[k].as_tuple() == act[k].as_tuple(), (name, band, bits, "ac", k)
+        assert got == want, (name, rows, band, bits, comps, len(got), len(want))
+
+
+def test_encode_basic_golden_through_gpu(manifest, H):
+    """examples/encode-basic end to end on the GPU: RGB -> pack -> decomposed -> fdct -> encode(scan:) must give the
+    reference's own DHT tables and entropy-coded bytes (digests from the 32 committed JPEG files)."""
+    from jpeg_b200 import lib
+    eb = manifest["encode_basic"]
+    w, h = eb["size"]
+    rgb = np.frombuffer(golden_bytes(eb["rgb"]), dtype=np.uint8).reshape(h, w, 3)
+    levels = {"0.0": 0.0, "0.25": 0.25, "1.0": 1.0, "8.0": 8.0}
+    for name, lum in (("4-4-4", (1, 1)), ("4-4-0", (1, 2)), ("4-2-2", (2, 1)), ("4-2-0", (2, 2))):
+        factors = [lum, (1, 1), (1, 1)]
+        planar = H.Rectangular.pack(rgb, factors).decomposed()
+        for tag, level in levels.items():
+            exp = eb["files"][f"{name}-{tag}"]
+            q = [np.array(exp["dqt"][0][1], np.uint16), np.array(exp["dqt"][1][1], np.uint16)]
+            sp = planar.fdct([q[0], q[1], q[1]])
+            for sc, comps in zip(exp["scans"], ([(0, 0, 0)], [(1, 1, 1), (2, 1, 1)])):
+                ecs, dct, act = sp.encode_scan((0, 64), (0, None), comps)
+                assert len(ecs) == sc["ecs_len"] and sha(ecs) == sc["ecs_sha256"], (name, tag)
+                for cls, tgt, counts, values in sc["dht"]:
+                    tab = (dct if cls == 0 else act)[tgt]
+                    assert tab.as_tuple() == (bytes.fromhex(counts), bytes.fromhex(values)), (name, tag)
+
+
+def test_reencode_in_memory_through_gpu(manifest, H):
+    """examples/in-memory: the 14-scan progressive file decoded to coefficients on the GPU and re-encoded from them."""
+    exp = manifest["reencode"]["in-memory"]
+    s = H.Spectral.decompress(golden_bytes(exp["source"]))
+    ids = [p.comp_id for p in s.planes]
+    for k, sc in enumerate(exp["scans"]):
+        sos = bytes.fromhex(sc["sos"])
+        n = sos[0]
+        comps = [(ids.index(sos[1 + 2 * i]), sos[2 + 2 * i] >> 4, sos[2 + 2 * i] & 15) for i in range(n)]
+        band = (sos[2 * n + 1], sos[2 * n + 2] + 1)
+        al, ah = sos[2 * n + 3] & 15, sos[2 * n + 3] >> 4
+        ecs, dct, act = s.encode_scan(band, (al, None if ah == 0 else ah), comps)
+        assert len(ecs) == sc["ecs_len"] and sha(ecs) == sc["ecs_sha256"], k
+        for cls, tgt, counts, values in sc["dht"]:
+            tab = (dct if cls == 0 else act)[tgt]
+            assert tab.as_tuple() == (bytes.fromhex(counts), bytes.fromhex(values)), k
+
+
+def test_compress_decompress_roundtrip_on_gpu(H, O):
+    """Spectral.compress() with DRI -> Spectral.decompress(): coefficients survive; the oracle decodes our file to
+    the same pixels (the file is a valid JPEG for an independent decoder)."""
+    src = H.Spectral.decompress(golden_bytes("gold/color-sequential-2.jpg"))
+    blob = src.compress(scans=[H.Scan((0, 64), (0, None), [(0, 0, 0), (1, 1, 1), (2, 1, 1)])],
+                        interval_mcus=src.blocks[0])
+    back = H.Spectral.decompress(blob)
+    for a, b in zip(src.planes, back.planes):
+        assert np.array_equal(a.coef, b.coef)
+    rgb, _, _ = O.decode_rgb(blob)
+    assert np.array_equal(rgb, back.to_rgb8())
