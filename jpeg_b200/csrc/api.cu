@@ -60,6 +60,13 @@ JPEG_API void jpeg_sm100_destroy(jpeg_sm100_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
+    for (auto &p : ctx->pinned) {
+        if (p.ptr) cudaFreeHost(p.ptr);
+        if (p.done) cudaEventDestroy(p.done);
+    }
+    for (auto &e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -464,7 +471,11 @@ JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_p
     return JPEG_SM100_OK;
 }
 
-// batched host-buffer decode: H2D -> K3 -> K1 -> K2 -> D2H on the ctx stream
+// batched host-buffer decode.  Entropy decoding is latency-bound (one thread per restart interval), so it runs once
+// for the whole batch; the bandwidth-bound back half is cut into chunks whose device->host copies (the e2e limiter:
+// 3 bytes of RGB per pixel leave the device) overlap the kernels of the next chunk:
+//     stream  : H2D ecs -> memset -> K3 (whole batch) -> per chunk k: K1 -> K2 into RGB buffer (k & 1)
+//     copy_out: D2H of chunk k's RGB (waits for its K2; K2 of chunk k + 2 waits for this copy)
 JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
                                           const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs,
                                           uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
@@ -483,8 +494,21 @@ JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_
         scy = scan->comp[c].factor_y > scy ? scan->comp[c].factor_y : scy;
     }
     if (scx < 1 || scy < 1) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (!ctx->copy_out) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+
+    // chunk size: ~100 MB of RGB per chunk, at least 1 image, at most the batch
+    const size_t rgb_per_image = (size_t) sx * sy * 3;
+    uint32_t     chunk = (uint32_t) ((size_t) (100u << 20) / (rgb_per_image ? rgb_per_image : 1));
+    chunk = chunk < 1 ? 1 : (chunk > n_images ? n_images : chunk);
+    const uint32_t n_chunks = (n_images + chunk - 1) / chunk;
+    while (ctx->events.size() < (size_t) 2 * n_chunks) {
+        cudaEvent_t ev;
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->events.push_back(ev);
+    }
+    cudaEvent_t *ev_k = ctx->events.data(), *ev_out = ev_k + n_chunks;
+
     jpeg_sm100_dev_spectral sp;
-    jpeg_sm100_dev_planar   pl;
     memset(&sp, 0, sizeof sp);
     sp.n_images = n_images;
     sp.n_planes = n_planes;
@@ -502,25 +526,41 @@ JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_
     void *d_coef = nullptr, *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr, *d_rgb = nullptr;
     J_TRY(scratch_reserve(ctx, 0, coef_total + 1024, &d_coef));
     for (uint32_t p = 0; p < n_planes; ++p) sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(d_coef) + coef_off[p]);
-    J_TRY(alloc_planar(ctx, 4, sp, 1, pl));
+    jpeg_sm100_dev_spectral geo = sp;  // sample planes are only needed for one chunk at a time
+    geo.n_images = chunk;
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, geo, 1, pl));
     const uint64_t n_off = (uint64_t) n_images * n_ecs + 1;
     const uint64_t ecs_bytes = ecs_offsets[n_off - 1];
-    const size_t   rgb_bytes = (size_t) sx * sy * 3 * n_images;
+    const size_t   rgb_chunk = align_up(rgb_per_image * chunk, 256);
     J_TRY(scratch_reserve(ctx, 1, ecs_bytes + 64, &d_ecs));
     J_TRY(scratch_reserve(ctx, 2, n_off * 8, &d_off));
     J_TRY(scratch_reserve(ctx, 3, sizeof(int32_t) * n_images + 64, &d_status));
-    J_TRY(scratch_reserve(ctx, 6, rgb_bytes + 64, &d_rgb));
+    J_TRY(scratch_reserve(ctx, 6, 2 * rgb_chunk + 64, &d_rgb));
+
     if (ecs_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, ecs_concat, ecs_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(d_off, ecs_offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemsetAsync(d_coef, 0, coef_total, ctx->stream));  // Spectral planes start zeroed (decode.swift:2241-2256)
     J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
                                    interval, 0, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status)));
-    J_TRY(jpeg_sm100_dev_idct(ctx, &sp, quanta, 8, &pl));
-    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
-    if (rgb_bytes) CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    for (uint32_t k = 0; k < n_chunks; ++k) {
+        const uint32_t i0 = k * chunk, cnt = (i0 + chunk <= n_images) ? chunk : n_images - i0;
+        uint8_t       *rgb_buf = reinterpret_cast<uint8_t *>(d_rgb) + (k & 1) * rgb_chunk;
+        jpeg_sm100_dev_spectral spk = sp;
+        spk.n_images = pl.n_images = cnt;
+        for (uint32_t p = 0; p < n_planes; ++p) spk.plane[p].coef = sp.plane[p].coef + (size_t) i0 * sp.plane[p].image_stride;
+        if (k >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[k - 2], 0));  // RGB buffer (k & 1) is free again
+        J_TRY(jpeg_sm100_dev_idct(ctx, &spk, quanta, 8, &pl));
+        J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, rgb_buf));
+        CU_TRY(ctx, cudaEventRecord(ev_k[k], ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k[k], 0));
+        CU_TRY(ctx, cudaMemcpyAsync(rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CU_TRY(ctx, cudaEventRecord(ev_out[k], ctx->copy_out));
+    }
     std::vector<int32_t> st(n_images, 0);
     CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
     int first = 0;
     for (uint32_t i = 0; i < n_images; ++i) {
         if (status) status[i] = st[i];

@@ -19,6 +19,14 @@ struct DeviceBuffer {
     size_t cap = 0;
 };
 
+// pinned host staging slots: async H2D of small per-call metadata without a host-side stream sync
+struct PinnedSlot {
+    void       *ptr = nullptr;
+    size_t      cap = 0;
+    cudaEvent_t done = nullptr;
+    bool        in_flight = false;
+};
+
 struct jpeg_sm100_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
@@ -28,6 +36,11 @@ struct jpeg_sm100_ctx {
     std::string  last_error;
     // grow-only scratch used by layer A (host-buffer entry points)
     DeviceBuffer scratch[12];
+    PinnedSlot   pinned[4];
+    int          pinned_next = 0;
+    // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> events;
     // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda dependency)
     void *encode_tiled = nullptr;
 };
@@ -70,6 +83,36 @@ static inline int scratch_reserve(jpeg_sm100_ctx *ctx, int slot, size_t bytes, v
         b.cap = want;
     }
     *out = b.ptr;
+    return JPEG_SM100_OK;
+}
+
+// Acquire a pinned staging slot of at least `bytes`; blocks only if that slot's previous copy is still in flight.
+static inline int pinned_acquire(jpeg_sm100_ctx *ctx, size_t bytes, void **out, int *slot_out)
+{
+    const int   si = ctx->pinned_next;
+    PinnedSlot &s = ctx->pinned[si];
+    ctx->pinned_next = (si + 1) % 4;
+    if (s.in_flight) {
+        CU_TRY(ctx, cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    if (!s.done) CU_TRY(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (bytes > s.cap) {
+        if (s.ptr) CU_TRY(ctx, cudaFreeHost(s.ptr));
+        s.ptr = nullptr;
+        s.cap = 0;
+        CU_TRY(ctx, cudaMallocHost(&s.ptr, bytes + 4096));
+        s.cap = bytes + 4096;
+    }
+    *out = s.ptr;
+    *slot_out = si;
+    return JPEG_SM100_OK;
+}
+// call after the async copies that read the slot have been enqueued
+static inline int pinned_release(jpeg_sm100_ctx *ctx, int slot)
+{
+    CU_TRY(ctx, cudaEventRecord(ctx->pinned[slot].done, ctx->stream));
+    ctx->pinned[slot].in_flight = true;
     return JPEG_SM100_OK;
 }
 

@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int WARP = 32;
-constexpr int MAX_LUT_SMEM = 40 * 1024;
+constexpr int MAX_LUT_SMEM = 44 * 1024;  // entries staged in shared memory up to this size
 
 // ---- host: LUT construction (decode.swift:310-351 size, 1037-1240 decoder) ----------------------------------
 struct LutHeader {  // per image: 8 tables (dc0..3, ac0..3)
@@ -28,8 +28,10 @@ struct LutHeader {  // per image: 8 tables (dc0..3, ac0..3)
     int32_t  zeta[8];
     uint32_t offset[8];  // entry offset into the image's entry array
     int32_t  present[8];
-    uint32_t total_entries;
-    uint32_t pad[3];
+    uint32_t fast[8];        // entry offset of the table's 2048-entry 11-bit fast table
+    uint32_t total_entries;  // reference (two-level) entries
+    uint32_t total_all;      // reference + fast entries
+    uint32_t pad[2];
 };
 static_assert(sizeof(LutHeader) % 16 == 0, "header must keep 16-byte alignment");
 
@@ -50,27 +52,51 @@ bool huff_size(const uint8_t counts[16], int &n, int &z)
     return interior > 0;
 }
 
-// appends the table's entries (symbol | length << 8) to `entries`
-int build_lut(const jpeg_sm100_huff_table &t, std::vector<uint16_t> &entries, int &n, int &zeta)
+// host -> device hand-over of one table set: the sized header plus the raw BITS / HUFFVAL of its eight slots
+struct RawSet {
+    LutHeader header;
+    uint8_t   counts[8][16];
+    uint8_t   values[8][256];
+};
+
+// decode.swift:1037-1240 Table.Huffman.decoder(): level l (codes of l+1 bits) contributes `0x8080 >> l & 0xff` clones
+// of (symbol, l+1) per leaf: 128, 64, ... 1 in the level-0 table, then 128 ... 1 again in the 256-entry sub-tables.
+__global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ raw, uint8_t *__restrict__ luts, size_t stride)
 {
-    int z;
-    if (!huff_size(t.counts, n, z)) return JPEG_SM100_ERR_INVALID_HUFFMAN;
-    int total = 0;
-    for (int l = 0; l < 16; ++l) total += t.counts[l];
-    if (total > 256) return JPEG_SM100_ERR_INVALID_HUFFMAN;
-    zeta = z + n * 255;
-    const size_t start = entries.size();
-    int          base = 0;
+    const int        ti = blockIdx.x;
+    const RawSet    &r = raw[blockIdx.y];
+    uint8_t         *dst = luts + stride * blockIdx.y;
+    const LutHeader &h = r.header;
+    if (ti == 0)
+        for (uint32_t i = threadIdx.x; i < sizeof(LutHeader) / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(&h)[i];
+    if (!h.present[ti]) return;
+    uint16_t     *entries = reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.offset[ti];
+    const uint8_t *counts = r.counts[ti], *values = r.values[ti];
+    // leaf j of level l starts at  sum_{l' < l} counts[l'] * clones(l')  +  j * clones(l)
+    uint32_t level_start = 0, leaf_base = 0;
     for (int l = 0; l < 16; ++l) {
-        if (!((int) (entries.size() - start) < z)) break;
-        const int clones = (0x8080 >> l) & 0xff;
-        for (int s = 0; s < t.counts[l]; ++s)
-            for (int c = 0; c < clones && (int) (entries.size() - start) < z; ++c)
-                entries.push_back((uint16_t) (t.values[base + s] | ((l + 1) << 8)));
-        base += t.counts[l];
+        const uint32_t clones = (0x8080u >> l) & 0xffu;
+        for (uint32_t j = threadIdx.x; j < counts[l]; j += blockDim.x) {
+            const uint16_t e = (uint16_t) (values[leaf_base + j] | ((l + 1) << 8));
+            uint16_t      *o = entries + level_start + j * clones;
+            for (uint32_t c = 0; c < clones; ++c) o[c] = e;
+        }
+        level_start += counts[l] * clones;
+        leaf_base += counts[l];
     }
-    while ((int) (entries.size() - start) < z) entries.push_back(0x1000);  // unreachable for valid trees
-    return JPEG_SM100_OK;
+    // 11-bit fast table: (symbol | length << 8) for codes of <= 11 bits, 0 = longer / invalid code -> reference lookup
+    __syncthreads();
+    uint16_t *fast = reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti];
+    const int n = h.n[ti], zeta = h.zeta[ti];
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) {
+        const uint32_t cw = i << 5;
+        const int      hi = (int) (cw >> 8);
+        uint32_t       e = 0x1000u;
+        if (hi < n) e = entries[hi];
+        else if ((int) cw < zeta) e = entries[(int) cw - 255 * n];
+        fast[i] = (e >> 8) <= 11u ? (uint16_t) e : (uint16_t) 0;
+    }
 }
 
 // ---- device side ---------------------------------------------------------------------------------------------
@@ -337,6 +363,301 @@ __global__ void __launch_bounds__(WARP) k_decode_flat(const __grid_constant__ Sc
             }
         }
     }
+finished:
+    if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
+}
+
+// ---- latency-optimised decoder for sequential (kind 0) and DC-first (kind 1) scans ----------------------------------
+// Every restart interval already has its own thread, so the kernel's duration is ONE thread's dependent-instruction
+// chain times its symbol count.  The loop is therefore organised around that chain (ncu: a lone warp per scheduler
+// issues one instruction every ~5 cycles, and exposed load latency was 20 % of the first-generation kernel):
+//   * FAST PHASE (all but the last few bytes of an interval): no truncation bookkeeping at all -- while the next
+//     word to load lies entirely inside the interval every consumed bit is a real bit, so the reference's
+//     `i < count` / `i + n <= count` guards (decode.swift:2775-2862) cannot fire;
+//   * the bitstream word for the NEXT refill is loaded one refill ahead (double buffering) and lines are prefetched
+//     into L1 two lines ahead, so no load latency sits on the chain;
+//   * codes of <= 11 bits (all DC codes, > 99.9 % of AC codes) resolve with one shared-memory load from an 11-bit
+//     table derived from the reference's two-level LUT; longer or invalid codes take the reference lookup;
+//   * DC and AC symbols share one straight-line path; DC predictors live in shared memory (touched once per block);
+//   * the successor block's geometry is recomputed every trip off the critical path and swapped in with selects;
+//   * a CAREFUL PHASE with the full bookkeeping finishes the tail of the interval and raises the errors.
+struct CmpInfo {                // one per scan component, 48 bytes
+    uint32_t base_blk;          // block index (128-byte units from P.plane0) of the plane's block (0, 0) of this image
+    int32_t  ux, uy, fx, fy;
+    uint32_t dfast, afast;      // entry offsets of the 11-bit tables
+    int32_t  dci, aci;          // LUT indices for the reference lookup
+    int32_t  hasplane;
+    int32_t  pad[2];
+};
+static_assert(sizeof(CmpInfo) == 48, "CmpInfo is read with three 16-byte shared loads");
+
+__global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ ScanParams P, int16_t *const plane0)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t   img = blockIdx.y, lane = threadIdx.x;
+    const uint32_t   e = blockIdx.x * WARP + lane;
+    const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    CmpInfo         *s_cmp = reinterpret_cast<CmpInfo *>(smem + sizeof(LutHeader));
+    uint32_t        *s_blk = reinterpret_cast<uint32_t *>(smem + sizeof(LutHeader) + 4 * sizeof(CmpInfo));
+    int             *s_pred = reinterpret_cast<int *>(smem + sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64);
+    constexpr uint32_t PRE = sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64 + 4 * WARP * sizeof(int);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + PRE);
+    {
+        const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
+        const uint32_t   total = gh->total_all;
+        uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = lane; i < sizeof(LutHeader) / 4; i += WARP) dst[i] = src[i];
+        uint32_t *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
+        for (uint32_t i = lane; i < (total + 1) / 2; i += WARP) d2[i] = src[sizeof(LutHeader) / 4 + i];
+        if (lane < 4) {
+            const int c = lane;
+            CmpInfo   ci;
+            memset(&ci, 0, sizeof ci);
+            ci.hasplane = P.plane[c] != nullptr;
+            ci.base_blk = ci.hasplane ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
+            ci.ux = P.ux[c], ci.uy = P.uy[c], ci.fx = P.fx[c], ci.fy = P.fy[c];
+            ci.dci = P.dc[c], ci.aci = P.ac[c];
+            ci.dfast = gh->fast[P.dc[c]];
+            ci.afast = gh->fast[P.ac[c]];
+            s_cmp[c] = ci;
+        }
+        if (lane < 16)
+            s_blk[lane] = lane < 12 ? (uint32_t) P.blk_comp[lane] | ((uint32_t) P.blk_dx[lane] << 4) | ((uint32_t) P.blk_dy[lane] << 8) : 0u;
+        for (int c = 0; c < 4; ++c) s_pred[c * WARP + lane] = 0;
+        __syncwarp();
+    }
+    if (e >= P.n_ecs) return;
+
+    int     err = 0;
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    const uint64_t o0 = P.offsets[(size_t) img * P.n_ecs + e], o1 = P.offsets[(size_t) img * P.n_ecs + e + 1];
+    const uint8_t *base = P.ecs + o0;
+    if ((int64_t) (o1 - o0) > 0x0fffffff) {
+        if (P.status) P.status[(size_t) img * P.n_ecs + e] = JPEG_SM100_ERR_UNSUPPORTED;
+        return;
+    }
+    const int       nbytes = (int) (o1 - o0), count = 8 * nbytes;
+    const int       lead = (int) (reinterpret_cast<uintptr_t>(base) & 3);
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(base - lead);
+    const uint32_t *wsafe = w0 + (lead + nbytes) / 4;  // words [w0, wsafe) need no padding (w0's lead bytes are shifted out)
+    auto padded_word = [&](const uint32_t *p) -> uint32_t {
+        const int first = (int) (p - w0) * 4 - lead;
+        uint32_t  be = 0xffffffffu;
+        if (first < nbytes) {
+            be = __byte_perm(__ldg(p), 0, 0x0123);
+            const int valid = nbytes - first;
+            if (valid < 4) be |= 0xffffffffu >> (8 * valid);
+        }
+        return be;
+    };
+    const uint32_t *wp = w0;
+    uint64_t        acc;
+    int             navail;
+    {
+        const uint32_t b0 = nbytes > 0 ? padded_word(wp) : 0xffffffffu;
+        wp += 1;
+        acc = (uint64_t) b0 << (32 + 8 * lead);
+        navail = 32 - 8 * lead;
+        const uint32_t b1 = padded_word(wp);
+        wp += 1;
+        acc |= (uint64_t) b1 << (32 - navail);
+        navail += 32;
+    }
+    const bool dc_only = P.kind == 1;
+    const int  al = P.al, W = P.W, nblk = P.mcu_blocks, rend = (int) r1;
+
+    int  z = 0, blk = 0, mx = 0, my = (int) r0;
+    bool fresh_row = true;
+    // current block
+    uint32_t cur_idx = 0, cur_dfo = 0, cur_afo = 0;
+    int      cur_comp = 0, cur_flags = 0;  // flags: 1 = store allowed (block inside its plane), 2 = component has a plane
+
+#define NEXT_INFO(B, X, Y, O_IDX, O_DFO, O_AFO, O_COMP, O_FLAGS)                                                     \
+    do {                                                                                                             \
+        const uint32_t tb_ = s_blk[(B)];                                                                             \
+        const int      c_ = (int) (tb_ & 15u);                                                                       \
+        const CmpInfo &ci_ = s_cmp[c_];                                                                              \
+        const int      bx_ = (X) *ci_.fx + (int) ((tb_ >> 4) & 15u), by_ = (Y) *ci_.fy + (int) ((tb_ >> 8) & 15u);   \
+        const bool     in_ = ci_.hasplane && bx_ < ci_.ux && by_ < ci_.uy;                                           \
+        O_IDX = ci_.base_blk + (uint32_t) (ci_.ux * by_ + bx_);                                                      \
+        O_DFO = ci_.dfast, O_AFO = ci_.afast, O_COMP = c_;                                                           \
+        O_FLAGS = (in_ ? 1 : 0) | (ci_.hasplane ? 2 : 0);                                                            \
+    } while (0)
+
+    if (my >= rend) goto finished;
+    NEXT_INFO(blk, mx, my, cur_idx, cur_dfo, cur_afo, cur_comp, cur_flags);
+
+    // ================================ FAST PHASE ================================
+    if (wp + 1 < wsafe) {
+        uint32_t nextw = __ldg(wp);  // raw word at wp, consumed by the next refill
+        for (;;) {
+            // successor block: depends only on (blk, mx, my)
+            int nb = blk + 1, nx = mx, ny = my;
+            if (nb == nblk) {
+                nb = 0;
+                nx = mx + 1;
+            }
+            if (nx == W) {
+                nx = 0;
+                ny = my + 1;
+            }
+            uint32_t n_idx, n_dfo, n_afo;
+            int      n_comp, n_flags;
+            NEXT_INFO(nb, nx, ny, n_idx, n_dfo, n_afo, n_comp, n_flags);
+
+            if (navail <= 32) {  // refill from the word loaded one refill ago; fetch the one after it
+                const uint32_t be = __byte_perm(nextw, 0, 0x0123);
+                wp += 1;
+                nextw = __ldg(wp);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));
+                acc |= (uint64_t) be << (32 - navail);
+                navail += 32;
+            }
+            if (P.extend && fresh_row && z == 0) {  // decode.swift:3214-3220 (`pos < count` holds in this phase)
+                if ((uint32_t) (acc >> 48) == 0xffffu) goto finished;
+            }
+            fresh_row = false;
+
+            const bool     isdc = z == 0;
+            const uint32_t cw = (uint32_t) (acc >> 48);
+            uint32_t       ent = entries[(isdc ? cur_dfo : cur_afo) + (cw >> 5)];
+            if (__builtin_expect(ent == 0u, 0)) {  // code longer than 11 bits, or not a code: the reference lookup
+                const int ti = isdc ? s_cmp[cur_comp].dci : s_cmp[cur_comp].aci;
+                ent = lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw);
+            }
+            const int len = (int) (ent >> 8), sym = (int) (ent & 0xffu);
+            const int size = isdc ? sym : (sym & 15);
+            const int run = isdc ? 0 : (sym >> 4);
+            // corrupt DC symbols and EOBn in a sequential scan are finished (and diagnosed) by the careful phase
+            if (__builtin_expect(size > 16 || (!isdc && size == 0 && run != 0 && run != 15), 0)) break;
+            const uint32_t after = (uint32_t) ((acc << len) >> 32);
+            const uint32_t tail = size ? after >> (32 - size) : 0u;
+            const int      total = len + size;
+            acc <<= total;
+            navail -= total;
+            const int v = size ? extend16(size, tail) : 0;
+            int       outv = v;
+            if (isdc) {  // decode.swift:3248-3254: wrapping Int16 prediction, kept per lane in shared memory
+                int pr = s_pred[cur_comp * WARP + lane];
+                if (cur_flags & 2) pr = (int) (short) (pr + v);
+                s_pred[cur_comp * WARP + lane] = pr;
+                outv = (int) ((uint32_t) pr << al);
+            }
+            const bool eob = !isdc && sym == 0;
+            const int  zpos = isdc ? 0 : z + run;
+            if ((cur_flags & 1) && !eob && zpos < 64) plane0[(size_t) cur_idx * 64 + zpos] = (int16_t) outv;
+            z = eob ? 64 : zpos + 1;
+            if (isdc && dc_only) z = 64;
+
+            if (z >= 64) {  // block finished: swap in the successor
+                if (ny >= rend) goto finished;
+                fresh_row = (nb == 0) & (nx == 0);
+                z = 0;
+                blk = nb, mx = nx, my = ny;
+                cur_idx = n_idx, cur_dfo = n_dfo, cur_afo = n_afo, cur_comp = n_comp, cur_flags = n_flags;
+            }
+            if (!(wp + 1 < wsafe)) break;
+        }
+    }
+
+    // ================================ CAREFUL PHASE ================================
+    {
+        // bits handed to `acc` so far are all real: words [w0, wp) minus the lead bytes
+        int pos = 8 * ((int) (wp - w0) * 4 - lead) - navail;
+        for (;;) {
+            if (navail <= 32) {
+                const uint32_t be = padded_word(wp);
+                wp += 1;
+                acc |= (uint64_t) be << (32 - navail);
+                navail += 32;
+            }
+            if (P.extend && fresh_row && z == 0) {
+                if (!(pos < count) || (uint32_t) (acc >> 48) == 0xffffu) goto finished;
+            }
+            fresh_row = false;
+            const bool     isdc = z == 0;
+            const int      ti = isdc ? s_cmp[cur_comp].dci : s_cmp[cur_comp].aci;
+            const uint32_t ent = lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], (uint32_t) (acc >> 48));
+            const int      len = (int) (ent >> 8), sym = (int) (ent & 0xffu);
+            const int      size = isdc ? sym : (sym & 15);
+            const int      run = isdc ? 0 : (sym >> 4);
+            if (!(pos < count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+            int v = 0;
+            if (size > 16) {  // corrupt DC symbol: the reference's masked shifts, bit by bit (decode.swift:2742-2754, 2808-2818)
+                acc <<= len;
+                navail -= len;
+                pos += len;
+                if (!(pos + size <= count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                v = extend16(size, (uint32_t) (acc >> 48) >> ((16 - size) & 15));
+                int left = size;
+                while (left > 0) {
+                    if (navail <= 32) {
+                        const uint32_t be = padded_word(wp);
+                        wp += 1;
+                        acc |= (uint64_t) be << (32 - navail);
+                        navail += 32;
+                    }
+                    const int k = left < 16 ? left : 16;
+                    acc <<= k;
+                    navail -= k;
+                    pos += k;
+                    left -= k;
+                }
+            } else {
+                const bool eobn = !isdc && size == 0 && run != 0 && run != 15;
+                const int  need = eobn ? run : size;
+                if (need > 0 && !(pos + len + need <= count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
+                if (eobn) FAIL_LANE(JPEG_SM100_ERR_INVALID_BLOCK_RUN);
+                const uint32_t after = (uint32_t) ((acc << len) >> 32);
+                const uint32_t tail = size ? after >> (32 - size) : 0u;
+                const int      total = len + size;
+                acc <<= total;
+                navail -= total;
+                pos += total;
+                v = size ? extend16(size, tail) : 0;
+            }
+            int outv = v;
+            if (isdc) {
+                int pr = s_pred[cur_comp * WARP + lane];
+                if (cur_flags & 2) pr = (int) (short) (pr + v);
+                s_pred[cur_comp * WARP + lane] = pr;
+                outv = (int) ((uint32_t) pr << al);
+            }
+            const bool eob = !isdc && sym == 0;
+            const int  zpos = isdc ? 0 : z + run;
+            if ((cur_flags & 1) && !eob && zpos < 64) plane0[(size_t) cur_idx * 64 + zpos] = (int16_t) outv;
+            z = eob ? 64 : zpos + 1;
+            if (isdc && dc_only) z = 64;
+            if (z >= 64) {
+                int nb = blk + 1, nx = mx, ny = my;
+                if (nb == nblk) {
+                    nb = 0;
+                    nx = mx + 1;
+                }
+                if (nx == W) {
+                    nx = 0;
+                    ny = my + 1;
+                }
+                if (ny >= rend) goto finished;
+                fresh_row = (nb == 0) & (nx == 0);
+                z = 0;
+                blk = nb, mx = nx, my = ny;
+                NEXT_INFO(blk, mx, my, cur_idx, cur_dfo, cur_afo, cur_comp, cur_flags);
+            }
+        }
+    }
+#undef NEXT_INFO
 finished:
     if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
 }
@@ -612,16 +933,19 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     P.H = interleaved ? scan->blocks_y : P.uy[0];
     if (P.W <= 0 || P.H < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
 
-    // LUTs (host) -> device.  decode.swift:2884-2895, 3186-3203: a missing table is an error of the scan
-    const uint32_t          n_sets = tables_shared ? 1 : n_images;
-    std::vector<uint8_t>    blob;
-    std::vector<LutHeader>  headers(n_sets);
-    std::vector<std::vector<uint16_t>> all(n_sets);
-    size_t                  max_entries = 0;
+    // Tables: validated and sized on the host (16 additions per table), expanded into the reference's two-level LUT
+    // by k_build_luts on the device.  decode.swift:2884-2895, 3186-3203: a missing table is an error of the scan.
+    const uint32_t n_sets = tables_shared ? 1 : n_images;
     const bool need_dc = P.kind == 0 || P.kind == 1, need_ac = P.kind == 0 || P.kind == 3 || P.kind == 4;
+    void *staging = nullptr;
+    int   slot = 0;
+    J_TRY(pinned_acquire(ctx, sizeof(RawSet) * (size_t) n_sets, &staging, &slot));
+    RawSet *raw = reinterpret_cast<RawSet *>(staging);
+    size_t  max_entries = 0;
     for (uint32_t s = 0; s < n_sets; ++s) {
-        LutHeader &h = headers[s];
+        LutHeader &h = raw[s].header;
         memset(&h, 0, sizeof h);
+        uint32_t total = 0;
         for (int c = 0; c < scan->n_comp; ++c) {
             const int slots[2] = {need_dc ? P.dc[c] : -1, need_ac ? P.ac[c] : -1};
             for (int k = 0; k < 2; ++k) {
@@ -629,26 +953,39 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 if (ti < 0 || h.present[ti]) continue;
                 const jpeg_sm100_huff_table &t = tables[(size_t) s * 8 + ti];
                 if (!t.present) return k == 0 ? JPEG_SM100_ERR_UNDEFINED_DC : JPEG_SM100_ERR_UNDEFINED_AC;
-                h.offset[ti] = (uint32_t) all[s].size();
-                J_TRY(build_lut(t, all[s], h.n[ti], h.zeta[ti]));
+                int n, z, leaves = 0;
+                if (!huff_size(t.counts, n, z)) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+                for (int l = 0; l < 16; ++l) leaves += t.counts[l];
+                if (leaves > 256) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+                h.n[ti] = n;
+                h.zeta[ti] = z + n * 255;
+                h.offset[ti] = total;
                 h.present[ti] = 1;
+                total += (uint32_t) z;
+                total = (total + 1u) & ~1u;  // keep every table 4-byte aligned
+                memcpy(raw[s].counts[ti], t.counts, 16);
+                memcpy(raw[s].values[ti], t.values, 256);
             }
         }
-        h.total_entries = (uint32_t) all[s].size();
-        if (all[s].size() > max_entries) max_entries = all[s].size();
+        h.total_entries = total;
+        for (int ti = 0; ti < 8; ++ti)
+            if (h.present[ti]) {
+                h.fast[ti] = total;
+                total += 2048;
+            }
+        h.total_all = total;
+        if (total > max_entries) max_entries = total;
     }
     const size_t entry_bytes = (max_entries * 2 + 15) & ~size_t(15);
     const size_t stride = sizeof(LutHeader) + entry_bytes + 16;
-    blob.assign(stride * n_sets, 0);
-    for (uint32_t s = 0; s < n_sets; ++s) {
-        memcpy(blob.data() + stride * s, &headers[s], sizeof(LutHeader));
-        if (!all[s].empty()) memcpy(blob.data() + stride * s + sizeof(LutHeader), all[s].data(), all[s].size() * 2);
-    }
-    void *d_luts = nullptr;
-    J_TRY(scratch_reserve(ctx, 8, blob.size(), &d_luts));
-    // the blob is tiny (KBs); a synchronous-with-respect-to-host staged copy keeps `blob` reusable
-    CU_TRY(ctx, cudaMemcpyAsync(d_luts, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    void *d_raw = nullptr, *d_luts = nullptr;
+    J_TRY(scratch_reserve(ctx, 7, sizeof(RawSet) * (size_t) n_sets, &d_raw));
+    J_TRY(scratch_reserve(ctx, 8, stride * n_sets, &d_luts));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(RawSet) * (size_t) n_sets, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(pinned_release(ctx, slot));
+    k_build_luts<<<dim3(8, n_sets), 128, 0, ctx->stream>>>(reinterpret_cast<const RawSet *>(d_raw),
+                                                           reinterpret_cast<uint8_t *>(d_luts), stride);
+    LAUNCH_CHECK(ctx);
     P.luts = reinterpret_cast<const uint8_t *>(d_luts);
     P.lut_stride = tables_shared ? 0 : stride;
     P.lut_smem = entry_bytes <= (size_t) MAX_LUT_SMEM ? 1 : 0;
@@ -659,7 +996,25 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
 
     const dim3   grid((n_ecs + WARP - 1) / WARP, n_images);
     const size_t smem = sizeof(LutHeader) + (P.lut_smem ? entry_bytes : 0);
-    if (P.kind <= 1) {
+    static const bool use_flat = [] {
+        const char *e = getenv("JPEG_SM100_HUFF");
+        return e && strcmp(e, "flat") == 0;  // the first-generation kernel, kept for A/B validation
+    }();
+    // the fast kernel addresses all planes as 128-byte blocks relative to the lowest plane pointer (32-bit indices)
+    int16_t *plane0 = nullptr;
+    bool     fast_ok = P.lut_smem != 0;
+    for (int c = 0; c < scan->n_comp; ++c)
+        if (P.plane[c] && (!plane0 || P.plane[c] < plane0)) plane0 = P.plane[c];
+    for (int c = 0; c < scan->n_comp && plane0; ++c) {
+        if (!P.plane[c]) continue;
+        const uint64_t span = (uint64_t) (P.plane[c] - plane0) + P.image_stride[c] * (uint64_t) n_images;
+        if (((P.plane[c] - plane0) & 63) || (P.image_stride[c] & 63) || span / 64 > 0xfffffff0ull) fast_ok = false;
+    }
+    if (!plane0) fast_ok = false;
+    if (P.kind <= 1 && !use_flat && fast_ok) {
+        const size_t smem2 = sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64 + 4 * WARP * sizeof(int) + entry_bytes;
+        k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0);
+    } else if (P.kind <= 1) {
         if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
         else k_decode_flat<false><<<grid, WARP, smem, ctx->stream>>>(P);
     } else {
