@@ -59,6 +59,17 @@ struct RawSet {
     uint8_t   values[8][256];
 };
 
+// (symbol | length << 8) of the reference LUT -> the fast decoder's entry; 0 if the sequential decoders need the careful
+// path for it (DC magnitude category > 16, or EOBn with n > 0 in a sequential scan)
+__host__ __device__ inline uint32_t fast_entry(uint32_t ref, bool dc)
+{
+    const uint32_t len = ref >> 8, sym = ref & 0xffu;
+    if (dc) return sym > 16u ? 0u : (len | (sym << 8));
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    if (size == 0u && run != 0u && run != 15u) return 0u;
+    return len | (size << 8) | (run << 16) | ((sym == 0u ? 1u : 0u) << 24);
+}
+
 // decode.swift:1037-1240 Table.Huffman.decoder(): level l (codes of l+1 bits) contributes `0x8080 >> l & 0xff` clones
 // of (symbol, l+1) per leaf: 128, 64, ... 1 in the level-0 table, then 128 ... 1 again in the 256-entry sub-tables.
 __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ raw, uint8_t *__restrict__ luts, size_t stride)
@@ -85,9 +96,10 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         level_start += counts[l] * clones;
         leaf_base += counts[l];
     }
-    // 11-bit fast table: (symbol | length << 8) for codes of <= 11 bits, 0 = longer / invalid code -> reference lookup
+    // 11-bit fast table, one 32-bit entry per prefix: byte0 = code length (0: code longer than 11 bits, not a code, or
+    // a symbol the sequential decoders reject -> reference lookup), byte1 = extra bits, byte2 = zero run, byte3 = 1: EOB
     __syncthreads();
-    uint16_t *fast = reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti];
+    uint32_t *fast = reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti]);
     const int n = h.n[ti], zeta = h.zeta[ti];
     for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) {
         const uint32_t cw = i << 5;
@@ -95,7 +107,7 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         uint32_t       e = 0x1000u;
         if (hi < n) e = entries[hi];
         else if ((int) cw < zeta) e = entries[(int) cw - 255 * n];
-        fast[i] = (e >> 8) <= 11u ? (uint16_t) e : (uint16_t) 0;
+        fast[i] = (e >> 8) <= 11u ? fast_entry(e, ti < 4) : 0u;
     }
 }
 
@@ -381,15 +393,14 @@ finished:
 //   * DC and AC symbols share one straight-line path; DC predictors live in shared memory (touched once per block);
 //   * the successor block's geometry is recomputed every trip off the critical path and swapped in with selects;
 //   * a CAREFUL PHASE with the full bookkeeping finishes the tail of the interval and raises the errors.
-struct CmpInfo {                // one per scan component, 48 bytes
-    uint32_t base_blk;          // block index (128-byte units from P.plane0) of the plane's block (0, 0) of this image
-    int32_t  ux, uy, fx, fy;
-    uint32_t dfast, afast;      // entry offsets of the 11-bit tables
-    int32_t  dci, aci;          // LUT indices for the reference lookup
-    int32_t  hasplane;
-    int32_t  pad[2];
+struct BlkInfo {  // one per block of the MCU, read with three 16-byte shared loads
+    uint32_t base_blk, ux, uy, hasplane;  // base_blk: 128-byte block index of the plane's block (0,0) of this image
+    int32_t  fx, fy, dx, dy;
+    uint32_t dfast, afast;                // entry offsets (uint16 units) of the 11-bit tables
+    int32_t  tabs;                        // dci | aci << 8: LUT indices for the reference lookup
+    int32_t  pred;                        // byte offset of the component's predictor row in shared memory
 };
-static_assert(sizeof(CmpInfo) == 48, "CmpInfo is read with three 16-byte shared loads");
+static_assert(sizeof(BlkInfo) == 48, "BlkInfo is three uint4");
 
 __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ ScanParams P, int16_t *const plane0)
 {
@@ -398,10 +409,10 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
     const uint32_t   e = blockIdx.x * WARP + lane;
     const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
     const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
-    CmpInfo         *s_cmp = reinterpret_cast<CmpInfo *>(smem + sizeof(LutHeader));
-    uint32_t        *s_blk = reinterpret_cast<uint32_t *>(smem + sizeof(LutHeader) + 4 * sizeof(CmpInfo));
-    int             *s_pred = reinterpret_cast<int *>(smem + sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64);
-    constexpr uint32_t PRE = sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64 + 4 * WARP * sizeof(int);
+    BlkInfo         *s_blk = reinterpret_cast<BlkInfo *>(smem + sizeof(LutHeader));
+    constexpr uint32_t PRED0 = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
+    int             *s_pred = reinterpret_cast<int *>(smem + PRED0);
+    constexpr uint32_t PRE = PRED0 + 4 * WARP * sizeof(int);
     const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + PRE);
     {
         const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
@@ -411,20 +422,18 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
         for (uint32_t i = lane; i < sizeof(LutHeader) / 4; i += WARP) dst[i] = src[i];
         uint32_t *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
         for (uint32_t i = lane; i < (total + 1) / 2; i += WARP) d2[i] = src[sizeof(LutHeader) / 4 + i];
-        if (lane < 4) {
-            const int c = lane;
-            CmpInfo   ci;
-            memset(&ci, 0, sizeof ci);
-            ci.hasplane = P.plane[c] != nullptr;
-            ci.base_blk = ci.hasplane ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
-            ci.ux = P.ux[c], ci.uy = P.uy[c], ci.fx = P.fx[c], ci.fy = P.fy[c];
-            ci.dci = P.dc[c], ci.aci = P.ac[c];
-            ci.dfast = gh->fast[P.dc[c]];
-            ci.afast = gh->fast[P.ac[c]];
-            s_cmp[c] = ci;
+        if (lane < 12) {
+            const int b = lane, c = P.blk_comp[b];
+            BlkInfo   bi;
+            bi.hasplane = P.plane[c] != nullptr;
+            bi.base_blk = bi.hasplane ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
+            bi.ux = (uint32_t) P.ux[c], bi.uy = (uint32_t) P.uy[c];
+            bi.fx = P.fx[c], bi.fy = P.fy[c], bi.dx = P.blk_dx[b], bi.dy = P.blk_dy[b];
+            bi.dfast = gh->fast[P.dc[c]], bi.afast = gh->fast[P.ac[c]];
+            bi.tabs = P.dc[c] | (P.ac[c] << 8);
+            bi.pred = (int) (PRED0 + (uint32_t) c * WARP * sizeof(int));
+            s_blk[b] = bi;
         }
-        if (lane < 16)
-            s_blk[lane] = lane < 12 ? (uint32_t) P.blk_comp[lane] | ((uint32_t) P.blk_dx[lane] << 4) | ((uint32_t) P.blk_dy[lane] << 8) : 0u;
         for (int c = 0; c < 4; ++c) s_pred[c * WARP + lane] = 0;
         __syncwarp();
     }
@@ -450,135 +459,135 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
     const int       nbytes = (int) (o1 - o0), count = 8 * nbytes;
     const int       lead = (int) (reinterpret_cast<uintptr_t>(base) & 3);
     const uint32_t *w0 = reinterpret_cast<const uint32_t *>(base - lead);
-    const uint32_t *wsafe = w0 + (lead + nbytes) / 4;  // words [w0, wsafe) need no padding (w0's lead bytes are shifted out)
-    auto padded_word = [&](const uint32_t *p) -> uint32_t {
-        const int first = (int) (p - w0) * 4 - lead;
+    const uint32_t  wlim = (uint32_t) (lead + nbytes) / 4;  // words [0, wlim) need no padding (word 0's lead bytes are shifted out)
+    auto padded_word = [&](uint32_t i) -> uint32_t {
+        const int first = (int) i * 4 - lead;
         uint32_t  be = 0xffffffffu;
         if (first < nbytes) {
-            be = __byte_perm(__ldg(p), 0, 0x0123);
+            be = __byte_perm(__ldg(w0 + i), 0, 0x0123);
             const int valid = nbytes - first;
             if (valid < 4) be |= 0xffffffffu >> (8 * valid);
         }
         return be;
     };
-    const uint32_t *wp = w0;
-    uint64_t        acc;
-    int             navail;
+    uint32_t wi = 0;  // next word to hand to the bit buffer
+    uint64_t acc;
+    int      navail;
     {
-        const uint32_t b0 = nbytes > 0 ? padded_word(wp) : 0xffffffffu;
-        wp += 1;
+        const uint32_t b0 = nbytes > 0 ? padded_word(0) : 0xffffffffu;
         acc = (uint64_t) b0 << (32 + 8 * lead);
         navail = 32 - 8 * lead;
-        const uint32_t b1 = padded_word(wp);
-        wp += 1;
+        const uint32_t b1 = padded_word(1);
         acc |= (uint64_t) b1 << (32 - navail);
         navail += 32;
+        wi = 2;
     }
     const bool dc_only = P.kind == 1;
     const int  al = P.al, W = P.W, nblk = P.mcu_blocks, rend = (int) r1;
 
     int  z = 0, blk = 0, mx = 0, my = (int) r0;
     bool fresh_row = true;
-    // current block
-    uint32_t cur_idx = 0, cur_dfo = 0, cur_afo = 0;
-    int      cur_comp = 0, cur_flags = 0;  // flags: 1 = store allowed (block inside its plane), 2 = component has a plane
+    // current block: element pointer (nullptr: store suppressed), table offsets, predictor slot (bit 0: component has a plane)
+    int16_t *cur_ptr = nullptr;
+    uint32_t cur_dfo = 0, cur_afo = 0;
+    int      cur_tabs = 0, cur_pred = 0;
 
-#define NEXT_INFO(B, X, Y, O_IDX, O_DFO, O_AFO, O_COMP, O_FLAGS)                                                     \
+#define LOAD_BLOCK(B, X, Y, O_PTR, O_DFO, O_AFO, O_TABS, O_PRED)                                                     \
     do {                                                                                                             \
-        const uint32_t tb_ = s_blk[(B)];                                                                             \
-        const int      c_ = (int) (tb_ & 15u);                                                                       \
-        const CmpInfo &ci_ = s_cmp[c_];                                                                              \
-        const int      bx_ = (X) *ci_.fx + (int) ((tb_ >> 4) & 15u), by_ = (Y) *ci_.fy + (int) ((tb_ >> 8) & 15u);   \
-        const bool     in_ = ci_.hasplane && bx_ < ci_.ux && by_ < ci_.uy;                                           \
-        O_IDX = ci_.base_blk + (uint32_t) (ci_.ux * by_ + bx_);                                                      \
-        O_DFO = ci_.dfast, O_AFO = ci_.afast, O_COMP = c_;                                                           \
-        O_FLAGS = (in_ ? 1 : 0) | (ci_.hasplane ? 2 : 0);                                                            \
+        const uint4 *q_ = reinterpret_cast<const uint4 *>(&s_blk[(B)]);                                              \
+        const uint4  a_ = q_[0], g_ = q_[1], t_ = q_[2];                                                             \
+        const uint32_t bx_ = (uint32_t) (X) * g_.x + g_.z, by_ = (uint32_t) (Y) * g_.y + g_.w;                       \
+        const bool     in_ = (bx_ < a_.y) & (by_ < a_.z) & (a_.w != 0u);                                             \
+        const uint32_t idx_ = a_.x + a_.y * by_ + bx_;                                                               \
+        O_PTR = in_ ? plane0 + (size_t) idx_ * 64 : nullptr;                                                         \
+        O_DFO = t_.x, O_AFO = t_.y, O_TABS = (int) t_.z;                                                             \
+        O_PRED = (int) t_.w + (int) lane * 4 + (a_.w != 0u ? 1 : 0);                                                 \
     } while (0)
 
     if (my >= rend) goto finished;
-    NEXT_INFO(blk, mx, my, cur_idx, cur_dfo, cur_afo, cur_comp, cur_flags);
+    LOAD_BLOCK(blk, mx, my, cur_ptr, cur_dfo, cur_afo, cur_tabs, cur_pred);
 
     // ================================ FAST PHASE ================================
-    if (wp + 1 < wsafe) {
-        uint32_t nextw = __ldg(wp);  // raw word at wp, consumed by the next refill
+    if (wi + 1 < wlim) {
+        uint32_t nextw = __ldg(w0 + wi);  // raw word `wi`, consumed by the next refill
         for (;;) {
-            // successor block: depends only on (blk, mx, my)
-            int nb = blk + 1, nx = mx, ny = my;
-            if (nb == nblk) {
-                nb = 0;
-                nx = mx + 1;
-            }
-            if (nx == W) {
-                nx = 0;
-                ny = my + 1;
-            }
-            uint32_t n_idx, n_dfo, n_afo;
-            int      n_comp, n_flags;
-            NEXT_INFO(nb, nx, ny, n_idx, n_dfo, n_afo, n_comp, n_flags);
+            // ---- successor block: depends only on (blk, mx, my); overlaps the symbol chain ----
+            int       nb = blk + 1;
+            const int wb = nb == nblk;
+            nb = wb ? 0 : nb;
+            int       nx = mx + wb;
+            const int wx = nx == W;
+            nx = wx ? 0 : nx;
+            const int ny = my + wx;
+            int16_t  *n_ptr;
+            uint32_t  n_dfo, n_afo;
+            int       n_tabs, n_pred;
+            LOAD_BLOCK(nb, nx, ny, n_ptr, n_dfo, n_afo, n_tabs, n_pred);
 
-            if (navail <= 32) {  // refill from the word loaded one refill ago; fetch the one after it
+            // ---- refill from the word loaded one refill ago; fetch the one after it ----
+            if (navail <= 32) {
                 const uint32_t be = __byte_perm(nextw, 0, 0x0123);
-                wp += 1;
-                nextw = __ldg(wp);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));
+                wi += 1;
+                nextw = __ldg(w0 + wi);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + wi + 64));
                 acc |= (uint64_t) be << (32 - navail);
                 navail += 32;
             }
-            if (P.extend && fresh_row && z == 0) {  // decode.swift:3214-3220 (`pos < count` holds in this phase)
+            if (P.extend && fresh_row && z == 0) {  // decode.swift:3214-3220 (`pos < count` always holds in this phase)
                 if ((uint32_t) (acc >> 48) == 0xffffu) goto finished;
             }
             fresh_row = false;
 
+            // ---- one symbol ----
             const bool     isdc = z == 0;
             const uint32_t cw = (uint32_t) (acc >> 48);
-            uint32_t       ent = entries[(isdc ? cur_dfo : cur_afo) + (cw >> 5)];
-            if (__builtin_expect(ent == 0u, 0)) {  // code longer than 11 bits, or not a code: the reference lookup
-                const int ti = isdc ? s_cmp[cur_comp].dci : s_cmp[cur_comp].aci;
-                ent = lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw);
+            const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? cur_dfo : cur_afo));
+            uint32_t        ent = tab[cw >> 5];
+            if (__builtin_expect(ent == 0u, 0)) {  // long / invalid / rejected code: the reference lookup
+                const int ti = isdc ? (cur_tabs & 0xff) : (cur_tabs >> 8);
+                ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
+                if (ent == 0u) break;  // corrupt DC symbol or EOBn: finished (and diagnosed) by the careful phase
             }
-            const int len = (int) (ent >> 8), sym = (int) (ent & 0xffu);
-            const int size = isdc ? sym : (sym & 15);
-            const int run = isdc ? 0 : (sym >> 4);
-            // corrupt DC symbols and EOBn in a sequential scan are finished (and diagnosed) by the careful phase
-            if (__builtin_expect(size > 16 || (!isdc && size == 0 && run != 0 && run != 15), 0)) break;
+            const int      len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441);
+            const int      run = (int) __byte_perm(ent, 0, 0x4442);
+            const bool     eob = (ent >> 24) != 0u;
             const uint32_t after = (uint32_t) ((acc << len) >> 32);
             const uint32_t tail = size ? after >> (32 - size) : 0u;
             const int      total = len + size;
             acc <<= total;
             navail -= total;
             const int v = size ? extend16(size, tail) : 0;
-            int       outv = v;
-            if (isdc) {  // decode.swift:3248-3254: wrapping Int16 prediction, kept per lane in shared memory
-                int pr = s_pred[cur_comp * WARP + lane];
-                if (cur_flags & 2) pr = (int) (short) (pr + v);
-                s_pred[cur_comp * WARP + lane] = pr;
-                outv = (int) ((uint32_t) pr << al);
-            }
-            const bool eob = !isdc && sym == 0;
-            const int  zpos = isdc ? 0 : z + run;
-            if ((cur_flags & 1) && !eob && zpos < 64) plane0[(size_t) cur_idx * 64 + zpos] = (int16_t) outv;
-            z = eob ? 64 : zpos + 1;
-            if (isdc && dc_only) z = 64;
+            // decode.swift:3248-3254: wrapping Int16 prediction; the predictor lives in shared memory, one slot per lane
+            int *pslot = reinterpret_cast<int *>(smem + (cur_pred & ~3));
+            const int pr0 = *pslot;
+            const int pr1 = (isdc & (cur_pred & 1)) ? (int) (short) (pr0 + v) : pr0;
+            *pslot = pr1;
+            const int outv = isdc ? (int) ((uint32_t) pr1 << al) : v;
+            const int zpos = z + run;  // z == 0 for a DC symbol (run = 0)
+            if ((cur_ptr != nullptr) & !eob & (zpos < 64)) cur_ptr[zpos] = (int16_t) outv;
+            z = (eob | (isdc & dc_only)) ? 64 : zpos + 1;
 
-            if (z >= 64) {  // block finished: swap in the successor
-                if (ny >= rend) goto finished;
-                fresh_row = (nb == 0) & (nx == 0);
-                z = 0;
-                blk = nb, mx = nx, my = ny;
-                cur_idx = n_idx, cur_dfo = n_dfo, cur_afo = n_afo, cur_comp = n_comp, cur_flags = n_flags;
-            }
-            if (!(wp + 1 < wsafe)) break;
+            // ---- block finished: swap in the successor ----
+            const bool done = z >= 64;
+            if (done & (ny >= rend)) goto finished;
+            fresh_row = done & (nb == 0) & (nx == 0);
+            z = done ? 0 : z;
+            blk = done ? nb : blk, mx = done ? nx : mx, my = done ? ny : my;
+            cur_ptr = done ? n_ptr : cur_ptr;
+            cur_dfo = done ? n_dfo : cur_dfo, cur_afo = done ? n_afo : cur_afo;
+            cur_tabs = done ? n_tabs : cur_tabs, cur_pred = done ? n_pred : cur_pred;
+            if (!(wi + 1 < wlim)) break;
         }
     }
 
     // ================================ CAREFUL PHASE ================================
     {
-        // bits handed to `acc` so far are all real: words [w0, wp) minus the lead bytes
-        int pos = 8 * ((int) (wp - w0) * 4 - lead) - navail;
+        // bits handed to `acc` so far are all real: words [0, wi) minus the lead bytes
+        int pos = 8 * ((int) wi * 4 - lead) - navail;
         for (;;) {
             if (navail <= 32) {
-                const uint32_t be = padded_word(wp);
-                wp += 1;
+                const uint32_t be = padded_word(wi);
+                wi += 1;
                 acc |= (uint64_t) be << (32 - navail);
                 navail += 32;
             }
@@ -587,14 +596,14 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             }
             fresh_row = false;
             const bool     isdc = z == 0;
-            const int      ti = isdc ? s_cmp[cur_comp].dci : s_cmp[cur_comp].aci;
+            const int      ti = isdc ? (cur_tabs & 0xff) : (cur_tabs >> 8);
             const uint32_t ent = lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], (uint32_t) (acc >> 48));
             const int      len = (int) (ent >> 8), sym = (int) (ent & 0xffu);
             const int      size = isdc ? sym : (sym & 15);
             const int      run = isdc ? 0 : (sym >> 4);
             if (!(pos < count)) FAIL_LANE(JPEG_SM100_ERR_TRUNCATED_ECS);
             int v = 0;
-            if (size > 16) {  // corrupt DC symbol: the reference's masked shifts, bit by bit (decode.swift:2742-2754, 2808-2818)
+            if (size > 16) {  // corrupt DC symbol: the reference's masked shifts (decode.swift:2742-2754, 2808-2818)
                 acc <<= len;
                 navail -= len;
                 pos += len;
@@ -603,8 +612,8 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
                 int left = size;
                 while (left > 0) {
                     if (navail <= 32) {
-                        const uint32_t be = padded_word(wp);
-                        wp += 1;
+                        const uint32_t be = padded_word(wi);
+                        wi += 1;
                         acc |= (uint64_t) be << (32 - navail);
                         navail += 32;
                     }
@@ -629,14 +638,15 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             }
             int outv = v;
             if (isdc) {
-                int pr = s_pred[cur_comp * WARP + lane];
-                if (cur_flags & 2) pr = (int) (short) (pr + v);
-                s_pred[cur_comp * WARP + lane] = pr;
+                int *pslot = reinterpret_cast<int *>(smem + (cur_pred & ~3));
+                int  pr = *pslot;
+                if (cur_pred & 1) pr = (int) (short) (pr + v);
+                *pslot = pr;
                 outv = (int) ((uint32_t) pr << al);
             }
             const bool eob = !isdc && sym == 0;
             const int  zpos = isdc ? 0 : z + run;
-            if ((cur_flags & 1) && !eob && zpos < 64) plane0[(size_t) cur_idx * 64 + zpos] = (int16_t) outv;
+            if (cur_ptr != nullptr && !eob && zpos < 64) cur_ptr[zpos] = (int16_t) outv;
             z = eob ? 64 : zpos + 1;
             if (isdc && dc_only) z = 64;
             if (z >= 64) {
@@ -653,11 +663,11 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
                 fresh_row = (nb == 0) & (nx == 0);
                 z = 0;
                 blk = nb, mx = nx, my = ny;
-                NEXT_INFO(blk, mx, my, cur_idx, cur_dfo, cur_afo, cur_comp, cur_flags);
+                LOAD_BLOCK(blk, mx, my, cur_ptr, cur_dfo, cur_afo, cur_tabs, cur_pred);
             }
         }
     }
-#undef NEXT_INFO
+#undef LOAD_BLOCK
 finished:
     if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
 }
@@ -971,7 +981,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         for (int ti = 0; ti < 8; ++ti)
             if (h.present[ti]) {
                 h.fast[ti] = total;
-                total += 2048;
+                total += 4096;  // 2048 x 32-bit entries
             }
         h.total_all = total;
         if (total > max_entries) max_entries = total;
@@ -1012,7 +1022,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     }
     if (!plane0) fast_ok = false;
     if (P.kind <= 1 && !use_flat && fast_ok) {
-        const size_t smem2 = sizeof(LutHeader) + 4 * sizeof(CmpInfo) + 64 + 4 * WARP * sizeof(int) + entry_bytes;
+        const size_t smem2 = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + 4 * WARP * sizeof(int) + entry_bytes;
         k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0);
     } else if (P.kind <= 1) {
         if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
