@@ -110,12 +110,50 @@ __global__ void __launch_bounds__(256) k_planar_to_rgb8(const __grid_constant__ 
     }
 }
 
-// ---- fast path: 4:2:0, centred, 8-bit planes -> RGB8 -------------------------------------------------------------
-// Thread = 8 x 2 pixels (columns 8t..8t+7 of rows 2r+1, 2r+2; row 0 handled by r = -1).  For these factors every
-// interpolation weight is a multiple of 1/4, every float product/sum in decode.swift:4258-4264 is exact, and
-// `.rounded()` of the exact value equals (9a + 3b + 3c + d + 8) >> 4 -- integer arithmetic, bit-identical.
+// ---- fast paths: 8-bit planes -> RGB8 --------------------------------------------------------------------------------
+// jpeg.swift:441-453 with the two zero matrix entries dropped: Y + 0 * d == Y exactly (d finite), so
+//   r = Y + 1.402 dr,   g = (Y + -0.34414 db) + -0.71414 dr,   b = Y + 1.772 db     -- same binary32 values.
+// clamp(0..255) then truncate == truncate then saturate (F2I.TRUNC + saturating byte pack, as in the IDCT kernel).
+__device__ __forceinline__ void ycc_to_rgb_fast(float Y, float db, float dr, float &r, float &g, float &b)
+{
+    r = fadd(Y, fmul(1.40200f, dr));
+    g = fadd(fadd(Y, fmul(-0.34414f, db)), fmul(-0.71414f, dr));
+    b = fadd(Y, fmul(1.77200f, db));
+}
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+// 8 pixels (24 bytes) of one row: Y bytes in (y0, y1), chroma as integers cb[8], cr[8]
+__device__ __forceinline__ void emit_rgb8x8(uint2 yy, const int (&cb)[8], const int (&cr)[8], uint8_t *dst, bool vec,
+                                            int n_valid)
+{
+    float r[8], g[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float Y = (float) byte_of(j < 4 ? yy.x : yy.y, j & 3);
+        ycc_to_rgb_fast(Y, fsub((float) cb[j], 128.0f), fsub((float) cr[j], 128.0f), r[j], g[j], b[j]);
+    }
+    uint32_t w[6];
+    w[0] = pack4_u8_trunc(r[0], g[0], b[0], r[1]);
+    w[1] = pack4_u8_trunc(g[1], b[1], r[2], g[2]);
+    w[2] = pack4_u8_trunc(b[2], r[3], g[3], b[3]);
+    w[3] = pack4_u8_trunc(r[4], g[4], b[4], r[5]);
+    w[4] = pack4_u8_trunc(g[5], b[5], r[6], g[6]);
+    w[5] = pack4_u8_trunc(b[6], r[7], g[7], b[7]);
+    if (vec) {
+        uint2 *d = reinterpret_cast<uint2 *>(dst);
+        d[0] = make_uint2(w[0], w[1]);
+        d[1] = make_uint2(w[2], w[3]);
+        d[2] = make_uint2(w[4], w[5]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 24; ++q)
+            if (q < n_valid * 3) dst[q] = (uint8_t) (w[q >> 2] >> (8 * (q & 3)));
+    }
+}
+
+// 4:2:0, centred.  Thread = 8 x 2 pixels (columns 8t..8t+7 of rows 2r+1, 2r+2; row 0 is covered by r = -1).  For these
+// factors every interpolation weight is a multiple of 1/4, every float product/sum in decode.swift:4258-4264 is exact,
+// and `.rounded()` of the exact value equals (9a + 3b + 3c + d + 8) >> 4 -- integer arithmetic, bit-identical.
 __global__ void __launch_bounds__(128)
 k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
 {
@@ -125,12 +163,13 @@ k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb
     const uint64_t per_image = (uint64_t) groups_x * row_pairs;
     const uint64_t total = per_image * V.n_images;
     const int      yw = V.width[0], cw = V.width[1], ch = V.height[1];
+    const bool     vec = (W & 7) == 0;
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t img = (uint32_t) (i / per_image);
         const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
         const int      rp = (int) (rem / groups_x);
         const int      gx = (int) (rem - (uint32_t) rp * groups_x);
-        const int      r = rp - 1;         // chroma row pair (r, r+1) feeds luma rows 2r+1, 2r+2
+        const int      r = rp - 1;  // chroma row pair (r, r+1) feeds luma rows 2r+1, 2r+2
         const int      x0 = 8 * gx, c0 = 4 * gx;
         const uint8_t *Yp = reinterpret_cast<const uint8_t *>(V.samples[0]) + (size_t) img * V.image_stride[0];
         const uint8_t *Cp[2] = {reinterpret_cast<const uint8_t *>(V.samples[1]) + (size_t) img * V.image_stride[1],
@@ -143,15 +182,15 @@ k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const uint8_t *row = Cp[c] + (size_t) cw * (rr ? rb : ra);
-                const uint32_t mid = *reinterpret_cast<const uint32_t *>(row + c0);  // chroma c0..c0+3 (planes are padded to 8)
-                const int      left = row[max(c0 - 1, 0)];
-                const int      right = row[min(c0 + 4, cw - 1)];
-                int            s[6] = {left, (int) byte_of(mid, 0), (int) byte_of(mid, 1), (int) byte_of(mid, 2),
+                const uint32_t mid = __ldg(reinterpret_cast<const uint32_t *>(row + c0));  // chroma c0..c0+3
+                const int      left = __ldg(row + max(c0 - 1, 0));
+                const int      right = __ldg(row + min(c0 + 4, cw - 1));
+                const int      s[6] = {left, (int) byte_of(mid, 0), (int) byte_of(mid, 1), (int) byte_of(mid, 2),
                                        (int) byte_of(mid, 3), right};
                 // pixel x = 8g + j: even x = 2m uses (c[m-1], c[m]) weights (1, 3); odd x = 2m+1 uses (c[m], c[m+1]) weights (3, 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int m = j >> 1;  // chroma index relative to c0
+                    const int m = j >> 1;
                     hc[c][rr][j] = (j & 1) ? 3 * s[m + 1] + s[m + 2] : s[m] + 3 * s[m + 1];
                 }
                 if (x0 == 0) hc[c][rr][0] = 4 * s[1];  // x = 0: t clamps to 0 -> u[0] alone (decode.swift:4250)
@@ -162,31 +201,47 @@ k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb
             if (y < 0 || y >= H) continue;
             // vertical weights: row 2r+1 -> (3, 1), row 2r+2 -> (1, 3); for y = 0 (r = -1) both rows are c[0],
             // which reproduces the reference's t = 0 clamp; at the bottom rb clamps to the padded plane edge
-            const int wa = (k == 0) ? 3 : 1, wb = 4 - wa;
-            const uint2 yy = *reinterpret_cast<const uint2 *>(Yp + (size_t) yw * y + x0);
-            uint32_t    out[24];
+            const int   wa = (k == 0) ? 3 : 1, wb = 4 - wa;
+            const uint2 yy = __ldg(reinterpret_cast<const uint2 *>(Yp + (size_t) yw * y + x0));
+            int         cb[8], cr[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t Y = byte_of(j < 4 ? yy.x : yy.y, j & 3);
-                const uint32_t cb = (uint32_t) (wa * hc[0][0][j] + wb * hc[0][1][j] + 8) >> 4;
-                const uint32_t cr = (uint32_t) (wa * hc[1][0][j] + wb * hc[1][1][j] + 8) >> 4;
-                float rr_, gg_, bb_;
-                ycc_to_rgb(Y, cb, cr, rr_, gg_, bb_);
-                out[3 * j] = clamp_u8(rr_);
-                out[3 * j + 1] = clamp_u8(gg_);
-                out[3 * j + 2] = clamp_u8(bb_);
+                cb[j] = (wa * hc[0][0][j] + wb * hc[0][1][j] + 8) >> 4;
+                cr[j] = (wa * hc[1][0][j] + wb * hc[1][1][j] + 8) >> 4;
             }
             uint8_t *dst = rgb + ((size_t) img * H + y) * (size_t) W * 3 + (size_t) x0 * 3;
-            if ((W & 7) == 0) {
-                uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-#pragma unroll
-                for (int q = 0; q < 6; ++q)
-                    d32[q] = out[4 * q] | (out[4 * q + 1] << 8) | (out[4 * q + 2] << 16) | (out[4 * q + 3] << 24);
-            } else {
-                const int n = min(8, W - x0) * 3;
-                for (int q = 0; q < n; ++q) dst[q] = (uint8_t) out[q];
-            }
+            emit_rgb8x8(yy, cb, cr, dst, vec, min(8, W - x0));
         }
+    }
+}
+
+// 4:4:4 (and any layout whose planes all have factor == scale): no resampling; thread = 8 pixels of one row
+__global__ void __launch_bounds__(128)
+k_ycc444_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
+{
+    const int      W = V.size_x, H = V.size_y;
+    const int      groups_x = (W + 7) / 8;
+    const uint64_t per_image = (uint64_t) groups_x * H;
+    const uint64_t total = per_image * V.n_images;
+    const bool     vec = (W & 7) == 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      y = (int) (rem / groups_x), x0 = (int) (rem - (uint32_t) y * groups_x) * 8;
+        uint2          pl[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(V.samples[p]) + (size_t) img * V.image_stride[p];
+            pl[p] = __ldg(reinterpret_cast<const uint2 *>(base + (size_t) V.width[p] * y + x0));
+        }
+        int cb[8], cr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cb[j] = (int) byte_of(j < 4 ? pl[1].x : pl[1].y, j & 3);
+            cr[j] = (int) byte_of(j < 4 ? pl[2].x : pl[2].y, j & 3);
+        }
+        uint8_t *dst = rgb + ((size_t) img * H + y) * (size_t) W * 3 + (size_t) x0 * 3;
+        emit_rgb8x8(pl[0], cb, cr, dst, vec, min(8, W - x0));
     }
 }
 
@@ -346,7 +401,17 @@ int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *
                        (reinterpret_cast<uintptr_t>(V.samples[0]) & 7) == 0 && (V.image_stride[0] & 7) == 0 &&
                        (reinterpret_cast<uintptr_t>(V.samples[1]) & 3) == 0 && (V.image_stride[1] & 3) == 0 &&
                        (reinterpret_cast<uintptr_t>(V.samples[2]) & 3) == 0 && (V.image_stride[2] & 3) == 0 &&
-                       (reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0;
+                       (reinterpret_cast<uintptr_t>(d_rgb) & 7) == 0;
+    bool is444 = V.n_planes == 3 && pl->sample_bytes == 1 && (reinterpret_cast<uintptr_t>(d_rgb) & 7) == 0;
+    for (int p = 0; p < 3 && is444; ++p)
+        is444 = V.fx[p] == V.scale_x && V.fy[p] == V.scale_y && (reinterpret_cast<uintptr_t>(V.samples[p]) & 7) == 0 &&
+                (V.image_stride[p] & 7) == 0;
+    if (is444 && !no_fast) {
+        const uint64_t work = (uint64_t) ((sx + 7) / 8) * sy * pl->n_images;
+        k_ycc444_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
+        LAUNCH_CHECK(ctx);
+        return JPEG_SM100_OK;
+    }
     if (is420 && !no_fast) {
         const uint64_t work = (uint64_t) ((sx + 7) / 8) * (sy / 2 + 1) * pl->n_images;
         k_ycc420_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);

@@ -1,0 +1,178 @@
+"""Full-size configurations of BASELINE.json on the GPU, checked through size-independent properties (entropy coding is
+lossless, so encode -> decode must return the coefficients bit for bit; re-encoding decoded coefficients must return
+the bytes) plus a direct oracle comparison on one frame per configuration."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available()
+    from jpeg_b200 import batch, lib, synth
+    from oracle import oracle as O
+    dev = torch.device("cuda:0")
+    ctx = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    return dict(torch=torch, batch=batch, lib=lib, synth=synth, O=O, dev=dev, ctx=ctx)
+
+
+def _quanta(O, level=0.25):
+    return np.stack([O.quanta(level, 0), O.quanta(level, 1), O.quanta(level, 1)])
+
+
+def _tables_to_oracle(O, tabs, i):
+    mk = lambda t: O.HuffSpec.make(bytes(t.counts), bytes(t.values)) if t.present else O.HuffSpec()
+    return [mk(t) for t in tabs[8 * i:8 * i + 4]], [mk(t) for t in tabs[8 * i + 4:8 * i + 8]]
+
+
+def test_config2_4k_420_baseline_decode(env):
+    """config #2: 3840x2160 baseline 4:2:0, DRI = 240 MCUs: GPU encode -> lexer -> GPU batch decode -> RGB."""
+    t, b, lib, O, ctx, dev = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"], env["dev"]
+    W, H, N = 3840, 2160, 3
+    geo = b.Geometry((W, H), [(2, 2), (1, 1), (1, 1)])
+    assert geo.total_blocks == 194400 and geo.blocks == (240, 135)
+    q = _quanta(O)
+    frames = t.stack([env["synth"].frame(100 + i, W, H, dev) for i in range(N)])
+    ecs, tabs, enc = b.encode_frames(ctx, frames, geo, q, geo.blocks[0])
+    inputs = b.DecodeInputs(ecs, list(tabs), n_ecs_expected=135)
+    # host-buffer batch entry point (H2D + K3 + K1 + K2 + D2H)
+    rgb = np.zeros((N, H, W, 3), dtype=np.uint8)
+    status = np.zeros(N, dtype=np.int32)
+    desc = b.sequential_scan(geo)
+    tarr = (lib.HuffTable * (8 * N))(*list(tabs))
+    ctx.check(ctx.L.jpeg_sm100_decode_batch_rgb8(ctx.h, C.byref(desc), N, inputs.ecs.ctypes.data, inputs.offsets.ctypes.data,
+                                                 inputs.n_ecs, geo.blocks[0], tarr, 0, q.ctypes.data, W, H, 0,
+                                                 rgb.ctypes.data, status.ctypes.data))
+    assert status.tolist() == [0] * N
+    # layer B on the same inputs: coefficients must equal what the encoder was given
+    buf = b.DeviceBuffers(geo, N, dev)
+    d_ecs = t.from_numpy(inputs.ecs).to(dev)
+    d_off = t.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    d_st = t.zeros(N, dtype=t.int32, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
+                                               geo.blocks[0], 0, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    for p in range(3):
+        assert t.equal(buf.coef[p], enc.coef[p]), p
+    # one frame against the oracle, end to end (coefficients from the stream, then IDCT + upsample + colour)
+    dct, act = _tables_to_oracle(O, tabs, 1)
+    data, lens = b.unstuff_split(ecs[1])
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    parts = [data[offs[k]:offs[k + 1]].tobytes() for k in range(len(lens))]
+    s = O.Spectral.create((W, H), geo.factors)
+    for p in range(3):
+        s.set_quanta(p, q[p])
+    s.decode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], dct, act, parts, interval=240)
+    for p in range(3):
+        assert np.array_equal(s.coefficients(p), enc.coef[p][1].cpu().numpy()), p
+    assert np.array_equal(O.unpack_rgb(s.to_rectangular()), rgb[1])
+    # pixels stay close to the source (level 0.25 is mild): a sanity bound, not a parity claim
+    err = np.abs(rgb[1].astype(np.int32) - frames[1].cpu().numpy().astype(np.int32))
+    assert err.mean() < 12.0
+
+
+def test_config3_4k_420_encode(env):
+    """config #3: 3840x2160 baseline 4:2:0 encode at level 0.25: coefficients and ECS bytes equal the oracle's, with the
+    reference-faithful single ECS and with DRI = 240."""
+    t, b, O, ctx, dev = env["torch"], env["batch"], env["O"], env["ctx"], env["dev"]
+    W, H = 3840, 2160
+    geo = b.Geometry((W, H), [(2, 2), (1, 1), (1, 1)])
+    q = _quanta(O)
+    frame = env["synth"].frame(7, W, H, dev)
+    rgb = frame.cpu().numpy()
+    planes = O.decompose(O.pack_rgb(rgb), geo.factors)
+    s = O.Spectral.create((W, H), geo.factors)
+    for p in range(3):
+        s.coefficients(p)[...] = O.fdct_plane(planes[p], q[p])
+    for interval in (0, 240):
+        ecs, tabs, enc = b.encode_frames(ctx, frame[None], geo, q, interval)
+        for p in range(3):
+            assert np.array_equal(enc.coef[p][0].cpu().numpy(), s.coefficients(p)), p
+        want, dct, act = s.encode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], interval)
+        assert ecs[0].tobytes() == want, interval
+        for k in range(4):
+            if dct[k].present:
+                assert tabs[k].as_tuple() == dct[k].as_tuple()
+            if act[k].present:
+                assert tabs[4 + k].as_tuple() == act[k].as_tuple()
+
+
+def test_config4_1080p_progressive_decode(env):
+    """config #4: 1920x1080 4:2:0, the 4-scan progression of examples/recompress (DC all components, then Y / Cb / Cr
+    AC 1..<64), per-row DRI.  Y has 135 block rows while the MCU grid covers 136 (hazard H3)."""
+    t, b, lib, O, ctx, dev = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"], env["dev"]
+    from jpeg_b200 import host
+    W, H = 1920, 1080
+    geo = b.Geometry((W, H), [(2, 2), (1, 1), (1, 1)])
+    assert geo.blocks == (120, 68) and geo.units[0] == (240, 135)
+    q = _quanta(O)
+    frame = env["synth"].frame(11, W, H, dev)
+    _, _, enc = b.encode_frames(ctx, frame[None], geo, q, 0)  # coefficients via K4 + K5
+    src = host.Spectral((W, H), geo.factors, process=2)
+    for p in range(3):
+        src.planes[p].coef = enc.coef[p][0].cpu().numpy()
+    dst = host.Spectral((W, H), geo.factors, process=2)
+    ref = O.Spectral.create((W, H), geo.factors, progressive=True)
+    for p in range(3):
+        ref.coefficients(p)[...] = src.planes[p].coef
+    scans = [((0, 1), (0, None), [(0, 0, 0), (1, 1, 0), (2, 1, 0)], geo.blocks[0]),
+             ((1, 64), (0, None), [(0, 0, 0)], geo.units[0][0]),
+             ((1, 64), (0, None), [(1, 0, 0)], geo.units[1][0]),
+             ((1, 64), (0, None), [(2, 0, 0)], geo.units[2][0])]
+    import sys
+    sys.path.insert(0, __file__.rsplit("/", 1)[0])
+    import jpegfile as J
+    for band, bits, comps, width in scans:
+        ecs, dct, act = src.encode_scan(band, bits, comps, width)          # GPU encoder, DRI = one row
+        want, _, _ = ref.encode_scan(band, bits, [c[0] for c in comps], [c[1] for c in comps], [c[2] for c in comps], width)
+        assert ecs == want, (band, comps)
+        dst.decode_scan(band, bits, comps, list(dct), list(act), J.unstuff_split(ecs), width)
+    for p in range(3):
+        assert np.array_equal(dst.planes[p].coef, src.planes[p].coef), p
+
+
+def test_config5_12mpix_444_roundtrip(env):
+    """config #5: 4000x3000 4:4:4 baseline, DRI = 500 MCUs: decode to coefficients, re-encode from them: same bytes."""
+    t, b, lib, O, ctx, dev = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"], env["dev"]
+    W, H = 4000, 3000
+    geo = b.Geometry((W, H), [(1, 1), (1, 1), (1, 1)])
+    assert geo.blocks == (500, 375) and geo.total_blocks == 562500
+    q = _quanta(O)
+    frame = env["synth"].frame(5, W, H, dev)
+    ecs, tabs, enc = b.encode_frames(ctx, frame[None], geo, q, 500)
+    inputs = b.DecodeInputs(ecs, list(tabs), n_ecs_expected=375)
+    buf = b.DeviceBuffers(geo, 1, dev)
+    desc = b.sequential_scan(geo)
+    tarr = (lib.HuffTable * 8)(*list(tabs))
+    d_ecs = t.from_numpy(inputs.ecs).to(dev)
+    d_off = t.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    d_st = t.zeros(1, dtype=t.int32, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs, 500,
+                                               0, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    assert d_st.item() == 0
+    for p in range(3):
+        assert t.equal(buf.coef[p], enc.coef[p]), p
+    # re-encode from the decoded coefficients
+    stride = 64 << 20
+    out = t.zeros(stride, dtype=t.uint8, device=dev)
+    ln = t.zeros(1, dtype=t.int64, device=dev)
+    tabs2 = (lib.HuffTable * 8)()
+    ctx.check(ctx.L.jpeg_sm100_dev_encode_scan(ctx.h, C.byref(desc), C.byref(buf.sp), 500, tabs2, out.data_ptr(), stride,
+                                               ln.data_ptr()))
+    t.cuda.synchronize()
+    again = out[:ln.item()].cpu().numpy()
+    assert again.tobytes() == ecs[0].tobytes()
+    # 4:4:4 colour fast path against the generic kernel on the same planes
+    ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), q.ctypes.data, 8, C.byref(buf.pl)))
+    ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
+    il = t.zeros((H, W, 3), dtype=t.int16, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_interleave(ctx.h, C.byref(buf.pl), W, H, 0, il.data_ptr()))
+    rgb2 = t.zeros((H, W, 3), dtype=t.uint8, device=dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_unpack_rgb8(ctx.h, il.data_ptr(), W * H, 3, rgb2.data_ptr()))
+    t.cuda.synchronize()
+    assert t.equal(buf.rgb[0], rgb2)
