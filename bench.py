@@ -132,7 +132,7 @@ def run_reference(args):
     from jpeg_b200 import synth
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    sample = max(1, min(cores, 32))
+    sample = max(1, min(cores, 128))  # one frame per host thread
     q = [O.quanta(LEVEL, 0), O.quanta(LEVEL, 1), O.quanta(LEVEL, 1)]
 
     # inputs: the same synthetic frames, encoded by the oracle's reference-equivalent encoder (DRI = 240 MCUs)
