@@ -35,7 +35,7 @@ struct jpeg_sm100_ctx {
     uint64_t     launches = 0;
     std::string  last_error;
     // grow-only scratch used by layer A (host-buffer entry points)
-    DeviceBuffer scratch[12];
+    DeviceBuffer scratch[16];
     PinnedSlot   pinned[4];
     int          pinned_next = 0;
     // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)

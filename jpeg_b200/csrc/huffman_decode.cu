@@ -20,6 +20,8 @@
 namespace {
 
 constexpr int WARP = 32;
+constexpr int FAST_BITS = 10;               // codes of up to FAST_BITS bits resolve with one shared-memory load
+constexpr int FAST_ENTRIES = 1 << FAST_BITS;
 constexpr int MAX_LUT_SMEM = 44 * 1024;  // entries staged in shared memory up to this size
 
 // ---- host: LUT construction (decode.swift:310-351 size, 1037-1240 decoder) ----------------------------------
@@ -28,7 +30,7 @@ struct LutHeader {  // per image: 8 tables (dc0..3, ac0..3)
     int32_t  zeta[8];
     uint32_t offset[8];  // entry offset into the image's entry array
     int32_t  present[8];
-    uint32_t fast[8];        // entry offset of the table's 2048-entry 11-bit fast table
+    uint32_t fast[8];        // entry offset of the table's FAST_ENTRIES-entry fast table
     uint32_t total_entries;  // reference (two-level) entries
     uint32_t total_all;      // reference + fast entries
     uint32_t pad[2];
@@ -96,18 +98,18 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         level_start += counts[l] * clones;
         leaf_base += counts[l];
     }
-    // 11-bit fast table, one 32-bit entry per prefix: byte0 = code length (0: code longer than 11 bits, not a code, or
+    // FAST_BITS-bit fast table, one 32-bit entry per prefix: byte0 = code length (0: code longer than 11 bits, not a code, or
     // a symbol the sequential decoders reject -> reference lookup), byte1 = extra bits, byte2 = zero run, byte3 = 1: EOB
     __syncthreads();
     uint32_t *fast = reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti]);
     const int n = h.n[ti], zeta = h.zeta[ti];
-    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) {
-        const uint32_t cw = i << 5;
+    for (uint32_t i = threadIdx.x; i < (uint32_t) FAST_ENTRIES; i += blockDim.x) {
+        const uint32_t cw = i << (16 - FAST_BITS);
         const int      hi = (int) (cw >> 8);
         uint32_t       e = 0x1000u;
         if (hi < n) e = entries[hi];
         else if ((int) cw < zeta) e = entries[(int) cw - 255 * n];
-        fast[i] = (e >> 8) <= 11u ? fast_entry(e, ti < 4) : 0u;
+        fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? fast_entry(e, ti < 4) : 0u;
     }
 }
 
@@ -388,7 +390,7 @@ finished:
 //     `i < count` / `i + n <= count` guards (decode.swift:2775-2862) cannot fire;
 //   * the bitstream word for the NEXT refill is loaded one refill ahead (double buffering) and lines are prefetched
 //     into L1 two lines ahead, so no load latency sits on the chain;
-//   * codes of <= 11 bits (all DC codes, > 99.9 % of AC codes) resolve with one shared-memory load from an 11-bit
+//   * codes of <= FAST_BITS bits (all DC codes, > 99 % of AC codes) resolve with one shared-memory load from a FAST_BITS-bit
 //     table derived from the reference's two-level LUT; longer or invalid codes take the reference lookup;
 //   * DC and AC symbols share one straight-line path; DC predictors live in shared memory (touched once per block);
 //   * the successor block's geometry is recomputed every trip off the critical path and swapped in with selects;
@@ -396,17 +398,22 @@ finished:
 struct BlkInfo {  // one per block of the MCU, read with three 16-byte shared loads
     uint32_t base_blk, ux, uy, hasplane;  // base_blk: 128-byte block index of the plane's block (0,0) of this image
     int32_t  fx, fy, dx, dy;
-    uint32_t dfast, afast;                // entry offsets (uint16 units) of the 11-bit tables
+    uint32_t dfast, afast;                // entry offsets (uint16 units) of the fast tables
     int32_t  tabs;                        // dci | aci << 8: LUT indices for the reference lookup
     int32_t  pred;                        // byte offset of the component's predictor row in shared memory
 };
 static_assert(sizeof(BlkInfo) == 48, "BlkInfo is three uint4");
 
-__global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ ScanParams P, int16_t *const plane0)
+__global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ ScanParams P, int16_t *const plane0,
+                                                      const uint32_t *const only_flagged)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t   img = blockIdx.y, lane = threadIdx.x;
     const uint32_t   e = blockIdx.x * WARP + lane;
+    if (only_flagged) {  // fallback pass after k_decode_par: most warps have nothing to do
+        const bool mine = e < P.n_ecs && only_flagged[(size_t) img * P.n_ecs + e] != 0u;
+        if (!__any_sync(0xffffffffu, mine)) return;
+    }
     const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
     const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
     BlkInfo         *s_blk = reinterpret_cast<BlkInfo *>(smem + sizeof(LutHeader));
@@ -438,6 +445,7 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
         __syncwarp();
     }
     if (e >= P.n_ecs) return;
+    if (only_flagged && only_flagged[(size_t) img * P.n_ecs + e] == 0u) return;
 
     int     err = 0;
     int64_t r0, r1;
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             const bool     isdc = z == 0;
             const uint32_t cw = (uint32_t) (acc >> 48);
             const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? cur_dfo : cur_afo));
-            uint32_t        ent = tab[cw >> 5];
+            uint32_t        ent = tab[cw >> (16 - FAST_BITS)];
             if (__builtin_expect(ent == 0u, 0)) {  // long / invalid / rejected code: the reference lookup
                 const int ti = isdc ? (cur_tabs & 0xff) : (cur_tabs >> 8);
                 ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
@@ -670,6 +678,386 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
 #undef LOAD_BLOCK
 finished:
     if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
+}
+
+// ---- subsequence-parallel decoder for sequential scans (kind 0): intra-interval parallelism ------------------------------
+// The restart interval is the only parallel axis the FORMAT gives, and a lone thread per interval is bound by its own
+// dependency chain.  Huffman streams self-synchronise, so an interval can also be decoded speculatively in pieces
+// (Klein & Wiseman; Weissenberger & Schmidt for JPEG on GPUs):
+//   * one CTA per (image, interval); the interval's bits are cut into S <= 128 subsequences, one thread each;
+//   * the parse state at a symbol boundary is (bit position, zig-zag position z, block-in-MCU b) -- MCU position and DC
+//     predictors do not influence parsing;
+//   * round 0: every thread parses its subsequence from a guessed state (its first bit, z = 0, b = 0) and records the state
+//     it leaves with; round r: a thread whose predecessor's exit changed re-parses from that exit.  Thread 0 starts from the
+//     true state, so after round r the first r + 1 exits are exact, and because streams re-synchronise after a few hundred
+//     symbols almost every exit is already exact after one or two rounds.  No change anywhere => all entries exact;
+//   * an exclusive scan of the per-subsequence block counts gives every subsequence its first block, then ONE decoding pass
+//     writes the coefficients (AC values straight to their zig-zag slots, DC *differences* to a side array);
+//   * k_dc_resolve turns the DC differences into predictions with a wrapping 16-bit prefix sum per (interval, component);
+//   * anything irregular on the TRUE path (truncation, a symbol the sequential decoder rejects, a block count that does not
+//     match) flags the interval; flagged intervals are zeroed and re-decoded by k_decode_fast, which also produces the
+//     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
+constexpr int PAR_THREADS = 128;
+constexpr int PAR_MIN_BITS = 1024;
+
+struct ParseState {
+    uint32_t p;      // bit position of the next symbol
+    uint16_t z, b;   // zig-zag position (0 = DC next), block index within the MCU
+};
+__device__ __forceinline__ uint64_t pack_state(uint32_t p, int z, int b) { return (uint64_t) p | ((uint64_t) z << 32) | ((uint64_t) b << 40); }
+
+struct ParReader {
+    const uint32_t *w0;
+    uint32_t        wlim;   // words [0, wlim) need no padding
+    int             lead, nbytes;
+    uint64_t        acc;
+    int             navail;
+    uint32_t        wi;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const
+    {
+        if (i < wlim) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
+        const int first = (int) i * 4 - lead;
+        uint32_t  be = 0xffffffffu;
+        if (first < nbytes) {
+            be = __byte_perm(__ldg(w0 + i), 0, 0x0123);
+            const int valid = nbytes - first;
+            if (valid < 4) be |= 0xffffffffu >> (8 * valid);
+        }
+        return be;
+    }
+    __device__ __forceinline__ void seek(uint32_t p)
+    {
+        const uint32_t ab = (uint32_t) lead * 8u + p;
+        wi = ab >> 5;
+        const int sh = (int) (ab & 31u);
+        acc = (((uint64_t) word(wi) << 32) | word(wi + 1)) << sh;
+        navail = 64 - sh;
+        wi += 2;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (navail <= 32) {
+            acc |= (uint64_t) word(wi) << (32 - navail);
+            wi += 1;
+            navail += 32;
+        }
+    }
+};
+
+// Parses (FINAL = false) or decodes (FINAL = true) symbols from `st` until the bit position reaches `end_bit`.
+// Returns the number of completed blocks; `st` is the exit state.  `bad` is set when the TRUE decoder would not simply
+// carry on (truncation / rejected symbol); speculative callers ignore it.
+template <bool FINAL>
+__device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                            const uint16_t *entries, const LutHeader *hdr, const BlkInfo *s_blk, const int nblk,
+                                            bool &bad,
+                                            // FINAL only:
+                                            uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
+                                            int16_t *dcdiff)
+{
+    uint32_t p = st.p, done = 0;
+    int      z = st.z, b = st.b;
+    bad = false;
+    if (p >= end_bit) return 0;
+    rd.seek(p);
+    uint32_t dfo = s_blk[b].dfast, afo = s_blk[b].afast;
+    int      tabs = s_blk[b].tabs;
+    // FINAL: position and destination of the current block
+    int      mx = 0, my = 0;
+    int16_t *bptr = nullptr;
+    if (FINAL) {
+        const uint32_t mcu = N / (uint32_t) nblk;
+        my = my0 + (int) (mcu / (uint32_t) W);
+        mx = (int) (mcu - (mcu / (uint32_t) W) * (uint32_t) W);
+        const BlkInfo &bi = s_blk[b];
+        const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
+        bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
+        if (N >= N_total) return 0;
+    }
+    while (p < end_bit) {
+        rd.refill();
+        const bool      isdc = z == 0;
+        const uint32_t  cw = (uint32_t) (rd.acc >> 48);
+        const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? dfo : afo));
+        uint32_t        ent = tab[cw >> (16 - FAST_BITS)];
+        if (__builtin_expect(ent == 0u, 0)) {
+            const int ti = isdc ? (tabs & 0xff) : (tabs >> 8);
+            ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
+            if (ent == 0u) {
+                bad = true;
+                break;
+            }
+        }
+        const int len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441), run = (int) __byte_perm(ent, 0, 0x4442);
+        const bool eob = (ent >> 24) != 0u;
+        const int  total = len + size;
+        if (__builtin_expect(p + (uint32_t) total > count_bits, 0)) {  // decode.swift:2808-2811, 2859-2863 (and 2775 for the next symbol)
+            bad = true;
+            break;
+        }
+        if (FINAL) {
+            const uint32_t after = (uint32_t) ((rd.acc << len) >> 32);
+            const uint32_t tail = size ? after >> (32 - size) : 0u;
+            const int      v = size ? extend16(size, tail) : 0;
+            const int      zpos = z + run;
+            if (isdc) dcdiff[N] = (int16_t) v;                                          // resolved by k_dc_resolve
+            else if ((bptr != nullptr) & !eob & (zpos < 64)) bptr[zpos] = (int16_t) v;  // ZRL stores its 0 like the reference
+        }
+        rd.acc <<= total;
+        rd.navail -= total;
+        p += (uint32_t) total;
+        z = eob ? 64 : z + run + 1;
+        if (z >= 64) {  // block complete
+            z = 0;
+            done += 1;
+            b = (b + 1 == nblk) ? 0 : b + 1;
+            dfo = s_blk[b].dfast, afo = s_blk[b].afast, tabs = s_blk[b].tabs;
+            if (FINAL) {
+                N += 1;
+                if (N >= N_total) break;
+                if (b == 0) {
+                    mx += 1;
+                    if (mx == W) {
+                        mx = 0;
+                        my += 1;
+                    }
+                }
+                const BlkInfo &bi = s_blk[b];
+                const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
+                bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
+            }
+        }
+    }
+    st.p = p;
+    st.z = (uint16_t) z;
+    st.b = (uint16_t) b;
+    return done;
+}
+
+__global__ void __launch_bounds__(PAR_THREADS)
+k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
+             uint32_t *const flagged)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint64_t s_exit[PAR_THREADS];
+    __shared__ uint32_t s_cnt[PAR_THREADS];
+    __shared__ uint8_t  s_changed[PAR_THREADS];
+    __shared__ uint32_t s_warp[PAR_THREADS / 32];
+    __shared__ uint32_t s_total, s_bad;
+    const uint32_t   img = blockIdx.y, e = blockIdx.x, tid = threadIdx.x;
+    const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    BlkInfo         *s_blk = reinterpret_cast<BlkInfo *>(smem + sizeof(LutHeader));
+    constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + PRE);
+    {
+        const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
+        const uint32_t   total = gh->total_all;
+        uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += PAR_THREADS) dst[i] = src[i];
+        uint32_t *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
+        for (uint32_t i = tid; i < (total + 1) / 2; i += PAR_THREADS) d2[i] = src[sizeof(LutHeader) / 4 + i];
+        if (tid < 12) {
+            const int b = tid, c = P.blk_comp[b];
+            BlkInfo   bi;
+            bi.hasplane = P.plane[c] != nullptr;
+            bi.base_blk = bi.hasplane ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
+            bi.ux = (uint32_t) P.ux[c], bi.uy = (uint32_t) P.uy[c];
+            bi.fx = P.fx[c], bi.fy = P.fy[c], bi.dx = P.blk_dx[b], bi.dy = P.blk_dy[b];
+            bi.dfast = gh->fast[P.dc[c]], bi.afast = gh->fast[P.ac[c]];
+            bi.tabs = P.dc[c] | (P.ac[c] << 8);
+            bi.pred = 0;
+            s_blk[b] = bi;
+        }
+        if (tid == 0) s_total = 0, s_bad = 0;
+    }
+    __syncthreads();
+
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    const int      W = P.W, nblk = P.mcu_blocks;
+    const uint32_t N_total = (uint32_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
+    const size_t   slot = (size_t) img * P.n_ecs + e;
+    if (N_total == 0) {  // nothing to decode: the reference's row loop does not run
+        if (tid == 0) {
+            flagged[slot] = 0;
+            if (P.status) P.status[slot] = 0;
+        }
+        return;
+    }
+    const uint64_t o0 = P.offsets[slot], o1 = P.offsets[slot + 1];
+    const uint8_t *base = P.ecs + o0;
+    const bool     oversize = (o1 - o0) > 0x07ffffffull || N_total > dc_per_interval;
+    if (oversize) {  // 32-bit bit positions / side-array capacity: leave it to the sequential kernel
+        if (tid == 0) flagged[slot] = 1;
+        return;
+    }
+    ParReader rd;
+    rd.nbytes = (int) (o1 - o0);
+    rd.lead = (int) (reinterpret_cast<uintptr_t>(base) & 3);
+    rd.w0 = reinterpret_cast<const uint32_t *>(base - rd.lead);
+    rd.wlim = (uint32_t) (rd.lead + rd.nbytes) / 4;
+    const uint32_t count = 8u * (uint32_t) rd.nbytes;
+    uint32_t       B = (count + PAR_THREADS - 1) / PAR_THREADS;
+    B = (B + 31u) & ~31u;
+    if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
+    const uint32_t S = count ? (count + B - 1) / B : 1u;  // <= PAR_THREADS
+    const bool     active = tid < S;
+    const uint32_t start_bit = tid * B, end_bit = (tid + 1 == S) ? count : (tid + 1) * B;
+    int16_t *const dcdiff = dcdiff_all + slot * dc_per_interval;
+
+    // ---- round 0: parse from the guessed state --------------------------------------------------------------------
+    ParseState st;
+    st.p = start_bit, st.z = 0, st.b = 0;
+    uint32_t my_cnt = 0;
+    uint64_t my_exit = 0;
+    bool     bad;
+    if (active) {
+        my_cnt = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        my_exit = pack_state(st.p, st.z, st.b);
+    }
+    s_exit[tid] = my_exit;
+    s_cnt[tid] = my_cnt;
+    s_changed[tid] = active ? 1 : 0;
+    __syncthreads();
+    // ---- synchronisation rounds --------------------------------------------------------------------------------------
+    for (uint32_t round = 1; round <= S; ++round) {
+        const bool redo = active && tid >= 1 && s_changed[tid - 1];
+        uint64_t   entry = 0;
+        if (redo) entry = s_exit[tid - 1];
+        __syncthreads();  // everyone has read its predecessor's state of the previous round
+        bool ch = false;
+        if (redo) {
+            st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
+            const uint32_t c = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+            const uint64_t x = pack_state(st.p, st.z, st.b);
+            ch = (x != my_exit) | (c != my_cnt);
+            my_exit = x;
+            my_cnt = c;
+            s_exit[tid] = x;
+            s_cnt[tid] = c;
+        }
+        s_changed[tid] = ch ? 1 : 0;
+        if (!__syncthreads_or(ch ? 1 : 0)) break;
+    }
+    // ---- first block of every subsequence: exclusive scan of the block counts -----------------------------------------
+    uint32_t incl = my_cnt;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t before = incl - my_cnt;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    // ---- the one real decoding pass ---------------------------------------------------------------------------------------
+    if (active) {
+        if (tid == 0) st.p = 0, st.z = 0, st.b = 0;
+        else {
+            const uint64_t entry = s_exit[tid - 1];
+            st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
+        }
+        uint32_t done = 0;
+        bad = false;
+        if (before < N_total)
+            done = par_run<true>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, before, N_total, W, (int) r0, plane0, dcdiff);
+        if (bad) atomicOr(&s_bad, 1u);
+        atomicAdd(&s_total, done);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // every expected block must have been completed (a short stream is a truncation in the reference)
+        const uint32_t f = (s_bad != 0u || s_total != N_total) ? 1u : 0u;
+        flagged[slot] = f;
+        if (!f && P.status) P.status[slot] = 0;
+    }
+}
+
+// DC differences -> DC coefficients: decode.swift:3248-3254 (wrapping Int16 prediction, reset per interval), one warp per
+// (interval, component).  Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
+__global__ void __launch_bounds__(WARP)
+k_dc_resolve(const __grid_constant__ ScanParams P, const int16_t *const dcdiff_all, const uint32_t dc_per_interval,
+             const uint32_t *const flagged)
+{
+    const uint32_t e = blockIdx.x, img = blockIdx.y, c = blockIdx.z, lane = threadIdx.x;
+    const size_t   slot = (size_t) img * P.n_ecs + e;
+    if (flagged[slot]) return;  // re-decoded sequentially, DC included
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    const uint32_t W = (uint32_t) P.W, nblk = (uint32_t) P.mcu_blocks;
+    const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
+    uint32_t       fb = 0;
+    for (uint32_t b = 0; b < nblk; ++b)
+        if (P.blk_comp[b] == c) {
+            fb = b;
+            break;
+        }
+    const uint32_t K = (uint32_t) (r1 - r0) * W * nc;
+    const int16_t *dc = dcdiff_all + slot * dc_per_interval;
+    int16_t       *pl = P.plane[c] ? P.plane[c] + (size_t) img * P.image_stride[c] : nullptr;
+    int            carry = 0;
+    for (uint32_t base = 0; base < K; base += WARP) {
+        const uint32_t k = base + lane;
+        const uint32_t mcu = k / nc, j = k - mcu * nc;
+        int            v = k < K ? (int) dc[mcu * nblk + fb + j] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= (uint32_t) d) v += y;
+        }
+        const int pred = (int) (short) (carry + v);
+        if (k < K && pl) {
+            const uint32_t my = (uint32_t) r0 + mcu / W, mx = mcu - (mcu / W) * W;
+            const uint32_t bx = mx * P.fx[c] + P.blk_dx[fb + j], by = my * P.fy[c] + P.blk_dy[fb + j];
+            if (bx < (uint32_t) P.ux[c] && by < (uint32_t) P.uy[c])
+                pl[64 * ((size_t) P.ux[c] * by + bx)] = (int16_t) ((uint32_t) pred << P.al);
+        }
+        carry = (int) (short) __shfl_sync(0xffffffffu, pred, 31);
+    }
+}
+
+// zero the blocks of flagged intervals before the sequential kernel re-decodes them
+__global__ void __launch_bounds__(128) k_zero_flagged(const __grid_constant__ ScanParams P, const uint32_t *const flagged)
+{
+    const uint32_t e = blockIdx.x, img = blockIdx.y;
+    if (!flagged[(size_t) img * P.n_ecs + e]) return;
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    for (int c = 0; c < P.n_comp; ++c) {
+        if (!P.plane[c]) continue;
+        int16_t  *pl = P.plane[c] + (size_t) img * P.image_stride[c];
+        const int y0 = min((int) r0 * P.fy[c], P.uy[c]), y1 = min((int) r1 * P.fy[c], P.uy[c]);
+        uint4    *q = reinterpret_cast<uint4 *>(pl + 64 * (size_t) P.ux[c] * y0);
+        const size_t n16 = (size_t) 8 * P.ux[c] * (y1 - y0);
+        for (size_t i = threadIdx.x; i < n16; i += blockDim.x) q[i] = make_uint4(0, 0, 0, 0);
+    }
 }
 
 // ---- straightforward per-thread decoders for the refinement / AC progressive scans ---------------------------------
@@ -981,7 +1369,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         for (int ti = 0; ti < 8; ++ti)
             if (h.present[ti]) {
                 h.fast[ti] = total;
-                total += 4096;  // 2048 x 32-bit entries
+                total += 2 * FAST_ENTRIES;  // FAST_ENTRIES x 32-bit entries
             }
         h.total_all = total;
         if (total > max_entries) max_entries = total;
@@ -1023,7 +1411,35 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     if (!plane0) fast_ok = false;
     if (P.kind <= 1 && !use_flat && fast_ok) {
         const size_t smem2 = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + 4 * WARP * sizeof(int) + entry_bytes;
-        k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0);
+        static const bool no_par = [] {
+            const char *e = getenv("JPEG_SM100_HUFF");
+            return e && strcmp(e, "seq") == 0;  // one thread per interval only (A/B validation of the parallel decoder)
+        }();
+        if (P.kind == 0 && !P.extend && !no_par) {
+            // subsequence-parallel decode, then the sequential kernel for whatever it flagged, then the DC prefix sums
+            const uint64_t rows_max = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W + 1;
+            const uint64_t dc_per_interval = rows_max * (uint64_t) P.W * (uint64_t) volume;
+            const uint64_t slots = (uint64_t) n_images * n_ecs;
+            void          *d_dc = nullptr, *d_flag = nullptr;
+            if (dc_per_interval <= 0x7fffffffull && slots * dc_per_interval * 2 <= (4ull << 30)) {
+                J_TRY(scratch_reserve(ctx, 12, (size_t) (slots * dc_per_interval * 2 + 256), &d_dc));
+                J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
+                const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + entry_bytes;
+                const dim3   grid_par(n_ecs, n_images);
+                k_decode_par<<<grid_par, PAR_THREADS, smem_par, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
+                                                                                (uint32_t) dc_per_interval,
+                                                                                reinterpret_cast<uint32_t *>(d_flag));
+                LAUNCH_CHECK(ctx);
+                k_zero_flagged<<<grid_par, 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+                LAUNCH_CHECK(ctx);
+                k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, reinterpret_cast<const uint32_t *>(d_flag));
+                LAUNCH_CHECK(ctx);
+                k_dc_resolve<<<dim3(n_ecs, n_images, scan->n_comp), WARP, 0, ctx->stream>>>(
+                    P, reinterpret_cast<const int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<const uint32_t *>(d_flag));
+            } else
+                k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, nullptr);
+        } else
+            k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, nullptr);
     } else if (P.kind <= 1) {
         if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
         else k_decode_flat<false><<<grid, WARP, smem, ctx->stream>>>(P);
