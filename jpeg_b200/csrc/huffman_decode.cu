@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int WARP = 32;
-constexpr int FAST_BITS = 10;               // codes of up to FAST_BITS bits resolve with one shared-memory load
+constexpr int FAST_BITS = 9;                // codes of up to FAST_BITS bits resolve with one shared-memory load
 constexpr int FAST_ENTRIES = 1 << FAST_BITS;
 constexpr int MAX_LUT_SMEM = 44 * 1024;  // entries staged in shared memory up to this size
 
@@ -699,6 +699,7 @@ finished:
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
 constexpr int PAR_THREADS = 128;
 constexpr int PAR_MIN_BITS = 1024;
+constexpr int PAR_WARMUP = 2;  // subsequences of speculative warm-up in round 0
 
 struct ParseState {
     uint32_t p;      // bit position of the next symbol
@@ -836,12 +837,11 @@ __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const
 
 __global__ void __launch_bounds__(PAR_THREADS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
-             uint32_t *const flagged)
+             uint32_t *const flagged, uint32_t *const stats)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t s_exit[PAR_THREADS];
     __shared__ uint32_t s_cnt[PAR_THREADS];
-    __shared__ uint8_t  s_changed[PAR_THREADS];
     __shared__ uint32_t s_warp[PAR_THREADS / 32];
     __shared__ uint32_t s_total, s_bad;
     const uint32_t   img = blockIdx.y, e = blockIdx.x, tid = threadIdx.x;
@@ -915,39 +915,42 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const uint32_t start_bit = tid * B, end_bit = (tid + 1 == S) ? count : (tid + 1) * B;
     int16_t *const dcdiff = dcdiff_all + slot * dc_per_interval;
 
-    // ---- round 0: parse from the guessed state --------------------------------------------------------------------
+    // ---- round 0: warm up over the preceding PAR_WARMUP subsequences from a guessed state, then parse the own one ----
+    // (by the time the speculative parse reaches its own first bit it has usually re-synchronised with the true parse, so
+    //  most subsequences never need a second look; thread 0 -- and every thread whose warm-up starts at bit 0 -- is exact)
     ParseState st;
-    st.p = start_bit, st.z = 0, st.b = 0;
-    uint32_t my_cnt = 0;
-    uint64_t my_exit = 0;
-    bool     bad;
+    uint32_t   my_cnt = 0;
+    uint64_t   my_exit = 0, my_entry = 0;
+    bool       bad;
     if (active) {
+        const uint32_t warm = tid >= (uint32_t) PAR_WARMUP ? (tid - PAR_WARMUP) * B : 0u;
+        st.p = warm, st.z = 0, st.b = 0;
+        if (tid > 0) par_run<false>(rd, st, start_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        my_entry = pack_state(st.p, st.z, st.b);
         my_cnt = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
         my_exit = pack_state(st.p, st.z, st.b);
     }
     s_exit[tid] = my_exit;
     s_cnt[tid] = my_cnt;
-    s_changed[tid] = active ? 1 : 0;
     __syncthreads();
-    // ---- synchronisation rounds --------------------------------------------------------------------------------------
-    for (uint32_t round = 1; round <= S; ++round) {
-        const bool redo = active && tid >= 1 && s_changed[tid - 1];
-        uint64_t   entry = 0;
-        if (redo) entry = s_exit[tid - 1];
-        __syncthreads();  // everyone has read its predecessor's state of the previous round
-        bool ch = false;
+    // ---- synchronisation rounds: re-parse wherever the entry that was used differs from the predecessor's exit ----------
+    uint32_t n_redo = 0, n_rounds = 0;
+    for (uint32_t round = 1; round <= S + 1; ++round) {
+        uint64_t entry = my_entry;
+        if (active && tid >= 1) entry = s_exit[tid - 1];
+        const bool redo = active && tid >= 1 && entry != my_entry;
+        n_redo += redo ? 1u : 0u;
+        n_rounds = round;
+        if (!__syncthreads_or(redo ? 1 : 0)) break;  // also: everyone has read its predecessor's exit
         if (redo) {
+            my_entry = entry;
             st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
-            const uint32_t c = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-            const uint64_t x = pack_state(st.p, st.z, st.b);
-            ch = (x != my_exit) | (c != my_cnt);
-            my_exit = x;
-            my_cnt = c;
-            s_exit[tid] = x;
-            s_cnt[tid] = c;
+            my_cnt = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+            my_exit = pack_state(st.p, st.z, st.b);
+            s_exit[tid] = my_exit;
+            s_cnt[tid] = my_cnt;
         }
-        s_changed[tid] = ch ? 1 : 0;
-        if (!__syncthreads_or(ch ? 1 : 0)) break;
+        __syncthreads();
     }
     // ---- first block of every subsequence: exclusive scan of the block counts -----------------------------------------
     uint32_t incl = my_cnt;
@@ -963,11 +966,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     for (int w = 0; w < wid; ++w) before += s_warp[w];
     // ---- the one real decoding pass ---------------------------------------------------------------------------------------
     if (active) {
-        if (tid == 0) st.p = 0, st.z = 0, st.b = 0;
-        else {
-            const uint64_t entry = s_exit[tid - 1];
-            st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
-        }
+        st.p = (uint32_t) my_entry, st.z = (uint16_t) ((my_entry >> 32) & 0xff), st.b = (uint16_t) ((my_entry >> 40) & 0xff);
         uint32_t done = 0;
         bad = false;
         if (before < N_total)
@@ -981,6 +980,15 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         const uint32_t f = (s_bad != 0u || s_total != N_total) ? 1u : 0u;
         flagged[slot] = f;
         if (!f && P.status) P.status[slot] = 0;
+    }
+    if (stats) {  // JPEG_SM100_PAR_STATS=1: rounds and re-parses per interval
+        atomicAdd(&stats[0], n_redo);
+        if (tid == 0) {
+            atomicAdd(&stats[1], n_rounds);
+            atomicAdd(&stats[2], S);
+            atomicAdd(&stats[3], 1u);
+            atomicMax(&stats[4], n_rounds);
+        }
     }
 }
 
@@ -1426,10 +1434,25 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
                 const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + entry_bytes;
                 const dim3   grid_par(n_ecs, n_images);
+                static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
+                uint32_t         *d_stats = nullptr;
+                if (want_stats) {
+                    void *p = nullptr;
+                    J_TRY(scratch_reserve(ctx, 14, 64, &p));
+                    d_stats = reinterpret_cast<uint32_t *>(p);
+                    CU_TRY(ctx, cudaMemsetAsync(d_stats, 0, 64, ctx->stream));
+                }
                 k_decode_par<<<grid_par, PAR_THREADS, smem_par, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
                                                                                 (uint32_t) dc_per_interval,
-                                                                                reinterpret_cast<uint32_t *>(d_flag));
+                                                                                reinterpret_cast<uint32_t *>(d_flag), d_stats);
                 LAUNCH_CHECK(ctx);
+                if (want_stats) {
+                    uint32_t h[5];
+                    CU_TRY(ctx, cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                    fprintf(stderr, "[k_decode_par] intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
+                            h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
+                }
                 k_zero_flagged<<<grid_par, 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
                 LAUNCH_CHECK(ctx);
                 k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, reinterpret_cast<const uint32_t *>(d_flag));
