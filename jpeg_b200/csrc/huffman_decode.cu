@@ -20,7 +20,10 @@
 namespace {
 
 constexpr int WARP = 32;
-constexpr int FAST_BITS = 9;                // codes of up to FAST_BITS bits resolve with one shared-memory load
+#ifndef FAST_BITS_N
+#define FAST_BITS_N 9
+#endif
+constexpr int FAST_BITS = FAST_BITS_N;               // codes of up to FAST_BITS bits resolve with one shared-memory load
 constexpr int FAST_ENTRIES = 1 << FAST_BITS;
 constexpr int MAX_LUT_SMEM = 44 * 1024;  // entries staged in shared memory up to this size
 
@@ -61,15 +64,19 @@ struct RawSet {
     uint8_t   values[8][256];
 };
 
-// (symbol | length << 8) of the reference LUT -> the fast decoder's entry; 0 if the sequential decoders need the careful
-// path for it (DC magnitude category > 16, or EOBn with n > 0 in a sequential scan)
+// (symbol | length << 8) of the reference LUT -> the fast decoders' entry:
+//     byte0 = code length, byte1 = extra bits, byte2 = zig-zag advance (run + 1; 64 for EOB), byte3 = length + extra bits
+// 0 if the sequential decoders need the careful path for it (DC magnitude category > 16, or EOBn with n > 0).
+// With z the zig-zag position before the symbol (0 for DC): the coefficient lands at z + advance - 1 (an EOB lands beyond
+// 63, i.e. nowhere) and the next position is z + advance.
 __host__ __device__ inline uint32_t fast_entry(uint32_t ref, bool dc)
 {
     const uint32_t len = ref >> 8, sym = ref & 0xffu;
-    if (dc) return sym > 16u ? 0u : (len | (sym << 8));
+    if (dc) return sym > 16u ? 0u : (len | (sym << 8) | (1u << 16) | ((len + sym) << 24));
     const uint32_t size = sym & 15u, run = sym >> 4;
     if (size == 0u && run != 0u && run != 15u) return 0u;
-    return len | (size << 8) | (run << 16) | ((sym == 0u ? 1u : 0u) << 24);
+    const uint32_t adv = sym == 0u ? 64u : run + 1u;
+    return len | (size << 8) | (adv << 16) | ((len + size) << 24);
 }
 
 // decode.swift:1037-1240 Table.Huffman.decoder(): level l (codes of l+1 bits) contributes `0x8080 >> l & 0xff` clones
@@ -557,11 +564,9 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
                 if (ent == 0u) break;  // corrupt DC symbol or EOBn: finished (and diagnosed) by the careful phase
             }
             const int      len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441);
-            const int      run = (int) __byte_perm(ent, 0, 0x4442);
-            const bool     eob = (ent >> 24) != 0u;
+            const int      adv = (int) __byte_perm(ent, 0, 0x4442), total = (int) (ent >> 24);
             const uint32_t after = (uint32_t) ((acc << len) >> 32);
             const uint32_t tail = size ? after >> (32 - size) : 0u;
-            const int      total = len + size;
             acc <<= total;
             navail -= total;
             const int v = size ? extend16(size, tail) : 0;
@@ -571,9 +576,9 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             const int pr1 = (isdc & (cur_pred & 1)) ? (int) (short) (pr0 + v) : pr0;
             *pslot = pr1;
             const int outv = isdc ? (int) ((uint32_t) pr1 << al) : v;
-            const int zpos = z + run;  // z == 0 for a DC symbol (run = 0)
-            if ((cur_ptr != nullptr) & !eob & (zpos < 64)) cur_ptr[zpos] = (int16_t) outv;
-            z = (eob | (isdc & dc_only)) ? 64 : zpos + 1;
+            const int zpos = z + adv - 1;  // z == 0 for a DC symbol (advance 1); an EOB lands beyond 63
+            if ((cur_ptr != nullptr) & (zpos < 64)) cur_ptr[zpos] = (int16_t) outv;
+            z = (isdc & dc_only) ? 64 : z + adv;
 
             // ---- block finished: swap in the successor ----
             const bool done = z >= 64;
@@ -699,7 +704,10 @@ finished:
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
 constexpr int PAR_THREADS = 128;
 constexpr int PAR_MIN_BITS = 1024;
-constexpr int PAR_WARMUP = 2;  // subsequences of speculative warm-up in round 0
+#ifndef PAR_WARMUP_N
+#define PAR_WARMUP_N 2
+#endif
+constexpr int PAR_WARMUP = PAR_WARMUP_N;  // subsequences of speculative warm-up in round 0
 
 struct ParseState {
     uint32_t p;      // bit position of the next symbol
@@ -735,20 +743,15 @@ struct ParReader {
         navail = 64 - sh;
         wi += 2;
     }
-    __device__ __forceinline__ void refill()
-    {
-        if (navail <= 32) {
-            acc |= (uint64_t) word(wi) << (32 - navail);
-            wi += 1;
-            navail += 32;
-        }
-    }
 };
 
 // Parses (FINAL = false) or decodes (FINAL = true) symbols from `st` until the bit position reaches `end_bit`.
 // Returns the number of completed blocks; `st` is the exit state.  `bad` is set when the TRUE decoder would not simply
 // carry on (truncation / rejected symbol); speculative callers ignore it.
-template <bool FINAL>
+// SAFE: the run (plus look-ahead) stays inside the words that need no padding, so every consumed bit is a real bit and the
+// reference's truncation guards cannot fire -- no padding logic, no bit-count checks.  The loop is written branch-free
+// (selects + predicated memory operations): lanes of a warp sit in different places of their blocks all the time.
+template <bool FINAL, bool SAFE>
 __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
                                             const uint16_t *entries, const LutHeader *hdr, const BlkInfo *s_blk, const int nblk,
                                             bool &bad,
@@ -760,9 +763,11 @@ __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const
     int      z = st.z, b = st.b;
     bad = false;
     if (p >= end_bit) return 0;
+    if (FINAL && N >= N_total) return 0;
     rd.seek(p);
-    uint32_t dfo = s_blk[b].dfast, afo = s_blk[b].afast;
-    int      tabs = s_blk[b].tabs;
+    uint64_t acc = rd.acc;
+    int      navail = rd.navail;
+    uint32_t wi = rd.wi;
     // FINAL: position and destination of the current block
     int      mx = 0, my = 0;
     int16_t *bptr = nullptr;
@@ -773,61 +778,72 @@ __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const
         const BlkInfo &bi = s_blk[b];
         const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
         bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
-        if (N >= N_total) return 0;
     }
     while (p < end_bit) {
-        rd.refill();
+        if (navail <= 32) {
+            const uint32_t be = SAFE ? __byte_perm(__ldg(rd.w0 + wi), 0, 0x0123) : rd.word(wi);
+            acc |= (uint64_t) be << (32 - navail);
+            wi += 1;
+            navail += 32;
+        }
+        const uint4     t3 = reinterpret_cast<const uint4 *>(&s_blk[b])[2];  // dfast, afast, tabs, -
         const bool      isdc = z == 0;
-        const uint32_t  cw = (uint32_t) (rd.acc >> 48);
-        const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? dfo : afo));
+        const uint32_t  cw = (uint32_t) (acc >> 48);
+        const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? t3.x : t3.y));
         uint32_t        ent = tab[cw >> (16 - FAST_BITS)];
         if (__builtin_expect(ent == 0u, 0)) {
-            const int ti = isdc ? (tabs & 0xff) : (tabs >> 8);
+            const int ti = isdc ? ((int) t3.z & 0xff) : ((int) t3.z >> 8);
             ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
             if (ent == 0u) {
                 bad = true;
                 break;
             }
         }
-        const int len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441), run = (int) __byte_perm(ent, 0, 0x4442);
-        const bool eob = (ent >> 24) != 0u;
-        const int  total = len + size;
-        if (__builtin_expect(p + (uint32_t) total > count_bits, 0)) {  // decode.swift:2808-2811, 2859-2863 (and 2775 for the next symbol)
-            bad = true;
-            break;
+        const int total = (int) (ent >> 24), adv = (int) __byte_perm(ent, 0, 0x4442);
+        if (!SAFE) {
+            if (__builtin_expect(p + (uint32_t) total > count_bits, 0)) {  // decode.swift:2808-2811, 2859-2863
+                bad = true;
+                break;
+            }
         }
         if (FINAL) {
-            const uint32_t after = (uint32_t) ((rd.acc << len) >> 32);
+            const int      len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441);
+            const uint32_t after = (uint32_t) ((acc << len) >> 32);
             const uint32_t tail = size ? after >> (32 - size) : 0u;
             const int      v = size ? extend16(size, tail) : 0;
-            const int      zpos = z + run;
-            if (isdc) dcdiff[N] = (int16_t) v;                                          // resolved by k_dc_resolve
-            else if ((bptr != nullptr) & !eob & (zpos < 64)) bptr[zpos] = (int16_t) v;  // ZRL stores its 0 like the reference
+            const int      zpos = z + adv - 1;
+            // DC differences go to the side array (resolved by k_dc_resolve); AC values to their zig-zag slot
+            int16_t *dst = isdc ? dcdiff + N : bptr + zpos;
+            if (isdc | ((bptr != nullptr) & (zpos < 64))) *dst = (int16_t) v;
         }
-        rd.acc <<= total;
-        rd.navail -= total;
+        acc <<= total;
+        navail -= total;
         p += (uint32_t) total;
-        z = eob ? 64 : z + run + 1;
-        if (z >= 64) {  // block complete
-            z = 0;
-            done += 1;
-            b = (b + 1 == nblk) ? 0 : b + 1;
-            dfo = s_blk[b].dfast, afo = s_blk[b].afast, tabs = s_blk[b].tabs;
-            if (FINAL) {
+        z += adv;
+        const bool fin = z >= 64;  // block complete
+        z = fin ? 0 : z;
+        done += fin ? 1u : 0u;
+        const int b1 = (b + 1 == nblk) ? 0 : b + 1;
+        if (FINAL) {
+            if (fin) {
                 N += 1;
-                if (N >= N_total) break;
-                if (b == 0) {
+                if (N >= N_total) {
+                    b = b1;
+                    break;
+                }
+                if (b1 == 0) {
                     mx += 1;
                     if (mx == W) {
                         mx = 0;
                         my += 1;
                     }
                 }
-                const BlkInfo &bi = s_blk[b];
+                const BlkInfo &bi = s_blk[b1];
                 const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
                 bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
             }
         }
+        b = fin ? b1 : b;
     }
     st.p = p;
     st.z = (uint16_t) z;
@@ -835,13 +851,32 @@ __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const
     return done;
 }
 
-__global__ void __launch_bounds__(PAR_THREADS)
+// picks the SAFE variant when the run, its overshoot (< 32 bits) and the 64-bit look-ahead stay in unpadded words
+template <bool FINAL>
+__device__ __forceinline__ uint32_t par_run_auto(ParReader &rd, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                                 const uint16_t *entries, const LutHeader *hdr, const BlkInfo *s_blk, const int nblk,
+                                                 bool &bad, uint32_t N, const uint32_t N_total, const int W, const int my0,
+                                                 int16_t *plane0, int16_t *dcdiff)
+{
+    // warp-uniform choice: a warp whose lanes disagree would execute both variants one after the other
+    const uint32_t last_word = ((uint32_t) rd.lead * 8u + end_bit + 32u + 64u) / 32u + 1u;
+    if (__all_sync(__activemask(), last_word < rd.wlim))
+        return par_run<FINAL, true>(rd, st, end_bit, count_bits, entries, hdr, s_blk, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
+    return par_run<FINAL, false>(rd, st, end_bit, count_bits, entries, hdr, s_blk, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
+}
+
+#ifndef PAR_MIN_CTAS
+#define PAR_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
              uint32_t *const flagged, uint32_t *const stats)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint64_t s_exit[PAR_THREADS];
+    __shared__ uint64_t s_exit[PAR_THREADS], s_entry[PAR_THREADS];
     __shared__ uint32_t s_cnt[PAR_THREADS];
+    __shared__ uint8_t  s_work[PAR_THREADS];
+    __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[PAR_THREADS / 32];
     __shared__ uint32_t s_total, s_bad;
     const uint32_t   img = blockIdx.y, e = blockIdx.x, tid = threadIdx.x;
@@ -919,39 +954,49 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // (by the time the speculative parse reaches its own first bit it has usually re-synchronised with the true parse, so
     //  most subsequences never need a second look; thread 0 -- and every thread whose warm-up starts at bit 0 -- is exact)
     ParseState st;
-    uint32_t   my_cnt = 0;
-    uint64_t   my_exit = 0, my_entry = 0;
     bool       bad;
     if (active) {
         const uint32_t warm = tid >= (uint32_t) PAR_WARMUP ? (tid - PAR_WARMUP) * B : 0u;
         st.p = warm, st.z = 0, st.b = 0;
-        if (tid > 0) par_run<false>(rd, st, start_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-        my_entry = pack_state(st.p, st.z, st.b);
-        my_cnt = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-        my_exit = pack_state(st.p, st.z, st.b);
+        if (tid > 0) par_run_auto<false>(rd, st, start_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        s_entry[tid] = pack_state(st.p, st.z, st.b);
+        s_cnt[tid] = par_run_auto<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        s_exit[tid] = pack_state(st.p, st.z, st.b);
+    } else {
+        s_entry[tid] = 0, s_exit[tid] = 0, s_cnt[tid] = 0;
     }
-    s_exit[tid] = my_exit;
-    s_cnt[tid] = my_cnt;
     __syncthreads();
-    // ---- synchronisation rounds: re-parse wherever the entry that was used differs from the predecessor's exit ----------
+    // ---- synchronisation rounds: re-parse wherever the entry that was used differs from the predecessor's exit.
+    // The subsequences to redo are compacted into a work list so that they occupy the lanes of as few warps as possible.
     uint32_t n_redo = 0, n_rounds = 0;
     for (uint32_t round = 1; round <= S + 1; ++round) {
-        uint64_t entry = my_entry;
-        if (active && tid >= 1) entry = s_exit[tid - 1];
-        const bool redo = active && tid >= 1 && entry != my_entry;
+        const bool redo = active && tid >= 1 && s_exit[tid - 1] != s_entry[tid];
         n_redo += redo ? 1u : 0u;
         n_rounds = round;
-        if (!__syncthreads_or(redo ? 1 : 0)) break;  // also: everyone has read its predecessor's exit
-        if (redo) {
-            my_entry = entry;
+        if (tid == 0) s_nwork = 0;
+        __syncthreads();
+        if (redo) s_work[atomicAdd(&s_nwork, 1u)] = (uint8_t) tid;
+        __syncthreads();
+        const uint32_t nwork = s_nwork;
+        if (nwork == 0) break;
+        if (tid < nwork) {
+            const uint32_t sid = s_work[tid];
+            const uint64_t entry = s_exit[sid - 1];
+            const uint32_t e_bit = (sid + 1 == S) ? count : (sid + 1) * B;
             st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
-            my_cnt = par_run<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-            my_exit = pack_state(st.p, st.z, st.b);
-            s_exit[tid] = my_exit;
-            s_cnt[tid] = my_cnt;
+            const uint32_t c = par_run_auto<false>(rd, st, e_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+            const uint64_t x = pack_state(st.p, st.z, st.b);
+            // every work item reads exit[sid - 1] before any item writes exit[sid]: the write is deferred past a barrier
+            s_cnt[sid] = c;
+            s_entry[sid] = entry;
+            st.p = (uint32_t) x, st.z = (uint16_t) ((x >> 32) & 0xff), st.b = (uint16_t) ((x >> 40) & 0xff);
         }
         __syncthreads();
+        if (tid < nwork) s_exit[s_work[tid]] = pack_state(st.p, st.z, st.b);
+        __syncthreads();
     }
+    const uint32_t my_cnt = s_cnt[tid];
+    const uint64_t my_entry = s_entry[tid];
     // ---- first block of every subsequence: exclusive scan of the block counts -----------------------------------------
     uint32_t incl = my_cnt;
     const int lane = tid & 31, wid = tid >> 5;
@@ -970,7 +1015,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         uint32_t done = 0;
         bad = false;
         if (before < N_total)
-            done = par_run<true>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, before, N_total, W, (int) r0, plane0, dcdiff);
+            done = par_run_auto<true>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, before, N_total, W, (int) r0, plane0, dcdiff);
         if (bad) atomicOr(&s_bad, 1u);
         atomicAdd(&s_total, done);
     }
