@@ -352,7 +352,7 @@ def run_ours(args):
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": k1_traffic() if n == BATCH else None,
                          "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5)},
-            "roofline_dominant": {"kernel": "k_decode_fast (K3, entropy decode: latency-bound, one thread per restart interval)",
+            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode, 128 threads per restart interval) + k_zero_flagged + k_decode_fast(flagged only) + k_dc_resolve + k_reduce_status; latency/issue-bound, not HBM-bound",
                                   "bound": "hbm", "achieved": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                   "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
                                   "bytes_per_launch": int(huff_bytes), "ms_per_launch": round(huff_ms, 4),
