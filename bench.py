@@ -4,10 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            our CUDA path (libjpeg_sm100.so)
     python bench.py --impl reference ...                      the reference's CPU path (restated oracle), host cores
 
-A "step" is one pass of the hot path over one batch: entropy decode (K3) -> dequantise + IDCT (K1) -> upsample +
-YCbCr->RGB + pack (K2).  `value` times it with every input already resident in HBM (CUDA events on the launching
-stream, max over ranks); `e2e` times the same work through the host-buffer C-ABI call
-jpeg_sm100_decode_batch_rgb8 with pinned host buffers, H2D and D2H copies inside the timed region.
+A "step" is one pass of the hot path over one batch: scan lexing (N1: unstuff + RSTn split) -> entropy decode (K3) ->
+dequantise + IDCT (K1) -> upsample + YCbCr->RGB + pack (K2).  `value` times it with every input (the raw scan bytes
+of the files) already resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` times the same work
+through the host-buffer C-ABI call jpeg_sm100_decode_batch_raw_rgb8 with pinned host buffers, H2D and D2H copies
+inside the timed region.
 Inputs are produced by our own GPU encoder (K4-K7) from deterministic synthetic frames, DRI = one MCU row.
 Multi-GPU: independent images are sharded across ranks, no collective on the data path ("weak": 64 frames per GPU).
 Prints ONE JSON line on rank 0.
@@ -215,32 +216,43 @@ def run_ours(args):
     tables = (lib.HuffTable * (8 * n))(*tables_all)
     desc = batch.sequential_scan(geo)
     buf = batch.DeviceBuffers(geo, n, dev)
-    d_ecs = torch.from_numpy(inputs.ecs).to(dev)
-    d_off = torch.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    # raw scan bytes (stuffed, RSTn-delimited) as they sit in the files; the GPU lexer (N1) is the first stage of a step
+    raw_len = np.array([len(e) for e in ecs_all], dtype=np.uint64)
+    raw_off = np.concatenate([[0], np.cumsum(raw_len)[:-1]]).astype(np.uint64)
+    raw_cat = np.concatenate(ecs_all + [np.zeros(64, np.uint8)])
+    d_raw = torch.from_numpy(raw_cat).to(dev)
+    d_ecs = torch.zeros(raw_cat.size + 64, dtype=torch.uint8, device=dev)
+    d_off = torch.zeros(n * inputs.n_ecs + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_lex_status = torch.zeros(n, dtype=torch.int32, device=dev)
     qz = np.ascontiguousarray(q, dtype=np.uint16)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"memset": [], "huffman": [], "idct": [], "color": []}
+    stage_ms = {"lexer": [], "memset": [], "huffman": [], "idct": [], "color": []}
+    STAGES = ("lexer", "memset", "huffman", "idct", "color")
 
     def step(record):
-        e = [ev() for _ in range(5)] if record else None
-        if record:
-            e[0].record(stream)
+        e = []
+
+        def mark():
+            if record:
+                e.append(ev())
+                e[-1].record(stream)
+
+        mark()
+        ctx.check(ctx.L.jpeg_sm100_dev_lex_scan(ctx.h, d_raw.data_ptr(), raw_off.ctypes.data, raw_len.ctypes.data, n, inputs.n_ecs,
+                                                d_ecs.data_ptr(), d_off.data_ptr(), d_lex_status.data_ptr()))
+        mark()
         for c in buf.coef:
             ctx.check(ctx.L.jpeg_sm100_memset(ctx.h, c.data_ptr(), 0, c.numel() * 2))
-        if record:
-            e[1].record(stream)
+        mark()
         ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
                                                    geo.blocks[0], 0, tables, 0, C.byref(buf.sp), d_status.data_ptr()))
-        if record:
-            e[2].record(stream)
+        mark()
         ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), qz.ctypes.data, 8, C.byref(buf.pl)))
-        if record:
-            e[3].record(stream)
+        mark()
         ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
-        if record:
-            e[4].record(stream)
+        mark()
         return e
 
     def barrier():
@@ -252,6 +264,8 @@ def run_ours(args):
         step(False)
     barrier()
     assert d_status.cpu().abs().sum().item() == 0, "decode reported an error"
+    assert d_lex_status.cpu().abs().sum().item() == 0, "lexer reported an error"
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), inputs.offsets), "GPU lexer offsets differ from the host lexer's"
     checksum = int(buf.rgb[0, ::97, ::89].to(torch.int64).sum().item())
 
     sampler = ClockSampler(local)
@@ -267,7 +281,7 @@ def run_ours(args):
     launches = ctx.launches - launches0
     total_ms = t0.elapsed_time(t1)
     for e in recs:
-        for k, name in enumerate(("memset", "huffman", "idct", "color")):
+        for k, name in enumerate(STAGES):
             stage_ms[name].append(e[k].elapsed_time(e[k + 1]))
     ms_per_step = total_ms / args.steps
 
@@ -280,13 +294,13 @@ def run_ours(args):
     halves = []
     for k in range(n_streams):
         i0, i1 = k * n // n_streams, (k + 1) * n // n_streams
-        b0, b1 = int(inputs.offsets[i0 * inputs.n_ecs]), int(inputs.offsets[i1 * inputs.n_ecs])
-        offs = (inputs.offsets[i0 * inputs.n_ecs:i1 * inputs.n_ecs + 1] - np.uint64(b0)).astype(np.uint64)
+        b0 = int(raw_off[i0])
+        b1 = int(raw_off[i1 - 1] + raw_len[i1 - 1])
         halves.append({
             "n": i1 - i0, "i0": i0,
             "ctx": lib.Context(local),  # own stream + own device staging
-            "ecs": torch.from_numpy(np.concatenate([inputs.ecs[b0:b1], np.zeros(64, np.uint8)])).pin_memory(),
-            "off": torch.from_numpy(offs.view(np.int64).copy()).pin_memory(),
+            "raw": torch.from_numpy(np.concatenate([raw_cat[b0:b1], np.zeros(64, np.uint8)])).pin_memory(),
+            "raw_off": (raw_off[i0:i1] - np.uint64(b0)).astype(np.uint64), "raw_len": raw_len[i0:i1].copy(),
             "rgb": torch.empty((i1 - i0) * W * H * 3, dtype=torch.uint8).pin_memory(),
             "status": np.zeros(i1 - i0, dtype=np.int32),
             "tables": (lib.HuffTable * (8 * (i1 - i0)))(*tables_all[8 * i0:8 * i1]),
@@ -295,9 +309,9 @@ def run_ours(args):
     def e2e_worker(h, steps):
         c = h["ctx"]
         for _ in range(steps):
-            c.check(c.L.jpeg_sm100_decode_batch_rgb8(c.h, C.byref(desc), h["n"], h["ecs"].data_ptr(), h["off"].data_ptr(),
-                                                     inputs.n_ecs, geo.blocks[0], h["tables"], 0, qz.ctypes.data, W, H, 0,
-                                                     h["rgb"].data_ptr(), h["status"].ctypes.data))
+            c.check(c.L.jpeg_sm100_decode_batch_raw_rgb8(c.h, C.byref(desc), h["n"], h["raw"].data_ptr(), h["raw_off"].ctypes.data,
+                                                         h["raw_len"].ctypes.data, inputs.n_ecs, geo.blocks[0], h["tables"], 0,
+                                                         qz.ctypes.data, W, H, 0, h["rgb"].data_ptr(), h["status"].ctypes.data))
 
     def e2e_run(steps):
         ths = [threading.Thread(target=e2e_worker, args=(h, steps)) for h in halves]
@@ -345,8 +359,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu": n, "ecs_bytes_per_frame": inputs.ecs_bytes // n,
                        "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective"},
             "e2e": {"value": round(px_per_step / e2e_s / 1e6, 1), "unit": "Mpixels/s",
-                    "h2d_bytes_per_step": int(inputs.ecs_bytes + inputs.offsets.nbytes), "d2h_bytes_per_step": int(rgb_bytes + 4 * n),
-                    "streams": n_streams, "call": "jpeg_sm100_decode_batch_rgb8 (host buffers, pinned)", "steps": e2e_steps},
+                    "h2d_bytes_per_step": int(raw_len.sum() + raw_len.nbytes * 2), "d2h_bytes_per_step": int(rgb_bytes + 4 * n),
+                    "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)", "steps": e2e_steps},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "roofline": {"kernel": "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -358,6 +372,7 @@ def run_ours(args):
                                   "bytes_per_launch": int(huff_bytes), "ms_per_launch": round(huff_ms, 4),
                                   "share_of_step": shares["huffman"]},
             "stages": {"ms": {k: round(statistics.mean(v), 4) for k, v in stage_ms.items()}, "share_of_step": shares,
+                       "lexer_GBps": round(3.0 * float(raw_len.sum()) / (statistics.mean(stage_ms["lexer"]) * 1e-3) / 1e9, 1),
                        "huffman_GBps": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1),
                        "color_GBps": round(color_bytes / (color_ms * 1e-3) / 1e9, 1)},
             "cpu_baseline": cpu,

@@ -47,6 +47,9 @@ enum {
     JPEG_SM100_ERR_UNDEFINED_AC            = -5,  /* DecodingError.undefinedScanHuffmanACReference decode.swift:2894,3198 */
     JPEG_SM100_ERR_PRECONDITION            = -7,  /* the reference would trap (preconditionFailure / Range2 bounds) */
     JPEG_SM100_ERR_INVALID_HUFFMAN         = -8,  /* ParsingError.invalidHuffmanTable              decode.swift:524 */
+    JPEG_SM100_ERR_RESTART_PHASE           = -9,  /* DecodingError.invalidRestartPhase             decode.swift:3931 */
+    JPEG_SM100_ERR_ECS_COUNT               = -10, /* batch lexer only: an image's RSTn count differs from the batch's n_ecs - 1 */
+    JPEG_SM100_ERR_MISSING_INTERVAL        = -11, /* DecodingError.missingRestartIntervalSegment   decode.swift:3719 */
     JPEG_SM100_ERR_INVALID_ARGUMENT        = -20,
     JPEG_SM100_ERR_UNSUPPORTED             = -21,
     JPEG_SM100_ERR_NO_MEMORY               = -22,
@@ -169,6 +172,34 @@ int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc
                                  const uint16_t *quanta_zigzag, uint32_t size_x, uint32_t size_y, int cosited,
                                  uint8_t *rgb, int32_t *status);
 
+/* ---- N1: the per-scan half of the lexer on the GPU ---- */
+
+/* replaces the  `for index in 0... { (ecs, marker) = try stream.segment(prefix: true) ... }`  loop of
+ * Context.decompress (decode.swift:3895-3933; Bytestream.segment decode.swift:130-190) for one scan:
+ * byte unstuffing (FF 00 -> FF), fill bytes, RSTn splitting, restart-phase validation.
+ *   raw / raw_len : the bytes that follow the SOS header up to (not including) the FF of the next non-RSTn marker
+ *   ecs           : out, unstuffed bytes of all entropy-coded segments back to back (capacity >= raw_len)
+ *   ecs_offsets   : out, *n_ecs + 1 offsets (capacity offsets_capacity entries; ERR_NO_MEMORY if too small)
+ * Errors: ERR_RESTART_PHASE; ERR_INVALID_ARGUMENT if raw contains a marker other than RSTn. */
+int jpeg_sm100_lex_scan(jpeg_sm100_ctx *ctx, const uint8_t *raw, uint64_t raw_len, uint8_t *ecs, uint64_t ecs_capacity,
+                        uint64_t *ecs_offsets, uint32_t offsets_capacity, uint32_t *n_ecs);
+
+/* lexer + Spectral.decode(ecss:...) in one call, the scan bytes never return to the host:
+ * same arguments as jpeg_sm100_decode_scan with the raw (stuffed, RSTn-delimited) scan bytes instead of ecss.
+ * interval = JPEG_SM100_INTERVAL_NONE with more than one segment -> ERR_MISSING_INTERVAL (decode.swift:3708-3720). */
+int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *raw, uint64_t raw_len,
+                               uint64_t interval, int extend,
+                               const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4],
+                               jpeg_sm100_plane_i16 *planes, uint32_t n_planes);
+
+/* jpeg_sm100_decode_batch_rgb8 fed with raw scan bytes: image i's scan data is raw_concat[raw_offsets[i] ..+ raw_lengths[i]).
+ * Every image must contain exactly n_ecs segments (else its status is ERR_ECS_COUNT). */
+int jpeg_sm100_decode_batch_raw_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
+                                     const uint8_t *raw_concat, const uint64_t *raw_offsets, const uint64_t *raw_lengths,
+                                     uint32_t n_ecs, uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
+                                     const uint16_t *quanta_zigzag, uint32_t size_x, uint32_t size_y, int cosited,
+                                     uint8_t *rgb, int32_t *status);
+
 /* ---- encode ---- */
 
 /* replaces  JPEG.RGB.pack(_:as:)   jpeg.swift:584-599 (RGB.ycc 463-478) */
@@ -223,6 +254,15 @@ int jpeg_sm100_dev_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *
                                uint64_t interval, int extend,
                                const jpeg_sm100_huff_table *tables, int tables_shared,
                                const jpeg_sm100_dev_spectral *spectral, int32_t *d_status);
+
+/* N1 on device memory: lex the scan bytes of n_images images into the inputs of jpeg_sm100_dev_decode_scan.
+ *   d_raw          : device, 16-byte aligned, readable for 16 bytes past the last image
+ *   raw_offsets / raw_lengths : HOST, n_images each (any alignment)
+ *   d_ecs          : device, 16-byte aligned, out: unstuffed bytes back to back; capacity >= sum(raw_lengths) + 16
+ *   d_ecs_offsets  : device, out: n_images * n_ecs + 1
+ *   d_status       : device, n_images int32: 0, ERR_RESTART_PHASE, ERR_ECS_COUNT or ERR_INVALID_ARGUMENT (foreign marker) */
+int jpeg_sm100_dev_lex_scan(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *raw_offsets, const uint64_t *raw_lengths,
+                            uint32_t n_images, uint32_t n_ecs, uint8_t *d_ecs, uint64_t *d_ecs_offsets, int32_t *d_status);
 
 /* dequantise + IDCT every plane of every image.  quanta: HOST, n_planes x 64 (shared by all images). */
 int jpeg_sm100_dev_idct(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *spectral,

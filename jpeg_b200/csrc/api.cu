@@ -12,6 +12,15 @@ int jpeg_color_pack_rgb(jpeg_sm100_ctx *, const uint8_t *, uint64_t, int, uint16
 int jpeg_color_decompose(jpeg_sm100_ctx *, const void *, bool, uint32_t, uint32_t, const jpeg_sm100_dev_planar *);
 int jpeg_huffman_decode_scan(jpeg_sm100_ctx *, const jpeg_sm100_scan_desc *, const uint8_t *, const uint64_t *, uint32_t,
                              uint64_t, int, const jpeg_sm100_huff_table *, int, const jpeg_sm100_dev_spectral *, int32_t *);
+struct LexPlan {
+    uint32_t  n_images, tiles_max;
+    uint64_t  n_tiles;
+    void     *d_images;
+    uint32_t *d_counts, *d_split_base, *d_foreign, *d_bad_phase, *d_n_splits;
+    uint64_t *d_emit_base;
+};
+int jpeg_lex_count(jpeg_sm100_ctx *, const uint8_t *, const uint64_t *, const uint64_t *, uint32_t, LexPlan *);
+int jpeg_lex_scatter(jpeg_sm100_ctx *, const uint8_t *, const LexPlan *, uint32_t, uint8_t *, uint64_t *, int32_t *);
 int jpeg_fdct_launch(jpeg_sm100_ctx *, const void *, int, uint64_t, uint32_t, uint32_t, uint32_t, const float[64], int,
                      int16_t *, uint64_t);
 int jpeg_huffman_encode_scan(jpeg_sm100_ctx *, const jpeg_sm100_scan_desc *, const jpeg_sm100_dev_spectral *, uint64_t,
@@ -87,6 +96,9 @@ JPEG_API const char *jpeg_sm100_error_string(int code)
     case JPEG_SM100_ERR_UNDEFINED_AC: return "undefinedScanHuffmanACReference";
     case JPEG_SM100_ERR_PRECONDITION: return "precondition failure in the reference";
     case JPEG_SM100_ERR_INVALID_HUFFMAN: return "invalidHuffmanTable";
+    case JPEG_SM100_ERR_RESTART_PHASE: return "invalidRestartPhase";
+    case JPEG_SM100_ERR_ECS_COUNT: return "restart marker count differs from the batch geometry";
+    case JPEG_SM100_ERR_MISSING_INTERVAL: return "missingRestartIntervalSegment";
     case JPEG_SM100_ERR_INVALID_ARGUMENT: return "invalid argument";
     case JPEG_SM100_ERR_UNSUPPORTED: return "unsupported";
     case JPEG_SM100_ERR_NO_MEMORY: return "out of memory / buffer too small";
@@ -476,14 +488,15 @@ JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_p
 // 3 bytes of RGB per pixel leave the device) overlap the kernels of the next chunk:
 //     stream  : H2D ecs -> memset -> K3 (whole batch) -> per chunk k: K1 -> K2 into RGB buffer (k & 1)
 //     copy_out: D2H of chunk k's RGB (waits for its K2; K2 of chunk k + 2 waits for this copy)
-JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
-                                          const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs,
-                                          uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
-                                          const uint16_t *quanta, uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb,
-                                          int32_t *status)
+namespace {
+
+// shared body of the two batch entry points.  raw_offsets == nullptr: `bytes` are unstuffed ECS bytes and `offsets` the
+// n_images * n_ecs + 1 ECS offsets; else `bytes` are raw scan bytes and the GPU lexer produces both.
+int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images, const uint8_t *bytes,
+                        const uint64_t *offsets, const uint64_t *raw_offsets, const uint64_t *raw_lengths, uint32_t n_ecs,
+                        uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared, const uint16_t *quanta,
+                        uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb, int32_t *status)
 {
-    REQUIRE_CTX(ctx);
-    if (!scan || !ecs_offsets || !tables || !quanta || !rgb || n_images == 0 || n_ecs == 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     if (scan->band_lo != 0 || scan->band_hi != 64 || scan->bit_hi >= 0) return JPEG_SM100_ERR_UNSUPPORTED;
     const uint32_t n_planes = (uint32_t) scan->n_comp;
     if (n_planes != 1 && n_planes != 3) return JPEG_SM100_ERR_UNSUPPORTED;
@@ -523,7 +536,7 @@ JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_
         coef_off[p] = coef_total;
         coef_total += align_up((size_t) sp.plane[p].image_stride * 2 * n_images, 1024);
     }
-    void *d_coef = nullptr, *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr, *d_rgb = nullptr;
+    void *d_coef = nullptr, *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr, *d_rgb = nullptr, *d_raw = nullptr;
     J_TRY(scratch_reserve(ctx, 0, coef_total + 1024, &d_coef));
     for (uint32_t p = 0; p < n_planes; ++p) sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(d_coef) + coef_off[p]);
     jpeg_sm100_dev_spectral geo = sp;  // sample planes are only needed for one chunk at a time
@@ -531,15 +544,30 @@ JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_
     jpeg_sm100_dev_planar pl;
     J_TRY(alloc_planar(ctx, 4, geo, 1, pl));
     const uint64_t n_off = (uint64_t) n_images * n_ecs + 1;
-    const uint64_t ecs_bytes = ecs_offsets[n_off - 1];
-    const size_t   rgb_chunk = align_up(rgb_per_image * chunk, 256);
-    J_TRY(scratch_reserve(ctx, 1, ecs_bytes + 64, &d_ecs));
+    uint64_t       in_bytes = 0;
+    if (raw_offsets)
+        for (uint32_t i = 0; i < n_images; ++i) in_bytes = raw_offsets[i] + raw_lengths[i] > in_bytes ? raw_offsets[i] + raw_lengths[i] : in_bytes;
+    else
+        in_bytes = offsets[n_off - 1];
+    const size_t rgb_chunk = align_up(rgb_per_image * chunk, 256);
+    J_TRY(scratch_reserve(ctx, 1, in_bytes + 64, &d_ecs));
     J_TRY(scratch_reserve(ctx, 2, n_off * 8, &d_off));
-    J_TRY(scratch_reserve(ctx, 3, sizeof(int32_t) * n_images + 64, &d_status));
+    J_TRY(scratch_reserve(ctx, 3, 2 * sizeof(int32_t) * n_images + 64, &d_status));
     J_TRY(scratch_reserve(ctx, 6, 2 * rgb_chunk + 64, &d_rgb));
+    int32_t *d_lex_status = reinterpret_cast<int32_t *>(d_status) + n_images;
 
-    if (ecs_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, ecs_concat, ecs_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_off, ecs_offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (raw_offsets) {
+        J_TRY(scratch_reserve(ctx, 5, in_bytes + 64, &d_raw));
+        if (in_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_raw, bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LexPlan plan;
+        J_TRY(jpeg_lex_count(ctx, reinterpret_cast<uint8_t *>(d_raw), raw_offsets, raw_lengths, n_images, &plan));
+        J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, n_ecs, reinterpret_cast<uint8_t *>(d_ecs),
+                               reinterpret_cast<uint64_t *>(d_off), d_lex_status));
+    } else {
+        if (in_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(d_off, offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(d_lex_status, 0, sizeof(int32_t) * n_images, ctx->stream));
+    }
     CU_TRY(ctx, cudaMemsetAsync(d_coef, 0, coef_total, ctx->stream));  // Spectral planes start zeroed (decode.swift:2241-2256)
     J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
                                    interval, 0, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status)));
@@ -557,16 +585,136 @@ JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_
         CU_TRY(ctx, cudaMemcpyAsync(rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
         CU_TRY(ctx, cudaEventRecord(ev_out[k], ctx->copy_out));
     }
-    std::vector<int32_t> st(n_images, 0);
-    CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> st(2 * (size_t) n_images, 0);
+    CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, 2 * sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
     int first = 0;
     for (uint32_t i = 0; i < n_images; ++i) {
-        if (status) status[i] = st[i];
-        if (st[i] && !first) first = st[i];
+        // a lexer error is raised before the scan is pushed (decode.swift:3929), so it wins over a decode error
+        const int32_t v = st[n_images + i] ? st[n_images + i] : st[i];
+        if (status) status[i] = v;
+        if (v && !first) first = v;
     }
     return first;
+}
+
+}  // namespace
+
+JPEG_API int jpeg_sm100_decode_batch_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
+                                          const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs,
+                                          uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared,
+                                          const uint16_t *quanta, uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb,
+                                          int32_t *status)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !ecs_offsets || !tables || !quanta || !rgb || n_images == 0 || n_ecs == 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    return decode_batch_common(ctx, scan, n_images, ecs_concat, ecs_offsets, nullptr, nullptr, n_ecs, interval, tables, tables_shared,
+                               quanta, sx, sy, cosited, rgb, status);
+}
+
+JPEG_API int jpeg_sm100_decode_batch_raw_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images,
+                                              const uint8_t *raw_concat, const uint64_t *raw_offsets, const uint64_t *raw_lengths,
+                                              uint32_t n_ecs, uint64_t interval, const jpeg_sm100_huff_table *tables,
+                                              int tables_shared, const uint16_t *quanta, uint32_t sx, uint32_t sy, int cosited,
+                                              uint8_t *rgb, int32_t *status)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !raw_concat || !raw_offsets || !raw_lengths || !tables || !quanta || !rgb || n_images == 0 || n_ecs == 0)
+        return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    return decode_batch_common(ctx, scan, n_images, raw_concat, nullptr, raw_offsets, raw_lengths, n_ecs, interval, tables,
+                               tables_shared, quanta, sx, sy, cosited, rgb, status);
+}
+
+// ---- N1: lexer entry points ----
+JPEG_API int jpeg_sm100_dev_lex_scan(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *raw_offsets,
+                                     const uint64_t *raw_lengths, uint32_t n_images, uint32_t n_ecs, uint8_t *d_ecs,
+                                     uint64_t *d_ecs_offsets, int32_t *d_status)
+{
+    REQUIRE_CTX(ctx);
+    if (!d_raw || !raw_offsets || !raw_lengths || !d_ecs || !d_ecs_offsets || n_images == 0 || n_ecs == 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_raw) & 15) || (reinterpret_cast<uintptr_t>(d_ecs) & 15)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    LexPlan plan;
+    J_TRY(jpeg_lex_count(ctx, d_raw, raw_offsets, raw_lengths, n_images, &plan));
+    return jpeg_lex_scatter(ctx, d_raw, &plan, n_ecs, d_ecs, d_ecs_offsets, d_status);
+}
+
+namespace {
+// uploads one image's raw scan bytes, lexes them on the device; leaves d_ecs (slot 1) / d_off (slot 2) ready
+int lex_one(jpeg_sm100_ctx *ctx, const uint8_t *raw, uint64_t raw_len, uint32_t *n_ecs, void **d_ecs, void **d_off, int32_t *lex_status)
+{
+    void *d_raw = nullptr, *d_st = nullptr;
+    J_TRY(scratch_reserve(ctx, 5, raw_len + 64, &d_raw));
+    J_TRY(scratch_reserve(ctx, 1, raw_len + 64, d_ecs));
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_st));
+    if (raw_len) CU_TRY(ctx, cudaMemcpyAsync(d_raw, raw, raw_len, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t off0 = 0;
+    LexPlan        plan;
+    J_TRY(jpeg_lex_count(ctx, reinterpret_cast<uint8_t *>(d_raw), &off0, &raw_len, 1, &plan));
+    // the number of segments is data: one 4-byte read-back before the scatter pass can lay out the offsets
+    J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, 0, nullptr, nullptr, nullptr));
+    uint32_t splits = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&splits, plan.d_n_splits, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_ecs = splits + 1;
+    J_TRY(scratch_reserve(ctx, 2, 8 * ((size_t) *n_ecs + 1), d_off));
+    J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, *n_ecs, reinterpret_cast<uint8_t *>(*d_ecs),
+                           reinterpret_cast<uint64_t *>(*d_off), reinterpret_cast<int32_t *>(d_st)));
+    CU_TRY(ctx, cudaMemcpyAsync(lex_status, d_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+}  // namespace
+
+JPEG_API int jpeg_sm100_lex_scan(jpeg_sm100_ctx *ctx, const uint8_t *raw, uint64_t raw_len, uint8_t *ecs, uint64_t ecs_capacity,
+                                 uint64_t *ecs_offsets, uint32_t offsets_capacity, uint32_t *n_ecs)
+{
+    REQUIRE_CTX(ctx);
+    if ((!raw && raw_len) || !ecs_offsets || !n_ecs) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    void   *d_ecs = nullptr, *d_off = nullptr;
+    int32_t st = 0;
+    J_TRY(lex_one(ctx, raw, raw_len, n_ecs, &d_ecs, &d_off, &st));
+    if (st) return st;
+    if (offsets_capacity < *n_ecs + 1) return JPEG_SM100_ERR_NO_MEMORY;
+    CU_TRY(ctx, cudaMemcpyAsync(ecs_offsets, d_off, 8 * ((size_t) *n_ecs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = ecs_offsets[*n_ecs];
+    if (total > ecs_capacity || (total && !ecs)) return JPEG_SM100_ERR_NO_MEMORY;
+    if (total) CU_TRY(ctx, cudaMemcpyAsync(ecs, d_ecs, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *raw, uint64_t raw_len,
+                                        uint64_t interval, int extend, const jpeg_sm100_huff_table dc[4],
+                                        const jpeg_sm100_huff_table ac[4], jpeg_sm100_plane_i16 *planes, uint32_t n_planes)
+{
+    REQUIRE_CTX(ctx);
+    if (!scan || !planes || !dc || !ac || (!raw && raw_len)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    void    *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr;
+    uint32_t n_ecs = 0;
+    int32_t  st = 0;
+    J_TRY(lex_one(ctx, raw, raw_len, &n_ecs, &d_ecs, &d_off, &st));
+    if (st) return st;
+    if (interval == JPEG_SM100_INTERVAL_NONE) {
+        if (n_ecs > 1) return JPEG_SM100_ERR_MISSING_INTERVAL;  // decode.swift:3708-3720
+        n_ecs = 1;
+    }
+    PlaneSet ps;
+    J_TRY(upload_spectral(ctx, 0, planes, n_planes, nullptr, ps));
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_status));
+    jpeg_sm100_huff_table tables[8];
+    memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
+    memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
+    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
+                                   interval, extend, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+    int32_t status = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+    for (uint32_t p = 0; p < n_planes; ++p)
+        if (ps.bytes[p])
+            CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return status;
 }
 
 // ---- encode ----

@@ -1,0 +1,342 @@
+// lexer.cu -- N1 (SURVEY §8 "next"): the per-scan half of the container lexer on the GPU.
+//
+// Replaces, for the bytes between an SOS header and the next non-RSTn marker, what Bytestream.segment(prefix: true)
+// (decode.swift:130-190) does one byte at a time inside the scan loop of Context.decompress (decode.swift:3895-3933):
+//   * byte unstuffing   FF 00 -> FF
+//   * fill bytes        FF FF .. FF x  ==  FF x
+//   * RSTn splitting    FF Dn ends an entropy-coded segment; n must equal (index mod 8), else
+//                       DecodingError.invalidRestartPhase (decode.swift:3929-3932)
+// and produces exactly the inputs jpeg_sm100_dev_decode_scan consumes: the unstuffed bytes of all images back to back
+// and n_images * n_ecs + 1 byte offsets.
+//
+// The lexer's automaton has one bit of state ("the previous byte was FF"), and that bit is a function of the previous
+// byte alone:   state(i) = (raw[i-1] == FF).   So every byte can be classified independently,
+//   emits(i)  = (prev != FF && cur != FF) || (prev == FF && cur == 00)        value = prev == FF ? FF : cur
+//   split(i)  =  prev == FF && (cur & F8) == D0
+//   foreign(i)=  prev == FF && cur not in {00, FF, D0..D7}                     (a marker the host should have cut at)
+// and the whole thing is a stream compaction: count (k_lex_count) -> scan (k_lex_scan) -> scatter (k_lex_scatter).
+// HBM-bound: 2 reads + 1 write of the scan bytes; 16 bytes per thread with SIMD-in-a-register byte compares (VSETxx),
+// output tiles staged in shared memory and stored as aligned 16-byte vectors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LEX_THREADS = 256;
+constexpr int LEX_CHUNK = 16;                        // raw bytes per thread
+constexpr int LEX_TILE = LEX_THREADS * LEX_CHUNK;    // 4 KB of raw bytes per CTA
+
+struct LexImage {
+    uint64_t raw_off, raw_len;
+};
+
+struct Chunk {
+    uint32_t emit[4];   // per byte 0xFF / 0x00
+    uint32_t split[4];
+    uint32_t out[4];    // output byte values
+    uint32_t cur[4];    // raw bytes (masked to the image)
+    uint32_t foreign;   // any foreign marker
+};
+
+__device__ __forceinline__ uint32_t bytes_below(int n)  // 0xFF in bytes j < n
+{
+    return n <= 0 ? 0u : (n >= 4 ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u));
+}
+
+// classify the 16 bytes at raw[base .. base+16); only bytes in [lo, hi) belong to the image
+__device__ __forceinline__ Chunk classify(const uint8_t *__restrict__ raw, uint64_t base, uint64_t lo, uint64_t hi)
+{
+    Chunk c;
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + base));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t prev = (base > lo) ? (uint32_t) __ldg(raw + base - 1) : 0u;
+    const int s = lo > base ? (int) (lo - base) : 0;
+    const int e = hi - base >= 16 ? 16 : (int) (hi - base);
+    c.foreign = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t valid = (s == 0 && e == 16) ? 0xFFFFFFFFu : (bytes_below(e - 4 * i) & ~bytes_below(s - 4 * i));
+        const uint32_t cur = w[i] & valid;
+        const uint32_t pw = (cur << 8) | prev;  // little endian: the byte before byte j sits 8 bits lower
+        prev = cur >> 24;
+        const uint32_t cur_ff = __vcmpeq4(cur, 0xFFFFFFFFu);
+        const uint32_t prev_ff = __vcmpeq4(pw, 0xFFFFFFFFu);
+        const uint32_t cur_00 = __vcmpeq4(cur, 0u);
+        const uint32_t cur_rst = __vcmpeq4(cur & 0xF8F8F8F8u, 0xD0D0D0D0u);
+        c.emit[i] = ((~prev_ff & ~cur_ff) | (prev_ff & cur_00)) & valid;
+        c.split[i] = prev_ff & cur_rst & valid;
+        c.out[i] = cur | prev_ff;
+        c.cur[i] = cur;
+        c.foreign |= prev_ff & ~cur_00 & ~cur_ff & ~cur_rst & valid;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint32_t count_bytes(const uint32_t m[4])
+{
+    return __popc(m[0] & 0x01010101u) + __popc(m[1] & 0x01010101u) + __popc(m[2] & 0x01010101u) + __popc(m[3] & 0x01010101u);
+}
+
+// block-wide exclusive scan of a packed (emit | split << 16) value; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t s_warp[LEX_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t  inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, sum = 0;
+#pragma unroll
+    for (int i = 0; i < LEX_THREADS / 32; ++i) {
+        const uint32_t t = s_warp[i];
+        if (i < warp) base += t;
+        sum += t;
+    }
+    *total = sum;
+    __syncthreads();
+    return base + inc - v;
+}
+
+// pass 1: per-tile totals.  grid = (tiles_max, n_images)
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_count(const uint8_t *__restrict__ raw, const LexImage *__restrict__ images,
+                                                            uint32_t tiles_max, uint32_t *__restrict__ tile_counts,
+                                                            uint32_t *__restrict__ foreign)
+{
+    const uint32_t img = blockIdx.y, tile = blockIdx.x;
+    const LexImage im = images[img];
+    const uint64_t lo = im.raw_off, hi = im.raw_off + im.raw_len;
+    const uint64_t base = (lo & ~15ull) + (uint64_t) tile * LEX_TILE + threadIdx.x * LEX_CHUNK;
+    uint32_t       v = 0, bad = 0;
+    if (base < hi) {
+        const Chunk c = classify(raw, base, lo, hi);
+        v = count_bytes(c.emit) | (count_bytes(c.split) << 16);
+        bad = c.foreign;
+    }
+    uint32_t total;
+    block_exclusive_scan(v, &total);
+    if (threadIdx.x == 0) tile_counts[(size_t) img * tiles_max + tile] = total;
+    if (bad) atomicOr(&foreign[img], 1u);
+}
+
+// pass 2: one CTA.  Exclusive scan over all (image-major) tile totals: 64-bit emitted-byte bases, 32-bit split bases.
+__global__ void __launch_bounds__(1024) k_lex_scan(const uint32_t *__restrict__ tile_counts, uint64_t n_tiles, uint64_t *__restrict__ emit_base,
+                                                   uint32_t *__restrict__ split_base)
+{
+    __shared__ uint64_t s_e[1024];
+    __shared__ uint32_t s_s[1024];
+    const uint64_t per = (n_tiles + 1023) / 1024;
+    const uint64_t b = threadIdx.x * per, e = (b + per < n_tiles) ? b + per : n_tiles;
+    uint64_t       se = 0;
+    uint32_t       ss = 0;
+    for (uint64_t i = b; i < e; ++i) {
+        const uint32_t c = tile_counts[i];
+        se += c & 0xFFFFu;
+        ss += c >> 16;
+    }
+    s_e[threadIdx.x] = se;
+    s_s[threadIdx.x] = ss;
+    __syncthreads();
+    // Hillis-Steele over 1024 partials
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint64_t ae = 0;
+        uint32_t as = 0;
+        if ((int) threadIdx.x >= d) {
+            ae = s_e[threadIdx.x - d];
+            as = s_s[threadIdx.x - d];
+        }
+        __syncthreads();
+        s_e[threadIdx.x] += ae;
+        s_s[threadIdx.x] += as;
+        __syncthreads();
+    }
+    uint64_t re = s_e[threadIdx.x] - se;
+    uint32_t rs = s_s[threadIdx.x] - ss;
+    for (uint64_t i = b; i < e; ++i) {
+        const uint32_t c = tile_counts[i];
+        emit_base[i] = re;
+        split_base[i] = rs;
+        re += c & 0xFFFFu;
+        rs += c >> 16;
+    }
+    if (threadIdx.x == 1023) {
+        emit_base[n_tiles] = s_e[1023];
+        split_base[n_tiles] = s_s[1023];
+    }
+}
+
+// pass 3: scatter.  grid = (tiles_max, n_images)
+__global__ void __launch_bounds__(LEX_THREADS) k_lex_scatter(const uint8_t *__restrict__ raw, const LexImage *__restrict__ images,
+                                                              uint32_t tiles_max, const uint64_t *__restrict__ emit_base,
+                                                              const uint32_t *__restrict__ split_base, uint32_t n_ecs,
+                                                              uint8_t *__restrict__ out, uint64_t *__restrict__ offsets,
+                                                              uint32_t *__restrict__ bad_phase)
+{
+    __shared__ __align__(16) uint8_t s_out[LEX_TILE + 32];
+    const uint32_t img = blockIdx.y, tile = blockIdx.x;
+    const LexImage im = images[img];
+    const uint64_t lo = im.raw_off, hi = im.raw_off + im.raw_len;
+    const uint64_t tile_base = (lo & ~15ull) + (uint64_t) tile * LEX_TILE;
+    if (tile_base >= hi) return;
+    const size_t   ti = (size_t) img * tiles_max + tile;
+    const uint64_t g0 = emit_base[ti];
+    const uint32_t k0 = split_base[ti] - split_base[(size_t) img * tiles_max];
+    const uint64_t base = tile_base + threadIdx.x * LEX_CHUNK;
+    Chunk          c;
+    uint32_t       v = 0;
+    if (base < hi) {
+        c = classify(raw, base, lo, hi);
+        v = count_bytes(c.emit) | (count_bytes(c.split) << 16);
+    }
+    uint32_t       total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    const uint32_t a = (uint32_t) (g0 & 15);  // keep the destination's alignment inside the staging tile
+    if (v) {
+        uint32_t pos = a + (ex & 0xFFFFu);
+        uint32_t k = k0 + (ex >> 16);
+        if ((v >> 16) == 0 && (v & 0xFFFFu) == 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_out[pos + 4 * i + j] = (uint8_t) (c.out[i] >> (8 * j));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((c.emit[i] >> (8 * j)) & 1u) s_out[pos++] = (uint8_t) (c.out[i] >> (8 * j));
+                    if ((c.split[i] >> (8 * j)) & 1u) {
+                        // the ECS that ends here has index k; the marker's phase must be k mod 8 (decode.swift:3929)
+                        const uint32_t phase = ((c.cur[i] >> (8 * j)) & 7u);
+                        if (phase != (k & 7u)) atomicMin(&bad_phase[img], k);
+                        if (k + 1 < n_ecs) offsets[(size_t) img * n_ecs + k + 1] = g0 + (pos - a);
+                        ++k;
+                    }
+                }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = total & 0xFFFFu;
+    if (n == 0) return;
+    uint8_t *gdst = out + (g0 - a);  // 16-byte aligned (out is)
+    for (uint32_t u = threadIdx.x; 16 * u < a + n; u += LEX_THREADS) {
+        const uint32_t p = 16 * u;
+        if (p >= a && p + 16 <= a + n)
+            *reinterpret_cast<uint4 *>(gdst + p) = *reinterpret_cast<const uint4 *>(s_out + p);
+        else
+            for (uint32_t q = (p > a ? p : a); q < p + 16 && q < a + n; ++q) gdst[q] = s_out[q];
+    }
+}
+
+// pass 4: one thread per image: first / missing / final offsets and the lexer status
+__global__ void k_lex_finish(uint32_t n_images, uint32_t tiles_max, uint32_t n_ecs, const uint64_t *__restrict__ emit_base,
+                             const uint32_t *__restrict__ split_base, const uint32_t *__restrict__ foreign,
+                             const uint32_t *__restrict__ bad_phase, uint64_t *__restrict__ offsets, int32_t *__restrict__ status,
+                             uint32_t *__restrict__ n_splits)
+{
+    const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= n_images) return;
+    const size_t   t0 = (size_t) img * tiles_max, t1 = t0 + tiles_max;
+    const uint64_t begin = emit_base[t0], end = emit_base[t1];
+    const uint32_t splits = split_base[t1] - split_base[t0];
+    if (n_splits) n_splits[img] = splits;
+    if (n_ecs) {
+        offsets[(size_t) img * n_ecs] = begin;
+        for (uint32_t k = splits + 1; k < n_ecs; ++k) offsets[(size_t) img * n_ecs + k] = end;
+        if (img == n_images - 1) offsets[(size_t) n_images * n_ecs] = end;
+    }
+    int32_t st = JPEG_SM100_OK;
+    if (foreign[img])
+        st = JPEG_SM100_ERR_INVALID_ARGUMENT;
+    else if (bad_phase[img] != 0xFFFFFFFFu)
+        st = JPEG_SM100_ERR_RESTART_PHASE;
+    else if (n_ecs && splits + 1 != n_ecs)
+        st = JPEG_SM100_ERR_ECS_COUNT;
+    if (status) status[img] = st;
+}
+
+}  // namespace
+
+// Device-side state of one lexing job: scratch slot 15 holds the image table, the tile tables and the flags.
+// (same definition in api.cu)
+struct LexPlan {
+    uint32_t  n_images, tiles_max;
+    uint64_t  n_tiles;
+    void     *d_images;
+    uint32_t *d_counts, *d_split_base, *d_foreign, *d_bad_phase, *d_n_splits;
+    uint64_t *d_emit_base;
+};
+
+// passes 1 + 2 (independent of n_ecs).  raw_offsets / raw_lengths are HOST arrays.
+int jpeg_lex_count(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *raw_offsets, const uint64_t *raw_lengths,
+                   uint32_t n_images, LexPlan *plan)
+{
+    uint64_t longest = 0;
+    for (uint32_t i = 0; i < n_images; ++i) {
+        const uint64_t span = (raw_offsets[i] & 15) + raw_lengths[i];
+        longest = span > longest ? span : longest;
+    }
+    const uint64_t tiles_max64 = longest ? (longest + LEX_TILE - 1) / LEX_TILE : 1;
+    if (tiles_max64 > 0x7FFFFFFFull || n_images > 65535) return JPEG_SM100_ERR_UNSUPPORTED;
+    plan->n_images = n_images;
+    plan->tiles_max = (uint32_t) tiles_max64;
+    plan->n_tiles = (uint64_t) n_images * plan->tiles_max;
+    // layout of slot 15: images | counts | emit_base | split_base | foreign | bad_phase | n_splits
+    size_t       off = 0;
+    const size_t o_images = off;
+    off += (sizeof(LexImage) * n_images + 255) & ~(size_t) 255;
+    const size_t o_counts = off;
+    off += (4 * plan->n_tiles + 255) & ~(size_t) 255;
+    const size_t o_emit = off;
+    off += (8 * (plan->n_tiles + 1) + 255) & ~(size_t) 255;
+    const size_t o_split = off;
+    off += (4 * (plan->n_tiles + 1) + 255) & ~(size_t) 255;
+    const size_t o_flags = off;
+    off += ((size_t) 12 * n_images + 255) & ~(size_t) 255;
+    void *base = nullptr;
+    J_TRY(scratch_reserve(ctx, 15, off, &base));
+    uint8_t *b = reinterpret_cast<uint8_t *>(base);
+    plan->d_images = b + o_images;
+    plan->d_counts = reinterpret_cast<uint32_t *>(b + o_counts);
+    plan->d_emit_base = reinterpret_cast<uint64_t *>(b + o_emit);
+    plan->d_split_base = reinterpret_cast<uint32_t *>(b + o_split);
+    plan->d_foreign = reinterpret_cast<uint32_t *>(b + o_flags);
+    plan->d_bad_phase = plan->d_foreign + n_images;
+    plan->d_n_splits = plan->d_bad_phase + n_images;
+
+    void *h = nullptr;
+    int   slot = 0;
+    J_TRY(pinned_acquire(ctx, sizeof(LexImage) * n_images, &h, &slot));
+    LexImage *hi = reinterpret_cast<LexImage *>(h);
+    for (uint32_t i = 0; i < n_images; ++i) hi[i] = LexImage{raw_offsets[i], raw_lengths[i]};
+    CU_TRY(ctx, cudaMemcpyAsync(plan->d_images, hi, sizeof(LexImage) * n_images, cudaMemcpyHostToDevice, ctx->stream));
+    J_TRY(pinned_release(ctx, slot));
+    CU_TRY(ctx, cudaMemsetAsync(plan->d_foreign, 0, 4 * (size_t) n_images, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(plan->d_bad_phase, 0xFF, 4 * (size_t) n_images, ctx->stream));
+    const dim3 grid(plan->tiles_max, n_images);
+    k_lex_count<<<grid, LEX_THREADS, 0, ctx->stream>>>(d_raw, reinterpret_cast<const LexImage *>(plan->d_images), plan->tiles_max, plan->d_counts, plan->d_foreign);
+    LAUNCH_CHECK(ctx);
+    k_lex_scan<<<1, 1024, 0, ctx->stream>>>(plan->d_counts, plan->n_tiles, plan->d_emit_base, plan->d_split_base);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}
+
+// n_ecs == 0: only the per-image split counts are produced (d_n_splits), nothing is written to d_ecs / d_offsets
+int jpeg_lex_scatter(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const LexPlan *plan, uint32_t n_ecs, uint8_t *d_ecs,
+                     uint64_t *d_offsets, int32_t *d_status)
+{
+    if (n_ecs) {
+        const dim3 grid(plan->tiles_max, plan->n_images);
+        k_lex_scatter<<<grid, LEX_THREADS, 0, ctx->stream>>>(d_raw, reinterpret_cast<const LexImage *>(plan->d_images), plan->tiles_max, plan->d_emit_base,
+                                                             plan->d_split_base, n_ecs, d_ecs, d_offsets, plan->d_bad_phase);
+        LAUNCH_CHECK(ctx);
+    }
+    k_lex_finish<<<(plan->n_images + 127) / 128, 128, 0, ctx->stream>>>(plan->n_images, plan->tiles_max, n_ecs, plan->d_emit_base,
+                                                                        plan->d_split_base, plan->d_foreign, plan->d_bad_phase,
+                                                                        d_offsets, d_status, plan->d_n_splits);
+    LAUNCH_CHECK(ctx);
+    return JPEG_SM100_OK;
+}

@@ -142,6 +142,19 @@ class Spectral:
                                                dcs, acs, planes, len(self.planes))
         self.ctx.check(rc)
 
+    def decode_scan_raw(self, band, bits, comps, dc_tables, ac_tables, raw, interval, extend=False):
+        """The same scan from its raw bytes (stuffed, RSTn-delimited): lexing (decode.swift:130-190, 3895-3933) and
+        decoding both on the GPU -> jpeg_sm100_decode_scan_raw."""
+        buf = np.frombuffer(bytes(raw) + b"\0" * 32, dtype=np.uint8)
+        dcs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in dc_tables])
+        acs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in ac_tables])
+        desc = self.scan_desc(band, bits, comps)
+        planes = self._plane_structs()
+        rc = self.ctx.L.jpeg_sm100_decode_scan_raw(self.ctx.h, C.byref(desc), _ptr(buf), len(raw),
+                                                   L.INTERVAL_NONE if interval is None else interval, int(extend),
+                                                   dcs, acs, planes, len(self.planes))
+        self.ctx.check(rc)
+
     def encode_scan(self, band, bits, comps, interval_mcus=0):
         """Spectral.encode(scan:) encode.swift:1559 -> jpeg_sm100_encode_scan.  Returns (ecs, dc[4], ac[4])."""
         desc = self.scan_desc(band, bits, comps)
@@ -191,8 +204,8 @@ class Spectral:
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod
-    def decompress(cls, data: bytes, ctx=None):
-        return _decompress(data, ctx or default_context())
+    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False):
+        return _decompress(data, ctx or default_context(), gpu_lexer)
 
     def compress(self, scans=None, quanta_slots=None, interval_mcus=0, jfif=True):
         return _compress(self, scans, quanta_slots, interval_mcus, jfif)
@@ -381,7 +394,7 @@ def _is_frame(m):
     return 0xC0 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC)
 
 
-def _decompress(data, ctx):
+def _decompress(data, ctx, gpu_lexer=False):
     lx = _Lexer(bytes(data))
     _, m, body = lx.segment()
     if m != 0xD8:
@@ -475,22 +488,43 @@ def _decompress(data, ctx):
                 ok = band[0] >= 1 and 2 <= band[1] <= 64 and (bits[1] is None or bits[1] == lo + 1) and count == 1
             if not ok:
                 raise ParsingError("invalidScanProgressiveSubset / component count")
-            ecss = []
-            index = 0
-            while True:
-                ecs, m, body = lx.segment(prefix=True)
-                ecss.append(ecs)
-                if not (0xD0 <= m <= 0xD7):
+            ecss, raw = [], None
+            if gpu_lexer:
+                # the host only finds the FF of the next non-RSTn marker; the GPU unstuffs, splits and checks the phases
+                d, p = lx.d, lx.pos
+                while True:
+                    k = d.find(b"\xff", p)
+                    if k < 0:
+                        raise LexingError("truncatedEntropyCodedSegment")
+                    q = k + 1
+                    while q < lx.n and d[q] == 0xFF:
+                        q += 1
+                    if q >= lx.n:
+                        raise LexingError("truncatedMarkerSegmentType")
+                    if d[q] == 0 or 0xD0 <= d[q] <= 0xD7:
+                        p = q + 1
+                        continue
                     break
-                if (m & 15) != index % 8:
-                    raise DecodingError("invalidRestartPhase")
-                index += 1
-            if interval is not None:
+                raw = d[lx.pos:k]
+                lx.pos = k
+                _, m, body = lx.segment()
                 ival = interval
-            elif len(ecss) == 1:
-                ival = None
             else:
-                raise DecodingError("missingRestartIntervalSegment")
+                index = 0
+                while True:
+                    ecs, m, body = lx.segment(prefix=True)
+                    ecss.append(ecs)
+                    if not (0xD0 <= m <= 0xD7):
+                        break
+                    if (m & 15) != index % 8:
+                        raise DecodingError("invalidRestartPhase")
+                    index += 1
+                if interval is not None:
+                    ival = interval
+                elif len(ecss) == 1:
+                    ival = None
+                else:
+                    raise DecodingError("missingRestartIntervalSegment")
             ids = [p.comp_id for p in s.planes]
             for cid, _, _ in hdr:  # Progression.update (jpeg.swift:1597-1634)
                 if cid not in ids:
@@ -520,7 +554,10 @@ def _decompress(data, ctx):
                     s.planes[ids.index(cid)].q = qslot[sel]
             if first and fh == 0:
                 raise DecodingError("DNL-defined height is resolved by the host before the call: unsupported here")
-            s.decode_scan(band, bits, comps_, dc, ac, ecss, ival, extend=first)
+            if gpu_lexer:
+                s.decode_scan_raw(band, bits, comps_, dc, ac, raw, ival, extend=first)
+            else:
+                s.decode_scan(band, bits, comps_, dc, ac, ecss, ival, extend=first)
             s.scans.append(Scan(band, bits, comps_))
             if first:
                 if m == 0xDC:

@@ -145,6 +145,18 @@ void Spectral::decode(const std::vector<std::vector<uint8_t>> &ecss, int64_t int
                                          views.data(), (uint32_t) views.size()));
 }
 
+void Spectral::decode_raw(const uint8_t *raw, size_t n, int64_t interval, const Scan &scan, const Table::HuffmanSlots &dc,
+                          const Table::HuffmanSlots &ac, bool extend)
+{
+    jpeg_sm100_huff_table d[4], a[4];
+    slots_to_array(dc, d);
+    slots_to_array(ac, a);
+    const jpeg_sm100_scan_desc desc = scan_desc(*this, scan);
+    auto                       views = plane_views(*this);
+    device->check(jpeg_sm100_decode_scan_raw(device->ctx(), &desc, raw, n, interval < 0 ? JPEG_SM100_INTERVAL_NONE : (uint64_t) interval,
+                                             extend ? 1 : 0, d, a, views.data(), (uint32_t) views.size()));
+}
+
 std::vector<uint8_t> Spectral::encode(const Scan &scan, Table::HuffmanSlots &dc, Table::HuffmanSlots &ac, uint64_t interval_mcus) const
 {
     const jpeg_sm100_scan_desc desc = scan_desc(*this, scan);
@@ -417,7 +429,7 @@ void put_segment(std::vector<uint8_t> &out, int marker, const std::vector<uint8_
 
 }  // namespace
 
-Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev)
+Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool gpu_lexer)
 {
     Lexer   lx{data, n};
     Segment sg = lx.segment();
@@ -530,19 +542,43 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev)
             if (!ok) parsing("invalidScanProgressiveSubset");
 
             std::vector<std::vector<uint8_t>> ecss;
-            for (int index = 0;; ++index) {
-                sg = lx.segment(true);
-                ecss.push_back(std::move(sg.ecs));
-                if (!is_restart(sg.marker)) break;
-                if ((sg.marker & 15) != index % 8) decoding("invalidRestartPhase");
+            const uint8_t                    *raw = lx.d + lx.pos;
+            size_t                            raw_len = 0;
+            int64_t                           ival;
+            if (gpu_lexer) {
+                // the host only finds where the scan ends (the FF of the next non-RSTn marker); unstuffing, splitting and
+                // the restart-phase check run on the GPU inside decode_raw
+                size_t p = lx.pos;
+                for (;;) {
+                    const uint8_t *ff = p < n ? (const uint8_t *) std::memchr(data + p, 0xFF, n - p) : nullptr;
+                    if (!ff) lexing("truncatedEntropyCodedSegment");
+                    size_t q = (size_t) (ff - data) + 1;
+                    while (q < n && data[q] == 0xFF) ++q;
+                    if (q >= n) lexing("truncatedMarkerSegmentType");
+                    if (data[q] == 0x00 || is_restart(data[q])) {
+                        p = q + 1;
+                        continue;
+                    }
+                    raw_len = (size_t) (ff - data) - lx.pos;
+                    lx.pos = (size_t) (ff - data);
+                    break;
+                }
+                sg = lx.segment();  // the marker that ended the scan
+                ival = interval;    // -1: none; decode_raw raises missingRestartIntervalSegment if it meets an RSTn then
+            } else {
+                for (int index = 0;; ++index) {
+                    sg = lx.segment(true);
+                    ecss.push_back(std::move(sg.ecs));
+                    if (!is_restart(sg.marker)) break;
+                    if ((sg.marker & 15) != index % 8) decoding("invalidRestartPhase");
+                }
+                if (interval >= 0)
+                    ival = interval;
+                else if (ecss.size() == 1)
+                    ival = -1;
+                else
+                    decoding("missingRestartIntervalSegment");
             }
-            int64_t ival;
-            if (interval >= 0)
-                ival = interval;
-            else if (ecss.size() == 1)
-                ival = -1;
-            else
-                decoding("missingRestartIntervalSegment");
 
             for (int i = 0; i < count; ++i) {  // Progression.update (jpeg.swift:1597-1634)
                 const int p = plane_of(hdr[i].key);
@@ -571,7 +607,10 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev)
                     s.planes[p].q = qslot[sel];
                 }
             if (first && fh == 0) decoding("unsupported: DNL-defined height must be resolved before the first scan is placed");
-            s.decode(ecss, ival, scan, dc, ac, first);
+            if (gpu_lexer)
+                s.decode_raw(raw, raw_len, ival, scan, dc, ac, first);
+            else
+                s.decode(ecss, ival, scan, dc, ac, first);
             s.scans.push_back(scan);
             if (first) {
                 if (sg.marker == 0xDC) {
@@ -692,12 +731,13 @@ template <class T> T *dup(const std::vector<T> &v)
 
 JPEGH_API void jpegh_free(void *p) { std::free(p); }
 
-// mode 0: staged  idct().interleaved(cosite).unpack(as: RGB)   1: same, YCbCr   2: fused to_rgb8
+// mode 0: staged  idct().interleaved(cosite).unpack(as: RGB)   1: same, YCbCr   2: fused to_rgb8;  +4: host lexer instead of the GPU's
 JPEGH_API int jpegh_decompress_pixels8(const uint8_t *data, size_t n, int mode, int cosite, uint8_t **pixels, int32_t *w, int32_t *h,
                                        char *err, size_t errcap)
 {
     try {
-        auto                 s = jpeg::Data::Spectral::decompress(data, n);
+        auto                 s = jpeg::Data::Spectral::decompress(data, n, nullptr, (mode & 4) == 0);
+        mode &= 3;
         std::vector<uint8_t> px;
         if (mode == 2)
             px = s.to_rgb8(cosite != 0);

@@ -99,13 +99,17 @@ public:
     // decode.swift:3476: one scan, already lexed (unstuffed, split at RSTn); interval < 0 = no DRI
     void decode(const std::vector<std::vector<uint8_t>> &ecss, int64_t interval, const Scan &scan,
                 const Table::HuffmanSlots &dc, const Table::HuffmanSlots &ac, bool extend);
+    // the same scan from its raw bytes (stuffed, RSTn-delimited): lexing (decode.swift:130-190, 3895-3933) happens on the GPU
+    void decode_raw(const uint8_t *raw, size_t n, int64_t interval, const Scan &scan, const Table::HuffmanSlots &dc,
+                    const Table::HuffmanSlots &ac, bool extend);
     // encode.swift:1559: returns the stuffed entropy-coded segment; tables by slot; interval_mcus = 0 -> reference form
     std::vector<uint8_t> encode(const Scan &scan, Table::HuffmanSlots &dc, Table::HuffmanSlots &ac, uint64_t interval_mcus = 0) const;
 
     Planar               idct() const;                       // decode.swift:4154
     std::vector<uint8_t> to_rgb8(bool cosite = false) const;  // fused idct().interleaved().unpack(as: RGB.self)
 
-    static Spectral      decompress(const uint8_t *data, size_t n, Device *device = nullptr);  // decode.swift:3728-3960
+    // decode.swift:3728-3960; gpu_lexer = false keeps byte unstuffing / RSTn splitting on the host (Bytestream.segment)
+    static Spectral      decompress(const uint8_t *data, size_t n, Device *device = nullptr, bool gpu_lexer = true);
     std::vector<uint8_t> compress(uint64_t interval_mcus = 0) const;                           // encode.swift:1918-1972
 
     Device *device;

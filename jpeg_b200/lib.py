@@ -18,6 +18,9 @@ ERR_UNDEFINED_DC = -4
 ERR_UNDEFINED_AC = -5
 ERR_PRECONDITION = -7
 ERR_INVALID_HUFFMAN = -8
+ERR_RESTART_PHASE = -9
+ERR_ECS_COUNT = -10
+ERR_MISSING_INTERVAL = -11
 ERR_INVALID_ARGUMENT = -20
 ERR_UNSUPPORTED = -21
 ERR_NO_MEMORY = -22
@@ -114,6 +117,10 @@ SYMBOLS = {
     "jpeg_sm100_unpack_ycc8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_spectral_to_rgb8": (_i, [_vp, C.POINTER(PlaneI16), _u32, _vp, _vp, _u32, _u32, _i, _vp]),
     "jpeg_sm100_decode_batch_rgb8": (_i, [_vp, _SD, _u32, _vp, _vp, _u32, _u64, _HT, _i, _vp, _u32, _u32, _i, _vp, _vp]),
+    "jpeg_sm100_lex_scan": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _u32, C.POINTER(_u32)]),
+    "jpeg_sm100_decode_scan_raw": (_i, [_vp, _SD, _vp, _u64, _u64, _i, _HT, _HT, C.POINTER(PlaneI16), _u32]),
+    "jpeg_sm100_decode_batch_raw_rgb8": (_i, [_vp, _SD, _u32, _vp, _vp, _vp, _u32, _u64, _HT, _i, _vp, _u32, _u32, _i, _vp, _vp]),
+    "jpeg_sm100_dev_lex_scan": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "jpeg_sm100_pack_rgb8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_decompose": (_i, [_vp, _vp, _u32, _u32, C.POINTER(PlaneU16), _u32]),
     "jpeg_sm100_fdct": (_i, [_vp, _vp, _u32, _u32, _vp, _i, _vp]),

@@ -155,6 +155,7 @@ def test_gold_files_through_cpp_host(manifest, hostlib, O):
         if "ycc_sha256" in v:
             assert sha(pixels(hostlib, data, 1).tobytes()) == v["ycc_sha256"], v["jpeg"]
         assert np.array_equal(pixels(hostlib, data, 2), rgb), v["jpeg"]  # fused Spectral -> RGB8
+        assert np.array_equal(pixels(hostlib, data, 4), rgb), v["jpeg"]  # host lexer instead of the GPU lexer
         ref = O.Spectral.decompress(data)
         for p in range(ref.ncomp):
             coef, q = coefficients(hostlib, data, p)
@@ -164,6 +165,7 @@ def test_gold_files_through_cpp_host(manifest, hostlib, O):
         data = golden_bytes(name)
         want, _, _ = O.decode_rgb(data)
         assert np.array_equal(pixels(hostlib, data, 0), want), name
+        assert np.array_equal(pixels(hostlib, data, 4), want), name
 
 
 @pytest.mark.gpu
