@@ -228,8 +228,8 @@ def run_ours(args):
     qz = np.ascontiguousarray(q, dtype=np.uint16)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"lexer": [], "memset": [], "huffman": [], "idct": [], "color": []}
-    STAGES = ("lexer", "memset", "huffman", "idct", "color")
+    stage_ms = {"lexer": [], "huffman": [], "idct": [], "color": []}
+    STAGES = ("lexer", "huffman", "idct", "color")
 
     def step(record):
         e = []
@@ -243,11 +243,9 @@ def run_ours(args):
         ctx.check(ctx.L.jpeg_sm100_dev_lex_scan(ctx.h, d_raw.data_ptr(), raw_off.ctypes.data, raw_len.ctypes.data, n, inputs.n_ecs,
                                                 d_ecs.data_ptr(), d_off.data_ptr(), d_lex_status.data_ptr()))
         mark()
-        for c in buf.coef:
-            ctx.check(ctx.L.jpeg_sm100_memset(ctx.h, c.data_ptr(), 0, c.numel() * 2))
-        mark()
+        # SCAN_FRESH: the coefficient planes are new Spectral planes; K3 clears the rows it decodes into (no separate memset)
         ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
-                                                   geo.blocks[0], 0, tables, 0, C.byref(buf.sp), d_status.data_ptr()))
+                                                   geo.blocks[0], lib.SCAN_FRESH, tables, 0, C.byref(buf.sp), d_status.data_ptr()))
         mark()
         ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), qz.ctypes.data, 8, C.byref(buf.pl)))
         mark()
@@ -284,6 +282,39 @@ def run_ours(args):
         for k, name in enumerate(STAGES):
             stage_ms[name].append(e[k].elapsed_time(e[k + 1]))
     ms_per_step = total_ms / args.steps
+
+    if args.quick:  # kernel A/B runs: device-resident stages only; --sweep "T:WARM,T:WARM,..." re-times K3p settings
+        if rank == 0:
+            sampler.stop()
+
+        def report(ms, stages):
+            if rank == 0:
+                print(json.dumps({"quick": True, "tag": os.environ.get("JPEG_SM100_LIB", ""), "ms_per_step": round(ms, 4),
+                                  "value": round(n * W * H * world / (ms * 1e-3) / 1e6, 1),
+                                  "stages_ms": {k: round(statistics.mean(v), 4) for k, v in stages.items()},
+                                  "env": {k: v for k, v in os.environ.items() if k.startswith("JPEG_SM100_")}}), flush=True)
+
+        report(ms_per_step, stage_ms)
+        for item in [x for x in args.sweep.split(",") if x]:
+            ts, warm = item.split(":")
+            os.environ["JPEG_SM100_PAR_T"], os.environ["JPEG_SM100_PAR_WARM"] = ts, warm
+            for _ in range(2):
+                step(False)
+            barrier()
+            assert d_status.cpu().abs().sum().item() == 0
+            a0, a1 = ev(), ev()
+            a0.record(stream)
+            rr = [step(True) for _ in range(args.steps)]
+            a1.record(stream)
+            barrier()
+            st2 = {k: [] for k in STAGES}
+            for e in rr:
+                for k, name in enumerate(STAGES):
+                    st2[name].append(e[k].elapsed_time(e[k + 1]))
+            report(a0.elapsed_time(a1) / args.steps, st2)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------------------
     # Images are independent, so the batch is sharded over two contexts (one stream each) driven by two host threads:
@@ -420,6 +451,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--sweep", default="", help="with --quick: K3p settings to re-time, log2(threads per interval):warm-up bits, ...")
+    ap.add_argument("--quick", action="store_true", help="device-resident stage times only (kernel A/B runs); not a bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

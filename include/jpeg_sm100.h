@@ -58,6 +58,11 @@ enum {
 
 #define JPEG_SM100_INTERVAL_NONE UINT64_MAX /* no DRI: interval = Int.max, decode.swift:3708-3720 */
 #define JPEG_SM100_BITS_MAX      (-1)       /* scan.bits.upperBound == .max (initial scan) */
+/* bits of the `extend` argument of the decode_scan entry points */
+#define JPEG_SM100_SCAN_EXTEND   1          /* the reference's `extend` flag (first scan, decode.swift:3214-3236) */
+#define JPEG_SM100_SCAN_FRESH    2          /* layer B only: the planes of the scan's components are newly created
+                                               Spectral planes (all zero, decode.swift:2241-2256) -- the library clears
+                                               them as part of the call, whatever they hold */
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
 typedef struct jpeg_sm100_ctx jpeg_sm100_ctx;

@@ -364,7 +364,7 @@ JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
     J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off),
-                                   n_ecs, interval, extend, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+                                   n_ecs, interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
     int32_t status = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)
@@ -568,9 +568,12 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
         CU_TRY(ctx, cudaMemcpyAsync(d_off, offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(d_lex_status, 0, sizeof(int32_t) * n_images, ctx->stream));
     }
-    CU_TRY(ctx, cudaMemsetAsync(d_coef, 0, coef_total, ctx->stream));  // Spectral planes start zeroed (decode.swift:2241-2256)
-    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
-                                   interval, 0, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status)));
+    // Spectral planes start zeroed (decode.swift:2241-2256): SCAN_FRESH lets K3 clear the rows it fills itself
+    ctx->hint_interval_bytes = in_bytes / ((uint64_t) n_images * n_ecs);
+    const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
+                                            interval, JPEG_SM100_SCAN_FRESH, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status));
+    ctx->hint_interval_bytes = 0;
+    J_TRY(k3);
     for (uint32_t k = 0; k < n_chunks; ++k) {
         const uint32_t i0 = k * chunk, cnt = (i0 + chunk <= n_images) ? chunk : n_images - i0;
         uint8_t       *rgb_buf = reinterpret_cast<uint8_t *>(d_rgb) + (k & 1) * rgb_chunk;
@@ -707,7 +710,7 @@ JPEG_API int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_sc
     memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
     J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
-                                   interval, extend, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+                                   interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
     int32_t status = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)

@@ -41,6 +41,8 @@ struct jpeg_sm100_ctx {
     // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // average bytes per restart interval of the next entropy-decode call, when the caller knows it (0: unknown); consumed by K3
+    uint64_t hint_interval_bytes = 0;
     // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda dependency)
     void *encode_tiled = nullptr;
 };

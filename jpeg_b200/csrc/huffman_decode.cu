@@ -66,17 +66,49 @@ struct RawSet {
 
 // (symbol | length << 8) of the reference LUT -> the fast decoders' entry:
 //     byte0 = code length, byte1 = extra bits, byte2 = zig-zag advance (run + 1; 64 for EOB), byte3 = length + extra bits
-// 0 if the sequential decoders need the careful path for it (DC magnitude category > 16, or EOBn with n > 0).
+// 0 if the sequential decoders need the careful path for it (DC magnitude category > 15, or EOBn with n > 0).
 // With z the zig-zag position before the symbol (0 for DC): the coefficient lands at z + advance - 1 (an EOB lands beyond
 // 63, i.e. nowhere) and the next position is z + advance.
+// A fast-table slot whose FAST_BITS-bit prefix is shared by longer codes holds a LINK instead: bit 7 set, bits 0..2 =
+// 16 - FAST_BITS - d, bits 8.. = byte offset (from the table base) of a 2^d-entry sub-table (same entry format) addressed
+// by the next d bits of the codeword.
 __host__ __device__ inline uint32_t fast_entry(uint32_t ref, bool dc)
 {
     const uint32_t len = ref >> 8, sym = ref & 0xffu;
-    if (dc) return sym > 16u ? 0u : (len | (sym << 8) | (1u << 16) | ((len + sym) << 24));
+    // category 16 takes the reference's masked-shift EXTEND (decode.swift:2742-2754), which is not the textbook one
+    if (dc) return sym > 15u ? 0u : (len | (sym << 8) | (1u << 16) | ((len + sym) << 24));
     const uint32_t size = sym & 15u, run = sym >> 4;
     if (size == 0u && run != 0u && run != 15u) return 0u;
     const uint32_t adv = sym == 0u ? 64u : run + 1u;
     return len | (size << 8) | (adv << 16) | ((len + size) << 24);
+}
+constexpr uint32_t FAST_LINK = 0x80u;
+constexpr uint32_t SUB_MAX = 1536;  // sub-table entries per Huffman table (6 KB); larger sets keep the reference lookup
+
+// Depth (bits beyond FAST_BITS) of the longest canonical code under every FAST_BITS-bit prefix (T.81 Annex C code
+// assignment == the leaf order of the reference's LUT, decode.swift:1037-1240).  Returns the number of sub-table entries.
+// Host (layout) and device (construction) run this same function, so both agree on every offset.
+__host__ __device__ inline uint32_t sub_depths(const uint8_t counts[16], uint8_t depth[FAST_ENTRIES])
+{
+    for (int i = 0; i < FAST_ENTRIES; ++i) depth[i] = 0;
+    uint32_t code = 0;
+    for (int l = 1; l <= 16; ++l) {
+        if (l > FAST_BITS && counts[l - 1]) {
+            const int      d = l - FAST_BITS;
+            const uint32_t p0 = code >> d, p1 = (code + counts[l - 1] - 1u) >> d;
+            for (uint32_t p = p0; p <= p1 && p < (uint32_t) FAST_ENTRIES; ++p)
+                if (depth[p] < d) depth[p] = (uint8_t) d;
+        }
+        code = (code + counts[l - 1]) << 1;
+    }
+    uint32_t total = 0;
+    for (int i = 0; i < FAST_ENTRIES; ++i)
+        if (depth[i]) total += 1u << depth[i];
+    if (total > SUB_MAX) {
+        for (int i = 0; i < FAST_ENTRIES; ++i) depth[i] = 0;
+        total = 0;
+    }
+    return total;
 }
 
 // decode.swift:1037-1240 Table.Huffman.decoder(): level l (codes of l+1 bits) contributes `0x8080 >> l & 0xff` clones
@@ -105,18 +137,44 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         level_start += counts[l] * clones;
         leaf_base += counts[l];
     }
-    // FAST_BITS-bit fast table, one 32-bit entry per prefix: byte0 = code length (0: code longer than 11 bits, not a code, or
-    // a symbol the sequential decoders reject -> reference lookup), byte1 = extra bits, byte2 = zero run, byte3 = 1: EOB
+    // FAST_BITS-bit fast table, one 32-bit entry per prefix (format: fast_entry), followed by the sub-tables of the
+    // prefixes that longer codes share.  Everything is derived from the reference LUT just written, entry for entry.
+    __shared__ uint8_t  s_depth[FAST_ENTRIES];
+    __shared__ uint16_t s_off[FAST_ENTRIES];
+    if (threadIdx.x == 0) {
+        sub_depths(counts, s_depth);
+        uint32_t o = FAST_ENTRIES;
+        for (int i = 0; i < FAST_ENTRIES; ++i) {
+            s_off[i] = (uint16_t) o;
+            if (s_depth[i]) o += 1u << s_depth[i];
+        }
+    }
     __syncthreads();
     uint32_t *fast = reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti]);
     const int n = h.n[ti], zeta = h.zeta[ti];
+    auto ref_lookup = [&](uint32_t cw, bool &valid) -> uint32_t {
+        const int hi = (int) (cw >> 8);
+        valid = true;
+        if (hi < n) return entries[hi];
+        if ((int) cw < zeta) return entries[(int) cw - 255 * n];
+        valid = false;
+        return 0x1000u;
+    };
     for (uint32_t i = threadIdx.x; i < (uint32_t) FAST_ENTRIES; i += blockDim.x) {
         const uint32_t cw = i << (16 - FAST_BITS);
-        const int      hi = (int) (cw >> 8);
-        uint32_t       e = 0x1000u;
-        if (hi < n) e = entries[hi];
-        else if ((int) cw < zeta) e = entries[(int) cw - 255 * n];
-        fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? fast_entry(e, ti < 4) : 0u;
+        const uint32_t d = s_depth[i];
+        if (d == 0u) {
+            bool           valid;
+            const uint32_t e = ref_lookup(cw, valid);
+            fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? fast_entry(e, ti < 4) : 0u;
+            continue;
+        }
+        fast[i] = FAST_LINK | (uint32_t) (16 - FAST_BITS - d) | ((uint32_t) s_off[i] << 10);  // shift, byte offset
+        for (uint32_t j = 0; j < (1u << d); ++j) {
+            bool           valid;
+            const uint32_t e = ref_lookup(cw | (j << (16 - FAST_BITS - d)), valid);
+            fast[s_off[i] + j] = (valid && (e >> 8) <= (uint32_t) FAST_BITS + d) ? fast_entry(e, ti < 4) : 0u;
+        }
     }
 }
 
@@ -237,6 +295,18 @@ __device__ __forceinline__ uint32_t lut_lookup(const uint16_t *entries, int n, i
     uint32_t   e = 0x1000u;  // (symbol 0, length 16)
     if (valid) e = entries[off + idx];
     return e;
+}
+
+// fast table + sub-table lookup: one shared-memory load for codes of up to FAST_BITS bits, a second (predicated) one for
+// longer codes.  0: not resolvable here (invalid codeword, or a symbol the sequential decoders treat specially).
+__device__ __forceinline__ uint32_t fast_lookup(const uint32_t *tab, uint32_t cw)
+{
+    uint32_t ent = tab[cw >> (16 - FAST_BITS)];
+    if (ent & FAST_LINK) {
+        const uint32_t rest = cw & ((1u << (16 - FAST_BITS)) - 1u);
+        ent = tab[(ent >> 10) + (rest >> (ent & 7u))];
+    }
+    return ent;
 }
 
 #define FAIL_LANE(code)                                                                                              \
@@ -557,8 +627,8 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             const bool     isdc = z == 0;
             const uint32_t cw = (uint32_t) (acc >> 48);
             const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? cur_dfo : cur_afo));
-            uint32_t        ent = tab[cw >> (16 - FAST_BITS)];
-            if (__builtin_expect(ent == 0u, 0)) {  // long / invalid / rejected code: the reference lookup
+            uint32_t        ent = fast_lookup(tab, cw);
+            if (__builtin_expect(ent == 0u, 0)) {  // invalid / rejected code (or oversized table set): the reference lookup
                 const int ti = isdc ? (cur_tabs & 0xff) : (cur_tabs >> 8);
                 ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
                 if (ent == 0u) break;  // corrupt DC symbol or EOBn: finished (and diagnosed) by the careful phase
@@ -703,25 +773,25 @@ finished:
 //     match) flags the interval; flagged intervals are zeroed and re-decoded by k_decode_fast, which also produces the
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
 constexpr int PAR_THREADS = 128;
+constexpr int PAR_MAX_GROUPS = PAR_THREADS / 16;
 constexpr int PAR_MIN_BITS = 1024;
-#ifndef PAR_WARMUP_N
-#define PAR_WARMUP_N 2
-#endif
-constexpr int PAR_WARMUP = PAR_WARMUP_N;  // subsequences of speculative warm-up in round 0
 
 struct ParseState {
     uint32_t p;      // bit position of the next symbol
     uint16_t z, b;   // zig-zag position (0 = DC next), block index within the MCU
 };
 __device__ __forceinline__ uint64_t pack_state(uint32_t p, int z, int b) { return (uint64_t) p | ((uint64_t) z << 32) | ((uint64_t) b << 40); }
+__device__ __forceinline__ ParseState unpack_state(uint64_t x)
+{
+    ParseState s;
+    s.p = (uint32_t) x, s.z = (uint16_t) ((x >> 32) & 0xff), s.b = (uint16_t) ((x >> 40) & 0xff);
+    return s;
+}
 
-struct ParReader {
-    const uint32_t *w0;
-    uint32_t        wlim;   // words [0, wlim) need no padding
-    int             lead, nbytes;
-    uint64_t        acc;
-    int             navail;
-    uint32_t        wi;
+struct ParIO {             // where the bytes of one restart interval live
+    const uint32_t *w0;    // the aligned word that holds its first byte
+    uint32_t        wlim;  // words [0, wlim) need no padding
+    int32_t         lead, nbytes;
     __device__ __forceinline__ uint32_t word(uint32_t i) const
     {
         if (i < wlim) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
@@ -734,66 +804,111 @@ struct ParReader {
         }
         return be;
     }
-    __device__ __forceinline__ void seek(uint32_t p)
-    {
-        const uint32_t ab = (uint32_t) lead * 8u + p;
-        wi = ab >> 5;
-        const int sh = (int) (ab & 31u);
-        acc = (((uint64_t) word(wi) << 32) | word(wi + 1)) << sh;
-        navail = 64 - sh;
-        wi += 2;
-    }
 };
+struct ParGroup {  // one restart interval of the CTA (the CTA decodes PAR_THREADS / T of them, T threads each)
+    ParIO    io;
+    uint32_t count, B, S;   // bits, bits per subsequence, subsequences (0: nothing to do in this kernel)
+    uint32_t N_total;       // blocks the interval must produce
+    int32_t  r0, r1;        // MCU rows
+    uint32_t slot, valid;   // img * n_ecs + e; interval exists
+    uint32_t total, bad;
+};
+
+// per block of the MCU: where its coefficients go and which tables decode it (two 16-byte shared loads)
+struct ParBlk {
+    uint32_t C, fx, R, lim;           // block index (128-byte units from plane0) = C + mx * fx + my * R; lim = LX | LY << 16:
+                                      // the block lies inside its plane iff mx < LX and my < LY (0 / 0: component without plane)
+    uint32_t dtab, atab, tabs, next;  // shared-memory addresses of the DC / AC fast tables; dc | ac << 8 | b << 16 | (b == 0) << 24;
+                                      // shared-memory address of the successor block's second quad
+};
+static_assert(sizeof(ParBlk) == 32 && 12 * sizeof(ParBlk) <= 12 * sizeof(BlkInfo), "ParBlk lives in the BlkInfo area");
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 
 // Parses (FINAL = false) or decodes (FINAL = true) symbols from `st` until the bit position reaches `end_bit`.
 // Returns the number of completed blocks; `st` is the exit state.  `bad` is set when the TRUE decoder would not simply
 // carry on (truncation / rejected symbol); speculative callers ignore it.
 // SAFE: the run (plus look-ahead) stays inside the words that need no padding, so every consumed bit is a real bit and the
-// reference's truncation guards cannot fire -- no padding logic, no bit-count checks.  The loop is written branch-free
-// (selects + predicated memory operations): lanes of a warp sit in different places of their blocks all the time.
+// reference's truncation guards cannot fire -- no padding logic, no bit-count checks.
+// The kernel is bound by instruction issue and the lanes of a warp sit in different places of their blocks all the time, so
+// the loop is branch-free (selects + predicated memory operations) and every instruction of it counts:
+//   * the bit window is two stream words (hi:lo) plus a consumed-bit count < 32: a symbol costs one funnel shift, a refill
+//     moves lo to hi and loads one word;
+//   * tables are addressed with 32-bit shared-memory addresses held in registers and reloaded (one LDS.128, which also brings
+//     the successor's address) only when a block ends.
 template <bool FINAL, bool SAFE>
-__device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                            const uint16_t *entries, const LutHeader *hdr, const BlkInfo *s_blk, const int nblk,
-                                            bool &bad,
+__device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                            const uint32_t blk0, const uint8_t *smem, const int nblk, bool &bad,
                                             // FINAL only:
                                             uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
                                             int16_t *dcdiff)
 {
-    uint32_t p = st.p, done = 0;
-    int      z = st.z, b = st.b;
+    int z = st.z;
     bad = false;
-    if (p >= end_bit) return 0;
+    if (st.p >= end_bit) return 0;
     if (FINAL && N >= N_total) return 0;
-    rd.seek(p);
-    uint64_t acc = rd.acc;
-    int      navail = rd.navail;
-    uint32_t wi = rd.wi;
+    const uint32_t N_start = N;
+    uint32_t       done = 0;
+    int            left = (int) (end_bit - st.p);            // bits up to the end of the run
+    const int      slack = (int) (count_bits - end_bit);     // bits between the end of the run and the end of the data
+    // bit window: (hi:lo) = the 64 stream bits that start at word wi - 2; cnt (< 32 at the loop top) of them are consumed
+    uint32_t wi, cnt, hi, lo;
+    {
+        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
+        wi = ab >> 5;
+        cnt = ab & 31u;
+        hi = io.word(wi), lo = io.word(wi + 1);
+        wi += 2;
+    }
+    uint32_t dtab, atab, tabs, next;
+    {
+        const uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
+        dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
+    }
     // FINAL: position and destination of the current block
     int      mx = 0, my = 0;
-    int16_t *bptr = nullptr;
+    int16_t *bptr = nullptr, *dcp = nullptr;
+    bool     inp = false;
     if (FINAL) {
+        dcp = dcdiff + N;
         const uint32_t mcu = N / (uint32_t) nblk;
         my = my0 + (int) (mcu / (uint32_t) W);
         mx = (int) (mcu - (mcu / (uint32_t) W) * (uint32_t) W);
-        const BlkInfo &bi = s_blk[b];
-        const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
-        bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
+        const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
+        inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+        bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
     }
-    while (p < end_bit) {
-        if (navail <= 32) {
-            const uint32_t be = SAFE ? __byte_perm(__ldg(rd.w0 + wi), 0, 0x0123) : rd.word(wi);
-            acc |= (uint64_t) be << (32 - navail);
+    while (left > 0) {
+        if (cnt >= 32u) {
+            hi = lo;
+            lo = SAFE ? __byte_perm(__ldg(io.w0 + wi), 0, 0x0123) : io.word(wi);
             wi += 1;
-            navail += 32;
+            cnt -= 32u;
         }
-        const uint4     t3 = reinterpret_cast<const uint4 *>(&s_blk[b])[2];  // dfast, afast, tabs, -
-        const bool      isdc = z == 0;
-        const uint32_t  cw = (uint32_t) (acc >> 48);
-        const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? t3.x : t3.y));
-        uint32_t        ent = tab[cw >> (16 - FAST_BITS)];
-        if (__builtin_expect(ent == 0u, 0)) {
-            const int ti = isdc ? ((int) t3.z & 0xff) : ((int) t3.z >> 8);
-            ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
+        const uint32_t top = __funnelshift_l(lo, hi, cnt);  // the next 32 bits of the stream
+        const bool     isdc = z == 0;
+        const uint32_t tab = isdc ? dtab : atab;
+        uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
+        if (ent & FAST_LINK) {  // longer code: its sub-table, addressed by the bits that follow the prefix
+            const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
+            ent = lds32(tab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
+        }
+        if (__builtin_expect(ent == 0u, 0)) {  // invalid codeword / symbol the sequential decoders single out: reference lookup
+            const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+            const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader) + 12 * sizeof(BlkInfo));
+            const int        ti = isdc ? (int) (tabs & 0xffu) : (int) ((tabs >> 8) & 0xffu);
+            ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);
             if (ent == 0u) {
                 bad = true;
                 break;
@@ -801,76 +916,74 @@ __device__ __forceinline__ uint32_t par_run(ParReader &rd, ParseState &st, const
         }
         const int total = (int) (ent >> 24), adv = (int) __byte_perm(ent, 0, 0x4442);
         if (!SAFE) {
-            if (__builtin_expect(p + (uint32_t) total > count_bits, 0)) {  // decode.swift:2808-2811, 2859-2863
+            if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2808-2811, 2859-2863
                 bad = true;
                 break;
             }
         }
         if (FINAL) {
-            const int      len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441);
-            const uint32_t after = (uint32_t) ((acc << len) >> 32);
-            const uint32_t tail = size ? after >> (32 - size) : 0u;
-            const int      v = size ? extend16(size, tail) : 0;
-            const int      zpos = z + adv - 1;
-            // DC differences go to the side array (resolved by k_dc_resolve); AC values to their zig-zag slot
-            int16_t *dst = isdc ? dcdiff + N : bptr + zpos;
-            if (isdc | ((bptr != nullptr) & (zpos < 64))) *dst = (int16_t) v;
+            const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441);
+            const uint32_t top2 = top << len;  // first extra bit in bit 31: it is the sign (0 = negative) of the value
+            const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
+            // T.81 EXTEND; identical to decode.swift:2742-2754 for categories 0..15 (16 never reaches this point)
+            const int v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;
+            const int zpos = z + adv - 1;
+            // DC differences go to the side array (resolved after the pass); AC values to their zig-zag slot
+            if (isdc) *dcp = (int16_t) v;
+            else if (inp & (zpos < 64)) bptr[zpos] = (int16_t) v;
         }
-        acc <<= total;
-        navail -= total;
-        p += (uint32_t) total;
+        cnt += (uint32_t) total;
+        left -= total;
         z += adv;
-        const bool fin = z >= 64;  // block complete
-        z = fin ? 0 : z;
-        done += fin ? 1u : 0u;
-        const int b1 = (b + 1 == nblk) ? 0 : b + 1;
-        if (FINAL) {
-            if (fin) {
+        if (z >= 64) {  // block complete: the successor's tables
+            z = 0;
+            const uint32_t cur = next;
+            const uint4    q = lds128(cur);
+            dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
+            if (FINAL) {
                 N += 1;
-                if (N >= N_total) {
-                    b = b1;
-                    break;
+                dcp += 1;
+                if (N >= N_total) break;
+                mx += (int) ((tabs >> 24) & 1u);
+                if (mx == W) {
+                    mx = 0;
+                    my += 1;
                 }
-                if (b1 == 0) {
-                    mx += 1;
-                    if (mx == W) {
-                        mx = 0;
-                        my += 1;
-                    }
-                }
-                const BlkInfo &bi = s_blk[b1];
-                const uint32_t bx = (uint32_t) mx * bi.fx + bi.dx, by = (uint32_t) my * bi.fy + bi.dy;
-                bptr = ((bx < bi.ux) & (by < bi.uy) & (bi.hasplane != 0u)) ? plane0 + (size_t) (bi.base_blk + bi.ux * by + bx) * 64 : nullptr;
+                const uint4 g = lds128(cur - 16u);
+                inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+                bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
+            } else {
+                done += 1;
             }
         }
-        b = fin ? b1 : b;
     }
-    st.p = p;
+    st.p = end_bit - (uint32_t) left;
     st.z = (uint16_t) z;
-    st.b = (uint16_t) b;
-    return done;
+    st.b = (uint16_t) ((tabs >> 16) & 0xffu);
+    return FINAL ? N - N_start : done;
 }
 
 // picks the SAFE variant when the run, its overshoot (< 32 bits) and the 64-bit look-ahead stay in unpadded words
 template <bool FINAL>
-__device__ __forceinline__ uint32_t par_run_auto(ParReader &rd, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                                 const uint16_t *entries, const LutHeader *hdr, const BlkInfo *s_blk, const int nblk,
-                                                 bool &bad, uint32_t N, const uint32_t N_total, const int W, const int my0,
-                                                 int16_t *plane0, int16_t *dcdiff)
+__device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                                 const uint32_t blk0, const uint8_t *smem, const int nblk, bool &bad, uint32_t N,
+                                                 const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff)
 {
     // warp-uniform choice: a warp whose lanes disagree would execute both variants one after the other
-    const uint32_t last_word = ((uint32_t) rd.lead * 8u + end_bit + 32u + 64u) / 32u + 1u;
-    if (__all_sync(__activemask(), last_word < rd.wlim))
-        return par_run<FINAL, true>(rd, st, end_bit, count_bits, entries, hdr, s_blk, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
-    return par_run<FINAL, false>(rd, st, end_bit, count_bits, entries, hdr, s_blk, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
+    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 32u + 64u) / 32u + 1u;
+    if (__all_sync(__activemask(), last_word < io.wlim))
+        return par_run<FINAL, true>(io, st, end_bit, count_bits, blk0, smem, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
+    return par_run<FINAL, false>(io, st, end_bit, count_bits, blk0, smem, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
 }
 
 #ifndef PAR_MIN_CTAS
 #define PAR_MIN_CTAS 1
 #endif
+// tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
+// zero_first: the CTA clears the coefficient rows of its intervals before it decodes into them (fresh Spectral planes)
 __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
-             uint32_t *const flagged, uint32_t *const stats)
+             uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits, const int zero_first)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t s_exit[PAR_THREADS], s_entry[PAR_THREADS];
@@ -878,13 +991,16 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     __shared__ uint8_t  s_work[PAR_THREADS];
     __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[PAR_THREADS / 32];
-    __shared__ uint32_t s_total, s_bad;
-    const uint32_t   img = blockIdx.y, e = blockIdx.x, tid = threadIdx.x;
+    __shared__ ParGroup s_grp[PAR_MAX_GROUPS];
+    const uint32_t   img = blockIdx.y, tid = threadIdx.x;
+    const uint32_t   T = 1u << tshift, G = PAR_THREADS >> tshift;
+    const uint32_t   g = tid >> tshift, l = tid & (T - 1u);
     const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
     const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
-    BlkInfo         *s_blk = reinterpret_cast<BlkInfo *>(smem + sizeof(LutHeader));
+    ParBlk          *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
     constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
-    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + PRE);
+    const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
+    const int        W = P.W, nblk = P.mcu_blocks;
     {
         const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
         const uint32_t   total = gh->total_all;
@@ -894,73 +1010,95 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         uint32_t *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
         for (uint32_t i = tid; i < (total + 1) / 2; i += PAR_THREADS) d2[i] = src[sizeof(LutHeader) / 4 + i];
         if (tid < 12) {
-            const int b = tid, c = P.blk_comp[b];
-            BlkInfo   bi;
-            bi.hasplane = P.plane[c] != nullptr;
-            bi.base_blk = bi.hasplane ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
-            bi.ux = (uint32_t) P.ux[c], bi.uy = (uint32_t) P.uy[c];
-            bi.fx = P.fx[c], bi.fy = P.fy[c], bi.dx = P.blk_dx[b], bi.dy = P.blk_dy[b];
-            bi.dfast = gh->fast[P.dc[c]], bi.afast = gh->fast[P.ac[c]];
-            bi.tabs = P.dc[c] | (P.ac[c] << 8);
-            bi.pred = 0;
-            s_blk[b] = bi;
+            const int      b = tid, c = P.blk_comp[b];
+            const bool     has = P.plane[c] != nullptr;
+            const uint32_t ux = (uint32_t) P.ux[c], uy = (uint32_t) P.uy[c], fx = (uint32_t) P.fx[c], fy = (uint32_t) P.fy[c];
+            const uint32_t dx = P.blk_dx[b], dy = P.blk_dy[b];
+            const uint32_t base_blk = has ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
+            ParBlk         pb;
+            pb.C = base_blk + dx + dy * ux, pb.fx = fx, pb.R = fy * ux;
+            const uint32_t LX = (has && ux > dx) ? min((ux - dx + fx - 1u) / fx, 0xffffu) : 0u;
+            const uint32_t LY = (has && uy > dy) ? min((uy - dy + fy - 1u) / fy, 0xffffu) : 0u;
+            pb.lim = LX | (LY << 16);
+            pb.dtab = sbase + PRE + 2u * gh->fast[P.dc[c]], pb.atab = sbase + PRE + 2u * gh->fast[P.ac[c]];
+            pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u);
+            pb.next = blk0 + (uint32_t) ((b + 1 == nblk) ? 0 : b + 1) * (uint32_t) sizeof(ParBlk) + 16u;
+            s_blk[b] = pb;
         }
-        if (tid == 0) s_total = 0, s_bad = 0;
+        if (tid >= 32 && tid < 32 + G) {  // one thread per interval of the CTA: where its bytes are, how it is cut
+            ParGroup       q;
+            const uint32_t e = blockIdx.x * G + (tid - 32);
+            memset(&q, 0, sizeof q);
+            q.valid = e < P.n_ecs;
+            if (q.valid) {
+                int64_t r0, r1;
+                if (P.interval == UINT64_MAX) {
+                    r0 = 0;
+                    r1 = P.H;
+                } else {
+                    r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) W);
+                    r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) W);
+                    if (r0 > P.H) r0 = P.H;
+                    if (r1 > P.H) r1 = P.H;
+                }
+                q.r0 = (int32_t) r0, q.r1 = (int32_t) r1;
+                q.slot = img * P.n_ecs + e;
+                const uint64_t n_total = (uint64_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
+                const uint64_t o0 = P.offsets[q.slot], o1 = P.offsets[q.slot + 1];
+                if (n_total == 0) {  // nothing to decode: the reference's row loop does not run
+                    flagged[q.slot] = 0;
+                    if (P.status) P.status[q.slot] = 0;
+                } else if ((o1 - o0) > 0x07ffffffull || n_total > dc_per_interval) {
+                    flagged[q.slot] = 1;  // 32-bit bit positions / side-array capacity: left to the sequential kernel
+                } else {
+                    const uint8_t *base = P.ecs + o0;
+                    q.N_total = (uint32_t) n_total;
+                    q.io.nbytes = (int32_t) (o1 - o0);
+                    q.io.lead = (int32_t) (reinterpret_cast<uintptr_t>(base) & 3);
+                    q.io.w0 = reinterpret_cast<const uint32_t *>(base - q.io.lead);
+                    q.io.wlim = (uint32_t) (q.io.lead + q.io.nbytes) / 4;
+                    q.count = 8u * (uint32_t) q.io.nbytes;
+                    uint32_t B = (q.count + T - 1) / T;
+                    B = (B + 31u) & ~31u;
+                    if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
+                    q.B = B;
+                    q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
+                }
+            }
+            s_grp[tid - 32] = q;
+        }
     }
     __syncthreads();
-
-    int64_t r0, r1;
-    if (P.interval == UINT64_MAX) {
-        r0 = 0;
-        r1 = P.H;
-    } else {
-        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
-        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
-        if (r0 > P.H) r0 = P.H;
-        if (r1 > P.H) r1 = P.H;
-    }
-    const int      W = P.W, nblk = P.mcu_blocks;
-    const uint32_t N_total = (uint32_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
-    const size_t   slot = (size_t) img * P.n_ecs + e;
-    if (N_total == 0) {  // nothing to decode: the reference's row loop does not run
-        if (tid == 0) {
-            flagged[slot] = 0;
-            if (P.status) P.status[slot] = 0;
+    // ---- fresh planes: clear the rows this CTA is about to fill (whole rows of whole intervals: 16-byte stores) ----------
+    if (zero_first) {
+        for (uint32_t gg = 0; gg < G; ++gg) {
+            if (!s_grp[gg].valid) continue;
+            const int r0 = s_grp[gg].r0, r1 = s_grp[gg].r1;
+            for (int c = 0; c < P.n_comp; ++c) {
+                if (!P.plane[c]) continue;
+                int16_t  *pl = P.plane[c] + (size_t) img * P.image_stride[c];
+                const int y0 = min(r0 * P.fy[c], P.uy[c]), y1 = min(r1 * P.fy[c], P.uy[c]);
+                uint4    *q = reinterpret_cast<uint4 *>(pl + 64 * (size_t) P.ux[c] * y0);
+                const uint32_t n16 = 8u * (uint32_t) P.ux[c] * (uint32_t) (y1 - y0);
+                for (uint32_t i = tid; i < n16; i += PAR_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+            }
         }
-        return;
     }
-    const uint64_t o0 = P.offsets[slot], o1 = P.offsets[slot + 1];
-    const uint8_t *base = P.ecs + o0;
-    const bool     oversize = (o1 - o0) > 0x07ffffffull || N_total > dc_per_interval;
-    if (oversize) {  // 32-bit bit positions / side-array capacity: leave it to the sequential kernel
-        if (tid == 0) flagged[slot] = 1;
-        return;
-    }
-    ParReader rd;
-    rd.nbytes = (int) (o1 - o0);
-    rd.lead = (int) (reinterpret_cast<uintptr_t>(base) & 3);
-    rd.w0 = reinterpret_cast<const uint32_t *>(base - rd.lead);
-    rd.wlim = (uint32_t) (rd.lead + rd.nbytes) / 4;
-    const uint32_t count = 8u * (uint32_t) rd.nbytes;
-    uint32_t       B = (count + PAR_THREADS - 1) / PAR_THREADS;
-    B = (B + 31u) & ~31u;
-    if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
-    const uint32_t S = count ? (count + B - 1) / B : 1u;  // <= PAR_THREADS
-    const bool     active = tid < S;
-    const uint32_t start_bit = tid * B, end_bit = (tid + 1 == S) ? count : (tid + 1) * B;
-    int16_t *const dcdiff = dcdiff_all + slot * dc_per_interval;
+    const ParIO    io = s_grp[g].io;
+    const uint32_t count = s_grp[g].count, B = s_grp[g].B, S = s_grp[g].S;
+    const bool     active = l < S;
+    const uint32_t start_bit = l * B, end_bit = (l + 1 == S) ? count : (l + 1) * B;
 
-    // ---- round 0: warm up over the preceding PAR_WARMUP subsequences from a guessed state, then parse the own one ----
+    // ---- round 0: warm up over the preceding warm_bits from a guessed state, then parse the own subsequence ----
     // (by the time the speculative parse reaches its own first bit it has usually re-synchronised with the true parse, so
-    //  most subsequences never need a second look; thread 0 -- and every thread whose warm-up starts at bit 0 -- is exact)
+    //  most subsequences never need a second look; every thread whose warm-up starts at bit 0 is exact)
     ParseState st;
     bool       bad;
     if (active) {
-        const uint32_t warm = tid >= (uint32_t) PAR_WARMUP ? (tid - PAR_WARMUP) * B : 0u;
-        st.p = warm, st.z = 0, st.b = 0;
-        if (tid > 0) par_run_auto<false>(rd, st, start_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
+        if (l > 0) par_run_auto<false>(io, st, start_bit, count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
         s_entry[tid] = pack_state(st.p, st.z, st.b);
-        s_cnt[tid] = par_run_auto<false>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        s_cnt[tid] = par_run_auto<false>(io, st, end_bit, count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
         s_exit[tid] = pack_state(st.p, st.z, st.b);
     } else {
         s_entry[tid] = 0, s_exit[tid] = 0, s_cnt[tid] = 0;
@@ -969,8 +1107,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // ---- synchronisation rounds: re-parse wherever the entry that was used differs from the predecessor's exit.
     // The subsequences to redo are compacted into a work list so that they occupy the lanes of as few warps as possible.
     uint32_t n_redo = 0, n_rounds = 0;
-    for (uint32_t round = 1; round <= S + 1; ++round) {
-        const bool redo = active && tid >= 1 && s_exit[tid - 1] != s_entry[tid];
+    for (uint32_t round = 1; round <= T + 1; ++round) {
+        const bool redo = active && l >= 1 && s_exit[tid - 1] != s_entry[tid];
         n_redo += redo ? 1u : 0u;
         n_rounds = round;
         if (tid == 0) s_nwork = 0;
@@ -979,112 +1117,109 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         __syncthreads();
         const uint32_t nwork = s_nwork;
         if (nwork == 0) break;
+        uint64_t x = 0;
         if (tid < nwork) {
-            const uint32_t sid = s_work[tid];
-            const uint64_t entry = s_exit[sid - 1];
-            const uint32_t e_bit = (sid + 1 == S) ? count : (sid + 1) * B;
-            st.p = (uint32_t) entry, st.z = (uint16_t) ((entry >> 32) & 0xff), st.b = (uint16_t) ((entry >> 40) & 0xff);
-            const uint32_t c = par_run_auto<false>(rd, st, e_bit, count, entries, hdr, s_blk, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-            const uint64_t x = pack_state(st.p, st.z, st.b);
+            const uint32_t  sid = s_work[tid];
+            const ParGroup &q = s_grp[sid >> tshift];
+            const uint32_t  ll = sid & (T - 1u);
+            const ParIO     qio = q.io;
+            const uint64_t  entry = s_exit[sid - 1];
+            const uint32_t  e_bit = (ll + 1 == q.S) ? q.count : (ll + 1) * q.B;
+            st = unpack_state(entry);
+            const uint32_t c = par_run_auto<false>(qio, st, e_bit, q.count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+            x = pack_state(st.p, st.z, st.b);
             // every work item reads exit[sid - 1] before any item writes exit[sid]: the write is deferred past a barrier
             s_cnt[sid] = c;
             s_entry[sid] = entry;
-            st.p = (uint32_t) x, st.z = (uint16_t) ((x >> 32) & 0xff), st.b = (uint16_t) ((x >> 40) & 0xff);
         }
         __syncthreads();
-        if (tid < nwork) s_exit[s_work[tid]] = pack_state(st.p, st.z, st.b);
+        if (tid < nwork) s_exit[s_work[tid]] = x;
         __syncthreads();
     }
     const uint32_t my_cnt = s_cnt[tid];
     const uint64_t my_entry = s_entry[tid];
-    // ---- first block of every subsequence: exclusive scan of the block counts -----------------------------------------
+    // ---- first block of every subsequence: exclusive scan of the block counts within the interval -------------------------
     uint32_t incl = my_cnt;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int      lane = tid & 31, wid = tid >> 5;
+    const uint32_t seg = (T < 32u ? T : 32u) - 1u;  // intervals of 16 threads share a warp: segmented scan
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += y;
+        if ((lane & seg) >= (uint32_t) d) incl += y;
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     uint32_t before = incl - my_cnt;
-    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    if (tshift > 5)
+        for (int w = (int) (g << (tshift - 5)); w < wid; ++w) before += s_warp[w];
     // ---- the one real decoding pass ---------------------------------------------------------------------------------------
+    const uint32_t N_total = s_grp[g].N_total, slot = s_grp[g].slot;
+    int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
     if (active) {
-        st.p = (uint32_t) my_entry, st.z = (uint16_t) ((my_entry >> 32) & 0xff), st.b = (uint16_t) ((my_entry >> 40) & 0xff);
+        st = unpack_state(my_entry);
         uint32_t done = 0;
         bad = false;
         if (before < N_total)
-            done = par_run_auto<true>(rd, st, end_bit, count, entries, hdr, s_blk, nblk, bad, before, N_total, W, (int) r0, plane0, dcdiff);
-        if (bad) atomicOr(&s_bad, 1u);
-        atomicAdd(&s_total, done);
+            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff);
+        if (bad) atomicOr(&s_grp[g].bad, 1u);
+        atomicAdd(&s_grp[g].total, done);
     }
     __syncthreads();
-    if (tid == 0) {
-        // every expected block must have been completed (a short stream is a truncation in the reference)
-        const uint32_t f = (s_bad != 0u || s_total != N_total) ? 1u : 0u;
-        flagged[slot] = f;
+    // every expected block must have been completed (a short stream is a truncation in the reference)
+    const bool mine = S != 0u;  // this interval was decoded here
+    if (mine && l == 0) {
+        const bool f = s_grp[g].bad != 0u || s_grp[g].total != N_total;
+        s_grp[g].bad = f ? 1u : 0u;
+        flagged[slot] = f ? 1u : 0u;
         if (!f && P.status) P.status[slot] = 0;
+    }
+    __syncthreads();
+    // ---- DC differences -> DC coefficients: decode.swift:3248-3254 (wrapping Int16 prediction, reset per interval); one warp
+    // per interval runs a 16-bit prefix sum per component over the side array the pass above filled (L2-resident).
+    // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
+    const uint32_t per_warp = T >= 32u ? 1u : 32u / T;  // intervals a warp resolves, one after the other
+    for (uint32_t k = 0; k < per_warp; ++k) {
+        const uint32_t gg = T >= 32u ? g : (uint32_t) wid * per_warp + k;
+        if (T >= 32u && l >= 32u) break;  // the first warp of the interval does it
+        const ParGroup &q = s_grp[gg];
+        if (q.S == 0u || q.bad != 0u) continue;
+        const int      r0 = q.r0, r1 = q.r1;
+        const uint32_t uW = (uint32_t) W, unblk = (uint32_t) nblk;
+        const int16_t *dcd = dcdiff_all + (size_t) q.slot * dc_per_interval;
+        uint32_t       fb = 0;
+        for (int c = 0; c < P.n_comp; ++c) {
+            const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
+            const uint32_t K = (uint32_t) (r1 - r0) * uW * nc;
+            int            carry = 0;
+            for (uint32_t base = 0; base < K && P.plane[c]; base += 32) {
+                const uint32_t i = base + (uint32_t) lane;
+                const uint32_t mcu = i / nc, j = i - mcu * nc;
+                int            v = i < K ? (int) __ldcg(dcd + mcu * unblk + fb + j) : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane >= d) v += y;
+                }
+                const int pred = (int) (short) (carry + v);
+                if (i < K) {
+                    const uint32_t my = (uint32_t) r0 + mcu / uW, mx = mcu - (mcu / uW) * uW;
+                    const ParBlk  &pb = s_blk[fb + j];
+                    if (mx < (pb.lim & 0xffffu) && my < (pb.lim >> 16))
+                        plane0[(int64_t) (int32_t) (pb.C + mx * pb.fx + my * pb.R) * 64] = (int16_t) ((uint32_t) pred << P.al);
+                }
+                carry = (int) (short) __shfl_sync(0xffffffffu, pred, 31);
+            }
+            fb += nc;
+        }
     }
     if (stats) {  // JPEG_SM100_PAR_STATS=1: rounds and re-parses per interval
         atomicAdd(&stats[0], n_redo);
-        if (tid == 0) {
+        if (mine && l == 0) {
             atomicAdd(&stats[1], n_rounds);
             atomicAdd(&stats[2], S);
             atomicAdd(&stats[3], 1u);
             atomicMax(&stats[4], n_rounds);
         }
-    }
-}
-
-// DC differences -> DC coefficients: decode.swift:3248-3254 (wrapping Int16 prediction, reset per interval), one warp per
-// (interval, component).  Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
-__global__ void __launch_bounds__(WARP)
-k_dc_resolve(const __grid_constant__ ScanParams P, const int16_t *const dcdiff_all, const uint32_t dc_per_interval,
-             const uint32_t *const flagged)
-{
-    const uint32_t e = blockIdx.x, img = blockIdx.y, c = blockIdx.z, lane = threadIdx.x;
-    const size_t   slot = (size_t) img * P.n_ecs + e;
-    if (flagged[slot]) return;  // re-decoded sequentially, DC included
-    int64_t r0, r1;
-    if (P.interval == UINT64_MAX) {
-        r0 = 0;
-        r1 = P.H;
-    } else {
-        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
-        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
-        if (r0 > P.H) r0 = P.H;
-        if (r1 > P.H) r1 = P.H;
-    }
-    const uint32_t W = (uint32_t) P.W, nblk = (uint32_t) P.mcu_blocks;
-    const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
-    uint32_t       fb = 0;
-    for (uint32_t b = 0; b < nblk; ++b)
-        if (P.blk_comp[b] == c) {
-            fb = b;
-            break;
-        }
-    const uint32_t K = (uint32_t) (r1 - r0) * W * nc;
-    const int16_t *dc = dcdiff_all + slot * dc_per_interval;
-    int16_t       *pl = P.plane[c] ? P.plane[c] + (size_t) img * P.image_stride[c] : nullptr;
-    int            carry = 0;
-    for (uint32_t base = 0; base < K; base += WARP) {
-        const uint32_t k = base + lane;
-        const uint32_t mcu = k / nc, j = k - mcu * nc;
-        int            v = k < K ? (int) dc[mcu * nblk + fb + j] : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= (uint32_t) d) v += y;
-        }
-        const int pred = (int) (short) (carry + v);
-        if (k < K && pl) {
-            const uint32_t my = (uint32_t) r0 + mcu / W, mx = mcu - (mcu / W) * W;
-            const uint32_t bx = mx * P.fx[c] + P.blk_dx[fb + j], by = my * P.fy[c] + P.blk_dy[fb + j];
-            if (bx < (uint32_t) P.ux[c] && by < (uint32_t) P.uy[c])
-                pl[64 * ((size_t) P.ux[c] * by + bx)] = (int16_t) ((uint32_t) pred << P.al);
-        }
-        carry = (int) (short) __shfl_sync(0xffffffffu, pred, 31);
     }
 }
 
@@ -1306,6 +1441,19 @@ __global__ void k_reduce_status(const int32_t *__restrict__ per_ecs, uint32_t n_
     if (threadIdx.x == 0) per_image[img] = first == 0xffffffffu ? 0 : per_ecs[(size_t) img * n_ecs + first];
 }
 
+// clear MCU rows [row0, H) of every plane of the scan, all images (cudaMemset2D: one row of the 2-D set per image)
+int zero_plane_rows(jpeg_sm100_ctx *ctx, const ScanParams &P, int n_comp, uint32_t n_images, int row0)
+{
+    for (int c = 0; c < n_comp; ++c) {
+        if (!P.plane[c]) continue;
+        const int y0 = row0 * P.fy[c] < P.uy[c] ? row0 * P.fy[c] : P.uy[c];
+        const size_t bytes = (size_t) 128 * P.ux[c] * (P.uy[c] - y0);
+        if (!bytes) continue;
+        CU_TRY(ctx, cudaMemset2DAsync(P.plane[c] + (size_t) 64 * P.ux[c] * y0, P.image_stride[c] * 2, 0, bytes, n_images, ctx->stream));
+    }
+    return JPEG_SM100_OK;
+}
+
 }  // namespace
 
 // Layer-B implementation.  scratch slots 8 (LUTs) and 9 (per-ECS status) belong to this file.
@@ -1343,7 +1491,8 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     P.band_hi = scan->band_hi;
     P.al = scan->bit_lo;
     P.n_comp = scan->n_comp;
-    P.extend = (extend && P.kind <= 1) ? 1 : 0;
+    const bool fresh = (extend & JPEG_SM100_SCAN_FRESH) != 0;  // planes are to be treated as newly created (all zero)
+    P.extend = ((extend & JPEG_SM100_SCAN_EXTEND) && P.kind <= 1) ? 1 : 0;
     P.n_ecs = n_ecs;
     P.interval = interval;
     P.ecs = d_ecs;
@@ -1421,8 +1570,9 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         h.total_entries = total;
         for (int ti = 0; ti < 8; ++ti)
             if (h.present[ti]) {
+                uint8_t depth[FAST_ENTRIES];
                 h.fast[ti] = total;
-                total += 2 * FAST_ENTRIES;  // FAST_ENTRIES x 32-bit entries
+                total += 2 * (FAST_ENTRIES + sub_depths(raw[s].counts[ti], depth));  // 32-bit entries: fast table + sub-tables
             }
         h.total_all = total;
         if (total > max_entries) max_entries = total;
@@ -1459,7 +1609,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     for (int c = 0; c < scan->n_comp && plane0; ++c) {
         if (!P.plane[c]) continue;
         const uint64_t span = (uint64_t) (P.plane[c] - plane0) + P.image_stride[c] * (uint64_t) n_images;
-        if (((P.plane[c] - plane0) & 63) || (P.image_stride[c] & 63) || span / 64 > 0xfffffff0ull) fast_ok = false;
+        if (((P.plane[c] - plane0) & 63) || (P.image_stride[c] & 63) || span / 64 > 0x7ffffff0ull) fast_ok = false;
     }
     if (!plane0) fast_ok = false;
     if (P.kind <= 1 && !use_flat && fast_ok) {
@@ -1468,8 +1618,9 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
             const char *e = getenv("JPEG_SM100_HUFF");
             return e && strcmp(e, "seq") == 0;  // one thread per interval only (A/B validation of the parallel decoder)
         }();
+        bool par_done = false;
         if (P.kind == 0 && !P.extend && !no_par) {
-            // subsequence-parallel decode, then the sequential kernel for whatever it flagged, then the DC prefix sums
+            // subsequence-parallel decode (+ fused row clearing and DC prefix sums), then the sequential kernel for whatever it flagged
             const uint64_t rows_max = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W + 1;
             const uint64_t dc_per_interval = rows_max * (uint64_t) P.W * (uint64_t) volume;
             const uint64_t slots = (uint64_t) n_images * n_ecs;
@@ -1478,7 +1629,21 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 J_TRY(scratch_reserve(ctx, 12, (size_t) (slots * dc_per_interval * 2 + 256), &d_dc));
                 J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
                 const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + entry_bytes;
-                const dim3   grid_par(n_ecs, n_images);
+                // Threads per interval (16 .. 128).  Every subsequence is parsed ~(2 + warm-up / length) times, so long
+                // subsequences (>= 3 Kbit) waste the least work; small batches take more threads per interval to fill the GPU.
+                // tuning / test overrides, read per call: log2(threads per interval), warm-up bits
+                const char *env_ts = getenv("JPEG_SM100_PAR_T"), *env_ws = getenv("JPEG_SM100_PAR_WARM");
+                const int   env_t = env_ts ? atoi(env_ts) : 0, env_warm = env_ws ? atoi(env_ws) : 0;
+                const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
+                const uint64_t est_bits = ctx->hint_interval_bytes ? 8 * ctx->hint_interval_bytes
+                                                                   : 96 * rows_typ * (uint64_t) P.W * (uint64_t) volume;
+                int tshift = 7;
+                while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
+                while (tshift < 7 && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
+                if (env_t >= 4 && env_t <= 7) tshift = env_t;
+                const uint32_t warm_bits = env_warm > 0 ? (uint32_t) env_warm : 2048u;
+                const uint32_t G = PAR_THREADS >> tshift;
+                const dim3     grid_par((n_ecs + G - 1) / G, n_images);
                 static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
                 uint32_t         *d_stats = nullptr;
                 if (want_stats) {
@@ -1487,31 +1652,37 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     d_stats = reinterpret_cast<uint32_t *>(p);
                     CU_TRY(ctx, cudaMemsetAsync(d_stats, 0, 64, ctx->stream));
                 }
+                // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
+                if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
+                    J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, (int) (((uint64_t) n_ecs * interval) / (uint64_t) P.W)));
                 k_decode_par<<<grid_par, PAR_THREADS, smem_par, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
                                                                                 (uint32_t) dc_per_interval,
-                                                                                reinterpret_cast<uint32_t *>(d_flag), d_stats);
+                                                                                reinterpret_cast<uint32_t *>(d_flag), d_stats, tshift,
+                                                                                warm_bits, fresh ? 1 : 0);
                 LAUNCH_CHECK(ctx);
                 if (want_stats) {
                     uint32_t h[5];
                     CU_TRY(ctx, cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
                     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-                    fprintf(stderr, "[k_decode_par] intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
-                            h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
+                    fprintf(stderr, "[k_decode_par] T %d, warm %u, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
+                            1 << tshift, warm_bits, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
                 }
-                k_zero_flagged<<<grid_par, 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+                k_zero_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
                 LAUNCH_CHECK(ctx);
                 k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, reinterpret_cast<const uint32_t *>(d_flag));
-                LAUNCH_CHECK(ctx);
-                k_dc_resolve<<<dim3(n_ecs, n_images, scan->n_comp), WARP, 0, ctx->stream>>>(
-                    P, reinterpret_cast<const int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<const uint32_t *>(d_flag));
-            } else
-                k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, nullptr);
-        } else
+                par_done = true;
+            }
+        }
+        if (!par_done) {
+            if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
             k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, nullptr);
+        }
     } else if (P.kind <= 1) {
+        if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
         if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
         else k_decode_flat<false><<<grid, WARP, smem, ctx->stream>>>(P);
     } else {
+        if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
         if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P);
         else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P);
     }

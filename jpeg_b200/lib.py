@@ -5,10 +5,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libjpeg_sm100.so")
+# JPEG_SM100_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+SO_PATH = os.environ.get("JPEG_SM100_LIB") or os.path.join(_HERE, "libjpeg_sm100.so")
 
 INTERVAL_NONE = (1 << 64) - 1
 BITS_MAX = -1
+SCAN_EXTEND = 1  # bits of the `extend` argument of the decode_scan entry points
+SCAN_FRESH = 2
 
 OK = 0
 ERR_TRUNCATED_ECS = -1

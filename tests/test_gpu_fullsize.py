@@ -75,6 +75,81 @@ def test_config2_4k_420_baseline_decode(env):
     assert err.mean() < 12.0
 
 
+@pytest.mark.parametrize("tshift", [0, 4, 5, 6, 7])
+def test_config2_fresh_planes_and_interval_threads(env, monkeypatch, tshift):
+    """SCAN_FRESH: the library clears the planes itself (here they hold garbage), for every threads-per-interval setting of
+    the parallel decoder (0 = the library's own choice) -- and for the sequential decoder."""
+    t, b, lib, O, ctx, dev = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"], env["dev"]
+    if tshift:
+        monkeypatch.setenv("JPEG_SM100_PAR_T", str(tshift))
+    W, H, N = 3840, 2160, 2
+    geo = b.Geometry((W, H), [(2, 2), (1, 1), (1, 1)])
+    q = _quanta(O)
+    frames = t.stack([env["synth"].frame(300 + i, W, H, dev) for i in range(N)])
+    ecs, tabs, enc = b.encode_frames(ctx, frames, geo, q, geo.blocks[0])
+    inputs = b.DecodeInputs(ecs, list(tabs), n_ecs_expected=135)
+    desc = b.sequential_scan(geo)
+    tarr = (lib.HuffTable * (8 * N))(*list(tabs))
+    buf = b.DeviceBuffers(geo, N, dev)
+    d_ecs = t.from_numpy(inputs.ecs).to(dev)
+    d_off = t.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    d_st = t.zeros(N, dtype=t.int32, device=dev)
+    for c in buf.coef:
+        c.fill_(0x5a5a)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
+                                               geo.blocks[0], lib.SCAN_FRESH, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    assert d_st.cpu().tolist() == [0] * N
+    for p in range(3):
+        assert t.equal(buf.coef[p], enc.coef[p]), p
+    # fewer intervals than the image has rows: the rows nobody decodes must still come out zero
+    short = 100
+    # (decode only the first image: with fewer intervals the offsets of consecutive images are no longer contiguous)
+    one = np.ascontiguousarray(inputs.offsets[:short + 1])
+    for c in buf.coef:
+        c.fill_(0x1234)
+    one_sp = lib.DevSpectral()
+    C.memmove(C.byref(one_sp), C.byref(buf.sp), C.sizeof(one_sp))
+    one_sp.n_images = 1
+    d_off1 = t.from_numpy(one.view(np.int64)).to(dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off1.data_ptr(), short,
+                                               geo.blocks[0], lib.SCAN_FRESH, tarr, 0, C.byref(one_sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    for p, (ux, uy) in enumerate(geo.units):
+        rows = short * geo.factors[p][1]
+        assert t.equal(buf.coef[p][0, :rows], enc.coef[p][0, :rows]), p
+        assert int(buf.coef[p][0, rows:].abs().sum().item()) == 0, p
+        assert int((buf.coef[p][1] != 0x1234).sum().item()) == 0, p  # the second image was not part of the call
+
+
+def test_single_ecs_without_restart_intervals(env, monkeypatch):
+    """a reference-faithful file (no DRI: one entropy-coded segment per scan) through the parallel decoder: one CTA cuts the
+    whole segment into 128 subsequences."""
+    t, b, lib, O, ctx, dev = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"], env["dev"]
+    W, H = 1920, 1080
+    geo = b.Geometry((W, H), [(2, 2), (1, 1), (1, 1)])
+    q = _quanta(O)
+    frames = t.stack([env["synth"].frame(400 + i, W, H, dev) for i in range(2)])
+    ecs, tabs, enc = b.encode_frames(ctx, frames, geo, q, 0)
+    inputs = b.DecodeInputs(ecs, list(tabs), n_ecs_expected=1)
+    desc = b.sequential_scan(geo)
+    tarr = (lib.HuffTable * 16)(*list(tabs))
+    buf = b.DeviceBuffers(geo, 2, dev)
+    d_ecs = t.from_numpy(inputs.ecs).to(dev)
+    d_off = t.from_numpy(inputs.offsets.view(np.int64)).to(dev)
+    d_st = t.zeros(2, dtype=t.int32, device=dev)
+    for warm in ("64", "2048"):
+        monkeypatch.setenv("JPEG_SM100_PAR_WARM", warm)
+        for c in buf.coef:
+            c.fill_(-1)
+        ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), 1,
+                                                   lib.INTERVAL_NONE, lib.SCAN_FRESH, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+        t.cuda.synchronize()
+        assert d_st.cpu().tolist() == [0, 0]
+        for p in range(3):
+            assert t.equal(buf.coef[p], enc.coef[p]), (warm, p)
+
+
 def test_config3_4k_420_encode(env):
     """config #3: 3840x2160 baseline 4:2:0 encode at level 0.25: coefficients and ECS bytes equal the oracle's, with the
     reference-faithful single ECS and with DRI = 240."""

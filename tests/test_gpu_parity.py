@@ -172,6 +172,49 @@ def test_scan_decode_all_kinds(H, O, name, progression, rows):
         assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (name, rows, p)
 
 
+@pytest.mark.parametrize("tshift", [4, 5, 6, 7])
+@pytest.mark.parametrize("warm", [32, 2048])
+def test_scan_decode_parallel_variants(H, O, monkeypatch, tshift, warm):
+    """the subsequence-parallel decoder (K3p) under every threads-per-interval setting and with a warm-up so short that the
+    synchronisation rounds have real work: same coefficients and same error codes as the oracle."""
+    from jpeg_b200 import lib
+    monkeypatch.setenv("JPEG_SM100_PAR_T", str(tshift))
+    monkeypatch.setenv("JPEG_SM100_PAR_WARM", str(warm))
+    src = O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))
+    fac = [src.factor(p) for p in range(3)]
+    for progression in (BASELINE, BASELINE_SPLIT):
+        for rows in (0, 1, 3):
+            dst = H.Spectral(src.size, fac, process=2)
+            for band, bits, comps, dct, act, parts, ival in _oracle_scans(O, src, progression, rows):
+                dst.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival)
+            for p in range(3):
+                assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (rows, p)
+    # corrupt intervals: flagged by the parallel decoder, diagnosed by the sequential one
+    (band, bits, comps, dct, act, parts, ival), = _oracle_scans(O, src, BASELINE, 1)
+    rng = np.random.default_rng(11)
+    for k in range(4):
+        junk = list(parts)
+        junk[k] = bytes(rng.integers(0, 256, len(parts[k]), dtype=np.uint8))
+        if k == 3:
+            junk[k] = junk[k][:len(junk[k]) // 3]
+        got = H.Spectral(src.size, fac)
+        want = O.Spectral.create(src.size, fac)
+        try:
+            got.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), junk, ival)
+            code = 0
+        except lib.JpegSm100Error as e:
+            code = e.code
+        try:
+            want.decode_scan(band, bits, comps, [0] * 3, [0] * 3, dct, act, junk, interval=ival)
+            wcode = 0
+        except O.OracleError as e:
+            wcode = e.code
+        assert code == wcode, k
+        if code == 0:
+            for p in range(3):
+                assert np.array_equal(got.planes[p].coef, want.coefficients(p)), (k, p)
+
+
 def test_scan_decode_errors(H, O):
     """Error parity: truncated data, undefined tables, EOB run in a sequential scan -- same code as the oracle."""
     from jpeg_b200 import lib
