@@ -775,6 +775,11 @@ finished:
 constexpr int PAR_THREADS = 128;
 constexpr int PAR_MAX_GROUPS = PAR_THREADS / 16;
 constexpr int PAR_MIN_BITS = 1024;
+#ifndef PAR_NSEG_N
+#define PAR_NSEG_N 2
+#endif
+constexpr int PAR_NSEG = PAR_NSEG_N;  // checkpoints per subsequence
+constexpr uint32_t PAR_BUF_STRIDE = 144;  // bytes between the threads' block buffers: 16-byte aligned, 4 banks apart
 
 struct ParseState {
     uint32_t p;      // bit position of the next symbol
@@ -792,6 +797,7 @@ struct ParIO {             // where the bytes of one restart interval live
     const uint32_t *w0;    // the aligned word that holds its first byte
     uint32_t        wlim;  // words [0, wlim) need no padding
     int32_t         lead, nbytes;
+    uint32_t        stage;  // shared-memory address of the staged copy (big-endian words, 1-padded past the end); 0: not staged
     __device__ __forceinline__ uint32_t word(uint32_t i) const
     {
         if (i < wlim) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
@@ -847,29 +853,36 @@ __device__ __forceinline__ uint4 lds128(uint32_t a)
 //     moves lo to hi and loads one word;
 //   * tables are addressed with 32-bit shared-memory addresses held in registers and reloaded (one LDS.128, which also brings
 //     the successor's address) only when a block ends.
-template <bool FINAL, bool SAFE>
+template <bool FINAL, bool STAGED, bool SAFE>
 __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                            const uint32_t blk0, const uint8_t *smem, const int nblk, bool &bad,
+                                            const uint32_t blk0, const uint8_t *smem, const uint16_t *ref_entries, const int nblk,
+                                            bool &bad,
                                             // FINAL only:
                                             uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                            int16_t *dcdiff)
+                                            int16_t *dcdiff, int16_t *buf)
 {
     int z = st.z;
     bad = false;
     if (st.p >= end_bit) return 0;
     if (FINAL && N >= N_total) return 0;
-    const uint32_t N_start = N;
     uint32_t       done = 0;
     int            left = (int) (end_bit - st.p);            // bits up to the end of the run
     const int      slack = (int) (count_bits - end_bit);     // bits between the end of the run and the end of the data
     // bit window: (hi:lo) = the 64 stream bits that start at word wi - 2; cnt (< 32 at the loop top) of them are consumed
-    uint32_t wi, cnt, hi, lo;
+    uint32_t wi, cnt, hi, lo, nxt = 0;  // nxt (global-memory path): the word after lo, loaded one refill ahead and still raw when SAFE
     {
         const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
         wi = ab >> 5;
         cnt = ab & 31u;
-        hi = io.word(wi), lo = io.word(wi + 1);
-        wi += 2;
+        if (STAGED) {
+            wi = io.stage + wi * 4u;  // STAGED: wi is the shared-memory address of the next word
+            hi = lds32(wi), lo = lds32(wi + 4u);
+            wi += 8u;
+        } else {
+            hi = io.word(wi), lo = io.word(wi + 1);
+            nxt = SAFE ? __ldg(io.w0 + wi + 2) : io.word(wi + 2);
+            wi += 3;
+        }
     }
     uint32_t dtab, atab, tabs, next;
     {
@@ -877,10 +890,17 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
         dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
     }
     // FINAL: position and destination of the current block
+    // A block is decoded by the thread in whose subsequence it STARTS: that thread runs past the end of its subsequence until the
+    // block is complete, and the thread that finds a block in progress at its entry skips to the block's end.  So every block is
+    // assembled by one thread, in that thread's 128-byte buffer in shared memory (zero-initialised, coefficient z at buf[z]), and
+    // leaves as eight 16-byte stores: whole lines, no read-modify-write of a cleared plane, an eighth of the store transactions
+    // that scattered 2-byte stores need (the pass is bound by L1TEX store transactions otherwise).
     int      mx = 0, my = 0;
     int16_t *bptr = nullptr, *dcp = nullptr;
-    bool     inp = false;
+    bool     inp = false, own = false;  // own: the DC symbol of the block in progress was decoded here
     if (FINAL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(buf)[i] = make_uint4(0, 0, 0, 0);
         dcp = dcdiff + N;
         const uint32_t mcu = N / (uint32_t) nblk;
         my = my0 + (int) (mcu / (uint32_t) W);
@@ -889,11 +909,18 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
         inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
         bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
     }
-    while (left > 0) {
+    while (left > 0 || (FINAL && own)) {
+        const bool in_range = left > 0;  // the symbol starts inside the subsequence (block completions are counted there)
         if (cnt >= 32u) {
             hi = lo;
-            lo = SAFE ? __byte_perm(__ldg(io.w0 + wi), 0, 0x0123) : io.word(wi);
-            wi += 1;
+            if (STAGED) {
+                lo = lds32(wi);
+                wi += 4u;
+            } else {  // the load issued here is consumed by the NEXT refill: its latency (L2: the lanes' streams thrash L1) is hidden
+                lo = SAFE ? __byte_perm(nxt, 0, 0x0123) : nxt;
+                nxt = SAFE ? __ldg(io.w0 + wi) : io.word(wi);
+                wi += 1;
+            }
             cnt -= 32u;
         }
         const uint32_t top = __funnelshift_l(lo, hi, cnt);  // the next 32 bits of the stream
@@ -906,9 +933,8 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
         }
         if (__builtin_expect(ent == 0u, 0)) {  // invalid codeword / symbol the sequential decoders single out: reference lookup
             const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
-            const uint16_t  *entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader) + 12 * sizeof(BlkInfo));
             const int        ti = isdc ? (int) (tabs & 0xffu) : (int) ((tabs >> 8) & 0xffu);
-            ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);
+            ent = fast_entry(lut_lookup(ref_entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);  // global memory
             if (ent == 0u) {
                 bad = true;
                 break;
@@ -928,9 +954,12 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
             // T.81 EXTEND; identical to decode.swift:2742-2754 for categories 0..15 (16 never reaches this point)
             const int v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;
             const int zpos = z + adv - 1;
-            // DC differences go to the side array (resolved after the pass); AC values to their zig-zag slot
-            if (isdc) *dcp = (int16_t) v;
-            else if (inp & (zpos < 64)) bptr[zpos] = (int16_t) v;
+            // DC differences go to the side array (resolved after the pass); AC values to their zig-zag slot of the block buffer
+            if (isdc) {
+                *dcp = (int16_t) v;
+                own = true;
+            } else if (own & (zpos < 64))
+                buf[zpos] = (int16_t) v;
         }
         cnt += (uint32_t) total;
         left -= total;
@@ -941,6 +970,16 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
             const uint4    q = lds128(cur);
             dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
             if (FINAL) {
+                if (own) {
+                    uint4 *src = reinterpret_cast<uint4 *>(buf), *dst = reinterpret_cast<uint4 *>(bptr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (inp) dst[i] = src[i];
+                        src[i] = make_uint4(0, 0, 0, 0);
+                    }
+                    own = false;
+                }
+                done += in_range ? 1u : 0u;
                 N += 1;
                 dcp += 1;
                 if (N >= N_total) break;
@@ -960,30 +999,43 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
     st.p = end_bit - (uint32_t) left;
     st.z = (uint16_t) z;
     st.b = (uint16_t) ((tabs >> 16) & 0xffu);
-    return FINAL ? N - N_start : done;
+    return done;
 }
 
-// picks the SAFE variant when the run, its overshoot (< 32 bits) and the 64-bit look-ahead stay in unpadded words
+// Picks the variant, warp-uniformly (a warp whose lanes disagree would execute both one after the other):
+//   STAGED  every lane's interval has a copy in shared memory (big-endian, 1-padded): refills are shared-memory loads;
+//   SAFE    no symbol that starts inside the run can reach past the end of the data (and, reading global memory, the run, its
+//           overshoot of < 32 bits and the 64-bit look-ahead stay in unpadded words).
 template <bool FINAL>
 __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                                 const uint32_t blk0, const uint8_t *smem, const int nblk, bool &bad, uint32_t N,
-                                                 const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff)
+                                                 const uint32_t blk0, const uint8_t *smem, const uint16_t *ref_entries, const int nblk,
+                                                 bool &bad, uint32_t N, const uint32_t N_total, const int W, const int my0,
+                                                 int16_t *plane0, int16_t *dcdiff, int16_t *buf)
 {
-    // warp-uniform choice: a warp whose lanes disagree would execute both variants one after the other
-    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 32u + 64u) / 32u + 1u;
-    if (__all_sync(__activemask(), last_word < io.wlim))
-        return par_run<FINAL, true>(io, st, end_bit, count_bits, blk0, smem, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
-    return par_run<FINAL, false>(io, st, end_bit, count_bits, blk0, smem, nblk, bad, N, N_total, W, my0, plane0, dcdiff);
+    const uint32_t mask = __activemask();
+    // the decoding pass may run past end_bit by the rest of one block: 63 symbols of at most 31 bits
+    const uint32_t reach = end_bit + (FINAL ? 2048u : 0u);
+    if (__all_sync(mask, io.stage != 0u)) {
+        if (__all_sync(mask, reach + 32u <= count_bits))
+            return par_run<FINAL, true, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
+        return par_run<FINAL, true, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
+    }
+    const uint32_t last_word = ((uint32_t) io.lead * 8u + reach + 32u + 64u) / 32u + 2u;  // incl. the word loaded ahead
+    if (__all_sync(mask, last_word < io.wlim))
+        return par_run<FINAL, false, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
+    return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
 }
 
 #ifndef PAR_MIN_CTAS
 #define PAR_MIN_CTAS 1
 #endif
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
-// zero_first: the CTA clears the coefficient rows of its intervals before it decodes into them (fresh Spectral planes)
+// stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
+// block buffers (PAR_BUF_STRIDE bytes each)
 __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
-             uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits, const int zero_first)
+             uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits,
+             const uint32_t stage_off, const uint32_t stage_bytes, const uint32_t buf_off)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t s_exit[PAR_THREADS], s_entry[PAR_THREADS];
@@ -992,14 +1044,30 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[PAR_THREADS / 32];
     __shared__ ParGroup s_grp[PAR_MAX_GROUPS];
+    __shared__ uint64_t s_ck_state[PAR_NSEG][PAR_THREADS];  // checkpoints of every subsequence's recorded parse
+    __shared__ uint32_t s_ck_cnt[PAR_NSEG][PAR_THREADS];
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
     const uint32_t   T = 1u << tshift, G = PAR_THREADS >> tshift;
+#ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
+    long long        t_phase = stats ? clock64() : 0;
+#define PAR_PHASE(k)                                                                                                 \
+    do {                                                                                                             \
+        if (stats && tid == 0) {                                                                                     \
+            const long long now_ = clock64();                                                                        \
+            atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 4 + (k), (unsigned long long) (now_ - t_phase)); \
+            t_phase = now_;                                                                                          \
+        }                                                                                                            \
+    } while (0)
+#else
+#define PAR_PHASE(k)
+#endif
     const uint32_t   g = tid >> tshift, l = tid & (T - 1u);
     const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
     const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
     ParBlk          *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
     constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
     const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
+    const uint16_t  *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
     const int        W = P.W, nblk = P.mcu_blocks;
     {
         const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
@@ -1007,8 +1075,10 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
         const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
         for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += PAR_THREADS) dst[i] = src[i];
-        uint32_t *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
-        for (uint32_t i = tid; i < (total + 1) / 2; i += PAR_THREADS) d2[i] = src[sizeof(LutHeader) / 4 + i];
+        // only the fast tables (and their sub-tables) live in shared memory; the reference LUT behind them stays in global memory
+        const uint32_t ref_total = gh->total_entries;
+        uint32_t      *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
+        for (uint32_t i = tid; i < (total - ref_total + 1) / 2; i += PAR_THREADS) d2[i] = src[(sizeof(LutHeader) + 2 * ref_total) / 4 + i];
         if (tid < 12) {
             const int      b = tid, c = P.blk_comp[b];
             const bool     has = P.plane[c] != nullptr;
@@ -1020,7 +1090,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             const uint32_t LX = (has && ux > dx) ? min((ux - dx + fx - 1u) / fx, 0xffffu) : 0u;
             const uint32_t LY = (has && uy > dy) ? min((uy - dy + fy - 1u) / fy, 0xffffu) : 0u;
             pb.lim = LX | (LY << 16);
-            pb.dtab = sbase + PRE + 2u * gh->fast[P.dc[c]], pb.atab = sbase + PRE + 2u * gh->fast[P.ac[c]];
+            pb.dtab = sbase + PRE + 2u * (gh->fast[P.dc[c]] - ref_total), pb.atab = sbase + PRE + 2u * (gh->fast[P.ac[c]] - ref_total);
             pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u);
             pb.next = blk0 + (uint32_t) ((b + 1 == nblk) ? 0 : b + 1) * (uint32_t) sizeof(ParBlk) + 16u;
             s_blk[b] = pb;
@@ -1063,49 +1133,77 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
                     if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
                     q.B = B;
                     q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
+                    // shared-memory copy: the words of the interval plus four words of 1-padding, if its share of the stage holds them
+                    const uint32_t cap = (stage_bytes / G) & ~15u, need = ((uint32_t) (q.io.lead + q.io.nbytes + 3) / 4u + 4u) * 4u;
+                    q.io.stage = need <= cap ? sbase + stage_off + (tid - 32) * cap : 0u;
                 }
             }
             s_grp[tid - 32] = q;
         }
     }
     __syncthreads();
-    // ---- fresh planes: clear the rows this CTA is about to fill (whole rows of whole intervals: 16-byte stores) ----------
-    if (zero_first) {
-        for (uint32_t gg = 0; gg < G; ++gg) {
-            if (!s_grp[gg].valid) continue;
-            const int r0 = s_grp[gg].r0, r1 = s_grp[gg].r1;
-            for (int c = 0; c < P.n_comp; ++c) {
-                if (!P.plane[c]) continue;
-                int16_t  *pl = P.plane[c] + (size_t) img * P.image_stride[c];
-                const int y0 = min(r0 * P.fy[c], P.uy[c]), y1 = min(r1 * P.fy[c], P.uy[c]);
-                uint4    *q = reinterpret_cast<uint4 *>(pl + 64 * (size_t) P.ux[c] * y0);
-                const uint32_t n16 = 8u * (uint32_t) P.ux[c] * (uint32_t) (y1 - y0);
-                for (uint32_t i = tid; i < n16; i += PAR_THREADS) q[i] = make_uint4(0, 0, 0, 0);
-            }
-        }
+    // ---- stage the intervals in shared memory: every byte is read from global memory once (coalesced), byte-swapped and
+    // 1-padded (jpeg.swift:1881-1887) on the way; all parsing passes then refill from shared memory
+    for (uint32_t gg = 0; gg < G; ++gg) {
+        const ParIO qio = s_grp[gg].io;
+        if (qio.stage == 0u) continue;
+        const uint32_t nw = (uint32_t) (qio.lead + qio.nbytes + 3) / 4u + 4u;
+        uint32_t      *dst = reinterpret_cast<uint32_t *>(smem + (qio.stage - sbase));
+        for (uint32_t i = tid; i < nw; i += PAR_THREADS) dst[i] = qio.word(i);
     }
+    __syncthreads();
+    PAR_PHASE(0);
     const ParIO    io = s_grp[g].io;
     const uint32_t count = s_grp[g].count, B = s_grp[g].B, S = s_grp[g].S;
     const bool     active = l < S;
     const uint32_t start_bit = l * B, end_bit = (l + 1 == S) ? count : (l + 1) * B;
 
-    // ---- round 0: warm up over the preceding warm_bits from a guessed state, then parse the own subsequence ----
-    // (by the time the speculative parse reaches its own first bit it has usually re-synchronised with the true parse, so
-    //  most subsequences never need a second look; every thread whose warm-up starts at bit 0 is exact)
+    // ---- synchronisation.  Every subsequence is parsed once from a guessed state (optionally after a speculative warm-up over
+    // the warm_bits before it) and leaves checkpoints -- parse state and block count at PAR_NSEG positions.  Then, round by
+    // round, every subsequence whose entry differs from its predecessor's exit is re-parsed from that exit, but only until
+    // the new parse MERGES with the recorded one (same state at a checkpoint: Huffman streams self-synchronise after a few
+    // hundred bits); the rest of the record stays valid, so a correction costs a fraction of a subsequence.  Thread 0 of an
+    // interval starts from the true state; once no entry differs from its predecessor's exit every record is exact.
+    // The subsequences to redo are compacted into a work list so that they occupy the lanes of as few warps as possible.
     ParseState st;
     bool       bad;
+    // parses subsequence `sid` = [s_bit, e_bit) of `qio` from `st`, checkpoint by checkpoint; returns its block count and exit
+    auto parse_sub = [&](const ParIO &qio, const uint32_t qcount, const uint32_t s_bit, const uint32_t e_bit, const uint32_t sid,
+                         const bool first_time, uint64_t &exit_out) -> uint32_t {
+        const uint32_t seglen = (e_bit - s_bit) / PAR_NSEG;
+        uint32_t       cum = 0;
+        uint64_t       x = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
+            const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
+            cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            x = pack_state(st.p, st.z, st.b);
+            if (!first_time && x == s_ck_state[k][sid]) {  // merged: from here on the recorded parse is this parse
+                const uint32_t delta = cum - s_ck_cnt[k][sid];  // the later checkpoints keep their states; their counts shift
+                for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) s_ck_cnt[kk][sid] += delta;
+                exit_out = s_exit[sid];
+                return s_cnt[sid] + delta;
+            }
+            s_ck_state[k][sid] = x;
+            s_ck_cnt[k][sid] = cum;
+        }
+        exit_out = x;
+        return cum;
+    };
     if (active) {
         st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
-        if (l > 0) par_run_auto<false>(io, st, start_bit, count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
+        if (l > 0 && warm_bits) par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+        if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
-        s_cnt[tid] = par_run_auto<false>(io, st, end_bit, count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-        s_exit[tid] = pack_state(st.p, st.z, st.b);
+        uint64_t       x;
+        const uint32_t c = parse_sub(io, count, start_bit, end_bit, tid, true, x);
+        s_cnt[tid] = c;
+        s_exit[tid] = x;
     } else {
         s_entry[tid] = 0, s_exit[tid] = 0, s_cnt[tid] = 0;
     }
     __syncthreads();
-    // ---- synchronisation rounds: re-parse wherever the entry that was used differs from the predecessor's exit.
-    // The subsequences to redo are compacted into a work list so that they occupy the lanes of as few warps as possible.
+    PAR_PHASE(1);
     uint32_t n_redo = 0, n_rounds = 0;
     for (uint32_t round = 1; round <= T + 1; ++round) {
         const bool redo = active && l >= 1 && s_exit[tid - 1] != s_entry[tid];
@@ -1126,8 +1224,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             const uint64_t  entry = s_exit[sid - 1];
             const uint32_t  e_bit = (ll + 1 == q.S) ? q.count : (ll + 1) * q.B;
             st = unpack_state(entry);
-            const uint32_t c = par_run_auto<false>(qio, st, e_bit, q.count, blk0, smem, nblk, bad, 0, 0, W, 0, nullptr, nullptr);
-            x = pack_state(st.p, st.z, st.b);
+            const uint32_t c = parse_sub(qio, q.count, ll * q.B, e_bit, sid, false, x);
             // every work item reads exit[sid - 1] before any item writes exit[sid]: the write is deferred past a barrier
             s_cnt[sid] = c;
             s_entry[sid] = entry;
@@ -1136,6 +1233,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         if (tid < nwork) s_exit[s_work[tid]] = x;
         __syncthreads();
     }
+    PAR_PHASE(2);
     const uint32_t my_cnt = s_cnt[tid];
     const uint64_t my_entry = s_entry[tid];
     // ---- first block of every subsequence: exclusive scan of the block counts within the interval -------------------------
@@ -1149,6 +1247,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
+    PAR_PHASE(3);
     uint32_t before = incl - my_cnt;
     if (tshift > 5)
         for (int w = (int) (g << (tshift - 5)); w < wid; ++w) before += s_warp[w];
@@ -1160,11 +1259,15 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         uint32_t done = 0;
         bad = false;
         if (before < N_total)
-            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff);
-        if (bad) atomicOr(&s_grp[g].bad, 1u);
+            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff,
+                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+        // a subsequence that does not produce the blocks the synchronisation counted for it (or that was cut short because the
+        // interval is complete while data remains) leaves the interval to the sequential decoder
+        if (bad || (before < N_total && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
         atomicAdd(&s_grp[g].total, done);
     }
     __syncthreads();
+    PAR_PHASE(4);
     // every expected block must have been completed (a short stream is a truncation in the reference)
     const bool mine = S != 0u;  // this interval was decoded here
     if (mine && l == 0) {
@@ -1177,41 +1280,52 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // ---- DC differences -> DC coefficients: decode.swift:3248-3254 (wrapping Int16 prediction, reset per interval); one warp
     // per interval runs a 16-bit prefix sum per component over the side array the pass above filled (L2-resident).
     // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
-    const uint32_t per_warp = T >= 32u ? 1u : 32u / T;  // intervals a warp resolves, one after the other
-    for (uint32_t k = 0; k < per_warp; ++k) {
-        const uint32_t gg = T >= 32u ? g : (uint32_t) wid * per_warp + k;
-        if (T >= 32u && l >= 32u) break;  // the first warp of the interval does it
+    // Work items (interval, component) are dealt to the warps; a lane owns a contiguous run of the component's blocks: it sums its
+    // differences, the warp scans the lane sums, the lane walks its run again and stores the predictions.
+    for (uint32_t item = (uint32_t) wid; item < G * (uint32_t) P.n_comp; item += PAR_THREADS / 32) {
+        const uint32_t  gg = item / (uint32_t) P.n_comp;
+        const int       c = (int) (item - gg * (uint32_t) P.n_comp);
         const ParGroup &q = s_grp[gg];
-        if (q.S == 0u || q.bad != 0u) continue;
-        const int      r0 = q.r0, r1 = q.r1;
+        if (q.S == 0u || q.bad != 0u || !P.plane[c]) continue;
+        uint32_t fb = 0;
+        for (int cc = 0; cc < c; ++cc) fb += (uint32_t) (P.fx[cc] * P.fy[cc]);
         const uint32_t uW = (uint32_t) W, unblk = (uint32_t) nblk;
+        const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
+        const uint32_t K = (uint32_t) (q.r1 - q.r0) * uW * nc;
         const int16_t *dcd = dcdiff_all + (size_t) q.slot * dc_per_interval;
-        uint32_t       fb = 0;
-        for (int c = 0; c < P.n_comp; ++c) {
-            const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
-            const uint32_t K = (uint32_t) (r1 - r0) * uW * nc;
-            int            carry = 0;
-            for (uint32_t base = 0; base < K && P.plane[c]; base += 32) {
-                const uint32_t i = base + (uint32_t) lane;
-                const uint32_t mcu = i / nc, j = i - mcu * nc;
-                int            v = i < K ? (int) __ldcg(dcd + mcu * unblk + fb + j) : 0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, v, d);
-                    if (lane >= d) v += y;
-                }
-                const int pred = (int) (short) (carry + v);
-                if (i < K) {
-                    const uint32_t my = (uint32_t) r0 + mcu / uW, mx = mcu - (mcu / uW) * uW;
-                    const ParBlk  &pb = s_blk[fb + j];
-                    if (mx < (pb.lim & 0xffffu) && my < (pb.lim >> 16))
-                        plane0[(int64_t) (int32_t) (pb.C + mx * pb.fx + my * pb.R) * 64] = (int16_t) ((uint32_t) pred << P.al);
-                }
-                carry = (int) (short) __shfl_sync(0xffffffffu, pred, 31);
+        const uint32_t R = (K + 31u) / 32u, k0 = min((uint32_t) lane * R, K), k1 = min(k0 + R, K);
+        int            sum = 0;
+        {
+            uint32_t mcu = k0 / nc, j = k0 - mcu * nc;
+#pragma unroll 4
+            for (uint32_t k = k0; k < k1; ++k) {
+                sum += (int) dcd[mcu * unblk + fb + j];
+                if (++j == nc) j = 0, ++mcu;
             }
-            fb += nc;
+        }
+        int incl2 = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl2, d);
+            if (lane >= d) incl2 += y;
+        }
+        int      run = incl2 - sum;
+        uint32_t mcu = k0 / nc, j = k0 - mcu * nc;
+        uint32_t my = (uint32_t) q.r0 + mcu / uW, mx = mcu - (mcu / uW) * uW;
+#pragma unroll 4
+        for (uint32_t k = k0; k < k1; ++k) {
+            run += (int) dcd[mcu * unblk + fb + j];
+            const ParBlk &pb = s_blk[fb + j];
+            if (mx < (pb.lim & 0xffffu) && my < (pb.lim >> 16))
+                plane0[(int64_t) (int32_t) (pb.C + mx * pb.fx + my * pb.R) * 64] = (int16_t) ((uint32_t) (int) (short) run << P.al);
+            if (++j == nc) {
+                j = 0, ++mcu;
+                if (++mx == uW) mx = 0, ++my;
+            }
         }
     }
+    __syncthreads();
+    PAR_PHASE(5);
     if (stats) {  // JPEG_SM100_PAR_STATS=1: rounds and re-parses per interval
         atomicAdd(&stats[0], n_redo);
         if (mine && l == 0) {
@@ -1541,7 +1655,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     int   slot = 0;
     J_TRY(pinned_acquire(ctx, sizeof(RawSet) * (size_t) n_sets, &staging, &slot));
     RawSet *raw = reinterpret_cast<RawSet *>(staging);
-    size_t  max_entries = 0;
+    size_t  max_entries = 0, max_fast = 0;  // uint16 units: whole LUT set / its fast tables only
     for (uint32_t s = 0; s < n_sets; ++s) {
         LutHeader &h = raw[s].header;
         memset(&h, 0, sizeof h);
@@ -1576,6 +1690,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
             }
         h.total_all = total;
         if (total > max_entries) max_entries = total;
+        if (total - h.total_entries > max_fast) max_fast = total - h.total_entries;
     }
     const size_t entry_bytes = (max_entries * 2 + 15) & ~size_t(15);
     const size_t stride = sizeof(LutHeader) + entry_bytes + 16;
@@ -1628,7 +1743,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
             if (dc_per_interval <= 0x7fffffffull && slots * dc_per_interval * 2 <= (4ull << 30)) {
                 J_TRY(scratch_reserve(ctx, 12, (size_t) (slots * dc_per_interval * 2 + 256), &d_dc));
                 J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
-                const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + entry_bytes;
+                const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + ((max_fast * 2 + 15) & ~size_t(15));
                 // Threads per interval (16 .. 128).  Every subsequence is parsed ~(2 + warm-up / length) times, so long
                 // subsequences (>= 3 Kbit) waste the least work; small batches take more threads per interval to fill the GPU.
                 // tuning / test overrides, read per call: log2(threads per interval), warm-up bits
@@ -1641,31 +1756,49 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
                 while (tshift < 7 && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
                 if (env_t >= 4 && env_t <= 7) tshift = env_t;
-                const uint32_t warm_bits = env_warm > 0 ? (uint32_t) env_warm : 2048u;
+                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 2048u;
                 const uint32_t G = PAR_THREADS >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
+                // shared-memory stage: twice the expected interval size per interval (larger intervals are read from global
+                // memory), within what leaves a few CTAs per SM
+                const char    *env_ss = getenv("JPEG_SM100_PAR_STAGE");  // KB per interval, 0 = no staging
+                uint64_t       per_interval = env_ss ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
+                if (per_interval * G > 96 * 1024) per_interval = (96 * 1024 / G) & ~(uint64_t) 1023;
+                const uint32_t stage_bytes = (uint32_t) (per_interval * G);
+                const size_t   smem_total = smem_par + stage_bytes + (size_t) PAR_THREADS * PAR_BUF_STRIDE;
+                if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB)
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                    ctx->par_smem_set = 160 * 1024;
+                }
                 static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
                 uint32_t         *d_stats = nullptr;
                 if (want_stats) {
                     void *p = nullptr;
-                    J_TRY(scratch_reserve(ctx, 14, 64, &p));
+                    J_TRY(scratch_reserve(ctx, 14, 128, &p));
                     d_stats = reinterpret_cast<uint32_t *>(p);
-                    CU_TRY(ctx, cudaMemsetAsync(d_stats, 0, 64, ctx->stream));
+                    CU_TRY(ctx, cudaMemsetAsync(d_stats, 0, 128, ctx->stream));
                 }
                 // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
                 if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
                     J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, (int) (((uint64_t) n_ecs * interval) / (uint64_t) P.W)));
-                k_decode_par<<<grid_par, PAR_THREADS, smem_par, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
-                                                                                (uint32_t) dc_per_interval,
-                                                                                reinterpret_cast<uint32_t *>(d_flag), d_stats, tshift,
-                                                                                warm_bits, fresh ? 1 : 0);
+                k_decode_par<<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
+                                                                                  (uint32_t) dc_per_interval,
+                                                                                  reinterpret_cast<uint32_t *>(d_flag), d_stats, tshift,
+                                                                                  warm_bits, (uint32_t) smem_par, stage_bytes,
+                                                                                  (uint32_t) smem_par + stage_bytes);
                 LAUNCH_CHECK(ctx);
                 if (want_stats) {
-                    uint32_t h[5];
+                    uint32_t h[32];
                     CU_TRY(ctx, cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
                     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-                    fprintf(stderr, "[k_decode_par] T %d, warm %u, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
-                            1 << tshift, warm_bits, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
+                    {
+                        const unsigned long long *ph = reinterpret_cast<const unsigned long long *>(h) + 4;
+                        const double ctas = (double) grid_par.x * grid_par.y;
+                        fprintf(stderr, "[k_decode_par] cycles per CTA: stage %.0f, round0 %.0f, rounds %.0f, zero+scan %.0f, final %.0f, dc %.0f\n",
+                                ph[0] / ctas, ph[1] / ctas, ph[2] / ctas, ph[3] / ctas, ph[4] / ctas, ph[5] / ctas);
+                    }
+                    fprintf(stderr, "[k_decode_par] T %d, warm %u, stage %u B, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
+                            1 << tshift, warm_bits, stage_bytes, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
                 }
                 k_zero_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
                 LAUNCH_CHECK(ctx);
