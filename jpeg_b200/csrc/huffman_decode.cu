@@ -798,6 +798,15 @@ struct ParIO {             // where the bytes of one restart interval live
     uint32_t        wlim;  // words [0, wlim) need no padding
     int32_t         lead, nbytes;
     uint32_t        stage;  // shared-memory address of the staged copy (big-endian words, 1-padded past the end); 0: not staged
+    uint32_t        wlast;  // index of the last word that holds a byte of the interval (loads are clamped to it)
+    // jpeg.swift:1881-1887: bytes past the end of the interval read as 1-bits; `be` = word i, already big-endian
+    __device__ __forceinline__ uint32_t pad(uint32_t be, uint32_t i) const
+    {
+        const int first = (int) i * 4 - lead;
+        if (first >= nbytes) return 0xffffffffu;
+        const int valid = nbytes - first;
+        return valid < 4 ? be | (0xffffffffu >> (8 * valid)) : be;
+    }
     __device__ __forceinline__ uint32_t word(uint32_t i) const
     {
         if (i < wlim) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
@@ -880,7 +889,7 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
             wi += 8u;
         } else {
             hi = io.word(wi), lo = io.word(wi + 1);
-            nxt = SAFE ? __ldg(io.w0 + wi + 2) : io.word(wi + 2);
+            nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));  // raw: swapped (and padded) when it becomes lo
             wi += 3;
         }
     }
@@ -917,8 +926,10 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
                 lo = lds32(wi);
                 wi += 4u;
             } else {  // the load issued here is consumed by the NEXT refill: its latency (L2: the lanes' streams thrash L1) is hidden
-                lo = SAFE ? __byte_perm(nxt, 0, 0x0123) : nxt;
-                nxt = SAFE ? __ldg(io.w0 + wi) : io.word(wi);
+                // (the byte swap is a volatile asm so that it stays HERE, one refill after its load, instead of being hoisted to it)
+                asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));
+                if (!SAFE && wi - 1 >= io.wlim) lo = io.pad(lo, wi - 1);  // the last words of the interval: 1-padding
+                nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
                 wi += 1;
             }
             cnt -= 32u;
@@ -1127,6 +1138,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
                     q.io.lead = (int32_t) (reinterpret_cast<uintptr_t>(base) & 3);
                     q.io.w0 = reinterpret_cast<const uint32_t *>(base - q.io.lead);
                     q.io.wlim = (uint32_t) (q.io.lead + q.io.nbytes) / 4;
+                    q.io.wlast = q.io.nbytes ? (uint32_t) (q.io.lead + q.io.nbytes - 1) / 4 : 0u;
                     q.count = 8u * (uint32_t) q.io.nbytes;
                     uint32_t B = (q.count + T - 1) / T;
                     B = (B + 31u) & ~31u;
