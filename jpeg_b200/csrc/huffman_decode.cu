@@ -776,7 +776,7 @@ constexpr int PAR_THREADS = 128;
 constexpr int PAR_MAX_GROUPS = PAR_THREADS / 16;
 constexpr int PAR_MIN_BITS = 1024;
 #ifndef PAR_NSEG_N
-#define PAR_NSEG_N 2
+#define PAR_NSEG_N 4
 #endif
 constexpr int PAR_NSEG = PAR_NSEG_N;  // checkpoints per subsequence
 constexpr uint32_t PAR_BUF_STRIDE = 144;  // bytes between the threads' block buffers: 16-byte aligned, 4 banks apart
@@ -1038,7 +1038,7 @@ __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st
 }
 
 #ifndef PAR_MIN_CTAS
-#define PAR_MIN_CTAS 1
+#define PAR_MIN_CTAS 7
 #endif
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
 // stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
@@ -1055,8 +1055,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[PAR_THREADS / 32];
     __shared__ ParGroup s_grp[PAR_MAX_GROUPS];
-    __shared__ uint64_t s_ck_state[PAR_NSEG][PAR_THREADS];  // checkpoints of every subsequence's recorded parse
-    __shared__ uint32_t s_ck_cnt[PAR_NSEG][PAR_THREADS];
+    __shared__ uint32_t s_ck[PAR_NSEG][PAR_THREADS];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
     const uint32_t   T = 1u << tshift, G = PAR_THREADS >> tshift;
 #ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
@@ -1184,22 +1183,27 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
                          const bool first_time, uint64_t &exit_out) -> uint32_t {
         const uint32_t seglen = (e_bit - s_bit) / PAR_NSEG;
         uint32_t       cum = 0;
-        uint64_t       x = 0;
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
             cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
-            x = pack_state(st.p, st.z, st.b);
-            if (!first_time && x == s_ck_state[k][sid]) {  // merged: from here on the recorded parse is this parse
-                const uint32_t delta = cum - s_ck_cnt[k][sid];  // the later checkpoints keep their states; their counts shift
-                for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) s_ck_cnt[kk][sid] += delta;
+            // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
+            const uint32_t over = st.p - seg_end;
+            const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
+            const uint32_t old = s_ck[k][sid];
+            if (!first_time && code != 0xffffffffu && old != 0xffffffffu && (code & 0xffffu) == (old & 0xffffu)) {
+                // merged: from here on the recorded parse is this parse; the later checkpoints keep their states, their counts shift
+                const uint32_t delta = cum - (old >> 16);
+                for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) {
+                    const uint32_t o = s_ck[kk][sid], c2 = (o >> 16) + delta;
+                    s_ck[kk][sid] = (o == 0xffffffffu || c2 >= 0xffffu) ? 0xffffffffu : ((o & 0xffffu) | (c2 << 16));
+                }
                 exit_out = s_exit[sid];
                 return s_cnt[sid] + delta;
             }
-            s_ck_state[k][sid] = x;
-            s_ck_cnt[k][sid] = cum;
+            s_ck[k][sid] = code;
         }
-        exit_out = x;
+        exit_out = pack_state(st.p, st.z, st.b);
         return cum;
     };
     if (active) {
@@ -1768,7 +1772,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
                 while (tshift < 7 && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
                 if (env_t >= 4 && env_t <= 7) tshift = env_t;
-                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 2048u;
+                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 1024u;
                 const uint32_t G = PAR_THREADS >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
                 // shared-memory stage: twice the expected interval size per interval (larger intervals are read from global
