@@ -773,7 +773,7 @@ finished:
 //     match) flags the interval; flagged intervals are zeroed and re-decoded by k_decode_fast, which also produces the
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
 constexpr int PAR_THREADS = 128;
-constexpr int PAR_MAX_GROUPS = PAR_THREADS / 16;
+constexpr int PAR_BIG_THREADS = 512;  // CTA size for scans with few, large intervals (no DRI: one entropy-coded segment per image)
 constexpr int PAR_MIN_BITS = 1024;
 #ifndef PAR_NSEG_N
 #define PAR_NSEG_N 4
@@ -1043,21 +1043,22 @@ __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
 // stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
 // block buffers (PAR_BUF_STRIDE bytes each)
-__global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_CTAS)
+template <int NT, int MIN_CTAS>
+__global__ void __launch_bounds__(NT, MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
              uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits,
              const uint32_t stage_off, const uint32_t stage_bytes, const uint32_t buf_off)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint64_t s_exit[PAR_THREADS], s_entry[PAR_THREADS];
-    __shared__ uint32_t s_cnt[PAR_THREADS];
-    __shared__ uint8_t  s_work[PAR_THREADS];
+    __shared__ uint64_t s_exit[NT], s_entry[NT];
+    __shared__ uint32_t s_cnt[NT];
+    __shared__ uint16_t s_work[NT];
     __shared__ uint32_t s_nwork;
-    __shared__ uint32_t s_warp[PAR_THREADS / 32];
-    __shared__ ParGroup s_grp[PAR_MAX_GROUPS];
-    __shared__ uint32_t s_ck[PAR_NSEG][PAR_THREADS];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
+    __shared__ uint32_t s_warp[NT / 32];
+    __shared__ ParGroup s_grp[NT / 16];
+    __shared__ uint32_t s_ck[PAR_NSEG][NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
-    const uint32_t   T = 1u << tshift, G = PAR_THREADS >> tshift;
+    const uint32_t   T = 1u << tshift, G = NT >> tshift;
 #ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
     long long        t_phase = stats ? clock64() : 0;
 #define PAR_PHASE(k)                                                                                                 \
@@ -1084,11 +1085,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         const uint32_t   total = gh->total_all;
         uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
         const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
-        for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += PAR_THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += NT) dst[i] = src[i];
         // only the fast tables (and their sub-tables) live in shared memory; the reference LUT behind them stays in global memory
         const uint32_t ref_total = gh->total_entries;
         uint32_t      *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
-        for (uint32_t i = tid; i < (total - ref_total + 1) / 2; i += PAR_THREADS) d2[i] = src[(sizeof(LutHeader) + 2 * ref_total) / 4 + i];
+        for (uint32_t i = tid; i < (total - ref_total + 1) / 2; i += NT) d2[i] = src[(sizeof(LutHeader) + 2 * ref_total) / 4 + i];
         if (tid < 12) {
             const int      b = tid, c = P.blk_comp[b];
             const bool     has = P.plane[c] != nullptr;
@@ -1160,7 +1161,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         if (qio.stage == 0u) continue;
         const uint32_t nw = (uint32_t) (qio.lead + qio.nbytes + 3) / 4u + 4u;
         uint32_t      *dst = reinterpret_cast<uint32_t *>(smem + (qio.stage - sbase));
-        for (uint32_t i = tid; i < nw; i += PAR_THREADS) dst[i] = qio.word(i);
+        for (uint32_t i = tid; i < nw; i += NT) dst[i] = qio.word(i);
     }
     __syncthreads();
     PAR_PHASE(0);
@@ -1227,7 +1228,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         n_rounds = round;
         if (tid == 0) s_nwork = 0;
         __syncthreads();
-        if (redo) s_work[atomicAdd(&s_nwork, 1u)] = (uint8_t) tid;
+        if (redo) s_work[atomicAdd(&s_nwork, 1u)] = (uint16_t) tid;
         __syncthreads();
         const uint32_t nwork = s_nwork;
         if (nwork == 0) break;
@@ -1298,7 +1299,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
     // Work items (interval, component) are dealt to the warps; a lane owns a contiguous run of the component's blocks: it sums its
     // differences, the warp scans the lane sums, the lane walks its run again and stores the predictions.
-    for (uint32_t item = (uint32_t) wid; item < G * (uint32_t) P.n_comp; item += PAR_THREADS / 32) {
+    for (uint32_t item = (uint32_t) wid; item < G * (uint32_t) P.n_comp; item += NT / 32) {
         const uint32_t  gg = item / (uint32_t) P.n_comp;
         const int       c = (int) (item - gg * (uint32_t) P.n_comp);
         const ParGroup &q = s_grp[gg];
@@ -1768,12 +1769,15 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
                 const uint64_t est_bits = ctx->hint_interval_bytes ? 8 * ctx->hint_interval_bytes
                                                                    : 96 * rows_typ * (uint64_t) P.W * (uint64_t) volume;
-                int tshift = 7;
+                // few, large intervals (a file without DRI is ONE interval): a 512-thread CTA per interval
+                const bool big = (est_bits >> 7) >= 16384 && slots * 128 < (uint64_t) ctx->sm_count * 1024;
+                const int  nt = big ? PAR_BIG_THREADS : PAR_THREADS, tmax = big ? 9 : 7;
+                int        tshift = tmax;
                 while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
-                while (tshift < 7 && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
-                if (env_t >= 4 && env_t <= 7) tshift = env_t;
+                while (tshift < tmax && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
+                if (env_t >= 4 && env_t <= tmax) tshift = env_t;
                 const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 1024u;
-                const uint32_t G = PAR_THREADS >> tshift;
+                const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
                 // shared-memory stage: twice the expected interval size per interval (larger intervals are read from global
                 // memory), within what leaves a few CTAs per SM
@@ -1781,10 +1785,11 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 uint64_t       per_interval = env_ss ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
                 if (per_interval * G > 96 * 1024) per_interval = (96 * 1024 / G) & ~(uint64_t) 1023;
                 const uint32_t stage_bytes = (uint32_t) (per_interval * G);
-                const size_t   smem_total = smem_par + stage_bytes + (size_t) PAR_THREADS * PAR_BUF_STRIDE;
-                if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB)
-                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                    ctx->par_smem_set = 160 * 1024;
+                const size_t   smem_total = smem_par + stage_bytes + (size_t) nt * PAR_BUF_STRIDE;
+                if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    ctx->par_smem_set = 200 * 1024;
                 }
                 static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
                 uint32_t         *d_stats = nullptr;
@@ -1797,11 +1802,14 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
                 if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
                     J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, (int) (((uint64_t) n_ecs * interval) / (uint64_t) P.W)));
-                k_decode_par<<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(P, plane0, reinterpret_cast<int16_t *>(d_dc),
-                                                                                  (uint32_t) dc_per_interval,
-                                                                                  reinterpret_cast<uint32_t *>(d_flag), d_stats, tshift,
-                                                                                  warm_bits, (uint32_t) smem_par, stage_bytes,
-                                                                                  (uint32_t) smem_par + stage_bytes);
+                if (big)
+                    k_decode_par<PAR_BIG_THREADS, 1><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
+                        P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
+                        d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
+                else
+                    k_decode_par<PAR_THREADS, PAR_MIN_CTAS><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
+                        P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
+                        d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
                 LAUNCH_CHECK(ctx);
                 if (want_stats) {
                     uint32_t h[32];
