@@ -231,6 +231,20 @@ int jpeg_sm100_rgb8_to_spectral(jpeg_sm100_ctx *ctx, const uint8_t *rgb, uint32_
                                 jpeg_sm100_plane_i16 *planes, uint32_t n_planes,
                                 const uint16_t *quanta_zigzag, const int32_t *factors_xy);
 
+/* ---- N3: spectral-domain operations (no reference library function; the loops of its examples) ---- */
+
+/* the requantisation loop of examples/recompress/main.swift:35-58, one plane:
+ *   out[z] = Int16(Double(Int16(q_old[z]) * coef[z]) / Double(q_new[z]) + 0.3 * sign)      (truncating conversion) */
+int jpeg_sm100_requantize(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t units_x, uint32_t units_y,
+                          const uint16_t q_old[64], const uint16_t q_new[64], int16_t *out);
+/* the block loop of examples/rotate/main.swift:164-190, one plane: source block s lands at offset + M s, where
+ * M = ((matrix[0], matrix[1]), (matrix[2], matrix[3])) and mirrored axes start at the far end of the source plane
+ * (main.swift:168-172); destination coefficient z = source coefficient zmap[z] * mul[z] (Block.transform, main.swift:13-99).
+ * Destination blocks outside out_units are dropped, blocks nothing lands on are zero. */
+int jpeg_sm100_transform_blocks(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t units_x, uint32_t units_y,
+                                const int32_t matrix[4], const uint8_t zmap[64], const int8_t mul[64],
+                                int16_t *out, uint32_t out_units_x, uint32_t out_units_y);
+
 /* =============================================================================================================
  * LAYER B -- device pointers, asynchronous on the ctx stream, batched over images of identical geometry
  * ============================================================================================================= */
@@ -300,6 +314,13 @@ int jpeg_sm100_dev_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *
                                const jpeg_sm100_dev_spectral *spectral, uint64_t interval_mcus,
                                jpeg_sm100_huff_table *tables_out,
                                uint8_t *d_ecs, uint64_t ecs_image_stride, uint64_t *d_ecs_len);
+
+/* N3 on device batches.  q_old / q_new: HOST, n_planes x 64.  in and out must have the same plane count and image count;
+ * for requantize also the same units (in-place, out == in, is allowed); for transform_blocks `out` has its own geometry. */
+int jpeg_sm100_dev_requantize(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *in, const uint16_t *q_old,
+                              const uint16_t *q_new, const jpeg_sm100_dev_spectral *out);
+int jpeg_sm100_dev_transform_blocks(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *in, const int32_t matrix[4],
+                                    const uint8_t zmap[64], const int8_t mul[64], const jpeg_sm100_dev_spectral *out);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,15 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def _zigzag(k, h):
+    """JPEG.Table.Quantization.z(k:h:) decode.swift:1289-1298"""
+    p = 1 if k + h < 8 else 0
+    q = (k + h) & 1
+    a, b = 72 * (p ^ 1), 2 * p - 1
+    n = b * (k + h) - 14 * p + 15
+    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # data types
 # ---------------------------------------------------------------------------------------------------------------
@@ -201,6 +210,63 @@ class Spectral:
         self.ctx.check(self.ctx.L.jpeg_sm100_spectral_to_rgb8(self.ctx.h, planes, len(self.planes), _ptr(q), _ptr(f),
                                                               self.size[0], self.size[1], int(cosited), _ptr(rgb)))
         return rgb
+
+    # ---- N3: spectral-domain operations (the loops of the reference's examples, as kernels) -------------------------
+    def requantized(self, new_quanta):
+        """examples/recompress/main.swift:35-58: the same image with other quantisation tables, without leaving the
+        coefficient domain.  new_quanta: one 64-entry table (zig-zag) per entry of self.quanta."""
+        out = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx)
+        out.quanta = [np.ascontiguousarray(q, dtype=np.uint16) for q in new_quanta]
+        for src, dst in zip(self.planes, out.planes):
+            dst.q = src.q
+            coef = np.ascontiguousarray(src.coef)
+            res = np.zeros_like(coef)
+            qo = np.ascontiguousarray(self.quanta[src.q], dtype=np.uint16)
+            self.ctx.check(self.ctx.L.jpeg_sm100_requantize(self.ctx.h, _ptr(coef), src.units[0], src.units[1], _ptr(qo),
+                                                            _ptr(out.quanta[src.q]), _ptr(res)))
+            dst.coef = res
+        return out
+
+    @staticmethod
+    def block_mapping(kind):
+        """examples/rotate/main.swift:13-99, 113-152: (zmap, mul, matrix) of the rotation into quadrant 'ii' | 'iii' | 'iv'."""
+        zz = [[_zigzag(k, h) for k in range(8)] for h in range(8)]
+        blank = [(zz[y][x], 1) for y in range(8) for x in range(8)]
+        transpose = lambda a: [a[8 * x + y] for y in range(8) for x in range(8)]
+        reflect_v = lambda a: [(a[8 * y + x][0], a[8 * y + x][1] * (1 - 2 * (y & 1))) for y in range(8) for x in range(8)]
+        reflect_h = lambda a: [(a[8 * y + x][0], a[8 * y + x][1] * (1 - 2 * (x & 1))) for y in range(8) for x in range(8)]
+        result, matrix = {"ii": (reflect_v(transpose(blank)), (0, 1, -1, 0)),
+                          "iii": (reflect_v(reflect_h(blank)), (-1, 0, 0, -1)),
+                          "iv": (reflect_h(transpose(blank)), (0, -1, 1, 0))}[kind]
+        zmap, mul = np.zeros(64, dtype=np.uint8), np.zeros(64, dtype=np.int8)
+        for h in range(8):
+            for k in range(8):
+                zmap[zz[h][k]], mul[zz[h][k]] = result[8 * h + k]
+        return zmap, mul, np.array(matrix, dtype=np.int32)
+
+    def rotated(self, kind):
+        """examples/rotate/main.swift:101-199: lossless rotation; the axes that get mirrored are first cropped to whole MCUs."""
+        zmap, mul, matrix = self.block_mapping(kind)
+        w, h = self.size
+        if kind in ("ii", "iii"):
+            w -= w % (8 * self.scale[0])
+        if kind in ("iii", "iv"):
+            h -= h % (8 * self.scale[1])
+        src = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx)
+        for a, b in zip(self.planes, src.planes):
+            b.coef, b.q = a.coef, a.q
+        src.set_size((w, h))                                       # Spectral.set(width:) / set(height:)
+        out = Spectral((w, h) if kind == "iii" else (h, w), [p.factor for p in self.planes],
+                       [p.comp_id for p in self.planes], self.process, self.ctx)
+        out.quanta = [np.ascontiguousarray(q, dtype=np.uint16)[zmap] for q in self.quanta]
+        for a, b in zip(src.planes, out.planes):
+            b.q = a.q
+            coef = np.ascontiguousarray(a.coef)
+            res = np.zeros((b.units[1], b.units[0], 64), dtype=np.int16)
+            self.ctx.check(self.ctx.L.jpeg_sm100_transform_blocks(self.ctx.h, _ptr(coef), a.units[0], a.units[1], _ptr(matrix),
+                                                                  _ptr(zmap), _ptr(mul), _ptr(res), b.units[0], b.units[1]))
+            b.coef = res
+        return out
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod

@@ -140,6 +140,10 @@ SYMBOLS = {
     "jpeg_sm100_dev_decompose": (_i, [_vp, _vp, _u32, _u32, C.POINTER(DevPlanar)]),
     "jpeg_sm100_dev_fdct": (_i, [_vp, C.POINTER(DevPlanar), _vp, _i, C.POINTER(DevSpectral)]),
     "jpeg_sm100_dev_encode_scan": (_i, [_vp, _SD, C.POINTER(DevSpectral), _u64, _HT, _vp, _u64, _vp]),
+    "jpeg_sm100_requantize": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "jpeg_sm100_transform_blocks": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _u32]),
+    "jpeg_sm100_dev_requantize": (_i, [_vp, C.POINTER(DevSpectral), _vp, _vp, C.POINTER(DevSpectral)]),
+    "jpeg_sm100_dev_transform_blocks": (_i, [_vp, C.POINTER(DevSpectral), _vp, _vp, _vp, C.POINTER(DevSpectral)]),
 }
 
 _lib = None

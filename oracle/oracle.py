@@ -328,3 +328,76 @@ def decode_rgb(data: bytes):
     s = Spectral.decompress(data)
     rect = s.to_rectangular()
     return unpack_rgb(rect), unpack_ycc(rect), s
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# N3: spectral-domain operations.  The reference has no library function for these; its examples spell them out as loops
+# over Spectral.Plane subscripts, and the files those examples committed pin the arithmetic.
+# ----------------------------------------------------------------------------------------------------------------------
+def requantize(coef, q_old, q_new):
+    """examples/recompress/main.swift:46-52: Int16(q_old[z]) * c, as Double / Double(q_new[z]), + 0.3 * sign, truncated."""
+    c = coef.astype(np.int64) * np.asarray(q_old, dtype=np.int64)
+    c = c.astype(np.int16).astype(np.float64)                      # `let coefficient:Int16 = ...` (no overflow in valid files)
+    r = c / np.asarray(q_new, dtype=np.float64)
+    return np.trunc(r + 0.3 * np.where(r < 0, -1.0, 1.0)).astype(np.int16)
+
+
+def block_mapping(kind):
+    """examples/rotate/main.swift:13-99 (Block.transform) and 113-152: per output zig-zag index z the source index and the
+    sign, plus the block matrix ((xx, xy), (yx, yy)).  kind: 'ii' | 'iii' | 'iv' (quadrant the x axis is rotated into)."""
+    zz = zigzag_table()                                            # zz[h][k] = z(k: k, h: h)
+    blank = [(int(zz[y][x]), 1) for y in range(8) for x in range(8)]
+    transpose = lambda a: [a[8 * x + y] for y in range(8) for x in range(8)]
+    reflect_v = lambda a: [(a[8 * y + x][0], a[8 * y + x][1] * (1 - 2 * (y & 1))) for y in range(8) for x in range(8)]
+    reflect_h = lambda a: [(a[8 * y + x][0], a[8 * y + x][1] * (1 - 2 * (x & 1))) for y in range(8) for x in range(8)]
+    if kind == "ii":
+        result, matrix = reflect_v(transpose(blank)), ((0, 1), (-1, 0))
+    elif kind == "iii":
+        result, matrix = reflect_v(reflect_h(blank)), ((-1, 0), (0, -1))
+    elif kind == "iv":
+        result, matrix = reflect_h(transpose(blank)), ((0, -1), (1, 0))
+    else:
+        raise ValueError(kind)
+    zmap, mul = np.zeros(64, dtype=np.uint8), np.zeros(64, dtype=np.int8)
+    for h in range(8):
+        for k in range(8):
+            zmap[zz[h][k]], mul[zz[h][k]] = result[8 * h + k]
+    return zmap, mul, matrix
+
+
+def transform_blocks(src, matrix, zmap, mul, dst_units):
+    """examples/rotate/main.swift:164-190: block s of the source lands at offset + M s; coefficient z of the destination block is
+    source coefficient zmap[z] times mul[z].  src: (uy, ux, 64); destination blocks outside dst_units are dropped
+    (decode.swift:1470-1475), blocks nothing lands on stay zero."""
+    uy, ux = src.shape[:2]
+    (xx, xy), (yx, yy) = matrix
+    ox = (ux - 1 if xx < 0 else 0) + (uy - 1 if xy < 0 else 0)
+    oy = (ux - 1 if yx < 0 else 0) + (uy - 1 if yy < 0 else 0)
+    dst = np.zeros((dst_units[1], dst_units[0], 64), dtype=np.int16)
+    sy, sx = np.mgrid[0:uy, 0:ux]
+    dx, dy = ox + xx * sx + xy * sy, oy + yx * sx + yy * sy
+    ok = (dx >= 0) & (dx < dst_units[0]) & (dy >= 0) & (dy < dst_units[1])
+    vals = (src[:, :, zmap].astype(np.int32) * mul.astype(np.int32)).astype(np.int16)
+    dst[dy[ok], dx[ok]] = vals[ok]
+    return dst
+
+
+def rotated(s, kind):
+    """examples/rotate/main.swift:101-199 on an oracle Spectral: crop to whole MCUs along the axes that get mirrored
+    (Spectral.set(width:/height:), decode.swift:2456-2495), transform every plane, permute the quantisation tables."""
+    zmap, mul, matrix = block_mapping(kind)
+    w, h = s.size
+    if kind in ("ii", "iii"):
+        w -= w % (8 * s.scale[0])
+    if kind in ("iii", "iv"):
+        h -= h % (8 * s.scale[1])
+    size = (w, h) if kind == "iii" else (h, w)
+    factors = [s.factor(p) for p in range(s.ncomp)]
+    out = Spectral.create(size, factors, progressive=bool(s.process))
+    for p in range(s.ncomp):
+        fx, fy = factors[p]
+        cux, cuy = units(w * fx, 8 * s.scale[0]), units(h * fy, 8 * s.scale[1])   # plane units after the crop
+        src = s.coefficients(p)[:cuy, :cux]
+        out.coefficients(p)[...] = transform_blocks(src, matrix, zmap, mul, out.units(p))
+        out.set_quanta(p, s.quanta(p)[zmap])
+    return out

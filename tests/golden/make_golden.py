@@ -8,6 +8,7 @@ sha256 digests in manifest.json, so the fixtures stay small while remaining bit-
   * examples/decode-basic, decode-advanced (+ per-plane IDCT dumps), in-memory (.rgb and re-encoded .jpg.jpg)
   * examples/encode-basic: 32 JPEGs produced from karlie-milan-sp12-2011.rgb   (main.swift:22-57)
   * examples/recompress: original.jpg -> recompressed-requantized.jpg
+  * examples/rotate: karlie-kwk-wwdc-2017.jpg -> -ii / -iii / -iv .jpg (lossless rotations in the spectral domain)
   * examples/encode-advanced: 11-scan progressive 4:2:2 (input 1.6 MB, not copied: digest-only, checked when
     /root/reference is present)
   * tests/integration/decode/*-restart.jpg (no reference output exists; inputs only)
@@ -77,6 +78,11 @@ def main():
     rel = copy("examples/recompress/original.jpg", "examples")
     man["reencode"]["recompress-requantized"] = {
         "source": rel, **scans_of(rd("examples/recompress/recompressed-requantized.jpg"))}
+    # examples/rotate: lossless rotation in the spectral domain (N3); the three committed outputs pin the block mapping,
+    # the crop (Spectral.set(width:/height:)) and the quantisation-table permutation
+    rel = copy("examples/rotate/karlie-kwk-wwdc-2017.jpg", "examples")
+    man["rotate"] = {"source": rel, "outputs": {k: scans_of(rd(f"examples/rotate/karlie-kwk-wwdc-2017-{k}.jpg"))
+                                                 for k in ("ii", "iii", "iv")}}
     man["restart"] = [copy(f"tests/integration/decode/{n}", "restart")
                       for n in sorted(os.listdir(os.path.join(REF, "tests/integration/decode")))
                       if n.endswith("-restart.jpg")]

@@ -423,3 +423,86 @@ def test_compress_decompress_roundtrip_on_gpu(H, O):
         assert np.array_equal(a.coef, b.coef)
     rgb, _, _ = O.decode_rgb(blob)
     assert np.array_equal(rgb, back.to_rgb8())
+
+
+# ------------------------------------------------------------------------------------------------ N3: spectral-domain operations
+@pytest.mark.parametrize("kind", ["ii", "iii", "iv"])
+def test_rotate_through_gpu(manifest, H, O, kind):
+    """examples/rotate: the block-transform kernel against the oracle (itself pinned to the reference's three rotated files):
+    coefficients, permuted quantisation tables, and the re-encoded scans byte for byte."""
+    data = golden_bytes(manifest["rotate"]["source"])
+    got = H.Spectral.decompress(data).rotated(kind)
+    want = O.rotated(O.Spectral.decompress(data), kind)
+    assert got.size == want.size
+    for p in range(3):
+        assert np.array_equal(got.planes[p].coef, want.coefficients(p)), (kind, p)
+        assert np.array_equal(got.quanta[got.planes[p].q], want.quanta(p)), (kind, p)
+    exp = manifest["rotate"]["outputs"][kind]
+    for k, sc in enumerate(exp["scans"]):
+        sos = bytes.fromhex(sc["sos"])
+        n = sos[0]
+        ids = [sos[1 + 2 * i] for i in range(n)]
+        cid = [pl.comp_id for pl in got.planes]
+        comps = [(cid.index(ids[i]), sos[2 + 2 * i] >> 4, sos[2 + 2 * i] & 15) for i in range(n)]
+        band = (sos[2 * n + 1], sos[2 * n + 2] + 1)
+        al, ah = sos[2 * n + 3] & 15, sos[2 * n + 3] >> 4
+        ecs, _, _ = got.encode_scan(band, (al, None if ah == 0 else ah), comps)
+        assert len(ecs) == sc["ecs_len"] and sha(ecs) == sc["ecs_sha256"], (kind, k)
+
+
+def test_requantize_through_gpu(manifest, H, O):
+    """examples/recompress: the requantisation kernel against the oracle's restatement (pinned to recompressed-requantized.jpg)."""
+    data = golden_bytes(manifest["reencode"]["recompress-requantized"]["source"])
+    s = H.Spectral.decompress(data)
+    ref = O.Spectral.decompress(data)
+    new_q = [np.concatenate([q[:1], np.minimum(q[1:].astype(np.int64) * 3, 255)]).astype(np.uint16) for q in s.quanta]
+    got = s.requantized(new_q)
+    for p in range(3):
+        q = ref.quanta(p)
+        nq = np.concatenate([q[:1], np.minimum(q[1:].astype(np.int64) * 3, 255)]).astype(np.uint16)
+        assert np.array_equal(got.planes[p].coef, O.requantize(ref.coefficients(p), q, nq)), p
+    # random coefficients and tables, including negative values and quotients that land on the rounding boundary
+    rng = np.random.default_rng(3)
+    coef = rng.integers(-1024, 1024, (5, 7, 64), dtype=np.int16)
+    qo = rng.integers(1, 31, 64).astype(np.uint16)
+    qn = rng.integers(1, 256, 64).astype(np.uint16)
+    t = H.Spectral((56, 40), [(1, 1)])
+    t.planes[0].coef = coef
+    t.quanta = [qo]
+    assert np.array_equal(t.requantized([qn]).planes[0].coef, O.requantize(coef, qo, qn))
+
+
+def test_spectral_ops_on_device_batches(H, O):
+    """layer B of N3: a batch of two images, planes with an image stride, requantise in place, then a rotation."""
+    import ctypes as C
+
+    import torch
+    from jpeg_b200 import batch, lib
+    ctx, dev = H.default_context(), torch.device("cuda:0")
+    geo = batch.Geometry((200, 128), [(2, 2), (1, 1), (1, 1)])
+    src = batch.DeviceBuffers(geo, 2, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
+    for c in src.coef:
+        c.copy_(torch.randint(-300, 300, c.shape, generator=g, device=dev, dtype=torch.int16))
+    host = [c.cpu().numpy().copy() for c in src.coef]
+    qo = np.stack([np.arange(1, 65), np.arange(2, 66), np.arange(3, 67)]).astype(np.uint16)
+    qn = np.stack([np.arange(64, 0, -1), np.full(64, 7), np.full(64, 255)]).astype(np.uint16)
+    ctx.check(ctx.L.jpeg_sm100_dev_requantize(ctx.h, C.byref(src.sp), qo.ctypes.data, qn.ctypes.data, C.byref(src.sp)))
+    torch.cuda.synchronize()
+    req = [np.stack([O.requantize(host[p][i], qo[p], qn[p]) for i in range(2)]) for p in range(3)]
+    for p in range(3):
+        assert np.array_equal(src.coef[p].cpu().numpy(), req[p]), p
+    zmap, mul, matrix = H.Spectral.block_mapping("iv")
+    rot = batch.Geometry((128, 200), [(2, 2), (1, 1), (1, 1)])  # (the height is a whole number of MCUs: no crop)
+    dst = batch.DeviceBuffers(rot, 2, dev)
+    for c in dst.coef:
+        c.fill_(77)
+    ctx.check(ctx.L.jpeg_sm100_dev_transform_blocks(ctx.h, C.byref(src.sp), matrix.ctypes.data, zmap.ctypes.data, mul.ctypes.data,
+                                                    C.byref(dst.sp)))
+    torch.cuda.synchronize()
+    m = ((int(matrix[0]), int(matrix[1])), (int(matrix[2]), int(matrix[3])))
+    for p in range(3):
+        for i in range(2):
+            want = O.transform_blocks(req[p][i], m, zmap, mul, rot.units[p])
+            assert np.array_equal(dst.coef[p][i].cpu().numpy(), want), (p, i)

@@ -220,6 +220,19 @@ def test_recompress_requantized(manifest):
     _check_scans(rec, exp)
 
 
+@pytest.mark.parametrize("kind", ["ii", "iii", "iv"])
+def test_rotate_golden(manifest, kind):
+    """examples/rotate/main.swift: lossless rotation in the spectral domain; the re-encoded scans (tables + entropy-coded
+    bytes) and the permuted quantisation tables equal the reference's committed outputs."""
+    exp = manifest["rotate"]["outputs"][kind]
+    s = O.Spectral.decompress(golden_bytes(manifest["rotate"]["source"]))
+    r = O.rotated(s, kind)
+    cid = [r.plane_info(p)[2] for p in range(r.ncomp)]
+    assert [t[1] for t in exp["dqt"]][:2] == [r.quanta(0).tolist(), r.quanta(1).tolist()] or \
+        all(r.quanta(p).tolist() in [t[1] for t in exp["dqt"]] for p in range(r.ncomp)), cid
+    _check_scans(r, exp)
+
+
 @pytest.mark.skipif(not have_reference(), reason="input (1.6 MB) lives only in the reference checkout")
 def test_encode_advanced_golden(manifest):
     """examples/encode-advanced: 4:2:2, 11-scan progressive with successive approximation, custom quanta."""
