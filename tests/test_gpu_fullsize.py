@@ -268,7 +268,7 @@ def test_colour_kernels_agree(env, monkeypatch, size, factors):
     for s_ in buf.samples:
         s_.copy_(t.randint(0, 256, s_.shape, generator=g, device=dev, dtype=t.uint8))
     out = {}
-    for mode in ("tma", "direct", "generic"):
+    for mode in ("tma", "direct", "default", "generic"):
         monkeypatch.setenv("JPEG_SM100_COLOR", mode)
         rgb = t.full((2, H, W, 3), 7, dtype=t.uint8, device=dev)
         ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, rgb.data_ptr()))
@@ -276,3 +276,4 @@ def test_colour_kernels_agree(env, monkeypatch, size, factors):
         out[mode] = rgb
     assert t.equal(out["tma"], out["generic"])
     assert t.equal(out["direct"], out["generic"])
+    assert t.equal(out["default"], out["generic"])
