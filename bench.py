@@ -321,7 +321,7 @@ def run_ours(args):
     # while one half-batch is copying its RGB back over PCIe the other is uploading / entropy-decoding.  Every step of
     # every half-batch uploads its entropy-coded bytes from pinned memory and reads its RGB back (Bi + Bo per step).
     rgb_bytes = n * W * H * 3
-    n_streams = 2 if n >= 2 else 1
+    n_streams = max(1, min(n, int(os.environ.get("JPEG_BENCH_STREAMS", "4"))))
     halves = []
     for k in range(n_streams):
         i0, i1 = k * n // n_streams, (k + 1) * n // n_streams
@@ -364,6 +364,23 @@ def run_ours(args):
     assert int(got) == checksum, "e2e result differs from the device-resident result"
     e2e_launches = sum(h["ctx"].launches for h in halves)
 
+    # the e2e bound: every frame's 3 bytes per pixel cross PCIe once.  Measure what this link sustains device -> pinned host,
+    # same buffer size as a half-batch, so that e2e can be read as a fraction of ITS roofline (the kernels are ~7x faster).
+    d2h_gbs = None
+    try:
+        src = buf.rgb.view(-1)[:halves[0]["rgb"].numel()]
+        a0, a1 = ev(), ev()
+        halves[0]["rgb"].copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a0.record(stream)
+        for _ in range(3):
+            halves[0]["rgb"].copy_(src, non_blocking=True)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        d2h_gbs = 3 * src.numel() / (a0.elapsed_time(a1) * 1e-3) / 1e9
+    except Exception:
+        pass
+
     if world > 1:
         t = torch.tensor([ms_per_step, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -391,6 +408,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective"},
             "e2e": {"value": round(px_per_step / e2e_s / 1e6, 1), "unit": "Mpixels/s",
                     "h2d_bytes_per_step": int(raw_len.sum() + raw_len.nbytes * 2), "d2h_bytes_per_step": int(rgb_bytes + 4 * n),
+                    "pcie_d2h_GBps_measured": None if d2h_gbs is None else round(d2h_gbs, 1),
+                    "pcie_d2h_GBps_achieved": round((rgb_bytes * world / max(world, 1)) / e2e_s / 1e9, 1),
                     "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)", "steps": e2e_steps},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "roofline": {"kernel": "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",

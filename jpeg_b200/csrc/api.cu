@@ -513,7 +513,7 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
     const size_t rgb_per_image = (size_t) sx * sy * 3;
     uint32_t     chunk = (uint32_t) ((size_t) (100u << 20) / (rgb_per_image ? rgb_per_image : 1));
     chunk = chunk < 1 ? 1 : (chunk > n_images ? n_images : chunk);
-    const uint32_t n_chunks = (n_images + chunk - 1) / chunk;
+    const uint32_t n_chunks = (n_images + chunk - 1) / chunk + 4;  // (+ the partial chunk each group of images may end with)
     while (ctx->events.size() < (size_t) 2 * n_chunks) {
         cudaEvent_t ev;
         CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -549,44 +549,77 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
         for (uint32_t i = 0; i < n_images; ++i) in_bytes = raw_offsets[i] + raw_lengths[i] > in_bytes ? raw_offsets[i] + raw_lengths[i] : in_bytes;
     else
         in_bytes = offsets[n_off - 1];
+    // The batch is cut into groups of images that go through the whole pipeline one after the other on the stream, so that the
+    // first RGB leaves the device after one group's upload + entropy decode instead of the whole batch's: the device -> host
+    // copy of 3 bytes per pixel is what bounds this call, and it should start early and never pause.
+    uint32_t group = (n_images + 3) / 4;
+    group = group < 8 ? 8 : group;
+    group = (group + chunk - 1) / chunk * chunk;  // whole chunks
+    group = group > n_images ? n_images : group;
+    const uint32_t n_groups = (n_images + group - 1) / group;
     const size_t rgb_chunk = align_up(rgb_per_image * chunk, 256);
-    J_TRY(scratch_reserve(ctx, 1, in_bytes + 64, &d_ecs));
-    J_TRY(scratch_reserve(ctx, 2, n_off * 8, &d_off));
+    J_TRY(scratch_reserve(ctx, 1, in_bytes + 16 * ((size_t) n_groups + 1) + 64, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 2, (n_off + n_groups) * 8, &d_off));
     J_TRY(scratch_reserve(ctx, 3, 2 * sizeof(int32_t) * n_images + 64, &d_status));
     J_TRY(scratch_reserve(ctx, 6, 2 * rgb_chunk + 64, &d_rgb));
+    if (raw_offsets) J_TRY(scratch_reserve(ctx, 5, in_bytes + 64, &d_raw));
     int32_t *d_lex_status = reinterpret_cast<int32_t *>(d_status) + n_images;
+    if (!raw_offsets) CU_TRY(ctx, cudaMemsetAsync(d_lex_status, 0, sizeof(int32_t) * n_images, ctx->stream));
 
-    if (raw_offsets) {
-        J_TRY(scratch_reserve(ctx, 5, in_bytes + 64, &d_raw));
-        if (in_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_raw, bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        LexPlan plan;
-        J_TRY(jpeg_lex_count(ctx, reinterpret_cast<uint8_t *>(d_raw), raw_offsets, raw_lengths, n_images, &plan));
-        J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, n_ecs, reinterpret_cast<uint8_t *>(d_ecs),
-                               reinterpret_cast<uint64_t *>(d_off), d_lex_status));
-    } else {
-        if (in_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CU_TRY(ctx, cudaMemcpyAsync(d_off, offsets, n_off * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU_TRY(ctx, cudaMemsetAsync(d_lex_status, 0, sizeof(int32_t) * n_images, ctx->stream));
-    }
-    // Spectral planes start zeroed (decode.swift:2241-2256): SCAN_FRESH lets K3 clear the rows it fills itself
-    ctx->hint_interval_bytes = in_bytes / ((uint64_t) n_images * n_ecs);
-    const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
-                                            interval, JPEG_SM100_SCAN_FRESH, tables, tables_shared, &sp, reinterpret_cast<int32_t *>(d_status));
-    ctx->hint_interval_bytes = 0;
-    J_TRY(k3);
-    for (uint32_t k = 0; k < n_chunks; ++k) {
-        const uint32_t i0 = k * chunk, cnt = (i0 + chunk <= n_images) ? chunk : n_images - i0;
-        uint8_t       *rgb_buf = reinterpret_cast<uint8_t *>(d_rgb) + (k & 1) * rgb_chunk;
-        jpeg_sm100_dev_spectral spk = sp;
-        spk.n_images = pl.n_images = cnt;
-        for (uint32_t p = 0; p < n_planes; ++p) spk.plane[p].coef = sp.plane[p].coef + (size_t) i0 * sp.plane[p].image_stride;
-        if (k >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[k - 2], 0));  // RGB buffer (k & 1) is free again
-        J_TRY(jpeg_sm100_dev_idct(ctx, &spk, quanta, 8, &pl));
-        J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, rgb_buf));
-        CU_TRY(ctx, cudaEventRecord(ev_k[k], ctx->stream));
-        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k[k], 0));
-        CU_TRY(ctx, cudaMemcpyAsync(rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
-        CU_TRY(ctx, cudaEventRecord(ev_out[k], ctx->copy_out));
+    uint32_t k = 0;  // running chunk index (the two RGB buffers alternate over the whole call)
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const uint32_t g0 = g * group, gn = (g0 + group <= n_images) ? group : n_images - g0;
+        // ---- this group's bytes: host -> device, at the same offsets they have on the host
+        uint64_t b0, b1;
+        if (raw_offsets) {
+            b0 = UINT64_MAX, b1 = 0;
+            for (uint32_t i = g0; i < g0 + gn; ++i) {
+                b0 = raw_offsets[i] < b0 ? raw_offsets[i] : b0;
+                b1 = raw_offsets[i] + raw_lengths[i] > b1 ? raw_offsets[i] + raw_lengths[i] : b1;
+            }
+            if (b1 < b0) b0 = b1 = 0;
+        } else {
+            b0 = offsets[(uint64_t) g0 * n_ecs], b1 = offsets[(uint64_t) (g0 + gn) * n_ecs];
+        }
+        uint8_t  *g_ecs;
+        uint64_t *g_off = reinterpret_cast<uint64_t *>(d_off) + (uint64_t) g0 * n_ecs + g;  // gn * n_ecs + 1 entries
+        if (raw_offsets) {
+            if (b1 > b0) CU_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_raw) + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
+            // the lexer writes the group's unstuffed bytes (never more than the raw ones) to a 16-byte aligned region of its own
+            g_ecs = reinterpret_cast<uint8_t *>(d_ecs) + align_up(b0, 16) + 16 * (size_t) g;
+            LexPlan plan;
+            J_TRY(jpeg_lex_count(ctx, reinterpret_cast<uint8_t *>(d_raw), raw_offsets + g0, raw_lengths + g0, gn, &plan));
+            J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, n_ecs, g_ecs, g_off, d_lex_status + g0));
+        } else {
+            g_ecs = reinterpret_cast<uint8_t *>(d_ecs);  // offsets stay absolute
+            if (b1 > b0) CU_TRY(ctx, cudaMemcpyAsync(g_ecs + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(g_off, offsets + (uint64_t) g0 * n_ecs, ((uint64_t) gn * n_ecs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        // ---- entropy decode of the group.  Spectral planes start zeroed (decode.swift:2241-2256): SCAN_FRESH
+        jpeg_sm100_dev_spectral spg = sp;
+        spg.n_images = gn;
+        for (uint32_t p = 0; p < n_planes; ++p) spg.plane[p].coef = sp.plane[p].coef + (size_t) g0 * sp.plane[p].image_stride;
+        ctx->hint_interval_bytes = (b1 - b0) / ((uint64_t) gn * n_ecs);
+        const int k3 = jpeg_huffman_decode_scan(ctx, scan, g_ecs, g_off, n_ecs, interval, JPEG_SM100_SCAN_FRESH,
+                                                tables + (tables_shared ? 0 : (size_t) 8 * g0), tables_shared, &spg,
+                                                reinterpret_cast<int32_t *>(d_status) + g0);
+        ctx->hint_interval_bytes = 0;
+        J_TRY(k3);
+        // ---- transform + colour, chunk by chunk; each chunk's RGB goes home on the copy stream while the next is computed
+        for (uint32_t c0 = 0; c0 < gn; c0 += chunk, ++k) {
+            const uint32_t i0 = g0 + c0, cnt = (c0 + chunk <= gn) ? chunk : gn - c0;
+            uint8_t       *rgb_buf = reinterpret_cast<uint8_t *>(d_rgb) + (k & 1) * rgb_chunk;
+            jpeg_sm100_dev_spectral spk = sp;
+            spk.n_images = pl.n_images = cnt;
+            for (uint32_t p = 0; p < n_planes; ++p) spk.plane[p].coef = sp.plane[p].coef + (size_t) i0 * sp.plane[p].image_stride;
+            if (k >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[k - 2], 0));  // RGB buffer (k & 1) is free again
+            J_TRY(jpeg_sm100_dev_idct(ctx, &spk, quanta, 8, &pl));
+            J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, rgb_buf));
+            CU_TRY(ctx, cudaEventRecord(ev_k[k], ctx->stream));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k[k], 0));
+            CU_TRY(ctx, cudaMemcpyAsync(rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CU_TRY(ctx, cudaEventRecord(ev_out[k], ctx->copy_out));
+        }
     }
     std::vector<int32_t> st(2 * (size_t) n_images, 0);
     CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, 2 * sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
