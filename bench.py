@@ -3,12 +3,14 @@
 
     python bench.py --gpus N --steps K --warmup W            our CUDA path (libjpeg_sm100.so)
     python bench.py --impl reference ...                      the reference's CPU path (restated oracle), host cores
+    python bench.py --quick [--sweep T:WARM,...]              device-resident stage times only (kernel A/B runs; not a bench line)
 
-A "step" is one pass of the hot path over one batch: scan lexing (N1: unstuff + RSTn split) -> entropy decode (K3) ->
-dequantise + IDCT (K1) -> upsample + YCbCr->RGB + pack (K2).  `value` times it with every input (the raw scan bytes
-of the files) already resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` times the same work
-through the host-buffer C-ABI call jpeg_sm100_decode_batch_raw_rgb8 with pinned host buffers, H2D and D2H copies
-inside the timed region.
+A "step" is one pass of the hot path over one batch: scan lexing (N1: unstuff + RSTn split) -> entropy decode (K3, which also
+clears the fresh coefficient planes and resolves the DC predictions) -> dequantise + IDCT (K1) -> upsample + YCbCr->RGB +
+pack (K2).  `value` times it with every input (the raw scan bytes of the files) already resident in HBM (CUDA events on the
+launching stream, max over ranks); `e2e` times the same work through the host-buffer C-ABI call
+jpeg_sm100_decode_batch_raw_rgb8 with pinned host buffers, H2D and D2H copies inside the timed region, and reports next to
+it what the PCIe link itself sustains device -> host (the e2e bound: 3 bytes of RGB per pixel leave the device).
 Inputs are produced by our own GPU encoder (K4-K7) from deterministic synthetic frames, DRI = one MCU row.
 Multi-GPU: independent images are sharded across ranks, no collective on the data path ("weak": 64 frames per GPU).
 Prints ONE JSON line on rank 0.
@@ -42,6 +44,15 @@ def k1_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
             return int(json.load(f)["dram_bytes_per_launch_avg"])
+    except Exception:
+        return None
+
+
+def k3_traffic():
+    """DRAM bytes of one k_decode_par launch (64 frames) from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
+            return int(json.load(f)["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -317,9 +328,10 @@ def run_ours(args):
         return
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------------------
-    # Images are independent, so the batch is sharded over two contexts (one stream each) driven by two host threads:
-    # while one half-batch is copying its RGB back over PCIe the other is uploading / entropy-decoding.  Every step of
-    # every half-batch uploads its entropy-coded bytes from pinned memory and reads its RGB back (Bi + Bo per step).
+    # Images are independent, so the batch is sharded over a few contexts (one stream each) driven by as many host threads:
+    # while one share is copying its RGB back over PCIe another is uploading / entropy-decoding.  (One call for the whole
+    # batch reaches ~95 % of this by itself: the entry point pipelines groups of images internally; JPEG_BENCH_STREAMS=1.)
+    # Every step of every share uploads its raw scan bytes from pinned memory and reads its RGB back (Bi + Bo per step).
     rgb_bytes = n * W * H * 3
     n_streams = max(1, min(n, int(os.environ.get("JPEG_BENCH_STREAMS", "4"))))
     halves = []
@@ -416,9 +428,9 @@ def run_ours(args):
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": k1_traffic() if n == BATCH else None,
                          "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5)},
-            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode, 128 threads per restart interval) + k_zero_flagged + k_decode_fast(flagged only) + k_dc_resolve + k_reduce_status; latency/issue-bound, not HBM-bound",
+            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 32 threads per restart interval, blocks assembled in shared memory and stored as whole lines, DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; bound by instruction issue and the LSU pipe (ncu: profiles/), not by HBM",
                                   "bound": "hbm", "achieved": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                                  "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                                  "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": k3_traffic() if n == BATCH else None,
                                   "bytes_per_launch": int(huff_bytes), "ms_per_launch": round(huff_ms, 4),
                                   "share_of_step": shares["huffman"]},
             "stages": {"ms": {k: round(statistics.mean(v), 4) for k, v in stage_ms.items()}, "share_of_step": shares,
