@@ -558,6 +558,63 @@ k_decompose(const void *__restrict__ src, const __grid_constant__ PlanarView V, 
     }
 }
 
+// K4 fast paths: RGB8 -> 8-bit YCbCr planes in one pass (RGB.pack jpeg.swift:584-599 fused with decomposed() encode.swift:389-425)
+// for 4:2:0 (SUB = true: thread = 8 x 2 pixels -> 16 Y, 4 Cb, 4 Cr) and 4:4:4 (thread = 8 pixels), image sizes that are whole
+// MCUs (so the planes have no padding to fill and no edge to clamp).  Each pixel is converted to integer YCbCr first, exactly
+// as RGB.pack does; the 2 x 2 box mean UInt16(Float(sum) / Float(4)) of encode.swift:413-420 is exact and truncating: sum >> 2.
+// The generic kernel reads every RGB pixel three times (once per plane) with 1-byte loads: 8.0 ms per 64 4K frames; this
+// reads them once with 8-byte loads.
+template <bool SUB>
+__global__ void __launch_bounds__(128)
+k_rgb8_to_ycc_planes(const uint8_t *__restrict__ rgb, const __grid_constant__ PlanarView V)
+{
+    constexpr int  ROWS = SUB ? 2 : 1;
+    const int      W = V.size_x, H = V.size_y;
+    const int      groups_x = W / 8, rows_y = H / ROWS;
+    const uint64_t per_image = (uint64_t) groups_x * rows_y;
+    const uint64_t total = per_image * V.n_images;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per_image);
+        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
+        const int      ry = (int) (rem / groups_x), gx = (int) (rem - (uint32_t) ry * groups_x);
+        const int      x0 = 8 * gx, y0 = ROWS * ry;
+        uint32_t       cbs[ROWS][8], crs[ROWS][8];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const uint2 *src = reinterpret_cast<const uint2 *>(rgb + (((size_t) img * H + y0 + k) * W + x0) * 3);
+            const uint2  a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            uint32_t       yv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t R = byte_of(w[(3 * j) >> 2], (3 * j) & 3), G = byte_of(w[(3 * j + 1) >> 2], (3 * j + 1) & 3),
+                               B = byte_of(w[(3 * j + 2) >> 2], (3 * j + 2) & 3);
+                rgb_to_ycc(R, G, B, yv[j], cbs[k][j], crs[k][j]);
+            }
+            uint8_t *Yp = reinterpret_cast<uint8_t *>(const_cast<void *>(V.samples[0])) + (size_t) img * V.image_stride[0];
+            *reinterpret_cast<uint2 *>(Yp + (size_t) V.width[0] * (y0 + k) + x0) =
+                make_uint2(yv[0] | yv[1] << 8 | yv[2] << 16 | yv[3] << 24, yv[4] | yv[5] << 8 | yv[6] << 16 | yv[7] << 24);
+        }
+        uint8_t *Cb = reinterpret_cast<uint8_t *>(const_cast<void *>(V.samples[1])) + (size_t) img * V.image_stride[1];
+        uint8_t *Cr = reinterpret_cast<uint8_t *>(const_cast<void *>(V.samples[2])) + (size_t) img * V.image_stride[2];
+        if (SUB) {
+            uint32_t pb = 0, pr = 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                pb |= ((cbs[0][2 * m] + cbs[0][2 * m + 1] + cbs[ROWS - 1][2 * m] + cbs[ROWS - 1][2 * m + 1]) >> 2) << (8 * m);
+                pr |= ((crs[0][2 * m] + crs[0][2 * m + 1] + crs[ROWS - 1][2 * m] + crs[ROWS - 1][2 * m + 1]) >> 2) << (8 * m);
+            }
+            *reinterpret_cast<uint32_t *>(Cb + (size_t) V.width[1] * ry + 4 * gx) = pb;
+            *reinterpret_cast<uint32_t *>(Cr + (size_t) V.width[2] * ry + 4 * gx) = pr;
+        } else {
+            *reinterpret_cast<uint2 *>(Cb + (size_t) V.width[1] * y0 + x0) =
+                make_uint2(cbs[0][0] | cbs[0][1] << 8 | cbs[0][2] << 16 | cbs[0][3] << 24, cbs[0][4] | cbs[0][5] << 8 | cbs[0][6] << 16 | cbs[0][7] << 24);
+            *reinterpret_cast<uint2 *>(Cr + (size_t) V.width[2] * y0 + x0) =
+                make_uint2(crs[0][0] | crs[0][1] << 8 | crs[0][2] << 16 | crs[0][3] << 24, crs[0][4] | crs[0][5] << 8 | crs[0][6] << 16 | crs[0][7] << 24);
+        }
+    }
+}
+
 int fill_view(const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy, int cosited, PlanarView &V)
 {
     if (!pl || pl->n_planes < 1 || pl->n_planes > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
@@ -685,6 +742,25 @@ int jpeg_color_decompose(jpeg_sm100_ctx *ctx, const void *d_src, bool src_is_rgb
     PlanarView V;
     J_TRY(fill_view(pl, sx, sy, 0, V));
     if (src_is_rgb8 && V.n_planes != 1 && V.n_planes != 3) return JPEG_SM100_ERR_UNSUPPORTED;
+    {   // fused fast paths (see k_rgb8_to_ycc_planes)
+        const char *e = getenv("JPEG_SM100_COLOR");
+        const bool  generic = e && strcmp(e, "generic") == 0;
+        bool        ok = src_is_rgb8 && !generic && V.n_planes == 3 && pl->sample_bytes == 1 && pl->n_images > 0 &&
+                  (reinterpret_cast<uintptr_t>(d_src) & 7) == 0 && V.fx[1] == 1 && V.fy[1] == 1 && V.fx[2] == 1 && V.fy[2] == 1;
+        const bool sub = ok && V.fx[0] == 2 && V.fy[0] == 2, full = ok && V.fx[0] == 1 && V.fy[0] == 1;
+        const int  mx = sub ? 16 : 8;
+        ok = (sub || full) && sx % mx == 0 && sy % mx == 0 && sx > 0 && sy > 0;
+        for (int p = 0; p < 3 && ok; ++p)
+            ok = V.width[p] == (int) (sx * V.fx[p] / V.scale_x) && V.height[p] == (int) (sy * V.fy[p] / V.scale_y) &&
+                 (reinterpret_cast<uintptr_t>(V.samples[p]) & 7) == 0 && (V.image_stride[p] & 7) == 0;
+        if (ok) {
+            const uint64_t work = (uint64_t) (sx / 8) * (sy / (sub ? 2 : 1)) * pl->n_images;
+            if (sub) k_rgb8_to_ycc_planes<true><<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(reinterpret_cast<const uint8_t *>(d_src), V);
+            else k_rgb8_to_ycc_planes<false><<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(reinterpret_cast<const uint8_t *>(d_src), V);
+            LAUNCH_CHECK(ctx);
+            return JPEG_SM100_OK;
+        }
+    }
     for (int p = 0; p < V.n_planes; ++p) {
         if (V.scale_x % V.fx[p] || V.scale_y % V.fy[p]) return JPEG_SM100_ERR_UNSUPPORTED;
         const uint64_t work = (uint64_t) V.width[p] * V.height[p] * V.n_images;

@@ -277,3 +277,28 @@ def test_colour_kernels_agree(env, monkeypatch, size, factors):
     assert t.equal(out["tma"], out["generic"])
     assert t.equal(out["direct"], out["generic"])
     assert t.equal(out["default"], out["generic"])
+
+
+@pytest.mark.parametrize("size,factors", [((3840, 2160), [(2, 2), (1, 1), (1, 1)]), ((4000, 3000), [(1, 1), (1, 1), (1, 1)]),
+                                          ((64, 48), [(2, 2), (1, 1), (1, 1)]), ((40, 24), [(1, 1), (1, 1), (1, 1)]),
+                                          ((50, 34), [(2, 2), (1, 1), (1, 1)])])
+def test_forward_colour_kernels_agree(env, monkeypatch, size, factors):
+    """K4: the fused RGB8 -> YCbCr-planes kernels against the reference-literal per-plane kernel (itself checked against the
+    oracle in test_gpu_parity) on random pixels; (50, 34) is not a whole number of MCUs and must take the generic path."""
+    t, b, ctx, dev = env["torch"], env["batch"], env["ctx"], env["dev"]
+    W, H = size
+    geo = b.Geometry(size, factors)
+    g = t.Generator(device=dev)
+    g.manual_seed(17)
+    rgb = t.randint(0, 256, (2, H, W, 3), generator=g, device=dev, dtype=t.uint8)
+    out = {}
+    for mode in ("default", "generic"):
+        monkeypatch.setenv("JPEG_SM100_COLOR", mode)
+        buf = b.DeviceBuffers(geo, 2, dev)
+        for s_ in buf.samples:
+            s_.fill_(9)
+        ctx.check(ctx.L.jpeg_sm100_dev_rgb8_to_planar(ctx.h, rgb.data_ptr(), W, H, C.byref(buf.pl)))
+        t.cuda.synchronize()
+        out[mode] = [s_.clone() for s_ in buf.samples]
+    for p in range(3):
+        assert t.equal(out["default"][p], out["generic"][p]), p
