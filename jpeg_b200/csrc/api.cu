@@ -74,6 +74,8 @@ JPEG_API void jpeg_sm100_destroy(jpeg_sm100_ctx *ctx)
         if (p.done) cudaEventDestroy(p.done);
     }
     for (auto &e : ctx->events) cudaEventDestroy(e);
+    for (auto &e : ctx->idle)
+        if (e) cudaEventDestroy(e);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -623,8 +625,22 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
     }
     std::vector<int32_t> st(2 * (size_t) n_images, 0);
     CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, 2 * sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+    // the batch call waits tens of milliseconds for PCIe: sleep on blocking events instead of spinning on the stream, so that
+    // several of these calls (one per context / per GPU process) do not fight over host cores
+    static const bool spin = getenv("JPEG_SM100_SPIN") != nullptr;  // A/B: plain stream synchronisation
+    if (spin) {
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+    } else {
+    if (!ctx->idle[0]) {
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->idle[0], cudaEventBlockingSync | cudaEventDisableTiming));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->idle[1], cudaEventBlockingSync | cudaEventDisableTiming));
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->idle[0], ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->idle[1], ctx->copy_out));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->idle[0]));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->idle[1]));
+    }
     int first = 0;
     for (uint32_t i = 0; i < n_images; ++i) {
         // a lexer error is raised before the scan is pushed (decode.swift:3929), so it wins over a decode error
