@@ -110,6 +110,30 @@ def test_idct_random_blocks(H, O, ux, uy):
     assert np.array_equal(s.idct_u8()[0], ref.astype(np.uint8))
 
 
+@pytest.mark.parametrize("precision", [8, 12, 16])
+def test_idct_fdct_other_precisions(H, O, precision):
+    """N4 (first step): Plane.idct(quanta:precision:) / Plane.fdct(_:quanta:precision:) with the precision of a 12-bit or 16-bit
+    frame (level shift 2^(P-1), clamp to 2^P - 1) and 16-bit quantisation tables, 16-bit samples in and out."""
+    import ctypes as C
+    ctx = H.default_context()
+    rng = np.random.default_rng(precision)
+    ux, uy = 19, 7
+    top = (1 << precision) - 1
+    coef = rng.integers(-40, 40, size=(uy, ux, 64)).astype(np.int16)
+    coef[..., 0] = rng.integers(-top // 16, top // 16, size=(uy, ux))
+    coef[rng.random((uy, ux)) < 0.1] *= 20
+    q = rng.integers(1, 600 if precision > 8 else 255, size=64).astype(np.uint16)
+    got = np.zeros((8 * uy, 8 * ux), dtype=np.uint16)
+    ctx.check(ctx.L.jpeg_sm100_idct(ctx.h, C.c_void_p(coef.ctypes.data), ux, uy, C.c_void_p(q.ctypes.data), precision,
+                                    C.c_void_p(got.ctypes.data)))
+    assert np.array_equal(got, O.idct_plane(coef, q, precision)), precision
+    samples = rng.integers(0, top + 1, size=(8 * uy, 8 * ux)).astype(np.uint16)
+    back = np.zeros((uy, ux, 64), dtype=np.int16)
+    ctx.check(ctx.L.jpeg_sm100_fdct(ctx.h, C.c_void_p(samples.ctypes.data), ux, uy, C.c_void_p(q.ctypes.data), precision,
+                                    C.c_void_p(back.ctypes.data)))
+    assert np.array_equal(back, O.fdct_plane(samples, q, precision)), precision
+
+
 def test_idct_empty_plane(H):
     s = H.Spectral((8, 8), [(1, 1)])
     s.planes[0].coef = np.zeros((0, 0, 64), np.int16)
