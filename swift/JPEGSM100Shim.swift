@@ -233,6 +233,48 @@ extension JPEG.RGB
     }
 }
 
+// MARK: spectral-domain operations (N3)
+//
+// The reference has no library function for these: examples/recompress/main.swift:35-58 and examples/rotate/main.swift:164-190
+// write them as loops over `Plane[x:y:z:]`.  These conveniences run the same arithmetic on the GPU, plane by plane.
+extension JPEG.Data.Spectral.Plane
+{
+    /// examples/recompress/main.swift:46-52: Int16(Double(Int16(old[z]) * c) / Double(new[z]) + 0.3 * sign)
+    func sm100Requantized(from old:JPEG.Table.Quantization, to new:JPEG.Table.Quantization) throws -> [Int16]
+    {
+        let count:Int = 64 * self.units.x * self.units.y
+        return try .init(unsafeUninitializedCapacity: count)
+        {
+            (out:inout UnsafeMutableBufferPointer<Int16>, initialized:inout Int) in
+            try self.withUnsafeCoefficients
+            {
+                try JPEG.SM100.check(jpeg_sm100_requantize(JPEG.SM100.shared.ctx, $0.baseAddress,
+                    .init(self.units.x), .init(self.units.y), old.storage, new.storage, out.baseAddress))
+            }
+            initialized = count
+        }
+    }
+    /// examples/rotate/main.swift:164-190: block s lands at offset + M s, coefficient z = source[mapping[z].z] * multiplier
+    func sm100Transformed(matrix:(x:(x:Int, y:Int), y:(x:Int, y:Int)), mapping:[(z:Int, multiplier:Int16)],
+        units:(x:Int, y:Int)) throws -> [Int16]
+    {
+        let count:Int       = 64 * units.x * units.y
+        let m:[Int32]       = [.init(matrix.x.x), .init(matrix.x.y), .init(matrix.y.x), .init(matrix.y.y)]
+        let zmap:[UInt8]    = mapping.map{ .init($0.z) }
+        let mul:[Int8]      = mapping.map{ .init($0.multiplier) }
+        return try .init(unsafeUninitializedCapacity: count)
+        {
+            (out:inout UnsafeMutableBufferPointer<Int16>, initialized:inout Int) in
+            try self.withUnsafeCoefficients
+            {
+                try JPEG.SM100.check(jpeg_sm100_transform_blocks(JPEG.SM100.shared.ctx, $0.baseAddress,
+                    .init(self.units.x), .init(self.units.y), m, zmap, mul, out.baseAddress, .init(units.x), .init(units.y)))
+            }
+            initialized = count
+        }
+    }
+}
+
 // MARK: encode seams (mirror image; same pattern)
 //
 //   JPEG.RGB.pack(_:as:)                 jpeg.swift:584   -> jpeg_sm100_pack_rgb8
