@@ -141,13 +141,49 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
     // prefixes that longer codes share.  Everything is derived from the reference LUT just written, entry for entry.
     __shared__ uint8_t  s_depth[FAST_ENTRIES];
     __shared__ uint16_t s_off[FAST_ENTRIES];
+    __shared__ uint32_t s_total;
+    // the same layout sub_depths() computes on the host, spread over the CTA: clear, mark the (few) prefixes under long codes,
+    // prefix-sum the sub-table sizes (warp 0, FAST_ENTRIES / 32 slots per lane)
+    for (uint32_t i = threadIdx.x; i < (uint32_t) FAST_ENTRIES; i += blockDim.x) s_depth[i] = 0;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        sub_depths(counts, s_depth);
-        uint32_t o = FAST_ENTRIES;
-        for (int i = 0; i < FAST_ENTRIES; ++i) {
-            s_off[i] = (uint16_t) o;
-            if (s_depth[i]) o += 1u << s_depth[i];
+        uint32_t code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            if (l > FAST_BITS && counts[l - 1]) {
+                const int      d = l - FAST_BITS;
+                const uint32_t p0 = code >> d, p1 = (code + counts[l - 1] - 1u) >> d;
+                for (uint32_t p = p0; p <= p1 && p < (uint32_t) FAST_ENTRIES; ++p)
+                    if (s_depth[p] < d) s_depth[p] = (uint8_t) d;
+            }
+            code = (code + counts[l - 1]) << 1;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        constexpr int PER = FAST_ENTRIES / 32;
+        uint32_t      sum = 0;
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t d = s_depth[threadIdx.x * PER + k];
+            sum += d ? 1u << d : 0u;
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (threadIdx.x >= (uint32_t) d) inc += y;
+        }
+        if (threadIdx.x == 31) s_total = inc;
+        uint32_t o = FAST_ENTRIES + inc - sum;
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t d = s_depth[threadIdx.x * PER + k];
+            s_off[threadIdx.x * PER + k] = (uint16_t) o;
+            o += d ? 1u << d : 0u;
+        }
+    }
+    __syncthreads();
+    if (s_total > SUB_MAX) {  // too many sub-table entries: this table keeps the reference lookup for its long codes
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < (uint32_t) FAST_ENTRIES; i += blockDim.x) s_depth[i] = 0;
     }
     __syncthreads();
     uint32_t *fast = reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(dst + sizeof(LutHeader)) + h.fast[ti]);

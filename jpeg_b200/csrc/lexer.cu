@@ -104,7 +104,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 // pass 1: per-tile totals.  grid = (tiles_max, n_images)
 __global__ void __launch_bounds__(LEX_THREADS) k_lex_count(const uint8_t *__restrict__ raw, const LexImage *__restrict__ images,
                                                             uint32_t tiles_max, uint32_t *__restrict__ tile_counts,
-                                                            uint32_t *__restrict__ foreign)
+                                                            uint32_t *__restrict__ foreign, unsigned long long *__restrict__ img_emit,
+                                                            uint32_t *__restrict__ img_split)
 {
     const uint32_t img = blockIdx.y, tile = blockIdx.x;
     const LexImage im = images[img];
@@ -118,53 +119,67 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_count(const uint8_t *__rest
     }
     uint32_t total;
     block_exclusive_scan(v, &total);
-    if (threadIdx.x == 0) tile_counts[(size_t) img * tiles_max + tile] = total;
+    if (threadIdx.x == 0) {
+        tile_counts[(size_t) img * tiles_max + tile] = total;
+        if (total) {  // per-image totals: the second level of the scan
+            atomicAdd(&img_emit[img], (unsigned long long) (total & 0xFFFFu));
+            if (total >> 16) atomicAdd(&img_split[img], total >> 16);
+        }
+    }
     if (bad) atomicOr(&foreign[img], 1u);
 }
 
-// pass 2: one CTA.  Exclusive scan over all (image-major) tile totals: 64-bit emitted-byte bases, 32-bit split bases.
-__global__ void __launch_bounds__(1024) k_lex_scan(const uint32_t *__restrict__ tile_counts, uint64_t n_tiles, uint64_t *__restrict__ emit_base,
-                                                   uint32_t *__restrict__ split_base)
+// pass 2: one CTA per image.  Exclusive scan over all (image-major) tile totals -- 64-bit emitted-byte bases, 32-bit split bases --
+// in two levels: the image's base is the sum of the totals of the images before it (k_lex_count accumulated them), its tiles
+// are scanned by the CTA.  (A single CTA walking all n_images * tiles_max totals took 70 us of the lexer's 360.)
+__global__ void __launch_bounds__(1024) k_lex_scan(const uint32_t *__restrict__ tile_counts, uint32_t tiles_max, uint32_t n_images,
+                                                   const unsigned long long *__restrict__ img_emit, const uint32_t *__restrict__ img_split,
+                                                   uint64_t *__restrict__ emit_base, uint32_t *__restrict__ split_base)
 {
-    __shared__ uint64_t s_e[1024];
-    __shared__ uint32_t s_s[1024];
-    const uint64_t per = (n_tiles + 1023) / 1024;
-    const uint64_t b = threadIdx.x * per, e = (b + per < n_tiles) ? b + per : n_tiles;
-    uint64_t       se = 0;
-    uint32_t       ss = 0;
-    for (uint64_t i = b; i < e; ++i) {
-        const uint32_t c = tile_counts[i];
-        se += c & 0xFFFFu;
-        ss += c >> 16;
-    }
-    s_e[threadIdx.x] = se;
-    s_s[threadIdx.x] = ss;
+    __shared__ unsigned long long s_base_e;
+    __shared__ uint32_t           s_base_s, s_we[32], s_ws[32];
+    const uint32_t img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base_e = 0, s_base_s = 0;
     __syncthreads();
-    // Hillis-Steele over 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint64_t ae = 0;
-        uint32_t as = 0;
-        if ((int) threadIdx.x >= d) {
-            ae = s_e[threadIdx.x - d];
-            as = s_s[threadIdx.x - d];
+    {
+        unsigned long long e = 0;
+        uint32_t           sp = 0;
+        for (uint32_t j = tid; j < img; j += 1024) e += img_emit[j], sp += img_split[j];
+        if (e) atomicAdd(&s_base_e, e);
+        if (sp) atomicAdd(&s_base_s, sp);
+    }
+    __syncthreads();
+    uint64_t carry_e = s_base_e;
+    uint32_t carry_s = s_base_s;
+    for (uint32_t t0 = 0; t0 < tiles_max; t0 += 1024) {
+        const uint32_t t = t0 + tid;
+        const uint32_t c = t < tiles_max ? tile_counts[(size_t) img * tiles_max + t] : 0u;
+        uint32_t       e = c & 0xFFFFu, sp = c >> 16;  // a chunk of 1024 tiles emits < 2^22 bytes
+        const uint32_t e0 = e, s0 = sp;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, e, d), os = __shfl_up_sync(0xFFFFFFFFu, sp, d);
+            if (lane >= (uint32_t) d) e += oe, sp += os;
         }
+        if (lane == 31) s_we[warp] = e, s_ws[warp] = sp;
         __syncthreads();
-        s_e[threadIdx.x] += ae;
-        s_s[threadIdx.x] += as;
+        uint32_t be = 0, bs = 0, te = 0, ts = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t we = s_we[i], ws = s_ws[i];
+            if ((uint32_t) i < warp) be += we, bs += ws;
+            te += we, ts += ws;
+        }
+        if (t < tiles_max) {
+            emit_base[(size_t) img * tiles_max + t] = carry_e + be + e - e0;
+            split_base[(size_t) img * tiles_max + t] = carry_s + bs + sp - s0;
+        }
+        carry_e += te, carry_s += ts;
         __syncthreads();
     }
-    uint64_t re = s_e[threadIdx.x] - se;
-    uint32_t rs = s_s[threadIdx.x] - ss;
-    for (uint64_t i = b; i < e; ++i) {
-        const uint32_t c = tile_counts[i];
-        emit_base[i] = re;
-        split_base[i] = rs;
-        re += c & 0xFFFFu;
-        rs += c >> 16;
-    }
-    if (threadIdx.x == 1023) {
-        emit_base[n_tiles] = s_e[1023];
-        split_base[n_tiles] = s_s[1023];
+    if (img + 1 == n_images && tid == 0) {
+        emit_base[(size_t) n_images * tiles_max] = carry_e;
+        split_base[(size_t) n_images * tiles_max] = carry_s;
     }
 }
 
@@ -296,6 +311,8 @@ int jpeg_lex_count(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *ra
     off += (4 * (plan->n_tiles + 1) + 255) & ~(size_t) 255;
     const size_t o_flags = off;
     off += ((size_t) 12 * n_images + 255) & ~(size_t) 255;
+    const size_t o_totals = off;  // per image: emitted bytes (u64) | splits (u32)
+    off += ((size_t) 12 * n_images + 255) & ~(size_t) 255;
     void *base = nullptr;
     J_TRY(scratch_reserve(ctx, 15, off, &base));
     uint8_t *b = reinterpret_cast<uint8_t *>(base);
@@ -316,10 +333,15 @@ int jpeg_lex_count(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *ra
     J_TRY(pinned_release(ctx, slot));
     CU_TRY(ctx, cudaMemsetAsync(plan->d_foreign, 0, 4 * (size_t) n_images, ctx->stream));
     CU_TRY(ctx, cudaMemsetAsync(plan->d_bad_phase, 0xFF, 4 * (size_t) n_images, ctx->stream));
+    unsigned long long *d_img_emit = reinterpret_cast<unsigned long long *>(b + o_totals);
+    uint32_t           *d_img_split = reinterpret_cast<uint32_t *>(b + o_totals + 8 * (size_t) n_images);
+    CU_TRY(ctx, cudaMemsetAsync(d_img_emit, 0, 12 * (size_t) n_images, ctx->stream));
     const dim3 grid(plan->tiles_max, n_images);
-    k_lex_count<<<grid, LEX_THREADS, 0, ctx->stream>>>(d_raw, reinterpret_cast<const LexImage *>(plan->d_images), plan->tiles_max, plan->d_counts, plan->d_foreign);
+    k_lex_count<<<grid, LEX_THREADS, 0, ctx->stream>>>(d_raw, reinterpret_cast<const LexImage *>(plan->d_images), plan->tiles_max, plan->d_counts,
+                                                       plan->d_foreign, d_img_emit, d_img_split);
     LAUNCH_CHECK(ctx);
-    k_lex_scan<<<1, 1024, 0, ctx->stream>>>(plan->d_counts, plan->n_tiles, plan->d_emit_base, plan->d_split_base);
+    k_lex_scan<<<n_images, 1024, 0, ctx->stream>>>(plan->d_counts, plan->tiles_max, n_images, d_img_emit, d_img_split, plan->d_emit_base,
+                                                   plan->d_split_base);
     LAUNCH_CHECK(ctx);
     return JPEG_SM100_OK;
 }

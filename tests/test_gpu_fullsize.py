@@ -148,6 +148,39 @@ def test_single_ecs_without_restart_intervals(env, monkeypatch):
         assert d_st.cpu().tolist() == [0, 0]
         for p in range(3):
             assert t.equal(buf.coef[p], enc.coef[p]), (warm, p)
+    # the second image's segment cut short: the parallel decoder flags it, the sequential one reports the reference's error
+    # (DecodingError.truncatedEntropyCodedSegment); the first image is unaffected
+    cut = inputs.offsets.copy()
+    cut[2] = cut[1] + (cut[2] - cut[1]) // 2
+    d_cut = t.from_numpy(cut.view(np.int64)).to(dev)
+    for c in buf.coef:
+        c.fill_(-1)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_cut.data_ptr(), 1, lib.INTERVAL_NONE,
+                                               lib.SCAN_FRESH, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    assert d_st.cpu().tolist() == [0, lib.ERR_TRUNCATED_ECS]
+    for p in range(3):
+        assert t.equal(buf.coef[p][0], enc.coef[p][0]), p
+    # garbage in the middle of the first image's segment: same verdict and, if it decodes, the same coefficients as the oracle
+    junk = inputs.ecs.copy()
+    rng = np.random.default_rng(2)
+    mid = int(inputs.offsets[1]) // 2
+    junk[mid:mid + 4096] = rng.integers(0, 256, 4096, dtype=np.uint8)
+    d_junk = t.from_numpy(junk).to(dev)
+    ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_junk.data_ptr(), d_off.data_ptr(), 1, lib.INTERVAL_NONE,
+                                               lib.SCAN_FRESH, tarr, 0, C.byref(buf.sp), d_st.data_ptr()))
+    t.cuda.synchronize()
+    dct, act = _tables_to_oracle(O, tabs, 0)
+    ref = O.Spectral.create((W, H), geo.factors)
+    try:
+        ref.decode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], dct, act, [junk[:int(inputs.offsets[1])].tobytes()])
+        want = 0
+    except O.OracleError as e:
+        want = e.code
+    assert d_st.cpu().tolist()[0] == want
+    if want == 0:
+        for p in range(3):
+            assert np.array_equal(buf.coef[p][0].cpu().numpy(), ref.coefficients(p)), p
 
 
 def test_config3_4k_420_encode(env):
