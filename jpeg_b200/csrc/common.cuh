@@ -41,7 +41,6 @@ struct jpeg_sm100_ctx {
     // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> events;
-    cudaEvent_t idle[2] = {nullptr, nullptr};  // blocking-sync events the batch entry point sleeps on
     // average bytes per restart interval of the next entropy-decode call, when the caller knows it (0: unknown); consumed by K3
     uint64_t hint_interval_bytes = 0;
     size_t   par_smem_set = 0;  // largest dynamic shared-memory size k_decode_par has been opted into on this device
