@@ -92,6 +92,27 @@ def test_cosited_and_generic_upsampling(H, O, manifest):
             assert np.array_equal(got.unpack_rgb(), O.unpack_rgb(ref))
 
 
+def test_four_planes_of_12_bit_samples(H, O):
+    """N4 (kernel level): a custom JPEG.Format with four components and 12-bit samples (examples/custom-color) reaches the same
+    kernels -- interleaved(cosite:) over four 16-bit planes with mixed sampling factors, centred and co-sited -- and decomposed()
+    back."""
+    rng = np.random.default_rng(12)
+    size = (150, 70)
+    factors = [(2, 2), (1, 1), (1, 2), (2, 1)]
+    sx, sy = 2, 2
+    us = [(-(-size[0] * fx // (8 * sx)), -(-size[1] * fy // (8 * sy))) for fx, fy in factors]
+    planes = [rng.integers(0, 4096, size=(8 * uy, 8 * ux)).astype(np.uint16) for ux, uy in us]
+    for cosited in (False, True):
+        ref = O.interleave(planes, us, factors, size, cosited)
+        got = H.Planar(size, us, factors, [p.copy() for p in planes]).interleaved(cosite=cosited)
+        assert np.array_equal(got.values, ref), cosited
+    il = rng.integers(0, 4096, size=(size[1], size[0], 4)).astype(np.uint16)
+    back = H.Rectangular(size, factors, il).decomposed()
+    want = O.decompose(il, factors)
+    for p in range(4):
+        assert np.array_equal(back.planes[p], want[p]), p
+
+
 # ------------------------------------------------------------------------------------------------ single stages
 @pytest.mark.parametrize("ux,uy", [(1, 1), (3, 2), (17, 5), (128, 1), (129, 3), (40, 40)])
 def test_idct_random_blocks(H, O, ux, uy):
