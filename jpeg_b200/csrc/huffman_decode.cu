@@ -964,7 +964,9 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
             } else {  // the load issued here is consumed by the NEXT refill: its latency (L2: the lanes' streams thrash L1) is hidden
                 // (the byte swap is a volatile asm so that it stays HERE, one refill after its load, instead of being hoisted to it)
                 asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));
-                if (!SAFE && wi - 1 >= io.wlim) lo = io.pad(lo, wi - 1);  // the last words of the interval: 1-padding
+                // No 1-padding (jpeg.swift:1881-1887) here: a symbol that lies inside the interval is decoded from its own bits
+                // whatever follows them (prefix code), and a symbol that reaches past the end trips the check below and sends the
+                // interval to the sequential decoder, which pads.  Loads are only clamped to the interval's last word.
                 nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
                 wi += 1;
             }
