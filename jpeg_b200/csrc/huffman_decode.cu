@@ -15,6 +15,8 @@
 //   * The reference's two-level (8 + 8 bit) LUT is reproduced entry for entry and staged in shared memory
 //     (a few KB for real tables); oversized tables fall back to global memory.
 //   * Coefficients go straight to their final zig-zag slot in the Spectral.Plane layout, 64 * (units_x * y + x) + z.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -1075,6 +1077,95 @@ __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st
     return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
 }
 
+// ---- prologue shared by the subsequence-parallel kernels ---------------------------------------------------------------------
+// shared-memory image of one table set: LutHeader | ParBlk[12] (in the BlkInfo area) | fast tables + sub-tables.  The reference
+// LUT behind them stays in global memory (only invalid codewords, EOBn and DC category 16 ever look at it).
+template <int NT>
+__device__ __forceinline__ void par_stage_tables(const ScanParams &P, const int16_t *plane0, const uint32_t img, const uint32_t tid,
+                                                 uint8_t *smem, const uint8_t *lut_img)
+{
+    constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
+    const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
+    ParBlk          *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
+    const int        nblk = P.mcu_blocks;
+    const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
+    const uint32_t   total = gh->total_all;
+    uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
+    for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += NT) dst[i] = src[i];
+    const uint32_t ref_total = gh->total_entries;
+    uint32_t      *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
+    for (uint32_t i = tid; i < (total - ref_total + 1) / 2; i += NT) d2[i] = src[(sizeof(LutHeader) + 2 * ref_total) / 4 + i];
+    if (tid < 12) {
+        const int      b = tid, c = P.blk_comp[b];
+        const bool     has = P.plane[c] != nullptr;
+        const uint32_t ux = (uint32_t) P.ux[c], uy = (uint32_t) P.uy[c], fx = (uint32_t) P.fx[c], fy = (uint32_t) P.fy[c];
+        const uint32_t dx = P.blk_dx[b], dy = P.blk_dy[b];
+        const uint32_t base_blk = has ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
+        ParBlk         pb;
+        pb.C = base_blk + dx + dy * ux, pb.fx = fx, pb.R = fy * ux;
+        const uint32_t LX = (has && ux > dx) ? min((ux - dx + fx - 1u) / fx, 0xffffu) : 0u;
+        const uint32_t LY = (has && uy > dy) ? min((uy - dy + fy - 1u) / fy, 0xffffu) : 0u;
+        pb.lim = LX | (LY << 16);
+        pb.dtab = sbase + PRE + 2u * (gh->fast[P.dc[c]] - ref_total), pb.atab = sbase + PRE + 2u * (gh->fast[P.ac[c]] - ref_total);
+        pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u);
+        pb.next = blk0 + (uint32_t) ((b + 1 == nblk) ? 0 : b + 1) * (uint32_t) sizeof(ParBlk) + 16u;
+        s_blk[b] = pb;
+    }
+}
+
+// interval e of image img, cut into at most T subsequences; stage_addr / stage_cap: its share of the shared-memory stage (0: none)
+__device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const uint32_t img, const uint32_t e, const uint32_t T,
+                                                    const uint32_t dc_per_interval, uint32_t *flagged, const uint32_t stage_addr,
+                                                    const uint32_t stage_cap)
+{
+    ParGroup q;
+    memset(&q, 0, sizeof q);
+    q.valid = e < P.n_ecs;
+    if (!q.valid) return q;
+    const int W = P.W, nblk = P.mcu_blocks;
+    int64_t   r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    q.r0 = (int32_t) r0, q.r1 = (int32_t) r1;
+    q.slot = img * P.n_ecs + e;
+    const uint64_t n_total = (uint64_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
+    const uint64_t o0 = P.offsets[q.slot], o1 = P.offsets[q.slot + 1];
+    if (n_total == 0) {  // nothing to decode: the reference's row loop does not run
+        if (flagged) {
+            flagged[q.slot] = 0;
+            if (P.status) P.status[q.slot] = 0;
+        }
+    } else if ((o1 - o0) > 0x07ffffffull || n_total > dc_per_interval) {
+        if (flagged) flagged[q.slot] = 1;  // 32-bit bit positions / side-array capacity: left to the sequential kernel
+    } else {
+        const uint8_t *base = P.ecs + o0;
+        q.N_total = (uint32_t) n_total;
+        q.io.nbytes = (int32_t) (o1 - o0);
+        q.io.lead = (int32_t) (reinterpret_cast<uintptr_t>(base) & 3);
+        q.io.w0 = reinterpret_cast<const uint32_t *>(base - q.io.lead);
+        q.io.wlim = (uint32_t) (q.io.lead + q.io.nbytes) / 4;
+        q.io.wlast = q.io.nbytes ? (uint32_t) (q.io.lead + q.io.nbytes - 1) / 4 : 0u;
+        q.count = 8u * (uint32_t) q.io.nbytes;
+        uint32_t B = (q.count + T - 1) / T;
+        B = (B + 31u) & ~31u;
+        if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
+        q.B = B;
+        q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
+        // shared-memory copy: the words of the interval plus four words of 1-padding, if its share of the stage holds them
+        const uint32_t need = ((uint32_t) (q.io.lead + q.io.nbytes + 3) / 4u + 4u) * 4u;
+        q.io.stage = (stage_cap && need <= stage_cap) ? stage_addr : 0u;
+    }
+    return q;
+}
+
 #ifndef PAR_MIN_CTAS
 #define PAR_MIN_CTAS 7
 #endif
@@ -1118,79 +1209,10 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
     const uint16_t  *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
     const int        W = P.W, nblk = P.mcu_blocks;
-    {
-        const LutHeader *gh = reinterpret_cast<const LutHeader *>(lut_img);
-        const uint32_t   total = gh->total_all;
-        uint32_t        *dst = reinterpret_cast<uint32_t *>(smem);
-        const uint32_t  *src = reinterpret_cast<const uint32_t *>(lut_img);
-        for (uint32_t i = tid; i < sizeof(LutHeader) / 4; i += NT) dst[i] = src[i];
-        // only the fast tables (and their sub-tables) live in shared memory; the reference LUT behind them stays in global memory
-        const uint32_t ref_total = gh->total_entries;
-        uint32_t      *d2 = reinterpret_cast<uint32_t *>(smem + PRE);
-        for (uint32_t i = tid; i < (total - ref_total + 1) / 2; i += NT) d2[i] = src[(sizeof(LutHeader) + 2 * ref_total) / 4 + i];
-        if (tid < 12) {
-            const int      b = tid, c = P.blk_comp[b];
-            const bool     has = P.plane[c] != nullptr;
-            const uint32_t ux = (uint32_t) P.ux[c], uy = (uint32_t) P.uy[c], fx = (uint32_t) P.fx[c], fy = (uint32_t) P.fy[c];
-            const uint32_t dx = P.blk_dx[b], dy = P.blk_dy[b];
-            const uint32_t base_blk = has ? (uint32_t) ((P.plane[c] + (size_t) img * P.image_stride[c] - plane0) / 64) : 0u;
-            ParBlk         pb;
-            pb.C = base_blk + dx + dy * ux, pb.fx = fx, pb.R = fy * ux;
-            const uint32_t LX = (has && ux > dx) ? min((ux - dx + fx - 1u) / fx, 0xffffu) : 0u;
-            const uint32_t LY = (has && uy > dy) ? min((uy - dy + fy - 1u) / fy, 0xffffu) : 0u;
-            pb.lim = LX | (LY << 16);
-            pb.dtab = sbase + PRE + 2u * (gh->fast[P.dc[c]] - ref_total), pb.atab = sbase + PRE + 2u * (gh->fast[P.ac[c]] - ref_total);
-            pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u);
-            pb.next = blk0 + (uint32_t) ((b + 1 == nblk) ? 0 : b + 1) * (uint32_t) sizeof(ParBlk) + 16u;
-            s_blk[b] = pb;
-        }
-        if (tid >= 32 && tid < 32 + G) {  // one thread per interval of the CTA: where its bytes are, how it is cut
-            ParGroup       q;
-            const uint32_t e = blockIdx.x * G + (tid - 32);
-            memset(&q, 0, sizeof q);
-            q.valid = e < P.n_ecs;
-            if (q.valid) {
-                int64_t r0, r1;
-                if (P.interval == UINT64_MAX) {
-                    r0 = 0;
-                    r1 = P.H;
-                } else {
-                    r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) W);
-                    r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) W);
-                    if (r0 > P.H) r0 = P.H;
-                    if (r1 > P.H) r1 = P.H;
-                }
-                q.r0 = (int32_t) r0, q.r1 = (int32_t) r1;
-                q.slot = img * P.n_ecs + e;
-                const uint64_t n_total = (uint64_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
-                const uint64_t o0 = P.offsets[q.slot], o1 = P.offsets[q.slot + 1];
-                if (n_total == 0) {  // nothing to decode: the reference's row loop does not run
-                    flagged[q.slot] = 0;
-                    if (P.status) P.status[q.slot] = 0;
-                } else if ((o1 - o0) > 0x07ffffffull || n_total > dc_per_interval) {
-                    flagged[q.slot] = 1;  // 32-bit bit positions / side-array capacity: left to the sequential kernel
-                } else {
-                    const uint8_t *base = P.ecs + o0;
-                    q.N_total = (uint32_t) n_total;
-                    q.io.nbytes = (int32_t) (o1 - o0);
-                    q.io.lead = (int32_t) (reinterpret_cast<uintptr_t>(base) & 3);
-                    q.io.w0 = reinterpret_cast<const uint32_t *>(base - q.io.lead);
-                    q.io.wlim = (uint32_t) (q.io.lead + q.io.nbytes) / 4;
-                    q.io.wlast = q.io.nbytes ? (uint32_t) (q.io.lead + q.io.nbytes - 1) / 4 : 0u;
-                    q.count = 8u * (uint32_t) q.io.nbytes;
-                    uint32_t B = (q.count + T - 1) / T;
-                    B = (B + 31u) & ~31u;
-                    if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
-                    q.B = B;
-                    q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
-                    // shared-memory copy: the words of the interval plus four words of 1-padding, if its share of the stage holds them
-                    const uint32_t cap = (stage_bytes / G) & ~15u, need = ((uint32_t) (q.io.lead + q.io.nbytes + 3) / 4u + 4u) * 4u;
-                    q.io.stage = need <= cap ? sbase + stage_off + (tid - 32) * cap : 0u;
-                }
-            }
-            s_grp[tid - 32] = q;
-        }
-    }
+    par_stage_tables<NT>(P, plane0, img, tid, smem, lut_img);
+    if (tid >= 32 && tid < 32 + G)  // one thread per interval of the CTA: where its bytes are, how it is cut
+        s_grp[tid - 32] = par_setup_group(P, img, blockIdx.x * G + (tid - 32), T, dc_per_interval, flagged,
+                                          sbase + stage_off + (tid - 32) * ((stage_bytes / G) & ~15u), (stage_bytes / G) & ~15u);
     __syncthreads();
     // ---- stage the intervals in shared memory: every byte is read from global memory once (coalesced), byte-swapped and
     // 1-padded (jpeg.swift:1881-1887) on the way; all parsing passes then refill from shared memory
@@ -1390,6 +1412,223 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             atomicMax(&stats[4], n_rounds);
         }
     }
+}
+
+// ---- the same decoder for FEW, LARGE intervals: a thread-block cluster per interval -------------------------------------------
+// A file without DRI is one entropy-coded segment per scan (the reference's own encoder never emits DRI), i.e. ONE interval per
+// image.  A cluster of up to 8 CTAs x 128 threads shares it: subsequence l = cluster rank * 128 + thread.  Everything a thread
+// needs from a neighbour -- the predecessor's exit state across a CTA border, the other CTAs' work counts, block totals, DC
+// sums -- is read from the owner's shared memory through DSMEM (mapa / ld.shared::cluster) between barrier.cluster syncs;
+// nothing goes through global memory except the coefficients and the DC side array.  Same records, same rounds, same
+// decoding pass as k_decode_par (see there); grid = (cluster size * n_ecs, n_images), cluster = (cluster size, 1, 1).
+constexpr int CL_THREADS = 128;
+
+__global__ void __launch_bounds__(CL_THREADS, 4)
+k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
+                     uint32_t *const flagged, const uint32_t warm_bits, const uint32_t buf_off)
+{
+    namespace cg = cooperative_groups;
+    constexpr int NT = CL_THREADS;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t    crank = cluster.block_rank(), csize = cluster.num_blocks();
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint64_t s_exit[NT], s_entry[NT];
+    __shared__ uint32_t s_cnt[NT];
+    __shared__ uint16_t s_work[NT];
+    __shared__ uint32_t s_nwork, s_ctatotal, s_bad, s_total;
+    __shared__ uint32_t s_warp[NT / 32];
+    __shared__ int      s_dcw[4][NT / 32];
+    __shared__ ParGroup s_q;
+    __shared__ uint32_t s_ck[PAR_NSEG][NT];
+    const uint32_t  img = blockIdx.y, tid = threadIdx.x, e = blockIdx.x / csize;
+    const uint32_t  T = NT * csize, l = crank * NT + tid;
+    const int       lane = tid & 31, wid = tid >> 5;
+    const uint8_t  *lut_img = P.luts + (size_t) img * P.lut_stride;
+    ParBlk         *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
+    const uint32_t  sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
+    const uint16_t *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
+    const int       W = P.W, nblk = P.mcu_blocks;
+    // values other CTAs of the cluster hold in their shared memory
+    auto remote64 = [&](uint64_t *p_, uint32_t r) -> uint64_t { return *cluster.map_shared_rank(p_, r); };
+    auto remote32 = [&](uint32_t *p_, uint32_t r) -> uint32_t { return *cluster.map_shared_rank(p_, r); };
+    par_stage_tables<NT>(P, plane0, img, tid, smem, lut_img);
+    if (tid == 32) s_q = par_setup_group(P, img, e, T, dc_per_interval, crank == 0 ? flagged : nullptr, 0u, 0u);
+    if (tid == 0) s_nwork = 0, s_ctatotal = 0, s_bad = 0, s_total = 0;
+    __syncthreads();
+    const ParIO    io = s_q.io;
+    const uint32_t count = s_q.count, B = s_q.B, S = s_q.S, N_total = s_q.N_total, slot = s_q.slot;
+    const bool     active = l < S, mine = S != 0u;
+    const uint32_t start_bit = l * B, end_bit = (l + 1 == S) ? count : (l + 1) * B;
+    ParseState     st;
+    bool           bad;
+    auto parse_sub = [&](const uint32_t s_bit, const uint32_t e_bit, const uint32_t sid, const bool first_time, uint64_t &exit_out) -> uint32_t {
+        const uint32_t seglen = (e_bit - s_bit) / PAR_NSEG;
+        uint32_t       cum = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
+            const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
+            cum += par_run_auto<false>(io, st, seg_end, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            const uint32_t over = st.p - seg_end;
+            const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
+            const uint32_t old = s_ck[k][sid];
+            if (!first_time && code != 0xffffffffu && old != 0xffffffffu && (code & 0xffffu) == (old & 0xffffu)) {
+                const uint32_t delta = cum - (old >> 16);
+                for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) {
+                    const uint32_t o = s_ck[kk][sid], c2 = (o >> 16) + delta;
+                    s_ck[kk][sid] = (o == 0xffffffffu || c2 >= 0xffffu) ? 0xffffffffu : ((o & 0xffffu) | (c2 << 16));
+                }
+                exit_out = s_exit[sid];
+                return s_cnt[sid] + delta;
+            }
+            s_ck[k][sid] = code;
+        }
+        exit_out = pack_state(st.p, st.z, st.b);
+        return cum;
+    };
+    // ---- round 0 ----
+    if (active) {
+        st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
+        if (l > 0 && warm_bits) par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+        if (l > 0 && !warm_bits) st.p = start_bit;
+        s_entry[tid] = pack_state(st.p, st.z, st.b);
+        uint64_t       x;
+        const uint32_t c = parse_sub(start_bit, end_bit, tid, true, x);
+        s_cnt[tid] = c;
+        s_exit[tid] = x;
+    } else {
+        s_entry[tid] = 0, s_exit[tid] = 0, s_cnt[tid] = 0;
+    }
+    cluster.sync();
+    // ---- synchronisation rounds (the predecessor of a CTA's first subsequence lives in the previous CTA) ----
+    for (uint32_t round = 1; round <= T + 1; ++round) {
+        uint64_t prev = 0;
+        if (active && l >= 1) prev = tid > 0 ? s_exit[tid - 1] : remote64(&s_exit[NT - 1], crank - 1);
+        const bool redo = active && l >= 1 && prev != s_entry[tid];
+        if (tid == 0) s_nwork = 0;
+        __syncthreads();
+        if (redo) s_work[atomicAdd(&s_nwork, 1u)] = (uint16_t) tid;
+        cluster.sync();
+        uint32_t pending = 0;
+        for (uint32_t r = 0; r < csize; ++r) pending += remote32(&s_nwork, r);
+        if (pending == 0) break;  // (the same sum in every thread of the cluster)
+        const uint32_t nwork = s_nwork;
+        uint64_t       x = 0;
+        if (tid < nwork) {
+            const uint32_t sid = s_work[tid], ll = crank * NT + sid;
+            const uint64_t entry = sid > 0 ? s_exit[sid - 1] : remote64(&s_exit[NT - 1], crank - 1);
+            const uint32_t e_bit = (ll + 1 == S) ? count : (ll + 1) * B;
+            st = unpack_state(entry);
+            const uint32_t c = parse_sub(ll * B, e_bit, sid, false, x);
+            s_cnt[sid] = c;
+            s_entry[sid] = entry;
+        }
+        cluster.sync();  // every exit has been read ...
+        if (tid < nwork) s_exit[s_work[tid]] = x;
+        cluster.sync();  // ... before any is replaced
+    }
+    // ---- first block of every subsequence: scan inside the CTA, then the totals of the CTAs before this one ----
+    const uint32_t my_cnt = s_cnt[tid];
+    uint32_t       incl = my_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t before = incl - my_cnt;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    if (tid == NT - 1) s_ctatotal = before + my_cnt;
+    cluster.sync();
+    for (uint32_t r = 0; r < crank; ++r) before += remote32(&s_ctatotal, r);
+    // ---- the decoding pass ----
+    int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
+    if (active) {
+        st = unpack_state(s_entry[tid]);
+        uint32_t done = 0;
+        bad = false;
+        if (before < N_total)
+            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_q.r0, plane0, dcdiff,
+                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+        if (bad || (before < N_total && done != my_cnt)) atomicOr(&s_bad, 1u);
+        atomicAdd(&s_total, done);
+    }
+    cluster.sync();
+    uint32_t bad_all = 0, total_all = 0;
+    for (uint32_t r = 0; r < csize; ++r) bad_all |= remote32(&s_bad, r), total_all += remote32(&s_total, r);
+    const bool f = mine && (bad_all != 0u || total_all != N_total);
+    if (mine && crank == 0 && tid == 0) {
+        flagged[slot] = f ? 1u : 0u;
+        if (!f && P.status) P.status[slot] = 0;
+    }
+    // ---- DC differences -> DC coefficients.  Every warp of the cluster takes a contiguous range of each component's blocks:
+    // lane runs are summed, warps publish their totals, everybody adds up the totals before its own (DSMEM), second walk stores.
+    // The side array was written by other SMs: L2 loads (ld.global.cg), ordered by the cluster barrier above.
+    const bool     do_dc = mine && !f;
+    const uint32_t warps_cta = NT / 32, gw = crank * warps_cta + (uint32_t) wid, n_gw = csize * warps_cta;
+    int            lane_ex[4] = {0, 0, 0, 0};
+    uint32_t       rk0[4] = {0, 0, 0, 0}, rk1[4] = {0, 0, 0, 0};
+    {
+        uint32_t fb = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c >= P.n_comp) break;
+            const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
+            if (do_dc && P.plane[c]) {
+                const uint32_t K = (uint32_t) (s_q.r1 - s_q.r0) * (uint32_t) W * nc;
+                const uint32_t per = (K + n_gw - 1) / n_gw, w0 = min(gw * per, K), w1 = min(w0 + per, K);
+                const uint32_t R = (w1 - w0 + 31u) / 32u, k0 = min(w0 + (uint32_t) lane * R, w1), k1 = min(k0 + R, w1);
+                int            sum = 0;
+                uint32_t       mcu = k0 / nc, j = k0 - mcu * nc;
+                for (uint32_t k = k0; k < k1; ++k) {
+                    sum += (int) __ldcg(dcdiff + mcu * (uint32_t) nblk + fb + j);
+                    if (++j == nc) j = 0, ++mcu;
+                }
+                int inc2 = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, inc2, d);
+                    if (lane >= d) inc2 += y;
+                }
+                lane_ex[c] = inc2 - sum, rk0[c] = k0, rk1[c] = k1;
+                if (lane == 31) s_dcw[c][wid] = inc2;
+            } else if (lane == 31)
+                s_dcw[c][wid] = 0;
+            fb += nc;
+        }
+    }
+    cluster.sync();
+    if (do_dc) {
+        uint32_t fb = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c >= P.n_comp) break;
+            const uint32_t nc = (uint32_t) (P.fx[c] * P.fy[c]);
+            if (P.plane[c]) {
+                // totals of the warps before this one: lane j fetches warp j's (there are at most 32 warps in a cluster of 8)
+                int part = 0;
+                for (uint32_t j = (uint32_t) lane; j < gw; j += 32) part += *cluster.map_shared_rank(&s_dcw[c][j % warps_cta], j / warps_cta);
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                int            run = part + lane_ex[c];
+                const uint32_t uW = (uint32_t) W;
+                uint32_t       mcu = rk0[c] / nc, j = rk0[c] - mcu * nc;
+                uint32_t       my = (uint32_t) s_q.r0 + mcu / uW, mx = mcu - (mcu / uW) * uW;
+                for (uint32_t k = rk0[c]; k < rk1[c]; ++k) {
+                    run += (int) __ldcg(dcdiff + mcu * (uint32_t) nblk + fb + j);
+                    const ParBlk &pb = s_blk[fb + j];
+                    if (mx < (pb.lim & 0xffffu) && my < (pb.lim >> 16))
+                        plane0[(int64_t) (int32_t) (pb.C + mx * pb.fx + my * pb.R) * 64] = (int16_t) ((uint32_t) (int) (short) run << P.al);
+                    if (++j == nc) {
+                        j = 0, ++mcu;
+                        if (++mx == uW) mx = 0, ++my;
+                    }
+                }
+            }
+            fb += nc;
+        }
+    }
+    cluster.sync();  // no CTA leaves while another may still read its shared memory
 }
 
 // zero the blocks of flagged intervals before the sequential kernel re-decodes them
@@ -1840,7 +2079,25 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
                 if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
                     J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, (int) (((uint64_t) n_ecs * interval) / (uint64_t) P.W)));
-                if (big)
+                // few, large intervals: a cluster of CTAs per interval (JPEG_SM100_PAR_CLUSTER=0: one 512-thread CTA, kept for A/B)
+                const char *env_cl = getenv("JPEG_SM100_PAR_CLUSTER");
+                uint32_t    csize = big ? (env_cl ? (uint32_t) atoi(env_cl) : 8u) : 0u;
+                while (csize > 1 && (est_bits / (CL_THREADS * csize)) < 2048) csize >>= 1;
+                if (csize > 8 || (csize & (csize - 1))) csize = 8;
+                if (big && csize >= 1 && !(env_cl && atoi(env_cl) == 0)) {
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof cfg);
+                    cfg.gridDim = dim3(csize * n_ecs, n_images);
+                    cfg.blockDim = dim3(CL_THREADS);
+                    cfg.dynamicSmemBytes = smem_par + (size_t) CL_THREADS * PAR_BUF_STRIDE;
+                    cfg.stream = ctx->stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr, cfg.numAttrs = 1;
+                    CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_decode_par_cluster, P, plane0, reinterpret_cast<int16_t *>(d_dc),
+                                                   (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag), warm_bits, (uint32_t) smem_par));
+                } else if (big)
                     k_decode_par<PAR_BIG_THREADS, 1><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
                         d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
