@@ -505,6 +505,155 @@ __global__ void __launch_bounds__(1024) k_enc_stuff(const __grid_constant__ EncP
     if (threadIdx.x == 0) P.out_len[img] = carry;
 }
 
+// ---- the same byte stuffing as a two-kernel stream expansion over 4 KB tiles of the raw stream (k_enc_stuff walks an image
+// with ONE CTA: 1.26 ms per 64 4K frames; this is HBM-bound).  The output position of raw byte i is
+//     i  +  (FF bytes before i)  +  2 * (index of the interval i lies in)            [every interval but the first is led by RSTn]
+constexpr int STUFF_THREADS = 256, STUFF_CHUNK = 16, STUFF_TILE = STUFF_THREADS * STUFF_CHUNK;
+
+__global__ void __launch_bounds__(STUFF_THREADS) k_enc_stuff_count(const __grid_constant__ EncParams P, uint32_t tiles_max, uint32_t *tile_ff)
+{
+    const uint32_t  img = blockIdx.y, tile = blockIdx.x;
+    const uint64_t  total = P.ivl[(size_t) img * (P.n_intervals + 1) + P.n_intervals];
+    const uint8_t  *raw = reinterpret_cast<const uint8_t *>(P.raw) + (size_t) img * P.raw_stride;
+    const uint64_t  i0 = (uint64_t) tile * STUFF_TILE + threadIdx.x * STUFF_CHUNK;
+    uint32_t        n = 0;
+    if (i0 < total) {
+        const uint4    v = *reinterpret_cast<const uint4 *>(raw + i0);  // (raw_stride keeps the tail readable)
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t m = __vcmpeq4(w[k], 0xffffffffu) & 0x01010101u;
+            if (i0 + 4 * k + 4 > total) m &= (i0 + 4 * k >= total) ? 0u : (0xffffffffu >> (8 * (4 - (int) (total - i0 - 4 * k))));
+            n += __popc(m);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    __shared__ uint32_t s_w[STUFF_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < STUFF_THREADS / 32; ++i) t += s_w[i];
+        tile_ff[(size_t) img * tiles_max + tile] = t;
+    }
+}
+
+__global__ void __launch_bounds__(STUFF_THREADS) k_enc_stuff_scatter(const __grid_constant__ EncParams P, uint32_t tiles_max, const uint32_t *tile_ff)
+{
+    __shared__ __align__(16) uint8_t s_out[4 * STUFF_TILE + 64];  // worst case per raw byte: FF 00 preceded by a marker
+    __shared__ uint32_t s_w[STUFF_THREADS / 32], s_base, s_tile_total;
+    const uint32_t  img = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t *ivl = P.ivl + (size_t) img * (P.n_intervals + 1);
+    const uint64_t  total = ivl[P.n_intervals];
+    const uint64_t  t0 = (uint64_t) tile * STUFF_TILE;
+    if (t0 >= total && !(tile == 0 && total == 0)) return;
+    const uint8_t *raw = reinterpret_cast<const uint8_t *>(P.raw) + (size_t) img * P.raw_stride;
+    uint8_t       *out = P.out + (size_t) img * P.out_stride;
+    // FF bytes in the tiles before this one
+    {
+        uint32_t part = 0;
+        for (uint32_t t = tid; t < tile; t += STUFF_THREADS) part += tile_ff[(size_t) img * tiles_max + t];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0) s_w[wid] = part;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int i = 0; i < STUFF_THREADS / 32; ++i) t += s_w[i];
+            s_base = t;
+        }
+        __syncthreads();
+    }
+    const uint64_t i0 = t0 + (uint64_t) tid * STUFF_CHUNK;
+    uint8_t        b[STUFF_CHUNK];
+    uint32_t       n = 0, ff = 0, marks = 0;
+    uint32_t       e = 0;  // interval of the thread's first byte
+    if (i0 < total) {
+        const uint4    v = *reinterpret_cast<const uint4 *>(raw + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        n = total - i0 >= STUFF_CHUNK ? STUFF_CHUNK : (uint32_t) (total - i0);
+#pragma unroll
+        for (int k = 0; k < STUFF_CHUNK; ++k) {
+            b[k] = (uint8_t) (w[k >> 2] >> (8 * (k & 3)));
+            ff += ((uint32_t) k < n && b[k] == 0xff) ? 1u : 0u;
+        }
+        // upper_bound(ivl, i0) - 1 over the interval starts ivl[0 .. n_intervals)
+        uint32_t lo = 0, hi = P.n_intervals;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ivl[mid] <= i0) lo = mid;
+            else hi = mid;
+        }
+        e = lo;
+        // interval boundaries strictly inside (i0, i0 + n): the markers this thread emits (a boundary AT i0 belongs to it too)
+        uint32_t e2 = e;
+        while (e2 + 1 < P.n_intervals && ivl[e2 + 1] < i0 + n) ++e2;
+        marks = (e2 - e) + ((e > 0 && ivl[e] == i0) ? 1u : 0u);
+    }
+    // exclusive scan of the bytes each thread produces
+    const uint32_t v = n + ff + 2u * marks;
+    uint32_t       x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t) d) x += y;
+    }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    uint32_t before = x - v;
+    for (uint32_t i = 0; i < wid; ++i) before += s_w[i];
+    if (tid == STUFF_THREADS - 1) s_tile_total = before + v;
+    // where the tile's output starts: raw position + FFs before + 2 per interval boundary before the tile's first byte
+    uint32_t e_tile = 0;
+    {
+        uint32_t lo = 0, hi = P.n_intervals;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ivl[mid] <= t0) lo = mid;
+            else hi = mid;
+        }
+        e_tile = lo;
+    }
+    // markers before the tile: one per interval start in (0, t0); the one AT t0 (if any) is emitted by thread 0 of this tile
+    const uint32_t marks_before = e_tile - ((e_tile > 0 && ivl[e_tile] == t0) ? 1u : 0u);
+    const uint64_t g0 = t0 + s_base + 2ull * marks_before;
+    const uint32_t a = (uint32_t) ((reinterpret_cast<uintptr_t>(out) + g0) & 15);  // keep the destination's alignment in the tile
+    if (n) {
+        uint32_t pos = a + before, ee = e;
+        if (ee > 0 && ivl[ee] == i0) {  // the thread's first byte opens an interval
+            s_out[pos++] = 0xff;
+            s_out[pos++] = (uint8_t) (0xd0 + ((ee - 1) & 7));
+        }
+#pragma unroll
+        for (int k = 0; k < STUFF_CHUNK; ++k) {
+            if ((uint32_t) k < n) {
+                if (k > 0 && ee + 1 < P.n_intervals && ivl[ee + 1] == i0 + k) {
+                    ++ee;
+                    s_out[pos++] = 0xff;
+                    s_out[pos++] = (uint8_t) (0xd0 + ((ee - 1) & 7));
+                }
+                s_out[pos++] = b[k];
+                if (b[k] == 0xff) s_out[pos++] = 0x00;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t produced = s_tile_total;
+    // copy out: bytes up to the first 16-byte boundary, aligned vectors, tail bytes; nothing beyond the caller's capacity
+    const uint64_t cap = P.out_stride;
+    const uint32_t end = a + produced;
+    for (uint32_t p = tid * 16; p < end; p += STUFF_THREADS * 16) {
+        const uint64_t g = g0 - a + p;  // 16-byte aligned global offset of this piece
+        if (p >= a && p + 16 <= end && g + 16 <= cap)
+            *reinterpret_cast<uint4 *>(out + g) = *reinterpret_cast<const uint4 *>(s_out + p);
+        else
+            for (uint32_t q = p < a ? a : p; q < p + 16 && q < end; ++q)
+                if (g0 - a + q < cap) out[g0 - a + q] = s_out[q];
+    }
+    if (t0 + STUFF_TILE >= total && tid == 0) P.out_len[img] = g0 + produced;  // the last tile knows the stuffed length
+}
+
 // ---- progressive AC scans: one thread per restart interval (encode.swift:1060-1205) -------------------------------
 // `pure` = the block emits nothing but (a share of) an EOB run: AC first: every |c| >> al == 0 in the band;
 // AC refine: no coefficient becomes newly significant.
@@ -833,8 +982,20 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         else k_enc_ac<2><<<grid_ivl, 32, 0, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
-    k_enc_stuff<<<n_images, 1024, 0, ctx->stream>>>(P);
-    LAUNCH_CHECK(ctx);
+    static const bool serial_stuff = [] { const char *e = getenv("JPEG_SM100_STUFF"); return e && strcmp(e, "serial") == 0; }();
+    if (serial_stuff) {  // first generation (one CTA per image), kept for A/B validation
+        k_enc_stuff<<<n_images, 1024, 0, ctx->stream>>>(P);
+        LAUNCH_CHECK(ctx);
+    } else {
+        const uint32_t tiles_max = (uint32_t) std::max<uint64_t>(1, (max_raw + STUFF_TILE - 1) / STUFF_TILE);
+        void          *tf = nullptr;
+        J_TRY(scratch_reserve(ctx, 14, (size_t) n_images * tiles_max * 4 + 256, &tf));
+        const dim3 grid_t(tiles_max, n_images);
+        k_enc_stuff_count<<<grid_t, STUFF_THREADS, 0, ctx->stream>>>(P, tiles_max, reinterpret_cast<uint32_t *>(tf));
+        LAUNCH_CHECK(ctx);
+        k_enc_stuff_scatter<<<grid_t, STUFF_THREADS, 0, ctx->stream>>>(P, tiles_max, reinterpret_cast<const uint32_t *>(tf));
+        LAUNCH_CHECK(ctx);
+    }
     if (h_needed) {
         std::vector<uint64_t> lens(n_images);
         CU_TRY(ctx, cudaMemcpyAsync(lens.data(), d_ecs_len, n_images * 8, cudaMemcpyDeviceToHost, ctx->stream));
