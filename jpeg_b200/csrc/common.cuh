@@ -43,6 +43,7 @@ struct jpeg_sm100_ctx {
     std::vector<cudaEvent_t> events;
     // average bytes per restart interval of the next entropy-decode call, when the caller knows it (0: unknown); consumed by K3
     uint64_t hint_interval_bytes = 0;
+    int      par_smem_ac = 0;   // same for its progressive AC-first instantiation
     size_t   par_smem_set = 0;  // largest dynamic shared-memory size k_decode_par has been opted into on this device
     // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda dependency)
     void *encode_tiled = nullptr;

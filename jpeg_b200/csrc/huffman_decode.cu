@@ -84,6 +84,14 @@ __host__ __device__ inline uint32_t fast_entry(uint32_t ref, bool dc)
     const uint32_t adv = sym == 0u ? 64u : run + 1u;
     return len | (size << 8) | (adv << 16) | ((len + size) << 24);
 }
+// AC table of a progressive AC-first scan (decode.swift:2822-2872, 3038-3067): EOBn is a regular symbol there -- byte2 = 0x80 marks
+// it, byte1 = n = the number of extra bits; the run is (1 << n) + those bits (n = 0: the plain end-of-block)
+__host__ __device__ inline uint32_t fast_entry_prog(uint32_t ref)
+{
+    const uint32_t len = ref >> 8, sym = ref & 0xffu, size = sym & 15u, run = sym >> 4;
+    if (size == 0u && run != 15u) return len | (run << 8) | (0x80u << 16) | ((len + run) << 24);
+    return len | (size << 8) | ((run + 1u) << 16) | ((len + size) << 24);
+}
 constexpr uint32_t FAST_LINK = 0x80u;
 constexpr uint32_t SUB_MAX = 1536;  // sub-table entries per Huffman table (6 KB); larger sets keep the reference lookup
 
@@ -115,7 +123,7 @@ __host__ __device__ inline uint32_t sub_depths(const uint8_t counts[16], uint8_t
 
 // decode.swift:1037-1240 Table.Huffman.decoder(): level l (codes of l+1 bits) contributes `0x8080 >> l & 0xff` clones
 // of (symbol, l+1) per leaf: 128, 64, ... 1 in the level-0 table, then 128 ... 1 again in the 256-entry sub-tables.
-__global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ raw, uint8_t *__restrict__ luts, size_t stride)
+__global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ raw, uint8_t *__restrict__ luts, size_t stride, int prog)
 {
     const int        ti = blockIdx.x;
     const RawSet    &r = raw[blockIdx.y];
@@ -204,14 +212,14 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         if (d == 0u) {
             bool           valid;
             const uint32_t e = ref_lookup(cw, valid);
-            fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? fast_entry(e, ti < 4) : 0u;
+            fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? ((prog && ti >= 4) ? (valid ? fast_entry_prog(e) : 0u) : fast_entry(e, ti < 4)) : 0u;
             continue;
         }
         fast[i] = FAST_LINK | (uint32_t) (16 - FAST_BITS - d) | ((uint32_t) s_off[i] << 10);  // shift, byte offset
         for (uint32_t j = 0; j < (1u << d); ++j) {
             bool           valid;
             const uint32_t e = ref_lookup(cw | (j << (16 - FAST_BITS - d)), valid);
-            fast[s_off[i] + j] = (valid && (e >> 8) <= (uint32_t) FAST_BITS + d) ? fast_entry(e, ti < 4) : 0u;
+            fast[s_off[i] + j] = (valid && (e >> 8) <= (uint32_t) FAST_BITS + d) ? ((prog && ti >= 4) ? fast_entry_prog(e) : fast_entry(e, ti < 4)) : 0u;
         }
     }
 }
@@ -1077,6 +1085,98 @@ __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st
     return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
 }
 
+// ---- progressive AC-first scans (kind 3) on the same machinery ------------------------------------------------------------------
+// One component, one table, blocks in raster order of the plane; the parse state is (bit position, z) alone -- no place in an MCU
+// to agree on, so streams re-synchronise quickly.  An EOBn symbol ends its block AND the n-1 blocks after it without consuming
+// another bit, so the whole run counts as completed blocks at that symbol and never needs to be carried in the state.
+// Coefficients are scattered 2-byte stores (the block's other bands belong to other scans); an invalid codeword or a read past the
+// end flags the interval, which k_decode_progressive then redoes with the reference's error semantics.
+template <bool FINAL, bool SAFE>
+__device__ __forceinline__ uint32_t par_run_ac(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                               const uint32_t tab, const int band_lo, const int band_hi, const int al, bool &bad,
+                                               uint32_t N, const uint32_t N_total, int16_t *base /* block 0 of the interval */)
+{
+    int z = st.z;
+    bad = false;
+    if (st.p >= end_bit) return 0;
+    if (FINAL && N >= N_total) return 0;
+    uint32_t  done = 0;
+    int       left = (int) (end_bit - st.p);
+    const int slack = (int) (count_bits - end_bit);
+    uint32_t  wi, cnt, hi, lo, nxt;
+    {
+        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
+        wi = ab >> 5;
+        cnt = ab & 31u;
+        hi = io.word(wi), lo = io.word(wi + 1);
+        nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));
+        wi += 3;
+    }
+    while (left > 0) {
+        if (cnt >= 32u) {
+            hi = lo;
+            asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));
+            nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
+            wi += 1;
+            cnt -= 32u;
+        }
+        const uint32_t top = __funnelshift_l(lo, hi, cnt);
+        uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
+        if (ent & FAST_LINK) {
+            const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
+            ent = lds32(tab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
+        }
+        if (__builtin_expect(ent == 0u, 0)) {  // not a codeword of this table (or a table too large for sub-tables)
+            bad = true;
+            break;
+        }
+        const int total = (int) (ent >> 24);
+        if (!SAFE) {
+            if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2843-2846, 2859-2863
+                bad = true;
+                break;
+            }
+        }
+        const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441), adv = (int) __byte_perm(ent, 0, 0x4442);
+        const uint32_t top2 = top << len;
+        const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
+        cnt += (uint32_t) total;
+        left -= total;
+        if (adv & 0x80) {  // EOBn: this block and (1 << n) + tail - 1 more are done (decode.swift:3059-3064)
+            const uint32_t nb = (1u << size) + tail;
+            done += nb;
+            N += nb;
+            z = band_lo;
+        } else {
+            const int v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;
+            const int zpos = z + adv - 1;  // decode.swift:3047-3055: skip `run` coefficients, place the value (ZRL places a zero)
+            if (FINAL && zpos < band_hi) base[(size_t) N * 64 + zpos] = (int16_t) ((uint32_t) v << al);
+            z += adv;
+            if (z >= band_hi) {
+                done += 1;
+                N += 1;
+                z = band_lo;
+            }
+        }
+        if (FINAL && N >= N_total) break;
+    }
+    st.p = end_bit - (uint32_t) left;
+    st.z = (uint16_t) z;
+    st.b = 0;
+    return done;
+}
+
+template <bool FINAL>
+__device__ __forceinline__ uint32_t par_run_ac_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                                    const uint32_t tab, const int band_lo, const int band_hi, const int al, bool &bad,
+                                                    uint32_t N, const uint32_t N_total, int16_t *base)
+{
+    const uint32_t mask = __activemask();
+    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 32u + 64u) / 32u + 2u;
+    if (__all_sync(mask, last_word < io.wlim)) return par_run_ac<FINAL, true>(io, st, end_bit, count_bits, tab, band_lo, band_hi, al, bad, N, N_total, base);
+    return par_run_ac<FINAL, false>(io, st, end_bit, count_bits, tab, band_lo, band_hi, al, bad, N, N_total, base);
+}
+
 // ---- prologue shared by the subsequence-parallel kernels ---------------------------------------------------------------------
 // shared-memory image of one table set: LutHeader | ParBlk[12] (in the BlkInfo area) | fast tables + sub-tables.  The reference
 // LUT behind them stays in global memory (only invalid codewords, EOBn and DC category 16 ever look at it).
@@ -1138,10 +1238,12 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
     q.slot = img * P.n_ecs + e;
     const uint64_t n_total = (uint64_t) (r1 - r0) * (uint32_t) W * (uint32_t) nblk;
     const uint64_t o0 = P.offsets[q.slot], o1 = P.offsets[q.slot + 1];
-    if (n_total == 0) {  // nothing to decode: the reference's row loop does not run
+    if (n_total == 0) {
+        // sequential scans: nothing to decode, the reference's row loop does not run.  Progressive scans iterate through
+        // General.Range2, which yields one row even when empty (decode.swift:3031-3036): left to the sequential kernel.
         if (flagged) {
-            flagged[q.slot] = 0;
-            if (P.status) P.status[q.slot] = 0;
+            flagged[q.slot] = P.kind == 3 ? 1u : 0u;
+            if (P.kind != 3 && P.status) P.status[q.slot] = 0;
         }
     } else if ((o1 - o0) > 0x07ffffffull || n_total > dc_per_interval) {
         if (flagged) flagged[q.slot] = 1;  // 32-bit bit positions / side-array capacity: left to the sequential kernel
@@ -1172,7 +1274,7 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
 // stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
 // block buffers (PAR_BUF_STRIDE bytes each)
-template <int NT, int MIN_CTAS>
+template <int NT, int MIN_CTAS, bool AC>
 __global__ void __launch_bounds__(NT, MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
              uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits,
@@ -1247,7 +1349,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
-            cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            if (AC) cum += par_run_ac_auto<false>(qio, st, seg_end, qcount, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
+            else cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
             // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
@@ -1268,8 +1371,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         return cum;
     };
     if (active) {
-        st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
-        if (l > 0 && warm_bits) par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+        st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = AC ? (uint16_t) P.band_lo : 0, st.b = 0;
+        if (l > 0 && warm_bits) {
+            if (AC) par_run_ac_auto<false>(io, st, start_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
+            else par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+        }
         if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
         uint64_t       x;
@@ -1335,9 +1441,14 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         st = unpack_state(my_entry);
         uint32_t done = 0;
         bad = false;
-        if (before < N_total)
-            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff,
-                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+        if (before < N_total) {
+            if (AC)  // single component, blocks in raster order: block N of the interval is N blocks after its first
+                done = par_run_ac_auto<true>(io, st, end_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, before, N_total,
+                                             P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) s_grp[g].r0 * (size_t) W * 64);
+            else
+                done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff,
+                                          reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+        }
         // a subsequence that does not produce the blocks the synchronisation counted for it (or that was cut short because the
         // interval is complete while data remains) leaves the interval to the sequential decoder
         if (bad || (before < N_total && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
@@ -1359,7 +1470,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
     // Work items (interval, component) are dealt to the warps; a lane owns a contiguous run of the component's blocks: it sums its
     // differences, the warp scans the lane sums, the lane walks its run again and stores the predictions.
-    for (uint32_t item = (uint32_t) wid; item < G * (uint32_t) P.n_comp; item += NT / 32) {
+    for (uint32_t item = (uint32_t) wid; !AC && item < G * (uint32_t) P.n_comp; item += NT / 32) {
         const uint32_t  gg = item / (uint32_t) P.n_comp;
         const int       c = (int) (item - gg * (uint32_t) P.n_comp);
         const ParGroup &q = s_grp[gg];
@@ -1656,6 +1767,27 @@ __global__ void __launch_bounds__(128) k_zero_flagged(const __grid_constant__ Sc
     }
 }
 
+// the band of a progressive AC-first scan in the blocks of flagged intervals, before the sequential kernel re-decodes them (the
+// band is all zero before its first scan; the parallel decoder may have written part of it)
+__global__ void __launch_bounds__(128) k_zero_band_flagged(const __grid_constant__ ScanParams P, const uint32_t *const flagged)
+{
+    const uint32_t e = blockIdx.x, img = blockIdx.y;
+    if (!flagged[(size_t) img * P.n_ecs + e] || !P.plane[0]) return;
+    int64_t r0, r1;
+    if (P.interval == UINT64_MAX) {
+        r0 = 0;
+        r1 = P.H;
+    } else {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r0 > P.H) r0 = P.H;
+        if (r1 > P.H) r1 = P.H;
+    }
+    int16_t       *pl = P.plane[0] + (size_t) img * P.image_stride[0] + 64 * (size_t) P.ux[0] * (size_t) r0;
+    const uint32_t nb = (uint32_t) P.ux[0] * (uint32_t) (r1 - r0), band = (uint32_t) (P.band_hi - P.band_lo);
+    for (uint32_t i = threadIdx.x; i < nb * band; i += blockDim.x) pl[(size_t) (i / band) * 64 + P.band_lo + i % band] = 0;
+}
+
 // ---- straightforward per-thread decoders for the refinement / AC progressive scans ---------------------------------
 __device__ __forceinline__ int16_t coef_get(const int16_t *pl, int ux, int uy, int x, int y, int z)
 {
@@ -1669,7 +1801,7 @@ __device__ __forceinline__ void coef_set(int16_t *pl, int ux, int uy, int x, int
 }
 
 template <bool LUT_SMEM>
-__global__ void __launch_bounds__(WARP) k_decode_progressive(const __grid_constant__ ScanParams P)
+__global__ void __launch_bounds__(WARP) k_decode_progressive(const __grid_constant__ ScanParams P, const uint32_t *const only_flagged)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t img = blockIdx.y;
@@ -1688,6 +1820,7 @@ __global__ void __launch_bounds__(WARP) k_decode_progressive(const __grid_consta
         if (LUT_SMEM) entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader));
     }
     if (e >= P.n_ecs) return;
+    if (only_flagged && only_flagged[(size_t) img * P.n_ecs + e] == 0u) return;  // fallback pass after the parallel decoder
     int err = 0;
 
     // rows: lo / w ..< min(hi / w, limit), iterated through General.Range2 (common.swift:383-409): an empty y range
@@ -1994,7 +2127,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     CU_TRY(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(RawSet) * (size_t) n_sets, cudaMemcpyHostToDevice, ctx->stream));
     J_TRY(pinned_release(ctx, slot));
     k_build_luts<<<dim3(8, n_sets), 128, 0, ctx->stream>>>(reinterpret_cast<const RawSet *>(d_raw),
-                                                           reinterpret_cast<uint8_t *>(d_luts), stride);
+                                                           reinterpret_cast<uint8_t *>(d_luts), stride, P.kind == 3 ? 1 : 0);
     LAUNCH_CHECK(ctx);
     P.luts = reinterpret_cast<const uint8_t *>(d_luts);
     P.lut_stride = tables_shared ? 0 : stride;
@@ -2064,8 +2197,8 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 const uint32_t stage_bytes = (uint32_t) (per_interval * G);
                 const size_t   smem_total = smem_par + stage_bytes + (size_t) nt * PAR_BUF_STRIDE;
                 if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
-                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     ctx->par_smem_set = 200 * 1024;
                 }
                 static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
@@ -2098,11 +2231,11 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_decode_par_cluster, P, plane0, reinterpret_cast<int16_t *>(d_dc),
                                                    (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag), warm_bits, (uint32_t) smem_par));
                 } else if (big)
-                    k_decode_par<PAR_BIG_THREADS, 1><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
+                    k_decode_par<PAR_BIG_THREADS, 1, false><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
                         d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
                 else
-                    k_decode_par<PAR_THREADS, PAR_MIN_CTAS><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
+                    k_decode_par<PAR_THREADS, PAR_MIN_CTAS, false><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
                         d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
                 LAUNCH_CHECK(ctx);
@@ -2133,10 +2266,41 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
         if (P.lut_smem) k_decode_flat<true><<<grid, WARP, smem, ctx->stream>>>(P);
         else k_decode_flat<false><<<grid, WARP, smem, ctx->stream>>>(P);
+    } else if (P.kind == 3 && fast_ok && !(getenv("JPEG_SM100_HUFF") && strcmp(getenv("JPEG_SM100_HUFF"), "seq") == 0) &&
+               (uint64_t) n_images * n_ecs * 4 <= (1ull << 30) && interval != 0 &&
+               (interval == JPEG_SM100_INTERVAL_NONE || interval % (uint64_t) P.W == 0)) {
+        // progressive AC-first scan: the subsequence-parallel decoder (par_run_ac), then the sequential one for flagged intervals
+        if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
+        const uint64_t slots = (uint64_t) n_images * n_ecs;
+        void          *d_flag = nullptr;
+        J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
+        const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
+        const uint64_t est_bits = ctx->hint_interval_bytes ? 8 * ctx->hint_interval_bytes : 96 * rows_typ * (uint64_t) P.W;
+        const char    *env_ts = getenv("JPEG_SM100_PAR_T"), *env_ws = getenv("JPEG_SM100_PAR_WARM");
+        int            tshift = 7;
+        while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
+        while (tshift < 7 && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
+        if (env_ts && atoi(env_ts) >= 4 && atoi(env_ts) <= 7) tshift = atoi(env_ts);
+        const uint32_t warm_bits = env_ws ? (uint32_t) (atoi(env_ws) > 0 ? atoi(env_ws) : 0) : 512u;
+        const uint32_t G = (uint32_t) PAR_THREADS >> tshift;
+        const size_t   smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + ((max_fast * 2 + 15) & ~size_t(15));
+        if (!ctx->par_smem_ac) {
+            CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->par_smem_ac = 1;
+        }
+        // (the side array / block buffers of the sequential-scan variant are unused: dc_per_interval only bounds N_total)
+        k_decode_par<PAR_THREADS, PAR_MIN_CTAS, true><<<dim3((n_ecs + G - 1) / G, n_images), PAR_THREADS, smem_par, ctx->stream>>>(
+            P, plane0, nullptr, 0xffffffffu, reinterpret_cast<uint32_t *>(d_flag), nullptr, tshift, warm_bits, (uint32_t) smem_par, 0u,
+            (uint32_t) smem_par);
+        LAUNCH_CHECK(ctx);
+        k_zero_band_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+        LAUNCH_CHECK(ctx);
+        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
     } else {
         if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
-        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P);
-        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P);
+        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, nullptr);
+        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, nullptr);
     }
     LAUNCH_CHECK(ctx);
     if (d_status) {
