@@ -4,17 +4,23 @@
 // below it: the ten per-kind decoders (decode.swift:2880-3445), composites (2773-2872), EXTEND (2742-2754), the
 // two-level Huffman LUT (310-351, 1037-1265) and the 1-padded bitstream (jpeg.swift:1873-1916).
 //
-// B200 design
-//   * The only parallel axis the format offers is the restart interval (the reference decoder itself walks them in
-//     a serial loop, decode.swift:3500): one THREAD decodes one interval; a warp holds 32 intervals of one image.
-//   * Entropy decoding is a serial dependency chain per thread, so the kernel is latency- not bandwidth-bound.
-//     Each warp is its own CTA so that the ~n_images x n_intervals / 32 warps spread over all 148 x 4 schedulers.
-//   * The sequential / DC-first decoders are written as a flat per-symbol state machine: every loop trip decodes
-//     exactly one Huffman symbol whatever block the lane is in, so lanes never wait for each other at block or MCU
-//     boundaries (trip count = max over lanes of the interval's symbol count, not the sum of per-block maxima).
-//   * The reference's two-level (8 + 8 bit) LUT is reproduced entry for entry and staged in shared memory
-//     (a few KB for real tables); oversized tables fall back to global memory.
-//   * Coefficients go straight to their final zig-zag slot in the Spectral.Plane layout, 64 * (units_x * y + x) + z.
+// B200 design (DESIGN.md section 3 has the measurements behind each choice)
+//   * The format's own parallel axis is the restart interval (the reference decoder walks them in a serial loop,
+//     decode.swift:3500).  Sequential scans and progressive AC-first scans are additionally cut INSIDE every interval:
+//     Huffman streams self-synchronise, so k_decode_par parses subsequences of >= 1 Kbit speculatively, repairs the ones whose
+//     entry state was wrong (checkpointed re-parses that stop when they merge with the recorded parse), scans the block counts
+//     and then decodes every subsequence for real.  A CTA of 128 threads holds 1..8 intervals; an interval without DRI
+//     (one segment per image: everything the reference's own encoder writes) gets a thread-block cluster whose CTAs exchange
+//     neighbour state through distributed shared memory (k_decode_par_cluster).
+//   * The kernels are bound by instruction issue and the LSU pipe, not by HBM: the loops are branch-light flat state machines
+//     (one Huffman symbol per trip whatever block the lane is in), tables are 9-bit shared-memory LUTs with sub-tables for
+//     longer codes, stream words are loaded one refill ahead, and each block of a sequential scan is assembled in shared
+//     memory and stored as one 128-byte line.
+//   * Anything irregular only flags its interval; flagged intervals are redone by the one-thread-per-interval kernels below
+//     (k_decode_fast / k_decode_progressive), which evaluate every guard of the reference and produce its error codes.
+//     Those kernels also serve DC-first, refinement and `extend` scans.
+//   * The reference's two-level (8 + 8 bit) LUT is reproduced entry for entry on the GPU (k_build_luts).
+//   * Coefficients land in the Spectral.Plane layout, 64 * (units_x * y + x) + z.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -2189,8 +2195,8 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 1024u;
                 const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
-                // shared-memory stage: twice the expected interval size per interval (larger intervals are read from global
-                // memory), within what leaves a few CTAs per SM
+                // optional shared-memory stage for the intervals' bytes (measured slower than global reads one refill ahead: the
+                // shared memory costs occupancy; kept selectable for A/B)
                 const char    *env_ss = getenv("JPEG_SM100_PAR_STAGE");  // KB per interval, 0 = no staging
                 uint64_t       per_interval = env_ss ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
                 if (per_interval * G > 96 * 1024) per_interval = (96 * 1024 / G) & ~(uint64_t) 1023;
