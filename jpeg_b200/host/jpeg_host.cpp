@@ -84,6 +84,69 @@ void Spectral::set_size(std::pair<int, int> s)
     }
 }
 
+// ---- N3: spectral-domain operations ----------------------------------------------------------------------------------
+// JPEG.Table.Quantization.z(k:h:) decode.swift:1289-1298
+static int zigzag_of(int k, int h)
+{
+    const int p = (k + h < 8) ? 1 : 0, q = (k + h) & 1;
+    const int a = 72 * (p ^ 1), b = 2 * p - 1, n = b * (k + h) - 14 * p + 15;
+    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1;
+}
+
+Spectral Spectral::requantized(const std::vector<Table::Quantization> &nq) const
+{
+    if (nq.size() != quanta.size()) throw Error(Error::Kind::decoding, "requantized: one table per quantisation slot expected");
+    Spectral out = *this;
+    out.quanta = nq;
+    for (size_t p = 0; p < planes.size(); ++p) {
+        const Plane &src = planes[p];
+        if (src.coefficients.empty()) continue;
+        device->check(jpeg_sm100_requantize(device->ctx(), src.coefficients.data(), (uint32_t) src.units.first, (uint32_t) src.units.second,
+                                            quanta[src.q].data(), nq[src.q].data(), out.planes[p].coefficients.data()));
+    }
+    return out;
+}
+
+Spectral Spectral::rotated(Rotation r) const
+{
+    // Block.transform (examples/rotate/main.swift:13-99): per destination zig-zag index the source index and the sign
+    struct Co { int z, mul; };
+    std::array<Co, 64> blank, t, res;
+    for (int y = 0; y < 8; ++y)
+        for (int x = 0; x < 8; ++x) blank[8 * y + x] = {zigzag_of(x, y), 1};
+    auto transpose = [](const std::array<Co, 64> &a) { std::array<Co, 64> o; for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) o[8 * y + x] = a[8 * x + y]; return o; };
+    auto reflect_v = [](const std::array<Co, 64> &a) { std::array<Co, 64> o; for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) o[8 * y + x] = {a[8 * y + x].z, a[8 * y + x].mul * (1 - 2 * (y & 1))}; return o; };
+    auto reflect_h = [](const std::array<Co, 64> &a) { std::array<Co, 64> o; for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) o[8 * y + x] = {a[8 * y + x].z, a[8 * y + x].mul * (1 - 2 * (x & 1))}; return o; };
+    int32_t matrix[4];
+    int     w = size.first, h = size.second;
+    switch (r) {
+    case Rotation::ii: t = transpose(blank), res = reflect_v(t), matrix[0] = 0, matrix[1] = 1, matrix[2] = -1, matrix[3] = 0, w -= w % (8 * scale.first); break;
+    case Rotation::iii: t = reflect_h(blank), res = reflect_v(t), matrix[0] = -1, matrix[1] = 0, matrix[2] = 0, matrix[3] = -1, w -= w % (8 * scale.first), h -= h % (8 * scale.second); break;
+    default: t = transpose(blank), res = reflect_h(t), matrix[0] = 0, matrix[1] = -1, matrix[2] = 1, matrix[3] = 0, h -= h % (8 * scale.second); break;
+    }
+    uint8_t zmap[64];
+    int8_t  mul[64];
+    for (int hh = 0; hh < 8; ++hh)
+        for (int k = 0; k < 8; ++k) zmap[zigzag_of(k, hh)] = (uint8_t) res[8 * hh + k].z, mul[zigzag_of(k, hh)] = (int8_t) res[8 * hh + k].mul;
+    Spectral src = *this;
+    src.set_size({w, h});  // original.set(width:) / set(height:): whole MCUs along the mirrored axes (main.swift:117-139)
+    Spectral out = src;
+    out.set_size(r == Rotation::iii ? std::make_pair(w, h) : std::make_pair(h, w));
+    for (auto &q : out.quanta) {
+        const Table::Quantization old = q;
+        for (int z = 0; z < 64; ++z) q[z] = old[zmap[z]];
+    }
+    for (size_t p = 0; p < planes.size(); ++p) {
+        const Plane &a = src.planes[p];
+        Plane       &b = out.planes[p];
+        std::fill(b.coefficients.begin(), b.coefficients.end(), (int16_t) 0);
+        if (b.coefficients.empty()) continue;
+        device->check(jpeg_sm100_transform_blocks(device->ctx(), a.coefficients.data(), (uint32_t) a.units.first, (uint32_t) a.units.second, matrix,
+                                                  zmap, mul, b.coefficients.data(), (uint32_t) b.units.first, (uint32_t) b.units.second));
+    }
+    return out;
+}
+
 static jpeg_sm100_scan_desc scan_desc(const Spectral &s, const Scan &scan)
 {
     jpeg_sm100_scan_desc d{};
@@ -776,6 +839,22 @@ JPEGH_API int jpegh_recompress(const uint8_t *data, size_t n, uint64_t interval_
     try {
         auto s = jpeg::Data::Spectral::decompress(data, n);
         auto b = s.compress(interval_mcus);
+        *out = dup(b);
+        *out_n = b.size();
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e, err, errcap);
+    }
+}
+
+// examples/rotate: decompress -> rotate losslessly in the coefficient domain -> compress.  rotation: 2 (ii), 3 (iii), 4 (iv)
+JPEGH_API int jpegh_rotate(const uint8_t *data, size_t n, int rotation, uint8_t **out, size_t *out_n, char *err, size_t errcap)
+{
+    try {
+        auto s = jpeg::Data::Spectral::decompress(data, n);
+        auto r = s.rotated(rotation == 2 ? jpeg::Data::Spectral::Rotation::ii
+                                         : rotation == 3 ? jpeg::Data::Spectral::Rotation::iii : jpeg::Data::Spectral::Rotation::iv);
+        auto b = r.compress(0);
         *out = dup(b);
         *out_n = b.size();
         return 0;

@@ -12,6 +12,7 @@
 //   jpeg::Data::Planar::fdct(quanta)             Planar.fdct(quanta:)                      encode.swift:353    -> jpeg_sm100_fdct
 //   jpeg::Data::Spectral::encode(scan)           Spectral.encode(scan:)                    encode.swift:1559   -> jpeg_sm100_encode_scan
 //     .compress()                                 Spectral.compress(stream:)                encode.swift:1918
+//     .requantized(quanta) / .rotated(r)          examples/recompress, examples/rotate (N3)             -> jpeg_sm100_requantize / _transform_blocks
 //
 // Container lexing / parsing / serialisation (decode.swift:53-1005, 3554-3961; encode.swift:1623-1972) is host
 // bookkeeping the reference keeps in Swift; it is restated here so whole files can be driven through the GPU path.
@@ -104,6 +105,11 @@ public:
                     const Table::HuffmanSlots &ac, bool extend);
     // encode.swift:1559: returns the stuffed entropy-coded segment; tables by slot; interval_mcus = 0 -> reference form
     std::vector<uint8_t> encode(const Scan &scan, Table::HuffmanSlots &dc, Table::HuffmanSlots &ac, uint64_t interval_mcus = 0) const;
+
+    // spectral-domain operations (N3): the loops of examples/recompress/main.swift:35-58 and examples/rotate/main.swift:101-199
+    Spectral requantized(const std::vector<Table::Quantization> &new_quanta) const;  // one table per entry of `quanta`
+    enum class Rotation { ii, iii, iv };                                             // quadrant the x axis is rotated into
+    Spectral rotated(Rotation r) const;
 
     Planar               idct() const;                       // decode.swift:4154
     std::vector<uint8_t> to_rgb8(bool cosite = false) const;  // fused idct().interleaved().unpack(as: RGB.self)

@@ -35,6 +35,7 @@ def hostlib():
     lib.jpegh_compress_rgb8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(u8p), C.POINTER(C.c_size_t), C.c_char_p,
                                         C.c_size_t]
+    lib.jpegh_rotate.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(u8p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
     return lib
 
 
@@ -220,3 +221,27 @@ def test_encode_basic_golden_through_cpp_host(manifest, hostlib):
             for sc in exp["scans"]:
                 for cls, tgt, counts, values in sc["dht"]:
                     assert dht[(cls, tgt)] == (bytes.fromhex(counts), bytes.fromhex(values)), (name, tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,code", [("ii", 2), ("iii", 3), ("iv", 4)])
+def test_rotate_through_cpp_host(manifest, hostlib, kind, code):
+    """examples/rotate as one call of the C++ host (decompress -> Spectral::rotated -> compress): every scan of our file --
+    entropy-coded bytes and the Huffman tables in front of it -- and the permuted quantisation tables equal the reference's
+    committed output."""
+    data = golden_bytes(manifest["rotate"]["source"])
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    rc = hostlib.jpegh_rotate(data, len(data), code, C.byref(out), C.byref(n), err, 256)
+    assert rc == 0, err.value.decode()
+    blob = bytes(np.ctypeslib.as_array(out, shape=(n.value,)))
+    hostlib.jpegh_free(out)
+    exp = manifest["rotate"]["outputs"][kind]
+    segs = J.split(blob)
+    got = [(body, ecs) for m, body, ecs in segs if m == 0xDA]
+    assert len(got) == len(exp["scans"])
+    for (body, ecs), sc in zip(got, exp["scans"]):
+        assert body.hex() == sc["sos"]
+        assert len(ecs) == sc["ecs_len"] and sha(ecs) == sc["ecs_sha256"], kind
+    dqt = [[t, q] for m, body, _ in segs if m == 0xDB for t, q in J.parse_dqt(body)]
+    assert dqt == exp["dqt"]
