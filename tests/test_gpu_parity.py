@@ -260,6 +260,38 @@ def test_scan_decode_parallel_variants(H, O, monkeypatch, tshift, warm):
                 assert np.array_equal(got.planes[p].coef, want.coefficients(p)), (k, p)
 
 
+@pytest.mark.parametrize("size,factors", [((97, 61), [(1, 1)]), ((200, 120), [(2, 1), (1, 1), (1, 1)]),
+                                          ((131, 77), [(1, 2), (1, 1), (1, 1)]), ((160, 96), [(4, 1), (1, 1), (1, 1)]),
+                                          ((150, 70), [(4, 2), (1, 1), (2, 1)]), ((96, 64), [(2, 2), (1, 1), (1, 1), (2, 2)]),
+                                          ((1000, 40), [(1, 1), (1, 1), (1, 1)])])
+@pytest.mark.parametrize("rows", [0, 1, 2])
+def test_sequential_scan_geometries(H, O, size, factors, rows):
+    """K3p over the geometries the benchmark does not touch -- up to 12 blocks per MCU, four components, partial MCUs on both
+    edges, one interval per image or per 1-2 MCU rows -- on random sparse coefficients: entropy coding is lossless, so the
+    oracle's encoder followed by the GPU decoder must return the coefficients, and the GPU encoder the oracle's bytes."""
+    rng = np.random.default_rng(hash((size, len(factors), rows)) & 0xffff)
+    src = O.Spectral.create(size, factors)
+    n = len(factors)
+    for p in range(n):
+        c = src.coefficients(p)
+        dense = rng.random(c.shape) < 0.08
+        c[...] = np.where(dense, rng.integers(-60, 60, c.shape), 0).astype(np.int16)
+        c[..., 0] = rng.integers(-500, 500, c.shape[:2])
+        c[rng.random(c.shape[:2]) < 0.3, 1:] = 0           # DC-only blocks
+        hot = rng.random(c.shape[:2]) < 0.05
+        c[hot] = rng.integers(-1000, 1000, (int(hot.sum()), 64)).astype(np.int16)  # a few dense blocks with long codes
+    comps = list(range(n))
+    ival = rows * src.blocks[0] if n > 1 else rows * src.units(0)[0]
+    ecs, dct, act = src.encode_scan((0, 64), (0, None), comps, [0] * n, [0] * n, ival)
+    dst = H.Spectral(size, factors)
+    dst.decode_scan((0, 64), (0, None), [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act),
+                    J.unstuff_split(ecs), ival or None)
+    for p in range(n):
+        assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), p
+    got, _, _ = dst.encode_scan((0, 64), (0, None), [(c, 0, 0) for c in comps], ival)
+    assert got == ecs
+
+
 def test_scan_decode_errors(H, O):
     """Error parity: truncated data, undefined tables, EOB run in a sequential scan -- same code as the oracle."""
     from jpeg_b200 import lib
