@@ -225,21 +225,20 @@ k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb
 // reference computes (jpeg.swift:447) and the two subtractions per pixel disappear.
 __device__ __forceinline__ float s8_to_float(uint32_t v, int byte) { return (float) (int) (int8_t) (v >> (8 * byte)); }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ycc420_to_rgb8_v2(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
 {
+    // grid = (column groups / blockDim, row pairs (strided), images): no index divisions (a flat 64-bit index cost ~60 of the
+    // ~450 instructions a thread spends on its 16 pixels)
     const int      W = V.size_x, H = V.size_y;
     const int      groups_x = (W + 7) / 8;
     const int      row_pairs = H / 2 + 1;  // r = -1 .. ceil((H-1)/2)-1
-    const uint64_t per_image = (uint64_t) groups_x * row_pairs;
-    const uint64_t total = per_image * V.n_images;
     const int      yw = V.width[0], cw = V.width[1], ch = V.height[1];
     const bool     vec = (W & 7) == 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint32_t img = (uint32_t) (i / per_image);
-        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
-        const int      rp = (int) (rem / groups_x);
-        const int      gx = (int) (rem - (uint32_t) rp * groups_x);
+    const int      gx = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t img = blockIdx.z;
+    if (gx >= groups_x) return;
+    for (int rp = (int) blockIdx.y; rp < row_pairs; rp += (int) gridDim.y) {
         const int      r = rp - 1;  // chroma row pair (r, r+1) feeds luma rows 2r+1, 2r+2
         const int      x0 = 8 * gx, c0 = 4 * gx;
         const uint8_t *Yp = reinterpret_cast<const uint8_t *>(V.samples[0]) + (size_t) img * V.image_stride[0];
@@ -691,8 +690,23 @@ int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *
         const uint64_t work = (uint64_t) ((sx + 7) / 8) * (sy / 2 + 1) * pl->n_images;
         if (color_env && strcmp(color_env, "direct") == 0)  // first generation, kept for A/B validation
             k_ycc420_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
-        else
-            k_ycc420_to_rgb8_v2<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
+        else {
+            // threads per CTA: the multiple of 32 (64..256) that wastes the fewest lanes on the last CTA of a row
+            const uint32_t groups_x = (sx + 7) / 8, row_pairs = sy / 2 + 1;
+            uint32_t       bt = 128, best = ~0u;
+            for (uint32_t t = 256; t >= 64; t -= 32) {
+                const uint32_t waste = (groups_x + t - 1) / t * t - groups_x;
+                if (waste < best) best = waste, bt = t;
+            }
+            for (uint32_t i0 = 0; i0 < pl->n_images; i0 += 65535) {  // gridDim.z limit
+                PlanarView     Vz = V;
+                const uint32_t nz = std::min<uint32_t>(65535, pl->n_images - i0);
+                for (int p = 0; p < 3; ++p)
+                    Vz.samples[p] = reinterpret_cast<const uint8_t *>(V.samples[p]) + (size_t) i0 * V.image_stride[p];
+                const dim3 grid((groups_x + bt - 1) / bt, std::min<uint32_t>(row_pairs, 4096), nz);
+                k_ycc420_to_rgb8_v2<<<grid, bt, 0, ctx->stream>>>(Vz, d_rgb + (size_t) i0 * sx * sy * 3);
+            }
+        }
         LAUNCH_CHECK(ctx);
         return JPEG_SM100_OK;
     }
