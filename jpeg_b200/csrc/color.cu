@@ -423,19 +423,19 @@ k_ycc_to_rgb8_tma(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rg
 }
 
 // 4:4:4 (and any layout whose planes all have factor == scale): no resampling; thread = 8 pixels of one row
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ycc444_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)
 {
+    // grid = (column groups / blockDim, rows (strided), images): no index divisions (see k_ycc420_to_rgb8_v2)
     const int      W = V.size_x, H = V.size_y;
     const int      groups_x = (W + 7) / 8;
-    const uint64_t per_image = (uint64_t) groups_x * H;
-    const uint64_t total = per_image * V.n_images;
     const bool     vec = (W & 7) == 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint32_t img = (uint32_t) (i / per_image);
-        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
-        const int      y = (int) (rem / groups_x), x0 = (int) (rem - (uint32_t) y * groups_x) * 8;
-        uint2          pl[3];
+    const int      gx = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t img = blockIdx.z;
+    if (gx >= groups_x) return;
+    for (int y = (int) blockIdx.y; y < H; y += (int) gridDim.y) {
+        const int x0 = 8 * gx;
+        uint2     pl[3];
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             const uint8_t *base = reinterpret_cast<const uint8_t *>(V.samples[p]) + (size_t) img * V.image_stride[p];
@@ -564,18 +564,17 @@ k_decompose(const void *__restrict__ src, const __grid_constant__ PlanarView V, 
 // The generic kernel reads every RGB pixel three times (once per plane) with 1-byte loads: 8.0 ms per 64 4K frames; this
 // reads them once with 8-byte loads.
 template <bool SUB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_rgb8_to_ycc_planes(const uint8_t *__restrict__ rgb, const __grid_constant__ PlanarView V)
 {
     constexpr int  ROWS = SUB ? 2 : 1;
+    // grid = (column groups / blockDim, rows (strided), images): no index divisions (see k_ycc420_to_rgb8_v2)
     const int      W = V.size_x, H = V.size_y;
     const int      groups_x = W / 8, rows_y = H / ROWS;
-    const uint64_t per_image = (uint64_t) groups_x * rows_y;
-    const uint64_t total = per_image * V.n_images;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint32_t img = (uint32_t) (i / per_image);
-        const uint32_t rem = (uint32_t) (i - (uint64_t) img * per_image);
-        const int      ry = (int) (rem / groups_x), gx = (int) (rem - (uint32_t) ry * groups_x);
+    const int      gx = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t img = blockIdx.z;
+    if (gx >= groups_x) return;
+    for (int ry = (int) blockIdx.y; ry < rows_y; ry += (int) gridDim.y) {
         const int      x0 = 8 * gx, y0 = ROWS * ry;
         uint32_t       cbs[ROWS][8], crs[ROWS][8];
 #pragma unroll
@@ -612,6 +611,18 @@ k_rgb8_to_ycc_planes(const uint8_t *__restrict__ rgb, const __grid_constant__ Pl
                 make_uint2(crs[0][0] | crs[0][1] << 8 | crs[0][2] << 16 | crs[0][3] << 24, crs[0][4] | crs[0][5] << 8 | crs[0][6] << 16 | crs[0][7] << 24);
         }
     }
+}
+
+// threads per CTA for the kernels whose CTAs span a row of 8-pixel groups: the multiple of 32 (64..256) that wastes the fewest
+// lanes on the last CTA of the row
+inline uint32_t row_threads(uint32_t groups_x)
+{
+    uint32_t bt = 128, best = ~0u;
+    for (uint32_t t = 256; t >= 64; t -= 32) {
+        const uint32_t waste = (groups_x + t - 1) / t * t - groups_x;
+        if (waste < best) best = waste, bt = t;
+    }
+    return bt;
 }
 
 int fill_view(const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy, int cosited, PlanarView &V)
@@ -681,8 +692,15 @@ int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *
         return JPEG_SM100_OK;
     }
     if (is444 && !no_fast) {
-        const uint64_t work = (uint64_t) ((sx + 7) / 8) * sy * pl->n_images;
-        k_ycc444_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
+        const uint32_t groups_x = (sx + 7) / 8, bt = row_threads(groups_x);
+        for (uint32_t i0 = 0; i0 < pl->n_images; i0 += 65535) {
+            PlanarView     Vz = V;
+            const uint32_t nz = std::min<uint32_t>(65535, pl->n_images - i0);
+            for (int p = 0; p < 3; ++p)
+                Vz.samples[p] = reinterpret_cast<const uint8_t *>(V.samples[p]) + (size_t) i0 * V.image_stride[p];
+            const dim3 grid((groups_x + bt - 1) / bt, std::min<uint32_t>(sy, 4096), nz);
+            k_ycc444_to_rgb8<<<grid, bt, 0, ctx->stream>>>(Vz, d_rgb + (size_t) i0 * sx * sy * 3);
+        }
         LAUNCH_CHECK(ctx);
         return JPEG_SM100_OK;
     }
@@ -691,13 +709,7 @@ int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *
         if (color_env && strcmp(color_env, "direct") == 0)  // first generation, kept for A/B validation
             k_ycc420_to_rgb8<<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(V, d_rgb);
         else {
-            // threads per CTA: the multiple of 32 (64..256) that wastes the fewest lanes on the last CTA of a row
-            const uint32_t groups_x = (sx + 7) / 8, row_pairs = sy / 2 + 1;
-            uint32_t       bt = 128, best = ~0u;
-            for (uint32_t t = 256; t >= 64; t -= 32) {
-                const uint32_t waste = (groups_x + t - 1) / t * t - groups_x;
-                if (waste < best) best = waste, bt = t;
-            }
+            const uint32_t groups_x = (sx + 7) / 8, row_pairs = sy / 2 + 1, bt = row_threads(groups_x);
             for (uint32_t i0 = 0; i0 < pl->n_images; i0 += 65535) {  // gridDim.z limit
                 PlanarView     Vz = V;
                 const uint32_t nz = std::min<uint32_t>(65535, pl->n_images - i0);
@@ -768,9 +780,17 @@ int jpeg_color_decompose(jpeg_sm100_ctx *ctx, const void *d_src, bool src_is_rgb
             ok = V.width[p] == (int) (sx * V.fx[p] / V.scale_x) && V.height[p] == (int) (sy * V.fy[p] / V.scale_y) &&
                  (reinterpret_cast<uintptr_t>(V.samples[p]) & 7) == 0 && (V.image_stride[p] & 7) == 0;
         if (ok) {
-            const uint64_t work = (uint64_t) (sx / 8) * (sy / (sub ? 2 : 1)) * pl->n_images;
-            if (sub) k_rgb8_to_ycc_planes<true><<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(reinterpret_cast<const uint8_t *>(d_src), V);
-            else k_rgb8_to_ycc_planes<false><<<grid_for(ctx, work, 128, 16), 128, 0, ctx->stream>>>(reinterpret_cast<const uint8_t *>(d_src), V);
+            const uint32_t groups_x = sx / 8, rows_y = sy / (sub ? 2 : 1), bt = row_threads(groups_x);
+            for (uint32_t i0 = 0; i0 < pl->n_images; i0 += 65535) {
+                PlanarView     Vz = V;
+                const uint32_t nz = std::min<uint32_t>(65535, pl->n_images - i0);
+                for (int p = 0; p < 3; ++p)
+                    Vz.samples[p] = reinterpret_cast<const uint8_t *>(V.samples[p]) + (size_t) i0 * V.image_stride[p];
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(d_src) + (size_t) i0 * sx * sy * 3;
+                const dim3     grid((groups_x + bt - 1) / bt, std::min<uint32_t>(rows_y, 4096), nz);
+                if (sub) k_rgb8_to_ycc_planes<true><<<grid, bt, 0, ctx->stream>>>(src, Vz);
+                else k_rgb8_to_ycc_planes<false><<<grid, bt, 0, ctx->stream>>>(src, Vz);
+            }
             LAUNCH_CHECK(ctx);
             return JPEG_SM100_OK;
         }
