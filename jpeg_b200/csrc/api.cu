@@ -513,7 +513,8 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
 
     // chunk size: ~100 MB of RGB per chunk, at least 1 image, at most the batch
     const size_t rgb_per_image = (size_t) sx * sy * 3;
-    uint32_t     chunk = (uint32_t) ((size_t) (100u << 20) / (rgb_per_image ? rgb_per_image : 1));
+    static const size_t chunk_mb = [] { const char *e = getenv("JPEG_SM100_CHUNK_MB"); return e && atoi(e) > 0 ? (size_t) atoi(e) : (size_t) 100; }();
+    uint32_t     chunk = (uint32_t) ((chunk_mb << 20) / (rgb_per_image ? rgb_per_image : 1));
     chunk = chunk < 1 ? 1 : (chunk > n_images ? n_images : chunk);
     const uint32_t n_chunks = (n_images + chunk - 1) / chunk + 4;  // (+ the partial chunk each group of images may end with)
     while (ctx->events.size() < (size_t) 2 * n_chunks) {
