@@ -178,3 +178,70 @@ def test_batch_raw_equals_batch_prelexed_4k(env):
                                                      got.ctypes.data, st.ctypes.data))
     assert st.tolist() == [0] * N
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("size,factors,n", [((200, 120), [(2, 2), (1, 1), (1, 1)], 37), ((97, 61), [(1, 1)], 19),
+                                             ((136, 104), [(2, 1), (1, 1), (1, 1)], 9)])
+def test_batch_entry_points_many_small_images(env, size, factors, n):
+    """the host-buffer batch entry points with more images than one group of their internal pipeline (groups of >= 8 images go
+    through upload -> lexer -> K3 -> K1/K2 -> download one after the other), per-image tables, colour and greyscale, odd sizes:
+    RGB equals the oracle's for every image; a corrupted image reports its own error and leaves the others intact."""
+    t, b, lib, O, ctx = env["torch"], env["batch"], env["lib"], env["O"], env["ctx"]
+    W, H = size
+    rng = np.random.default_rng(n)
+    geo = b.Geometry(size, factors)
+    npl = len(factors)
+    q = [O.quanta(0.5, 0)] + [O.quanta(0.5, 1)] * (npl - 1)
+    ecs_list, tabs, want = [], [], []
+    comps = list(range(npl))
+    sel = [0, 1, 1][:npl]
+    ival = geo.blocks[0] if npl > 1 else geo.units[0][0]
+    for i in range(n):
+        s = O.Spectral.create(size, factors)
+        for p in range(npl):
+            c = s.coefficients(p)
+            c[...] = np.where(rng.random(c.shape) < 0.1, rng.integers(-40, 40, c.shape), 0).astype(np.int16)
+            c[..., 0] = rng.integers(-100, 100, c.shape[:2])
+            s.set_quanta(p, q[p])
+        ecs, dct, act = s.encode_scan((0, 64), (0, None), comps, sel, sel, ival)
+        ecs_list.append(np.frombuffer(ecs, np.uint8))
+        mk = lambda x: lib.HuffTable.make(bytes(x.counts), bytes(x.values)) if x.present else lib.HuffTable()
+        tabs += [mk(x) for x in dct] + [mk(x) for x in act]
+        want.append(O.unpack_rgb(s.to_rectangular()))
+    want = np.stack(want)
+    desc = b.sequential_scan(geo, dc=sel, ac=sel)
+    tarr = (lib.HuffTable * (8 * n))(*tabs)
+    qz = np.ascontiguousarray(np.stack(q), dtype=np.uint16)
+    # raw scan bytes at odd offsets
+    raw_off, cat = [], bytearray()
+    for e in ecs_list:
+        cat += bytes(len(cat) % 5)
+        raw_off.append(len(cat))
+        cat += e.tobytes()
+    raw = np.frombuffer(bytes(cat) + bytes(64), np.uint8)
+    ro, rl = np.array(raw_off, np.uint64), np.array([len(e) for e in ecs_list], np.uint64)
+    n_ecs = geo.blocks[1] if npl > 1 else geo.units[0][1]
+    got, st = np.zeros_like(want), np.zeros(n, np.int32)
+    ctx.check(ctx.L.jpeg_sm100_decode_batch_raw_rgb8(ctx.h, C.byref(desc), n, raw.ctypes.data, ro.ctypes.data, rl.ctypes.data, n_ecs, ival,
+                                                     tarr, 0, qz.ctypes.data, W, H, 0, got.ctypes.data, st.ctypes.data))
+    assert st.tolist() == [0] * n
+    assert np.array_equal(got, want)
+    # the pre-lexed entry point on the same images
+    inputs = b.DecodeInputs(ecs_list, tabs, n_ecs_expected=n_ecs)
+    got2, st2 = np.zeros_like(want), np.zeros(n, np.int32)
+    ctx.check(ctx.L.jpeg_sm100_decode_batch_rgb8(ctx.h, C.byref(desc), n, inputs.ecs.ctypes.data, inputs.offsets.ctypes.data, n_ecs, ival,
+                                                 tarr, 0, qz.ctypes.data, W, H, 0, got2.ctypes.data, st2.ctypes.data))
+    assert st2.tolist() == [0] * n and np.array_equal(got2, want)
+    # image n // 2 cut short inside its second interval: its status is the truncation error, every other image is unchanged
+    bad = n // 2
+    offs = inputs.offsets.copy()
+    cut = int(offs[bad * n_ecs + 2] - offs[bad * n_ecs + 1]) // 2 + 1
+    ecs_cut = np.concatenate([inputs.ecs[:int(offs[bad * n_ecs + 2]) - cut], inputs.ecs[int(offs[bad * n_ecs + 2]):]])
+    offs[bad * n_ecs + 2:] -= np.uint64(cut)
+    got3, st3 = np.zeros_like(want), np.zeros(n, np.int32)
+    rc = ctx.L.jpeg_sm100_decode_batch_rgb8(ctx.h, C.byref(desc), n, ecs_cut.ctypes.data, offs.ctypes.data, n_ecs, ival, tarr, 0,
+                                            qz.ctypes.data, W, H, 0, got3.ctypes.data, st3.ctypes.data)
+    assert rc == lib.ERR_TRUNCATED_ECS
+    assert st3.tolist() == [lib.ERR_TRUNCATED_ECS if i == bad else 0 for i in range(n)]
+    keep = [i for i in range(n) if i != bad]
+    assert np.array_equal(got3[keep], want[keep])
