@@ -267,7 +267,11 @@ typedef struct {
  *   d_ecs_offsets  : device, n_images * n_ecs + 1 byte offsets into d_ecs (image-major)
  *   tables         : HOST, n_images sets of (dc[4], ac[4]) -- tables[i*8 + 0..3] = dc, [i*8 + 4..7] = ac;
  *                    if tables_shared != 0 only set 0 is read and used for every image
- *   d_status       : device, n_images int32: 0 or the error of the lowest-index failing interval (may be NULL) */
+ *   d_status       : device, n_images int32: 0 or the error of the lowest-index failing interval (may be NULL)
+ *   extend         : JPEG_SM100_SCAN_EXTEND and/or JPEG_SM100_SCAN_FRESH (see above), 0 for neither
+ * A baseline scan (band 0..<64) defines every coefficient of every block it decodes: blocks leave the decoder as whole
+ * 128-byte lines, so whatever the planes held there before is replaced (for in-plane blocks of intervals that decode without
+ * error); progressive scans touch only their band. */
 int jpeg_sm100_dev_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan,
                                const uint8_t *d_ecs, const uint64_t *d_ecs_offsets, uint32_t n_ecs,
                                uint64_t interval, int extend,
