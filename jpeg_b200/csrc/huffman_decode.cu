@@ -1091,6 +1091,193 @@ __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st
     return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
 }
 
+// ---- the decoding pass, warp-synchronous: blocks leave through a warp-cooperative flush -------------------------------------------
+// Same symbol loop as par_run<true, false, SAFE>, but every lane of the warp calls it (`go`: the lane has a subsequence to decode)
+// and the lanes stay converged, iterating until the slowest one is done (they did so anyway, as a divergent warp).  ncu of the
+// per-lane flush: at every warp iteration about two lanes complete a block, so the 8 LDS.128 + 8 STG.128 + 8 STS.128 of the
+// flush ran at 2 of 32 lanes -- 42 % of the kernel's shared-memory wavefronts and 31 % of its global requests.  Here a lane that
+// completes a block only queues (buffer address | in-plane, block index) in the warp's queue; right after the symbol step the
+// warp flushes the queued blocks together, 8 lanes x 16 bytes per block, 4 blocks per LDS.128 / STG.128 / STS.128:
+// one shared wavefront per block and direction instead of eight, one global request per four blocks instead of eight per block.
+#ifndef PAR_DEFER_DEN
+#define PAR_DEFER_DEN 4  // block-end work runs when 1 / PAR_DEFER_DEN of the warp's live lanes wait for it (32: at once)
+#endif
+__device__ __forceinline__ void sts128_zero(uint32_t a)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+}
+template <bool SAFE>
+__device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
+                                                  const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
+                                                  const uint16_t *ref_entries, const int nblk, bool &bad, uint32_t N,
+                                                  const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff,
+                                                  const uint32_t buf /* shared address of the lane's block buffer */,
+                                                  const uint32_t fq /* shared address of the warp's 32-entry flush queue */)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    int            z = st.z;
+    bad = false;
+    bool           run = go && st.p < end_bit && N < N_total;
+    uint32_t       done = 0;
+    int            left = run ? (int) (end_bit - st.p) : 0;
+    const int      slack = (int) (count_bits - end_bit);
+    uint32_t       wi = 0, cnt = 0, hi = 0, lo = 0, nxt = 0;
+    uint32_t       dtab = 0, atab = 0, tabs = 0, next = 0;
+    int            mx = 0, my = 0;
+    uint32_t       bidx = 0;  // destination of the block in progress, in 128-byte units from plane0
+    bool           inp = false, own = false;
+    int16_t       *dcp = dcdiff + N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
+    if (run) {
+        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
+        wi = ab >> 5;
+        cnt = ab & 31u;
+        hi = io.word(wi), lo = io.word(wi + 1);
+        nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));
+        wi += 3;
+        const uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
+        dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
+        const uint32_t mcu = N / (uint32_t) nblk;
+        my = my0 + (int) (mcu / (uint32_t) W);
+        mx = (int) (mcu - (mcu / (uint32_t) W) * (uint32_t) W);
+        const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
+        inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+        bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
+    }
+    __syncwarp();
+    bool wait = false;  // the lane's block is complete; its block-end work is pending
+    for (;;) {
+        const bool     actv = run && !wait && (left > 0 || own);
+        const uint32_t ma = __ballot_sync(FULL, actv), mw = __ballot_sync(FULL, wait);
+        if ((ma | mw) == 0u) break;
+        // Block ends are deferred: ~2 of 32 lanes complete a block at every step, and the ~80 instructions of the block-end work
+        // (successor tables, geometry, flush) at 2 lanes cost the warp more than the symbol step itself.  A lane that completes a
+        // block idles until a share of the live lanes (1 / PAR_DEFER_DEN) is waiting -- or nobody can proceed.
+        if (__popc(mw) * PAR_DEFER_DEN >= __popc(ma | mw)) {
+            bool     fin = false;
+            uint32_t fin_bidx = 0, fin_buf = 0;
+            if (wait) {
+                wait = false;
+                const uint32_t cur = next;
+                const uint4    q = lds128(cur);
+                dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
+                if (own) {
+                    fin = true, fin_bidx = bidx, fin_buf = buf | (inp ? 1u : 0u);
+                    own = false;
+                }
+                N += 1;
+                dcp += 1;
+                if (N >= N_total)
+                    run = false;
+                else {
+                    mx += (int) ((tabs >> 24) & 1u);
+                    if (mx == W) {
+                        mx = 0;
+                        my += 1;
+                    }
+                    const uint4 g = lds128(cur - 16u);
+                    inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+                    bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
+                }
+            }
+            const uint32_t m = __ballot_sync(FULL, fin);
+            if (m) {
+                if (fin) {
+                    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(fq + 8u * rank), "r"(fin_buf), "r"(fin_bidx) : "memory");
+                }
+                __syncwarp();
+                const uint32_t n = __popc(m), chunk = (lane & 7u) * 16u;
+                for (uint32_t k = lane >> 3; k < n; k += 4u) {
+                    uint32_t src, dst;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(src), "=r"(dst) : "r"(fq + 8u * k) : "memory");
+                    const uint32_t a = (src & ~1u) + chunk;
+                    uint4          v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                    if (src & 1u)
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk) = v;
+                    sts128_zero(a);
+                }
+                __syncwarp();
+            }
+            continue;
+        }
+        if (actv) do {
+                const bool in_range = left > 0;
+                if (cnt >= 32u) {
+                    hi = lo;
+                    asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // see par_run: swap at the point of use
+                    nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
+                    wi += 1;
+                    cnt -= 32u;
+                }
+                const uint32_t top = __funnelshift_l(lo, hi, cnt);
+                const bool     isdc = z == 0;
+                const uint32_t tab = isdc ? dtab : atab;
+                uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
+                if (ent & FAST_LINK) {
+                    const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
+                    ent = lds32(tab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
+                }
+                if (__builtin_expect(ent == 0u, 0)) {
+                    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+                    const int        ti = isdc ? (int) (tabs & 0xffu) : (int) ((tabs >> 8) & 0xffu);
+                    ent = fast_entry(lut_lookup(ref_entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);
+                    if (ent == 0u) {
+                        bad = true, run = false;
+                        break;
+                    }
+                }
+                const int total = (int) (ent >> 24), adv = (int) __byte_perm(ent, 0, 0x4442);
+                if (!SAFE) {
+                    if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2808-2811, 2859-2863
+                        bad = true, run = false;
+                        break;
+                    }
+                }
+                {
+                    const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441);
+                    const uint32_t top2 = top << len;
+                    const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
+                    const int      v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;  // T.81 EXTEND
+                    const int      zpos = z + adv - 1;
+                    if (isdc) {
+                        *dcp = (int16_t) v;
+                        own = true;
+                    } else if (own & (zpos < 64))
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + 2u * (uint32_t) zpos), "h"((uint16_t) v) : "memory");
+                }
+                cnt += (uint32_t) total;
+                left -= total;
+                z += adv;
+                if (z >= 64) {  // block complete (counted where its last symbol starts); the rest of the block-end work is deferred
+                    z = 0;
+                    done += in_range ? 1u : 0u;
+                    wait = true;
+                }
+            } while (0);
+    }
+    return done;
+}
+
+#ifndef PAR_COOP
+#define PAR_COOP 1  // 0: the per-lane flush of par_run<true, ...> (kept for A/B)
+#endif
+// SAFE is picked for the whole warp (see par_run_auto); lanes without work do not constrain it
+__device__ __forceinline__ uint32_t par_run_final_auto(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
+                                                       const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
+                                                       const uint16_t *ref_entries, const int nblk, bool &bad, const uint32_t N,
+                                                       const uint32_t N_total, const int W, const int my0, int16_t *plane0,
+                                                       int16_t *dcdiff, const uint32_t buf, const uint32_t fq)
+{
+    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 2048u + 32u + 64u) / 32u + 2u;
+    if (__all_sync(0xffffffffu, !go || last_word < io.wlim))
+        return par_run_final<true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    return par_run_final<false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+}
+
 // ---- progressive AC-first scans (kind 3) on the same machinery ------------------------------------------------------------------
 // One component, one table, blocks in raster order of the plane; the parse state is (bit position, z) alone -- no place in an MCU
 // to agree on, so streams re-synchronise quickly.  An EOBn symbol ends its block AND the n-1 blocks after it without consuming
@@ -1293,7 +1480,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[NT / 32];
     __shared__ ParGroup s_grp[NT / 16];
-    __shared__ uint32_t s_ck[PAR_NSEG][NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
+    __shared__ __align__(16) uint32_t s_ck[PAR_NSEG][NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
     const uint32_t   T = 1u << tshift, G = NT >> tshift;
 #ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
@@ -1443,7 +1630,17 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // ---- the one real decoding pass ---------------------------------------------------------------------------------------
     const uint32_t N_total = s_grp[g].N_total, slot = s_grp[g].slot;
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
-    if (active) {
+    if (PAR_COOP && !AC && stage_bytes == 0u) {  // every lane of every warp takes part in the cooperative flush
+        static_assert(sizeof(s_ck) >= NT * 8, "the flush queues live in the checkpoint array");
+        const bool     go = active && before < N_total;
+        const uint32_t done = par_run_final_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
+                                                 N_total, W, s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
+                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u);
+        if (active) {
+            if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
+            atomicAdd(&s_grp[g].total, done);
+        }
+    } else if (active) {
         st = unpack_state(my_entry);
         uint32_t done = 0;
         bad = false;
@@ -1556,7 +1753,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     __shared__ uint32_t s_warp[NT / 32];
     __shared__ int      s_dcw[4][NT / 32];
     __shared__ ParGroup s_q;
-    __shared__ uint32_t s_ck[PAR_NSEG][NT];
+    __shared__ __align__(16) uint32_t s_ck[PAR_NSEG][NT];
     const uint32_t  img = blockIdx.y, tid = threadIdx.x, e = blockIdx.x / csize;
     const uint32_t  T = NT * csize, l = crank * NT + tid;
     const int       lane = tid & 31, wid = tid >> 5;
@@ -1660,7 +1857,17 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     for (uint32_t r = 0; r < crank; ++r) before += remote32(&s_ctatotal, r);
     // ---- the decoding pass ----
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
-    if (active) {
+    if (PAR_COOP) {
+        static_assert(sizeof(s_ck) >= NT * 8, "the flush queues live in the checkpoint array");
+        const bool     go = active && before < N_total;
+        const uint32_t done = par_run_final_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
+                                                 N_total, W, s_q.r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
+                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u);
+        if (active) {
+            if (bad || (go && done != my_cnt)) atomicOr(&s_bad, 1u);
+            atomicAdd(&s_total, done);
+        }
+    } else if (active) {
         st = unpack_state(s_entry[tid]);
         uint32_t done = 0;
         bad = false;
