@@ -1464,6 +1464,9 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
 #ifndef PAR_MIN_CTAS
 #define PAR_MIN_CTAS 7
 #endif
+#ifndef PAR_ALIAS
+#define PAR_ALIAS 1
+#endif
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
 // stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
 // block buffers (PAR_BUF_STRIDE bytes each)
@@ -1474,13 +1477,24 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
              const uint32_t stage_off, const uint32_t stage_bytes, const uint32_t buf_off)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint64_t s_exit[NT], s_entry[NT];
-    __shared__ uint32_t s_cnt[NT];
-    __shared__ uint16_t s_work[NT];
+    // The records of the synchronisation (exit / entry states, block counts, checkpoints, work list) are dead once the decoding
+    // pass starts, and the threads' block buffers are unused until then: with PAR_ALIAS the records live in the buffer area
+    // (4.9 KB less shared memory per CTA: 7 CTAs per SM instead of 6).  AC scans have no block buffers and keep static arrays.
+    constexpr bool ALIAS = PAR_ALIAS && !AC;
+    static_assert(NT * (8 + 8 + 4 + 2 + 4 * PAR_NSEG) <= NT * (int) PAR_BUF_STRIDE, "records fit in the block buffers");
+    __shared__ uint64_t s_exit_st[ALIAS ? 1 : NT], s_entry_st[ALIAS ? 1 : NT];
+    __shared__ uint32_t s_cnt_st[ALIAS ? 1 : NT];
+    __shared__ uint16_t s_work_st[ALIAS ? 1 : NT];
     __shared__ uint32_t s_nwork;
     __shared__ uint32_t s_warp[NT / 32];
     __shared__ ParGroup s_grp[NT / 16];
-    __shared__ __align__(16) uint32_t s_ck[PAR_NSEG][NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
+    __shared__ __align__(16) uint32_t s_ck_st[ALIAS ? 1 : PAR_NSEG][ALIAS ? 4 : NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
+    __shared__ __align__(16) uint2 s_fq[ALIAS ? NT : 1];  // the warps' flush queues (without ALIAS they reuse the checkpoint array)
+    uint64_t *const s_exit = ALIAS ? reinterpret_cast<uint64_t *>(smem + buf_off) : s_exit_st;
+    uint64_t *const s_entry = ALIAS ? s_exit + NT : s_entry_st;
+    uint32_t (*const s_ck)[NT] = ALIAS ? reinterpret_cast<uint32_t (*)[NT]>(s_entry + NT) : reinterpret_cast<uint32_t (*)[NT]>(&s_ck_st[0][0]);
+    uint32_t *const s_cnt = ALIAS ? &s_ck[PAR_NSEG][0] : s_cnt_st;
+    uint16_t *const s_work = ALIAS ? reinterpret_cast<uint16_t *>(s_cnt + NT) : s_work_st;
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
     const uint32_t   T = 1u << tshift, G = NT >> tshift;
 #ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
@@ -1631,11 +1645,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const uint32_t N_total = s_grp[g].N_total, slot = s_grp[g].slot;
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
     if (PAR_COOP && !AC && stage_bytes == 0u) {  // every lane of every warp takes part in the cooperative flush
-        static_assert(sizeof(s_ck) >= NT * 8, "the flush queues live in the checkpoint array");
+        static_assert(PAR_NSEG * 4 >= 8, "the flush queues fit in the checkpoint array");
         const bool     go = active && before < N_total;
         const uint32_t done = par_run_final_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
                                                  N_total, W, s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u);
+                                                 (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
             atomicAdd(&s_grp[g].total, done);
