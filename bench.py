@@ -430,7 +430,7 @@ def run_ours(args):
                          "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5),
                          "note": "the HBM-bound kernel BASELINE.json's north_star sets the >= 70 % target on; the kernel that takes most of the step "
                                  "(K3, bound by instruction issue / LSU, not HBM) is under roofline_dominant"},
-            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 32 threads per restart interval, blocks assembled in shared memory and stored as whole lines, DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; bound by instruction issue and the LSU pipe (ncu: profiles/), not by HBM",
+            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 32 threads per restart interval, 8 CTAs x 4 warps per SM, blocks assembled in shared memory and flushed by the whole warp as 128-byte lines, DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; latency-bound, then issue-bound (ncu: 66 % issue-active at 32 resident warps, profiles/), not HBM-bound",
                                   "bound": "hbm", "achieved": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                   "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": k3_traffic() if n == BATCH else None,
                                   "bytes_per_launch": int(huff_bytes), "ms_per_launch": round(huff_ms, 4),

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int WARP = 32;
 #ifndef FAST_BITS_N
-#define FAST_BITS_N 9
+#define FAST_BITS_N 8  // 8 (with PAR_MIN_CTAS 8) rather than 9: 4 KB less shared memory per CTA buys an eighth CTA per SM
 #endif
 constexpr int FAST_BITS = FAST_BITS_N;               // codes of up to FAST_BITS bits resolve with one shared-memory load
 constexpr int FAST_ENTRIES = 1 << FAST_BITS;
@@ -824,7 +824,10 @@ finished:
 //   * anything irregular on the TRUE path (truncation, a symbol the sequential decoder rejects, a block count that does not
 //     match) flags the interval; flagged intervals are zeroed and re-decoded by k_decode_fast, which also produces the
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
-constexpr int PAR_THREADS = 128;
+#ifndef PAR_THREADS_N
+#define PAR_THREADS_N 128
+#endif
+constexpr int PAR_THREADS = PAR_THREADS_N;  // 128: four 32-thread intervals share a CTA (and one copy of the tables)
 constexpr int PAR_BIG_THREADS = 512;  // CTA size for scans with few, large intervals (no DRI: one entropy-coded segment per image)
 constexpr int PAR_MIN_BITS = 1024;
 #ifndef PAR_NSEG_N
@@ -1461,8 +1464,11 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
     return q;
 }
 
+// The kernel is latency-bound (every lane walks its own dependent chain of table look-ups), so resident warps are what
+// counts: 8 CTAs per SM = 32 warps needs <= 64 registers (62 used, no spills) and <= 27.5 KB of shared memory per CTA
+// (8-bit first-level tables + PAR_ALIAS).  Measured on the bench workload: 6 CTAs 2.79 ms, 7 CTAs 2.71 ms, 8 CTAs 2.39 ms.
 #ifndef PAR_MIN_CTAS
-#define PAR_MIN_CTAS 7
+#define PAR_MIN_CTAS 8
 #endif
 #ifndef PAR_ALIAS
 #define PAR_ALIAS 1
