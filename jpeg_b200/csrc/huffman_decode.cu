@@ -1525,9 +1525,13 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const uint16_t  *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
     const int        W = P.W, nblk = P.mcu_blocks;
     par_stage_tables<NT>(P, plane0, img, tid, smem, lut_img);
-    if (tid >= 32 && tid < 32 + G)  // one thread per interval of the CTA: where its bytes are, how it is cut
-        s_grp[tid - 32] = par_setup_group(P, img, blockIdx.x * G + (tid - 32), T, dc_per_interval, flagged,
-                                          sbase + stage_off + (tid - 32) * ((stage_bytes / G) & ~15u), (stage_bytes / G) & ~15u);
+    if (tid >= 32 && tid < 32 + NT / 16) {  // one thread per interval of the CTA: where its bytes are, how it is cut
+        if (tid - 32 < G)
+            s_grp[tid - 32] = par_setup_group(P, img, blockIdx.x * G + (tid - 32), T, dc_per_interval, flagged,
+                                              sbase + stage_off + (tid - 32) * ((stage_bytes / G) & ~15u), (stage_bytes / G) & ~15u);
+        else  // NT is not a multiple of T: the threads past the last whole interval idle (S = 0)
+            memset(&s_grp[tid - 32], 0, sizeof(ParGroup));
+    }
     __syncthreads();
     // ---- stage the intervals in shared memory: every byte is read from global memory once (coalesced), byte-swapped and
     // 1-padded (jpeg.swift:1881-1887) on the way; all parsing passes then refill from shared memory
