@@ -250,6 +250,7 @@ typedef struct {
 
 struct orc_spectral {
     int    sx, sy, bx, by, ncomp, scx, scy, process;
+    int    precision;       /* Format.precision (8 for JPEG.Common) */
     splane pl[4];
     int    nquanta;
     uint16_t (*quanta)[64]; /* quanta[0] = default (zeros), decode.swift:1723-1728 */
@@ -312,6 +313,7 @@ API orc_spectral *orc_spectral_create(int size_x, int size_y, int ncomp, const i
     zz_init();
     orc_spectral *s = (orc_spectral *) calloc(1, sizeof *s);
     s->ncomp = ncomp;
+    s->precision = 8;
     s->process = progressive ? 2 : 0;
     for (int p = 0; p < ncomp; ++p) {
         s->pl[p].fx = factors_xy[2 * p];
@@ -864,7 +866,9 @@ static int parse_huffman(const uint8_t *data, size_t n, orc_huff_spec dc[4], orc
 }
 
 /* decode.swift:568-615  Table.parse(quantization:) + Context.push(quanta:) 3664-3672 */
-static int parse_and_push_quanta(const uint8_t *data, size_t n, uint16_t (*out)[64], int *targets, int *nout)
+/* Table.parse(quantization:) decode.swift:480-530; 16-bit tables: Quantization.init(precision:values:target:) decode.swift:431-438.
+ * prec_out[i] = 0 (8-bit) / 1 (16-bit); whether a 16-bit table is acceptable depends on the format (see quanta_allowed). */
+static int parse_and_push_quanta(const uint8_t *data, size_t n, uint16_t (*out)[64], int *targets, int *prec_out, int *nout)
 {
     size_t base = 0;
     while (base < n) {
@@ -876,14 +880,20 @@ static int parse_and_push_quanta(const uint8_t *data, size_t n, uint16_t (*out)[
             for (int i = 0; i < 64; ++i) out[*nout][i] = data[base + 1 + i];
             base += 65;
         } else if (prec == 1) {
-            /* 16-bit DQT with an 8-bit format: DecodingError.invalidScanQuantizationPrecision decode.swift:2548-2557 */
-            return ORC_ERR_DECODE;
+            if (n < base + 129) return ORC_ERR_PARSE;
+            for (int i = 0; i < 64; ++i)
+                out[*nout][i] = (uint16_t) ((data[base + 1 + 2 * i] << 8) | data[base + 2 + 2 * i]);
+            base += 129;
         } else
             return ORC_ERR_PARSE;
+        prec_out[*nout] = prec;
         targets[(*nout)++] = target;
     }
     return ORC_OK;
 }
+/* Spectral.push(qi:quanta:) decode.swift:2546-2557: "an 8-bit dct-based process shall not use a 16-bit quantization table"
+ * -> DecodingError.invalidScanQuantizationPrecision */
+static int quanta_allowed(int format_precision, int table_prec) { return table_prec == 0 || format_precision > 8; }
 
 typedef struct {
     int id, fx, fy, qsel;
@@ -905,8 +915,12 @@ static int progression_update(orc_spectral *s, int band_lo, int band_hi, int bit
     return ORC_OK;
 }
 
-/* decode.swift:3728-3960  Context.decompress(stream:) */
-API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
+/* decode.swift:3728-3960  Context.decompress(stream:), generic over JPEG.Format (jpeg.swift:300-340).
+ * fmt_ids == NULL: JPEG.Common (jpeg.swift:370-397).  Otherwise a user-defined format in the style of
+ * examples/custom-color/main.swift:41-63: recognised iff the frame's component keys are exactly fmt_ids (as a set) and
+ * its precision is fmt_precision; planes are ordered as fmt_ids lists them (Layout.init(format:process:components:),
+ * jpeg.swift:1286-1329). */
+static orc_spectral *decompress_impl(const uint8_t *jpeg, size_t n, const int *fmt_ids, int fmt_n, int fmt_precision, int *err_out)
 {
     zz_init();
     int           err = ORC_OK;
@@ -943,7 +957,7 @@ API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
     orc_huff_spec pend_dc[64], pend_ac[64];
     int           pend_dc_t[64], pend_ac_t[64], npdc = 0, npac = 0;
     uint16_t      pend_q[16][64];
-    int           pend_q_t[16], npq = 0;
+    int           pend_q_t[16], pend_q_prec[16], npq = 0;
     int64_t       pend_interval = -2; /* -2 = not seen */
     framecomp     fc[4];
     int           nfc = 0, process = -1, precision = 0, fw = 0, fh = 0;
@@ -989,7 +1003,7 @@ API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
         }
         switch (marker) {
         case 0xdb:
-            if ((err = parse_and_push_quanta(body, blen, pend_q, pend_q_t, &npq))) goto done;
+            if ((err = parse_and_push_quanta(body, blen, pend_q, pend_q_t, pend_q_prec, &npq))) goto done;
             break;
         case 0xc4:
             if ((err = parse_huffman(body, blen, NULL, NULL, pend_dc, &npdc, pend_ac, &npac, pend_dc_t, pend_ac_t)))
@@ -1011,28 +1025,46 @@ API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
     }
 
     /* Context.init(frame:) -> Spectral.decode(frame:) decode.swift:2359-2388; Common.recognize jpeg.swift:370-397 */
-    if (precision != 8) FAIL(ORC_ERR_UNSUPPORTED);
-    if (!(nfc == 1 || nfc == 3)) FAIL(ORC_ERR_DECODE); /* unrecognizedColorFormat */
-    /* planes are ordered by sorted component key (format.components) */
-    for (int i = 0; i < nfc; ++i)
-        for (int j = i + 1; j < nfc; ++j)
-            if (fc[j].id < fc[i].id) {
-                framecomp t = fc[i];
-                fc[i] = fc[j];
-                fc[j] = t;
-            }
-    if (nfc == 3 && !(fc[1].id == fc[0].id + 1 && fc[2].id == fc[0].id + 2)) FAIL(ORC_ERR_DECODE);
+    if (fmt_ids) {
+        /* Format.recognize(_:precision:) in the style of examples/custom-color/main.swift:43-53 */
+        if (precision != fmt_precision || nfc != fmt_n) FAIL(ORC_ERR_DECODE); /* unrecognizedColorFormat */
+        framecomp ordered[4];
+        for (int i = 0; i < fmt_n; ++i) {
+            int k = -1;
+            for (int j = 0; j < nfc; ++j)
+                if (fc[j].id == fmt_ids[i]) k = j;
+            if (k < 0) FAIL(ORC_ERR_DECODE);
+            ordered[i] = fc[k];
+        }
+        for (int i = 0; i < fmt_n; ++i) fc[i] = ordered[i];
+    } else {
+        if (precision != 8) FAIL(ORC_ERR_DECODE); /* Common.recognize: precision 8 only (jpeg.swift:370-397) */
+        if (!(nfc == 1 || nfc == 3)) FAIL(ORC_ERR_DECODE); /* unrecognizedColorFormat */
+        /* planes are ordered by sorted component key (format.components) */
+        for (int i = 0; i < nfc; ++i)
+            for (int j = i + 1; j < nfc; ++j)
+                if (fc[j].id < fc[i].id) {
+                    framecomp t = fc[i];
+                    fc[i] = fc[j];
+                    fc[j] = t;
+                }
+        if (nfc == 3 && !(fc[1].id == fc[0].id + 1 && fc[2].id == fc[0].id + 2)) FAIL(ORC_ERR_DECODE);
+    }
     {
         int factors[8];
         for (int i = 0; i < nfc; ++i) factors[2 * i] = fc[i].fx, factors[2 * i + 1] = fc[i].fy;
         s = orc_spectral_create(fw, fh, nfc, factors, process == 2);
         s->process = process;
+        s->precision = precision;
         for (int i = 0; i < nfc; ++i) s->pl[i].comp_id = fc[i].id;
     }
     ctx.s = s;
     for (int i = 0; i < npdc; ++i) ctx.dc[pend_dc_t[i]] = pend_dc[i];
     for (int i = 0; i < npac; ++i) ctx.ac[pend_ac_t[i]] = pend_ac[i];
-    for (int i = 0; i < npq; ++i) ctx.qslot[pend_q_t[i]] = spectral_push_quanta(s, pend_q[i]);
+    for (int i = 0; i < npq; ++i) {
+        if (!quanta_allowed(precision, pend_q_prec[i])) FAIL(ORC_ERR_DECODE); /* invalidScanQuantizationPrecision */
+        ctx.qslot[pend_q_t[i]] = spectral_push_quanta(s, pend_q[i]);
+    }
     if (pend_interval != -2) ctx.interval = pend_interval == 0 ? -1 : pend_interval;
 
     int first = 1;
@@ -1042,8 +1074,11 @@ API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
         switch (marker) {
         case 0xdb: {
             npq = 0;
-            if ((err = parse_and_push_quanta(body, blen, pend_q, pend_q_t, &npq))) goto done;
-            for (int i = 0; i < npq; ++i) ctx.qslot[pend_q_t[i]] = spectral_push_quanta(s, pend_q[i]);
+            if ((err = parse_and_push_quanta(body, blen, pend_q, pend_q_t, pend_q_prec, &npq))) goto done;
+            for (int i = 0; i < npq; ++i) {
+                if (!quanta_allowed(precision, pend_q_prec[i])) FAIL(ORC_ERR_DECODE);
+                ctx.qslot[pend_q_t[i]] = spectral_push_quanta(s, pend_q[i]);
+            }
             break;
         }
         case 0xc4: {
@@ -1172,6 +1207,26 @@ done:
     return s;
 #undef FAIL
 #undef NEXT
+}
+API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
+{
+    return decompress_impl(jpeg, n, NULL, 0, 8, err_out);
+}
+API orc_spectral *orc_decompress_format(const uint8_t *jpeg, size_t n, const int *format_components, int n_components,
+                                        int format_precision, int *err_out)
+{
+    if (!format_components || n_components < 1 || n_components > 4) {
+        if (err_out) *err_out = ORC_ERR_PRECONDITION;
+        return NULL;
+    }
+    return decompress_impl(jpeg, n, format_components, n_components, format_precision, err_out);
+}
+API int  orc_spectral_precision(const orc_spectral *s) { return s->precision; }
+/* a blank image of a user-defined format: component keys in plane order, sample precision */
+API void orc_spectral_set_format(orc_spectral *s, const int *component_ids, int precision)
+{
+    for (int p = 0; p < s->ncomp; ++p) s->pl[p].comp_id = component_ids[p];
+    s->precision = precision;
 }
 
 /* ========================================================================= */
@@ -1997,7 +2052,7 @@ API int orc_spectral_to_planes(orc_spectral *s, uint16_t **planes)
     for (int p = 0; p < s->ncomp; ++p) {
         size_t n = (size_t) 64 * s->pl[p].ux * s->pl[p].uy;
         planes[p] = (uint16_t *) malloc((n ? n : 1) * sizeof(uint16_t));
-        orc_idct_plane(s->pl[p].coef, s->pl[p].ux, s->pl[p].uy, s->quanta[s->pl[p].q], 8, planes[p]);
+        orc_idct_plane(s->pl[p].coef, s->pl[p].ux, s->pl[p].uy, s->quanta[s->pl[p].q], s->precision, planes[p]);
     }
     return ORC_OK;
 }

@@ -73,6 +73,12 @@ typedef struct orc_spectral orc_spectral;
 
 /* full container decode: lexer + parsers + JPEG.Context.decompress (decode.swift:130-190, 475-1005, 3728-3960) */
 orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err);
+/* the same for a user-defined JPEG.Format in the style of examples/custom-color/main.swift:41-63 (recognised iff the frame's
+ * component keys are exactly format_components and its precision is format_precision; planes in the listed order) */
+orc_spectral *orc_decompress_format(const uint8_t *jpeg, size_t n, const int *format_components, int n_components,
+                                    int format_precision, int *err);
+int  orc_spectral_precision(const orc_spectral *s);
+void orc_spectral_set_format(orc_spectral *s, const int *component_ids, int precision);
 /* build an empty spectral image (Spectral.init(size:layout:...), decode.swift:2413) */
 orc_spectral *orc_spectral_create(int size_x, int size_y, int ncomp, const int *factors_xy /*2*ncomp*/,
                                   int progressive);

@@ -75,6 +75,10 @@ def lib():
     L.orc_quanta.argtypes = [C.c_double, C.c_int, u16p]
     L.orc_decompress.restype = C.c_void_p
     L.orc_decompress.argtypes = [C.c_char_p, C.c_size_t, ip]
+    L.orc_decompress_format.restype = C.c_void_p
+    L.orc_decompress_format.argtypes = [C.c_char_p, C.c_size_t, ip, C.c_int, C.c_int, ip]
+    L.orc_spectral_precision.argtypes = [C.c_void_p]
+    L.orc_spectral_set_format.argtypes = [C.c_void_p, ip, C.c_int]
     L.orc_spectral_create.restype = C.c_void_p
     L.orc_spectral_create.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int]
     L.orc_spectral_free.argtypes = [C.c_void_p]
@@ -162,18 +166,32 @@ class Spectral:
         self.process = pr.value
 
     @classmethod
-    def decompress(cls, data: bytes):
+    def decompress(cls, data: bytes, format=None):
+        """format: None = JPEG.Common; (component keys in plane order, precision) = a user-defined JPEG.Format in the style of
+        examples/custom-color/main.swift:41-63."""
         err = C.c_int()
-        h = lib().orc_decompress(data, len(data), C.byref(err))
+        if format is None:
+            h = lib().orc_decompress(data, len(data), C.byref(err))
+        else:
+            ids, precision = format
+            h = lib().orc_decompress_format(data, len(data), _ints(list(ids)), len(ids), precision, C.byref(err))
         if not h:
             raise OracleError(err.value)
         return cls(h)
 
     @classmethod
-    def create(cls, size, factors, progressive=False):
+    def create(cls, size, factors, progressive=False, format=None):
         flat = [v for f in factors for v in f]
         h = lib().orc_spectral_create(size[0], size[1], len(factors), _ints(flat), int(progressive))
+        if format is not None:
+            ids, precision = format
+            assert len(ids) == len(factors)
+            lib().orc_spectral_set_format(h, _ints(list(ids)), precision)
         return cls(h)
+
+    @property
+    def precision(self):
+        return lib().orc_spectral_precision(self._h)
 
     def __del__(self):
         try:
@@ -248,7 +266,7 @@ class Spectral:
         planes = []
         for p in range(self.ncomp):
             (ux, uy), _, _ = self.plane_info(p)
-            planes.append(idct_plane(self.coefficients(p), self.quanta(p)))
+            planes.append(idct_plane(self.coefficients(p), self.quanta(p), self.precision))
         return planes
 
     def to_rectangular(self, cosited=False):

@@ -37,12 +37,13 @@ def rd(p):
         return f.read()
 
 
-def copy(p, sub):
+def copy(p, sub, name=None):
     os.makedirs(os.path.join(HERE, sub), exist_ok=True)
-    dst = os.path.join(HERE, sub, os.path.basename(p))
+    name = name or os.path.basename(p)
+    dst = os.path.join(HERE, sub, name)
     shutil.copyfile(os.path.join(REF, p), dst)
     os.chmod(dst, 0o644)
-    return os.path.join(sub, os.path.basename(p))
+    return os.path.join(sub, name)
 
 
 def scans_of(jpeg_bytes):
@@ -95,6 +96,13 @@ def main():
     man["encode_advanced"] = {"rgb_sha256": sha(rd("examples/encode-advanced/karlie-cfdas-2011.png.rgb")),
                               "size": [600, 900],
                               **scans_of(rd("examples/encode-advanced/karlie-cfdas-2011.png.rgb.jpg"))}
+    # examples/custom-color: a user-defined format (components 4-7, 12-bit samples, 16-bit DQT), 10-scan progression with
+    # two-component DC scans of unequal sampling; the .rgb is the INPUT of the encode (main.swift:206), 12 bits in 2 bytes
+    rel = copy("examples/custom-color/output.jpg", "examples", "custom-color-output.jpg")
+    man["custom_color"] = {"jpeg": rel, "size": [1000, 200], "format": [[4, 5, 6, 7], 12],
+                           "factors": [[2, 2], [2, 2], [2, 2], [1, 1]],
+                           "rgb_sha256": sha(rd("examples/custom-color/output.jpg.rgb")),
+                           **scans_of(rd("examples/custom-color/output.jpg"))}
     # tests/unit/tests.swift:170-340: 162 (length, codeword) pairs of the T.81 K.3.3.2 AC-luminance table, listed in
     # the order the unit test walks the symbols (run/size 0x00, 0x01..0x0A, 0x11.., 0xF0, ...)
     import re

@@ -80,10 +80,15 @@ def parse_dht(body: bytes):
 
 
 def parse_dqt(body: bytes):
+    """-> list of (target, 64 quanta in zig-zag order); 8-bit and 16-bit (Pq = 1, big-endian) tables"""
     out, i = [], 0
     while i < len(body):
         prec, tgt = body[i] >> 4, body[i] & 15
-        assert prec == 0
-        out.append((tgt, list(body[i + 1:i + 65])))
-        i += 65
+        assert prec in (0, 1)
+        if prec == 0:
+            out.append((tgt, list(body[i + 1:i + 65])))
+            i += 65
+        else:
+            out.append((tgt, [(body[i + 1 + 2 * k] << 8) | body[i + 2 + 2 * k] for k in range(64)]))
+            i += 129
     return out

@@ -2,7 +2,8 @@
 
 Mirrors tests/regression/tests.swift:39-138 (decode -> .ycc / .rgb byte compare), tests/unit/tests.swift
 (zig-zag, amplitude coding, Annex-K Huffman KAT, invalid codewords, Huffman round trip) and uses the committed
-outputs of examples/{decode-basic,decode-advanced,in-memory,encode-basic,recompress,encode-advanced} as vectors.
+outputs of examples/{decode-basic,decode-advanced,in-memory,encode-basic,recompress,encode-advanced,rotate,custom-color}
+as vectors.
 """
 import hashlib
 import os
@@ -249,6 +250,87 @@ def test_encode_advanced_golden(manifest):
     for p in range(3):
         s.coefficients(p)[...] = O.fdct_plane(planes[p], q0 if p == 0 else q1)
     _check_scans(s, exp)
+
+
+# ---------------------------------------------------------------- user-defined format, 12-bit samples (N4)
+
+def custom_color_pixels():
+    """examples/custom-color/main.swift:123-134: the gradient the example encodes, as 12-bit (r, g, b, a) samples."""
+    def stride(a, b, step):  # Swift's stride(from:to:by:) over Double: a + i * step
+        n = 0
+        while a + n * step < b:
+            n += 1
+        return a + np.arange(n, dtype=np.float64) * step
+
+    def wave(x):  # UInt16(0x0fff * (sin(2 pi x) * 0.5 + 0.5)): truncating conversion
+        return np.trunc(0x0fff * (np.sin(2.0 * np.pi * x) * 0.5 + 0.5)).astype(np.uint16)
+    t = stride(0.0, 1.0, 0.005)[:, None] + stride(0.0, 1.0, 0.001)[None, :]
+    return np.stack([wave(t - 0.15), wave(t), wave(t + 0.15), np.full(t.shape, 0x0fff, np.uint16)], axis=-1)
+
+
+def test_custom_color_golden(manifest):
+    """examples/custom-color: a user-defined JPEG.Format (components 4-7, 12-bit precision) written as a 10-scan
+    progression (two-component DC scans of unequal sampling, AC first + refinement per component, 16-bit DQT).
+    The committed output.jpg pins, bit for bit: Rectangular.decomposed() over four planes, the 12-bit FDCT + quantiser,
+    the progressive scan decoders on that file, and the progressive encoders (tables + entropy-coded bytes)."""
+    cc = manifest["custom_color"]
+    fmt = (cc["format"][0], cc["format"][1])
+    w, h = cc["size"]
+    factors = [tuple(f) for f in cc["factors"]]
+    px = custom_color_pixels()
+    assert px.shape == (h, w, 4)
+    # main.swift:196-204: the .rgb the example writes next to the file is its INPUT, 12 bits left-aligned in two bytes
+    rgb = px[..., :3]
+    dump = np.stack([(rgb >> 4).astype(np.uint8), ((rgb << 4) & 0xff).astype(np.uint8)], axis=-1)
+    assert sha(dump.tobytes()) == cc["rgb_sha256"]
+    q = [np.array([1, 2, 2, 3, 3, 3] + [10] * 58, dtype=np.uint16), np.array([1] + [100] * 63, dtype=np.uint16)]
+    assert [t[1] for t in cc["dqt"]] == [q[0].tolist(), q[1].tolist()]
+    jpeg = golden_bytes(cc["jpeg"])
+    # JPEG.Common does not recognise the file (jpeg.swift:370-397): DecodingError.unrecognizedColorFormat
+    with pytest.raises(O.OracleError) as e:
+        O.Spectral.decompress(jpeg)
+    assert e.value.code == -12
+    dec = O.Spectral.decompress(jpeg, format=fmt)
+    assert dec.size == (w, h) and dec.ncomp == 4 and dec.precision == 12
+    assert [dec.plane_info(p)[2] for p in range(4)] == fmt[0] and [dec.factor(p) for p in range(4)] == factors
+    # forward path from the pixels == what the decoders read back from the reference's file
+    planes = O.decompose(px, factors)
+    enc = O.Spectral.create((w, h), factors, progressive=True, format=fmt)
+    for p in range(4):
+        enc.set_quanta(p, q[1 if p == 3 else 0])
+        enc.coefficients(p)[...] = O.fdct_plane(planes[p], q[1 if p == 3 else 0], precision=12)
+        assert np.array_equal(enc.coefficients(p), dec.coefficients(p)), p
+        assert np.array_equal(dec.quanta(p), q[1 if p == 3 else 0]), p
+    _check_scans(enc, cc)
+    _check_scans(dec, cc)
+    # inverse path (no committed output for it: the example only shows a difference image): 12-bit samples, small error
+    out = dec.to_rectangular()
+    assert out.shape == (h, w, 4) and int(out.max()) <= 0x0fff
+    assert int(np.abs(out[..., :3].astype(np.int32) - rgb.astype(np.int32)).max()) <= 4
+    assert np.all(out[..., 3] == 0x0fff)
+
+
+def test_16bit_quanta_need_a_deep_format(manifest):
+    """Spectral.push(qi:quanta:) decode.swift:2546-2557: a 16-bit DQT in an 8-bit image is
+    DecodingError.invalidScanQuantizationPrecision; 8-bit tables in a 12-bit image are fine (examples/custom-color would
+    have written them had its format been 8-bit: decode.swift:2530)."""
+    src = golden_bytes(manifest["decode"][0]["jpeg"])
+    out = bytearray()
+    for m, body, ecs in J.split(src):
+        if m == 0xDB:  # rewrite every table as Pq = 1
+            wide = bytearray()
+            for tgt, vals in J.parse_dqt(body):
+                wide.append(0x10 | tgt)
+                for v in vals:
+                    wide += bytes([v >> 8, v & 0xff])
+            body = bytes(wide)
+        out += bytes([0xFF, m])
+        if m not in (0xD8, 0xD9):
+            out += (len(body) + 2).to_bytes(2, "big") + body + ecs
+    O.Spectral.decompress(src)
+    with pytest.raises(O.OracleError) as e:
+        O.Spectral.decompress(bytes(out))
+    assert e.value.code == -12
 
 
 # ---------------------------------------------------------------- our restart-interval extension of the encoder
