@@ -67,6 +67,18 @@ def _zigzag(k, h):
 # ---------------------------------------------------------------------------------------------------------------
 # data types
 # ---------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Format:
+    """A user-defined JPEG.Format (jpeg.swift:300-340) in the style of examples/custom-color/main.swift:41-63: recognised iff
+    the frame's component keys are exactly `components` and its precision is `precision`; `components` orders the planes.
+    `None` wherever a format is expected means JPEG.Common (jpeg.swift:370-397)."""
+    components: tuple
+    precision: int
+
+    def recognize(self, keys, precision):
+        return sorted(keys) == sorted(self.components) and precision == self.precision
+
+
 @dataclass
 class SpectralPlane:
     units: tuple
@@ -86,9 +98,10 @@ class Scan:
 class Spectral:
     """JPEG.Data.Spectral<JPEG.Common> (decode.swift:1397-1519)."""
 
-    def __init__(self, size, factors, comp_ids=None, process=0, ctx=None):
+    def __init__(self, size, factors, comp_ids=None, process=0, ctx=None, precision=8):
         self.ctx = ctx or default_context()
         self.process = process
+        self.precision = precision  # Format.precision: 8 for JPEG.Common, up to 16 for user-defined formats
         self.scale = (max(f[0] for f in factors), max(f[1] for f in factors))
         self.quanta = [np.zeros(64, dtype=np.uint16)]
         self.planes = [SpectralPlane((0, 0), tuple(f), np.zeros((0, 0, 64), np.int16), 0,
@@ -186,11 +199,14 @@ class Spectral:
             s = np.zeros((8 * uy, 8 * ux), dtype=np.uint16)
             coef = np.ascontiguousarray(p.coef)
             q = np.ascontiguousarray(self.quanta[p.q], dtype=np.uint16)
-            self.ctx.check(self.ctx.L.jpeg_sm100_idct(self.ctx.h, _ptr(coef), ux, uy, _ptr(q), 8, _ptr(s)))
+            self.ctx.check(self.ctx.L.jpeg_sm100_idct(self.ctx.h, _ptr(coef), ux, uy, _ptr(q), self.precision, _ptr(s)))
             out.append(s)
-        return Planar(self.size, [p.units for p in self.planes], [p.factor for p in self.planes], out, self.ctx)
+        return Planar(self.size, [p.units for p in self.planes], [p.factor for p in self.planes], out, self.ctx,
+                      self.precision)
 
     def idct_u8(self):
+        if self.precision != 8:
+            raise ValueError("8-bit sample planes exist for 8-bit formats only")
         out = []
         for p in self.planes:
             ux, uy = p.units
@@ -270,8 +286,8 @@ class Spectral:
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod
-    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False):
-        return _decompress(data, ctx or default_context(), gpu_lexer)
+    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None):
+        return _decompress(data, ctx or default_context(), gpu_lexer, format)
 
     def compress(self, scans=None, quanta_slots=None, interval_mcus=0, jfif=True):
         return _compress(self, scans, quanta_slots, interval_mcus, jfif)
@@ -280,9 +296,10 @@ class Spectral:
 class Planar:
     """JPEG.Data.Planar<JPEG.Common> (decode.swift:1543-1632); planes are uint16 (8uy, 8ux)."""
 
-    def __init__(self, size, units_list, factors, planes, ctx=None):
+    def __init__(self, size, units_list, factors, planes, ctx=None, precision=8):
         self.ctx = ctx or default_context()
         self.size, self.units, self.factors, self.planes = size, list(units_list), list(factors), planes
+        self.precision = precision
 
     def _structs(self):
         arr = (L.PlaneU16 * len(self.planes))()
@@ -299,17 +316,17 @@ class Planar:
         out = np.zeros((self.size[1], self.size[0], n), dtype=np.uint16)
         self.ctx.check(self.ctx.L.jpeg_sm100_interleave(self.ctx.h, self._structs(), n, self.size[0], self.size[1],
                                                         int(cosite), _ptr(out)))
-        return Rectangular(self.size, self.factors, out, self.ctx)
+        return Rectangular(self.size, self.factors, out, self.ctx, self.precision)
 
-    def fdct(self, quanta):
+    def fdct(self, quanta, comp_ids=None, process=0):
         """Planar.fdct(quanta:) encode.swift:353 -> jpeg_sm100_fdct per plane.  quanta: one 64-array per plane."""
-        sp = Spectral(self.size, self.factors, ctx=self.ctx)
+        sp = Spectral(self.size, self.factors, comp_ids, process, ctx=self.ctx, precision=self.precision)
         for i, pl in enumerate(self.planes):
             ux, uy = self.units[i]
             pl = np.ascontiguousarray(pl, dtype=np.uint16)
             q = np.ascontiguousarray(quanta[i], dtype=np.uint16)
             coef = np.zeros((uy, ux, 64), dtype=np.int16)
-            self.ctx.check(self.ctx.L.jpeg_sm100_fdct(self.ctx.h, _ptr(pl), ux, uy, _ptr(q), 8, _ptr(coef)))
+            self.ctx.check(self.ctx.L.jpeg_sm100_fdct(self.ctx.h, _ptr(pl), ux, uy, _ptr(q), self.precision, _ptr(coef)))
             sp.planes[i].coef = coef
             sp.quanta.append(q.copy())
             sp.planes[i].q = len(sp.quanta) - 1
@@ -319,9 +336,10 @@ class Planar:
 class Rectangular:
     """JPEG.Data.Rectangular<JPEG.Common> (decode.swift:1650-1718); values uint16 (h, w, n)."""
 
-    def __init__(self, size, factors, values, ctx=None):
+    def __init__(self, size, factors, values, ctx=None, precision=8):
         self.ctx = ctx or default_context()
         self.size, self.factors, self.values = size, list(factors), values
+        self.precision = precision
 
     def _unpack(self, fn):
         v = np.ascontiguousarray(self.values, dtype=np.uint16)
@@ -353,7 +371,7 @@ class Rectangular:
         scx, scy = max(f[0] for f in self.factors), max(f[1] for f in self.factors)
         us = [(units(w * fx, 8 * scx), units(h * fy, 8 * scy)) for fx, fy in self.factors]
         planes = [np.zeros((8 * uy, 8 * ux), dtype=np.uint16) for ux, uy in us]
-        pl = Planar(self.size, us, self.factors, planes, self.ctx)
+        pl = Planar(self.size, us, self.factors, planes, self.ctx, self.precision)
         v = np.ascontiguousarray(self.values, dtype=np.uint16)
         self.ctx.check(self.ctx.L.jpeg_sm100_decompose(self.ctx.h, _ptr(v), w, h, pl._structs(), len(planes)))
         return pl
@@ -447,10 +465,13 @@ def _parse_dqt(body):
         if prec == 0:
             if len(body) < base + 65:
                 raise ParsingError("mismatched quantization segment")
-            out.append((tgt, np.frombuffer(body[base + 1:base + 65], dtype=np.uint8).astype(np.uint16)))
+            out.append((tgt, np.frombuffer(body[base + 1:base + 65], dtype=np.uint8).astype(np.uint16), 0))
             base += 65
-        elif prec == 1:
-            raise DecodingError("invalidScanQuantizationPrecision")
+        elif prec == 1:  # decode.swift:431-438: 64 big-endian UInt16
+            if len(body) < base + 129:
+                raise ParsingError("mismatched quantization segment")
+            out.append((tgt, np.frombuffer(body[base + 1:base + 129], dtype=">u2").astype(np.uint16), 1))
+            base += 129
         else:
             raise ParsingError("invalidQuantizationPrecisionCode")
     return out
@@ -460,7 +481,16 @@ def _is_frame(m):
     return 0xC0 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC)
 
 
-def _decompress(data, ctx, gpu_lexer=False):
+def _push_quanta(s, qslot, tables):
+    """Spectral.push(qi:quanta:) decode.swift:2546-2557: an 8-bit image shall not use a 16-bit quantisation table"""
+    for tgt, q, prec in tables:
+        if prec == 1 and s.precision <= 8:
+            raise DecodingError("invalidScanQuantizationPrecision")
+        s.quanta.append(q)
+        qslot[tgt] = len(s.quanta) - 1
+
+
+def _decompress(data, ctx, gpu_lexer=False, format=None):
     lx = _Lexer(bytes(data))
     _, m, body = lx.segment()
     if m != 0xD8:
@@ -495,8 +525,8 @@ def _decompress(data, ctx, gpu_lexer=False):
                     raise ParsingError("invalidFrameQuantizationSelector")
             if process is None:
                 raise DecodingError("unsupportedFrameCodingProcess")
-            if precision != 8:
-                raise DecodingError("unsupported precision")
+            if (process == 0 and precision != 8) or precision not in (8, 12):
+                raise ParsingError("invalidFramePrecision")  # decode.swift:700-768
             _, m, body = lx.segment()
             break
         if m == 0xDB:
@@ -512,14 +542,18 @@ def _decompress(data, ctx, gpu_lexer=False):
             raise DecodingError("premature / unexpected segment")
         _, m, body = lx.segment()
 
-    comps.sort(key=lambda c: c[0])
-    if not (len(comps) == 1 or (len(comps) == 3 and comps[1][0] == comps[0][0] + 1 and comps[2][0] == comps[0][0] + 2)):
-        raise DecodingError("unrecognizedColorFormat")
-    s = Spectral((fw, fh), [(c[1], c[2]) for c in comps], [c[0] for c in comps], process, ctx)
+    if format is not None:  # Format.recognize; planes in the order format.components lists them (jpeg.swift:1286-1329)
+        if not format.recognize([c[0] for c in comps], precision):
+            raise DecodingError("unrecognizedColorFormat")
+        comps.sort(key=lambda c: list(format.components).index(c[0]))
+    else:  # JPEG.Common.recognize (jpeg.swift:370-397)
+        comps.sort(key=lambda c: c[0])
+        if precision != 8 or not (len(comps) == 1 or (len(comps) == 3 and comps[1][0] == comps[0][0] + 1
+                                                      and comps[2][0] == comps[0][0] + 2)):
+            raise DecodingError("unrecognizedColorFormat")
+    s = Spectral((fw, fh), [(c[1], c[2]) for c in comps], [c[0] for c in comps], process, ctx, precision)
     qsel = {c[0]: c[3] for c in comps}
-    for tgt, q in pend_q:
-        s.quanta.append(q)
-        qslot[tgt] = len(s.quanta) - 1
+    _push_quanta(s, qslot, pend_q)
     approx = [[None] * 64 for _ in comps]  # Progression, jpeg.swift:1581-1634
 
     first = True
@@ -527,9 +561,7 @@ def _decompress(data, ctx, gpu_lexer=False):
         if _is_frame(m):
             raise DecodingError("duplicateFrameHeaderSegment")
         if m == 0xDB:
-            for tgt, q in _parse_dqt(body):
-                s.quanta.append(q)
-                qslot[tgt] = len(s.quanta) - 1
+            _push_quanta(s, qslot, _parse_dqt(body))
         elif m == 0xC4:
             for cls, tgt, t in _parse_dht(body):
                 (dc if cls == 0 else ac)[tgt] = t
@@ -659,13 +691,16 @@ def _compress(s: Spectral, scans, quanta_slots, interval_mcus, jfif):
     if jfif:
         out += _seg(0xE0, b"JFIF\0" + bytes([1, 2, 2, 0, 1, 0, 1, 0, 0]))
     quanta_slots = quanta_slots or {p.q: min(i, 1) for i, p in enumerate(s.planes)}
-    sof = bytes([8, s.size[1] >> 8, s.size[1] & 255, s.size[0] >> 8, s.size[0] & 255, len(s.planes)])
+    sof = bytes([s.precision, s.size[1] >> 8, s.size[1] & 255, s.size[0] >> 8, s.size[0] & 255, len(s.planes)])
     for p in s.planes:
         sof += bytes([p.comp_id, (p.factor[0] << 4) | p.factor[1], quanta_slots[p.q]])
     out += _seg(0xC2 if s.process == 2 else (0xC1 if s.process == 1 else 0xC0), sof)
     dqt = b""
     for qi, slot in sorted(quanta_slots.items(), key=lambda kv: kv[1]):
-        dqt += bytes([slot]) + bytes(int(v) for v in s.quanta[qi])
+        if s.precision > 8:  # decode.swift:2528-2532: formats deeper than 8 bits write 16-bit tables
+            dqt += bytes([0x10 | slot]) + np.asarray(s.quanta[qi], dtype=">u2").tobytes()
+        else:
+            dqt += bytes([slot]) + bytes(int(v) for v in s.quanta[qi])
     out += _seg(0xDB, dqt)
     if interval_mcus:
         out += _seg(0xDD, bytes([interval_mcus >> 8, interval_mcus & 255]))

@@ -113,6 +113,47 @@ def test_four_planes_of_12_bit_samples(H, O):
         assert np.array_equal(back.planes[p], want[p]), p
 
 
+def test_custom_format_file_through_gpu(manifest, H, O):
+    """N4 (host level): examples/custom-color/output.jpg -- a user-defined JPEG.Format (components 4-7, 12-bit samples, 16-bit
+    DQT), ten progressive scans with two-component DC scans of unequal sampling -- decoded, inverse-transformed, forward-
+    transformed from the example's pixels and written back through the CUDA path.  The writer must return the reference's
+    file byte for byte."""
+    from test_oracle_golden import custom_color_pixels
+    cc = manifest["custom_color"]
+    fmt = H.Format(tuple(cc["format"][0]), cc["format"][1])
+    w, h = cc["size"]
+    factors = [tuple(f) for f in cc["factors"]]
+    data = golden_bytes(cc["jpeg"])
+    ref = O.Spectral.decompress(data, format=(list(fmt.components), fmt.precision))
+    with pytest.raises(H.DecodingError, match="unrecognizedColorFormat"):
+        H.Spectral.decompress(data)
+    for gpu_lexer in (False, True):
+        s = H.Spectral.decompress(data, format=fmt, gpu_lexer=gpu_lexer)
+        assert s.size == (w, h) and s.precision == 12 and [p.comp_id for p in s.planes] == [4, 5, 6, 7]
+        for p in range(4):
+            assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (gpu_lexer, p)
+            assert np.array_equal(s.quanta[s.planes[p].q], ref.quanta(p)), (gpu_lexer, p)
+    # inverse path: 12-bit IDCT, four planes interleaved
+    planar = s.idct()
+    for p, pl in enumerate(ref.idct()):
+        assert np.array_equal(planar.planes[p], pl), ("idct", p)
+    rect = planar.interleaved()
+    assert rect.precision == 12 and np.array_equal(rect.values, ref.to_rectangular())
+    # forward path from the example's pixels (main.swift:123-134): decomposed() over four planes, 12-bit FDCT + quantiser
+    px = custom_color_pixels()
+    q = [np.array([1, 2, 2, 3, 3, 3] + [10] * 58, dtype=np.uint16), np.array([1] + [100] * 63, dtype=np.uint16)]
+    pl = H.Rectangular((w, h), factors, px, precision=12).decomposed()
+    for p, want in enumerate(O.decompose(px, factors)):
+        assert np.array_equal(pl.planes[p], want), ("decomposed", p)
+    enc = pl.fdct([q[0], q[0], q[0], q[1]], comp_ids=list(fmt.components), process=2)
+    for p in range(4):
+        assert np.array_equal(enc.planes[p].coef, ref.coefficients(p)), ("fdct", p)
+    # the writer: same progression, quanta 0 shared by R, G, B (main.swift:143-149)
+    enc.planes[1].q = enc.planes[2].q = enc.planes[0].q
+    out = enc.compress(scans=s.scans, quanta_slots={enc.planes[0].q: 0, enc.planes[3].q: 1}, jfif=False)
+    assert out == data and sha(out) == cc["file_sha256"]
+
+
 # ------------------------------------------------------------------------------------------------ single stages
 @pytest.mark.parametrize("ux,uy", [(1, 1), (3, 2), (17, 5), (128, 1), (129, 3), (40, 40)])
 def test_idct_random_blocks(H, O, ux, uy):
