@@ -231,7 +231,8 @@ class Spectral:
     def requantized(self, new_quanta):
         """examples/recompress/main.swift:35-58: the same image with other quantisation tables, without leaving the
         coefficient domain.  new_quanta: one 64-entry table (zig-zag) per entry of self.quanta."""
-        out = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx)
+        out = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx,
+                       self.precision)
         out.quanta = [np.ascontiguousarray(q, dtype=np.uint16) for q in new_quanta]
         for src, dst in zip(self.planes, out.planes):
             dst.q = src.q
@@ -268,12 +269,13 @@ class Spectral:
             w -= w % (8 * self.scale[0])
         if kind in ("iii", "iv"):
             h -= h % (8 * self.scale[1])
-        src = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx)
+        src = Spectral(self.size, [p.factor for p in self.planes], [p.comp_id for p in self.planes], self.process, self.ctx,
+                       self.precision)
         for a, b in zip(self.planes, src.planes):
             b.coef, b.q = a.coef, a.q
         src.set_size((w, h))                                       # Spectral.set(width:) / set(height:)
         out = Spectral((w, h) if kind == "iii" else (h, w), [p.factor for p in self.planes],
-                       [p.comp_id for p in self.planes], self.process, self.ctx)
+                       [p.comp_id for p in self.planes], self.process, self.ctx, self.precision)
         out.quanta = [np.ascontiguousarray(q, dtype=np.uint16)[zmap] for q in self.quanta]
         for a, b in zip(src.planes, out.planes):
             b.q = a.q

@@ -45,14 +45,22 @@ void Device::check(int status) const
     throw Error(k, what, status);
 }
 
+bool Format::recognize(std::vector<int> keys, int frame_precision) const
+{
+    std::vector<int> mine = components;
+    std::sort(keys.begin(), keys.end());
+    std::sort(mine.begin(), mine.end());
+    return keys == mine && frame_precision == precision;
+}
+
 namespace Data {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Spectral
 // ---------------------------------------------------------------------------------------------------------------
 Spectral::Spectral(std::pair<int, int> size_, const std::vector<std::pair<int, int>> &factors, const std::vector<int> &keys,
-                   bool progressive_, Device *device_)
-    : progressive(progressive_), device(device_ ? device_ : &Device::shared())
+                   bool progressive_, Device *device_, int precision_)
+    : progressive(progressive_), precision(precision_), device(device_ ? device_ : &Device::shared())
 {
     scale = {1, 1};
     for (auto &f : factors) {
@@ -244,6 +252,7 @@ Planar Spectral::idct() const
     Planar out;
     out.size = size;
     out.device = device;
+    out.precision = precision;
     out.planes.resize(planes.size());
     for (size_t i = 0; i < planes.size(); ++i) {
         const auto &p = planes[i];
@@ -251,8 +260,8 @@ Planar Spectral::idct() const
         o.units = p.units;
         o.factor = p.factor;
         o.samples.assign((size_t) 64 * p.units.first * p.units.second, 0);
-        device->check(jpeg_sm100_idct(device->ctx(), p.coefficients.data(), p.units.first, p.units.second, quanta[p.q].data(), 8,
-                                      o.samples.data()));
+        device->check(jpeg_sm100_idct(device->ctx(), p.coefficients.data(), p.units.first, p.units.second, quanta[p.q].data(),
+                                      precision, o.samples.data()));
     }
     return out;
 }
@@ -294,6 +303,7 @@ Rectangular Planar::interleaved(bool cosite) const
     Rectangular r;
     r.size = size;
     r.device = device;
+    r.precision = precision;
     for (auto &p : planes) r.factors.push_back(p.factor);
     r.values.assign((size_t) size.first * size.second * planes.size(), 0);
     auto views = plane_views(*this);
@@ -302,14 +312,14 @@ Rectangular Planar::interleaved(bool cosite) const
     return r;
 }
 
-Spectral Planar::fdct(const std::vector<Table::Quantization> &q) const
+Spectral Planar::fdct(const std::vector<Table::Quantization> &q, const std::vector<int> &keys) const
 {
     std::vector<std::pair<int, int>> factors;
     for (auto &p : planes) factors.push_back(p.factor);
-    Spectral s(size, factors, {}, false, device);
+    Spectral s(size, factors, keys, false, device, precision);
     for (size_t i = 0; i < planes.size(); ++i) {
         const auto &p = planes[i];
-        device->check(jpeg_sm100_fdct(device->ctx(), p.samples.data(), p.units.first, p.units.second, q[i].data(), 8,
+        device->check(jpeg_sm100_fdct(device->ctx(), p.samples.data(), p.units.first, p.units.second, q[i].data(), precision,
                                       s.planes[i].coefficients.data()));
         s.quanta.push_back(q[i]);
         s.planes[i].q = (int) s.quanta.size() - 1;
@@ -344,6 +354,7 @@ Planar Rectangular::decomposed() const
     Planar pl;
     pl.size = size;
     pl.device = device;
+    pl.precision = precision;
     int sx = 1, sy = 1;
     for (auto &f : factors) {
         sx = std::max(sx, f.first);
@@ -453,22 +464,39 @@ void parse_dht(const Segment &s, Table::HuffmanSlots &dc, Table::HuffmanSlots &a
     }
 }
 
-void parse_dqt(const Segment &s, std::vector<std::pair<int, Table::Quantization>> &out)
+// Table.parse(quantization:) decode.swift:480-530; 16-bit tables (Pq = 1): 64 big-endian UInt16, decode.swift:431-438
+struct PendingQuanta {
+    int                 target;
+    Table::Quantization values;
+    bool                wide;  // Pq = 1
+};
+void parse_dqt(const Segment &s, std::vector<PendingQuanta> &out)
 {
     size_t base = 0;
     while (base < s.len) {
         const int tgt = s.body[base] & 15, prec = s.body[base] >> 4;
         if (tgt > 3) parsing("invalidQuantizationTargetCode");
+        Table::Quantization q;
         if (prec == 0) {
             if (s.len < base + 65) parsing("mismatchedQuantizationSegmentSize");
-            Table::Quantization q;
             for (int i = 0; i < 64; ++i) q[i] = s.body[base + 1 + i];
-            out.emplace_back(tgt, q);
             base += 65;
-        } else if (prec == 1)
-            decoding("invalidScanQuantizationPrecision");
-        else
+        } else if (prec == 1) {
+            if (s.len < base + 129) parsing("mismatchedQuantizationSegmentSize");
+            for (int i = 0; i < 64; ++i) q[i] = (uint16_t) ((s.body[base + 1 + 2 * i] << 8) | s.body[base + 2 + 2 * i]);
+            base += 129;
+        } else
             parsing("invalidQuantizationPrecisionCode");
+        out.push_back({tgt, q, prec == 1});
+    }
+}
+// Spectral.push(qi:quanta:) decode.swift:2546-2557: "an 8-bit dct-based process shall not use a 16-bit quantization table"
+void push_quanta(Spectral &s, int qslot[4], const std::vector<PendingQuanta> &tables)
+{
+    for (auto &t : tables) {
+        if (t.wide && s.precision <= 8) decoding("invalidScanQuantizationPrecision");
+        s.quanta.push_back(t.values);
+        qslot[t.target] = (int) s.quanta.size() - 1;
     }
 }
 
@@ -492,7 +520,7 @@ void put_segment(std::vector<uint8_t> &out, int marker, const std::vector<uint8_
 
 }  // namespace
 
-Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool gpu_lexer)
+Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool gpu_lexer, const Format *format)
 {
     Lexer   lx{data, n};
     Segment sg = lx.segment();
@@ -501,15 +529,16 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool g
     while ((0xE0 <= sg.marker && sg.marker <= 0xEF) || sg.marker == 0xFE) sg = lx.segment();
 
     Table::HuffmanSlots                              dc{}, ac{};
-    std::vector<std::pair<int, Table::Quantization>> pending;
+    std::vector<PendingQuanta>                       pending;
     int64_t                                          interval = -1;
     std::vector<Component>                           comps;
-    int                                              process = -1, fw = 0, fh = 0;
+    int                                              process = -1, fw = 0, fh = 0, precision = 0;
     for (;;) {
         const int m = sg.marker;
         if (is_frame(m)) {
             if (sg.len < 6) parsing("mismatchedFrameHeaderSegmentSize");
-            const int precision = sg.body[0], count = sg.body[5];
+            const int count = sg.body[5];
+            precision = sg.body[0];
             fh = (sg.body[1] << 8) | sg.body[2];
             fw = (sg.body[3] << 8) | sg.body[4];
             if (sg.len != (size_t) 3 * count + 6) parsing("mismatchedFrameHeaderSegmentSize");
@@ -527,7 +556,7 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool g
                 if (process == 0 && c.tq > 1) parsing("invalidFrameQuantizationSelector");
             }
             if (process < 0) decoding("unsupportedFrameCodingProcess");
-            if (precision != 8) decoding("unsupportedFramePrecision");
+            if ((process == 0 && precision != 8) || (precision != 8 && precision != 12)) parsing("invalidFramePrecision");  // decode.swift:700-768
             sg = lx.segment();
             break;
         }
@@ -542,21 +571,27 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool g
         sg = lx.segment();
     }
 
-    std::sort(comps.begin(), comps.end(), [](const Component &a, const Component &b) { return a.key < b.key; });
-    if (!(comps.size() == 1 || (comps.size() == 3 && comps[1].key == comps[0].key + 1 && comps[2].key == comps[0].key + 2)))
-        decoding("unrecognizedColorFormat");
+    if (format) {  // Format.recognize; planes in the order format.components lists them (jpeg.swift:1286-1329)
+        std::vector<int> keys;
+        for (auto &c : comps) keys.push_back(c.key);
+        if (!format->recognize(keys, precision)) decoding("unrecognizedColorFormat");
+        auto rank = [&](int key) { return std::find(format->components.begin(), format->components.end(), key) - format->components.begin(); };
+        std::sort(comps.begin(), comps.end(), [&](const Component &a, const Component &b) { return rank(a.key) < rank(b.key); });
+    } else {  // JPEG.Common.recognize (jpeg.swift:370-397)
+        std::sort(comps.begin(), comps.end(), [](const Component &a, const Component &b) { return a.key < b.key; });
+        if (precision != 8 ||
+            !(comps.size() == 1 || (comps.size() == 3 && comps[1].key == comps[0].key + 1 && comps[2].key == comps[0].key + 2)))
+            decoding("unrecognizedColorFormat");
+    }
     std::vector<std::pair<int, int>> factors;
     std::vector<int>                 keys;
     for (auto &c : comps) {
         factors.push_back({c.fx, c.fy});
         keys.push_back(c.key);
     }
-    Spectral s({fw, fh}, factors, keys, process == 2, dev);
+    Spectral s({fw, fh}, factors, keys, process == 2, dev, precision);
     int      qslot[4] = {-1, -1, -1, -1};
-    for (auto &pq : pending) {
-        s.quanta.push_back(pq.second);
-        qslot[pq.first] = (int) s.quanta.size() - 1;
-    }
+    push_quanta(s, qslot, pending);
     // JPEG.Layout progression state (jpeg.swift:1581-1634): approximation bit per coefficient, -2 = not yet seen, -1 = .max
     std::vector<std::array<int, 64>> approx(comps.size());
     for (auto &a : approx) a.fill(-2);
@@ -571,12 +606,9 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool g
         const int m = sg.marker;
         if (is_frame(m)) decoding("duplicateFrameHeaderSegment");
         if (m == 0xDB) {
-            std::vector<std::pair<int, Table::Quantization>> qs;
+            std::vector<PendingQuanta> qs;
             parse_dqt(sg, qs);
-            for (auto &pq : qs) {
-                s.quanta.push_back(pq.second);
-                qslot[pq.first] = (int) s.quanta.size() - 1;
-            }
+            push_quanta(s, qslot, qs);
         } else if (m == 0xC4)
             parse_dht(sg, dc, ac);
         else if (m == 0xDA) {
@@ -697,11 +729,11 @@ Spectral Spectral::decompress(const uint8_t *data, size_t n, Device *dev, bool g
 // Spectral.compress(stream:) encode.swift:1918-1972.  Table slots are assigned explicitly (quantisation: plane 0 ->
 // slot 0, others -> slot 1; Huffman: as named by each scan) -- the reference derives them from scan lifetimes through
 // a Dictionary whose iteration order is per-process random (jpeg.swift:1388-1441), so its byte layout is not a target.
-std::vector<uint8_t> Spectral::compress(uint64_t interval_mcus) const
+std::vector<uint8_t> Spectral::compress(uint64_t interval_mcus, bool jfif) const
 {
     std::vector<uint8_t> out;
     put_segment(out, 0xD8);
-    put_segment(out, 0xE0, {'J', 'F', 'I', 'F', 0, 1, 2, 2, 0, 1, 0, 1, 0, 0});
+    if (jfif) put_segment(out, 0xE0, {'J', 'F', 'I', 'F', 0, 1, 2, 2, 0, 1, 0, 1, 0, 0});
     std::vector<std::pair<int, int>> qs;  // (quanta index, slot)
     for (size_t i = 0; i < planes.size(); ++i) {
         bool seen = false;
@@ -713,7 +745,7 @@ std::vector<uint8_t> Spectral::compress(uint64_t interval_mcus) const
             if (e.first == q) return e.second;
         return 0;
     };
-    std::vector<uint8_t> sof = {8, (uint8_t) (size.second >> 8), (uint8_t) size.second, (uint8_t) (size.first >> 8), (uint8_t) size.first,
+    std::vector<uint8_t> sof = {(uint8_t) precision, (uint8_t) (size.second >> 8), (uint8_t) size.second, (uint8_t) (size.first >> 8), (uint8_t) size.first,
                                 (uint8_t) planes.size()};
     for (auto &p : planes) {
         sof.push_back((uint8_t) p.component);
@@ -724,8 +756,16 @@ std::vector<uint8_t> Spectral::compress(uint64_t interval_mcus) const
     std::sort(qs.begin(), qs.end(), [](auto &a, auto &b) { return a.second < b.second; });
     std::vector<uint8_t> dqt;
     for (auto &e : qs) {
-        dqt.push_back((uint8_t) e.second);
-        for (int i = 0; i < 64; ++i) dqt.push_back((uint8_t) quanta[e.first][i]);
+        if (precision > 8) {  // decode.swift:2528-2532: formats deeper than 8 bits write 16-bit tables
+            dqt.push_back((uint8_t) (0x10 | e.second));
+            for (int i = 0; i < 64; ++i) {
+                dqt.push_back((uint8_t) (quanta[e.first][i] >> 8));
+                dqt.push_back((uint8_t) quanta[e.first][i]);
+            }
+        } else {
+            dqt.push_back((uint8_t) e.second);
+            for (int i = 0; i < 64; ++i) dqt.push_back((uint8_t) quanta[e.first][i]);
+        }
     }
     put_segment(out, 0xDB, dqt);
     if (interval_mcus) put_segment(out, 0xDD, {(uint8_t) (interval_mcus >> 8), (uint8_t) interval_mcus});
@@ -841,6 +881,39 @@ JPEGH_API int jpegh_recompress(const uint8_t *data, size_t n, uint64_t interval_
         auto b = s.compress(interval_mcus);
         *out = dup(b);
         *out_n = b.size();
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e, err, errcap);
+    }
+}
+
+// The same two calls for a user-defined format (examples/custom-color): components = the format's keys in plane order.
+// jpegh_recompress_format: Spectral<Format>.decompress -> compress (no JFIF segment when jfif == 0);
+// jpegh_decompress_samples16: Rectangular<Format>.decompress -> the interleaved 16-bit values, stride = n_components.
+JPEGH_API int jpegh_recompress_format(const uint8_t *data, size_t n, const int32_t *components, int32_t n_components, int32_t precision,
+                                      int32_t jfif, uint8_t **out, size_t *out_n, char *err, size_t errcap)
+{
+    try {
+        jpeg::Format f{std::vector<int>(components, components + n_components), precision};
+        auto         s = jpeg::Data::Spectral::decompress(data, n, nullptr, true, &f);
+        auto         b = s.compress(0, jfif != 0);
+        *out = dup(b);
+        *out_n = b.size();
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e, err, errcap);
+    }
+}
+JPEGH_API int jpegh_decompress_samples16(const uint8_t *data, size_t n, const int32_t *components, int32_t n_components,
+                                         int32_t precision, uint16_t **values, int32_t *w, int32_t *h, char *err, size_t errcap)
+{
+    try {
+        jpeg::Format f{std::vector<int>(components, components + n_components), precision};
+        auto         s = jpeg::Data::Spectral::decompress(data, n, nullptr, true, &f);
+        auto         r = s.idct().interleaved(false);
+        *values = dup(r.values);
+        *w = s.size.first;
+        *h = s.size.second;
         return 0;
     } catch (const std::exception &e) {
         return fail(e, err, errcap);

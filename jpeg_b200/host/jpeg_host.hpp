@@ -70,6 +70,15 @@ struct Scan {
     std::vector<Component> components;
 };
 
+// A user-defined JPEG.Format (jpeg.swift:300-340) in the style of examples/custom-color/main.swift:41-63: recognised iff the
+// frame's component keys are exactly `components` and its precision is `precision`; `components` orders the planes.
+// Where a `const Format *` is expected, nullptr means JPEG.Common (jpeg.swift:370-397).
+struct Format {
+    std::vector<int> components;
+    int              precision = 8;
+    bool             recognize(std::vector<int> keys, int frame_precision) const;
+};
+
 namespace Data {
 
 class Planar;
@@ -87,10 +96,11 @@ public:
     };
 
     Spectral(std::pair<int, int> size, const std::vector<std::pair<int, int>> &factors, const std::vector<int> &keys = {},
-             bool progressive = false, Device *device = nullptr);
+             bool progressive = false, Device *device = nullptr, int precision = 8);
 
     std::pair<int, int>              size{0, 0}, blocks{0, 0}, scale{1, 1};
     bool                             progressive = false;
+    int                              precision = 8;  // Format.precision: 8 for JPEG.Common, 12 for deeper user-defined formats
     std::vector<Plane>               planes;
     std::vector<Table::Quantization> quanta;  // quanta[0] = default (zeros), decode.swift:1723
     std::vector<Scan>                scans;   // the progression this image was decoded from / is encoded with
@@ -115,8 +125,9 @@ public:
     std::vector<uint8_t> to_rgb8(bool cosite = false) const;  // fused idct().interleaved().unpack(as: RGB.self)
 
     // decode.swift:3728-3960; gpu_lexer = false keeps byte unstuffing / RSTn splitting on the host (Bytestream.segment)
-    static Spectral      decompress(const uint8_t *data, size_t n, Device *device = nullptr, bool gpu_lexer = true);
-    std::vector<uint8_t> compress(uint64_t interval_mcus = 0) const;                           // encode.swift:1918-1972
+    static Spectral      decompress(const uint8_t *data, size_t n, Device *device = nullptr, bool gpu_lexer = true,
+                                    const Format *format = nullptr);
+    std::vector<uint8_t> compress(uint64_t interval_mcus = 0, bool jfif = true) const;         // encode.swift:1918-1972
 
     Device *device;
 };
@@ -131,9 +142,11 @@ public:
     std::pair<int, int> size;
     std::vector<Plane>  planes;
     Device             *device;
+    int                 precision = 8;
 
     Rectangular interleaved(bool cosite = false) const;                          // decode.swift:4182
-    Spectral    fdct(const std::vector<Table::Quantization> &quanta) const;      // encode.swift:353 (one table per plane)
+    // encode.swift:353 (one table per plane); keys: the component key of every plane (default 1, 2, ...)
+    Spectral    fdct(const std::vector<Table::Quantization> &quanta, const std::vector<int> &keys = {}) const;
 };
 
 // JPEG.Data.Rectangular<JPEG.Common> (decode.swift:1650-1718): uint16 values, (y * size.x + x) * stride + p
@@ -143,6 +156,7 @@ public:
     std::vector<std::pair<int, int>>  factors;
     std::vector<uint16_t>             values;
     Device                           *device;
+    int                               precision = 8;
 
     int                  stride() const { return (int) factors.size(); }
     std::vector<uint8_t> unpack_rgb() const;  // [JPEG.RGB]   jpeg.swift:551

@@ -36,6 +36,11 @@ def hostlib():
                                         C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(u8p), C.POINTER(C.c_size_t), C.c_char_p,
                                         C.c_size_t]
     lib.jpegh_rotate.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(u8p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    i32p = C.POINTER(C.c_int32)
+    lib.jpegh_recompress_format.argtypes = [C.c_char_p, C.c_size_t, i32p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(u8p),
+                                            C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    lib.jpegh_decompress_samples16.argtypes = [C.c_char_p, C.c_size_t, i32p, C.c_int32, C.c_int32,
+                                               C.POINTER(C.POINTER(C.c_uint16)), i32p, i32p, C.c_char_p, C.c_size_t]
     return lib
 
 
@@ -127,6 +132,47 @@ def test_lexer_and_parser_errors_need_no_device(hostlib):
     with pytest.raises(HostError) as e:
         pixels(hostlib, b"\xff\xd8\xff\xe0\x00\x10")
     assert e.value.code == LEXING and e.value.what == "truncatedMarkerSegmentBody"
+
+
+def recompress_format(lib, data, components, precision, jfif=False):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    ids = (C.c_int32 * len(components))(*components)
+    rc = lib.jpegh_recompress_format(data, len(data), ids, len(components), precision, int(jfif), C.byref(out), C.byref(n), err, 256)
+    if rc:
+        raise HostError(rc, err.value.decode())
+    b = bytes(np.ctypeslib.as_array(out, shape=(n.value,)))
+    lib.jpegh_free(out)
+    return b
+
+
+def samples16(lib, data, components, precision):
+    out, w, h = C.POINTER(C.c_uint16)(), C.c_int32(), C.c_int32()
+    err = C.create_string_buffer(256)
+    ids = (C.c_int32 * len(components))(*components)
+    rc = lib.jpegh_decompress_samples16(data, len(data), ids, len(components), precision, C.byref(out), C.byref(w), C.byref(h),
+                                        err, 256)
+    if rc:
+        raise HostError(rc, err.value.decode())
+    a = np.ctypeslib.as_array(out, shape=(h.value, w.value, len(components))).copy()
+    lib.jpegh_free(out)
+    return a
+
+
+def test_format_recognition_needs_no_device(manifest, hostlib):
+    """jpeg::Format (examples/custom-color/main.swift:41-63): a file is decoded only by a format that recognises its component
+    keys and precision -- DecodingError.unrecognizedColorFormat otherwise (decode.swift:2374-2381), before any device work."""
+    data = golden_bytes(manifest["custom_color"]["jpeg"])
+    for comps, prec in (([4, 5, 6, 7], 8), ([4, 5, 6], 12), ([1, 2, 3, 4], 12)):
+        with pytest.raises(HostError) as e:
+            recompress_format(hostlib, data, comps, prec)
+        assert e.value.code == DECODING and e.value.what == "unrecognizedColorFormat", (comps, prec)
+    with pytest.raises(HostError) as e:
+        pixels(hostlib, data)  # JPEG.Common
+    assert e.value.code == DECODING and e.value.what == "unrecognizedColorFormat"
+    with pytest.raises(HostError) as e:  # an 8-bit file is not a 12-bit format's
+        recompress_format(hostlib, golden_bytes("gold/color-sequential-2.jpg"), [1, 2, 3], 12)
+    assert e.value.code == DECODING and e.value.what == "unrecognizedColorFormat"
 
 
 def test_no_cpu_fallback_without_device(hostlib):
@@ -245,3 +291,22 @@ def test_rotate_through_cpp_host(manifest, hostlib, kind, code):
         assert len(ecs) == sc["ecs_len"] and sha(ecs) == sc["ecs_sha256"], kind
     dqt = [[t, q] for m, body, _ in segs if m == 0xDB for t, q in J.parse_dqt(body)]
     assert dqt == exp["dqt"]
+
+
+@pytest.mark.gpu
+def test_custom_format_through_cpp_host(manifest, hostlib, O):
+    """examples/custom-color through jpeg::Data::Spectral with a jpeg::Format: components 4-7, 12-bit samples, 16-bit DQT, ten
+    progressive scans.  compress() of the decoded image returns the reference's file byte for byte; the decoded 16-bit values
+    equal the oracle's."""
+    cc = manifest["custom_color"]
+    comps, prec = cc["format"]
+    data = golden_bytes(cc["jpeg"])
+    out = recompress_format(hostlib, data, comps, prec, jfif=False)
+    assert out == data and sha(out) == cc["file_sha256"]
+    ref = O.Spectral.decompress(data, format=(comps, prec)).to_rectangular()
+    got = samples16(hostlib, data, comps, prec)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    # planes follow the format's order, not the frame header's
+    rev = samples16(hostlib, data, comps[::-1], prec)
+    assert np.array_equal(rev, ref[..., ::-1])
+
