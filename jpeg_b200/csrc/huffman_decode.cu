@@ -12,10 +12,12 @@
 //     and then decodes every subsequence for real.  A CTA of 128 threads holds 1..8 intervals; an interval without DRI
 //     (one segment per image: everything the reference's own encoder writes) gets a thread-block cluster whose CTAs exchange
 //     neighbour state through distributed shared memory (k_decode_par_cluster).
-//   * The kernels are bound by instruction issue and the LSU pipe, not by HBM: the loops are branch-light flat state machines
-//     (one Huffman symbol per trip whatever block the lane is in), tables are 9-bit shared-memory LUTs with sub-tables for
-//     longer codes, stream words are loaded one refill ahead, and each block of a sequential scan is assembled in shared
-//     memory and stored as one 128-byte line.
+//   * The kernels are bound by the latency of every lane's dependent chain of table look-ups, then by instruction issue -- not
+//     by HBM.  So: as many resident warps as the SM holds (8 CTAs x 4 warps: 62 registers, 8-bit shared-memory LUTs with
+//     sub-tables for longer codes, synchronisation records aliased onto the block buffers); branch-light flat state machines
+//     (one Huffman symbol per trip whatever block the lane is in); stream words loaded one refill ahead; and a warp-synchronous
+//     decoding pass in which lanes that complete a block wait for each other, do their block-end work together and have the
+//     whole warp flush the finished blocks from shared memory as 128-byte lines.
 //   * Anything irregular only flags its interval; flagged intervals are redone by the one-thread-per-interval kernels below
 //     (k_decode_fast / k_decode_progressive), which evaluate every guard of the reference and produce its error codes.
 //     Those kernels also serve DC-first, refinement and `extend` scans.
@@ -811,7 +813,8 @@ finished:
 // The restart interval is the only parallel axis the FORMAT gives, and a lone thread per interval is bound by its own
 // dependency chain.  Huffman streams self-synchronise, so an interval can also be decoded speculatively in pieces
 // (Klein & Wiseman; Weissenberger & Schmidt for JPEG on GPUs):
-//   * one CTA per (image, interval); the interval's bits are cut into S <= 128 subsequences, one thread each;
+//   * a CTA holds 128 / T intervals of one image, T = 16..128 threads each (or a cluster of CTAs holds one big interval); the
+//     interval's bits are cut into S <= T subsequences, one thread each;
 //   * the parse state at a symbol boundary is (bit position, zig-zag position z, block-in-MCU b) -- MCU position and DC
 //     predictors do not influence parsing;
 //   * round 0: every thread parses its subsequence from a guessed state (its first bit, z = 0, b = 0) and records the state
@@ -819,8 +822,9 @@ finished:
 //     true state, so after round r the first r + 1 exits are exact, and because streams re-synchronise after a few hundred
 //     symbols almost every exit is already exact after one or two rounds.  No change anywhere => all entries exact;
 //   * an exclusive scan of the per-subsequence block counts gives every subsequence its first block, then ONE decoding pass
-//     writes the coefficients (AC values straight to their zig-zag slots, DC *differences* to a side array);
-//   * k_dc_resolve turns the DC differences into predictions with a wrapping 16-bit prefix sum per (interval, component);
+//     (par_run_final) assembles every block in its owner's shared-memory buffer (DC *differences* go to a side array) and the
+//     warp stores completed blocks as whole 128-byte lines;
+//   * the CTA's warps then turn the DC differences into predictions with a wrapping 16-bit prefix sum per (interval, component);
 //   * anything irregular on the TRUE path (truncation, a symbol the sequential decoder rejects, a block count that does not
 //     match) flags the interval; flagged intervals are zeroed and re-decoded by k_decode_fast, which also produces the
 //     reference's error codes.  The speculative rounds never raise errors: garbage parses just end early.
