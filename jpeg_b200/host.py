@@ -288,8 +288,10 @@ class Spectral:
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod
-    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None):
-        return _decompress(data, ctx or default_context(), gpu_lexer, format)
+    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None, on_scan=None):
+        """on_scan(spectral, scan): called after every scan with the image as JPEG.Context holds it at that point -- the
+        capture closure of examples/decode-online/main.swift:252-282 (online / progressive display)."""
+        return _decompress(data, ctx or default_context(), gpu_lexer, format, on_scan)
 
     def compress(self, scans=None, quanta_slots=None, interval_mcus=0, jfif=True):
         return _compress(self, scans, quanta_slots, interval_mcus, jfif)
@@ -492,7 +494,7 @@ def _push_quanta(s, qslot, tables):
         qslot[tgt] = len(s.quanta) - 1
 
 
-def _decompress(data, ctx, gpu_lexer=False, format=None):
+def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None):
     lx = _Lexer(bytes(data))
     _, m, body = lx.segment()
     if m != 0xD8:
@@ -666,6 +668,8 @@ def _decompress(data, ctx, gpu_lexer=False, format=None):
                     s.set_size((fw, (body[0] << 8) | body[1]))
                     _, m, body = lx.segment()
                 first = False
+            if on_scan is not None:
+                on_scan(s, s.scans[-1])
             continue
         elif m == 0xDD:
             if len(body) != 2:

@@ -920,7 +920,8 @@ static int progression_update(orc_spectral *s, int band_lo, int band_hi, int bit
  * examples/custom-color/main.swift:41-63: recognised iff the frame's component keys are exactly fmt_ids (as a set) and
  * its precision is fmt_precision; planes are ordered as fmt_ids lists them (Layout.init(format:process:components:),
  * jpeg.swift:1286-1329). */
-static orc_spectral *decompress_impl(const uint8_t *jpeg, size_t n, const int *fmt_ids, int fmt_n, int fmt_precision, int *err_out)
+static orc_spectral *decompress_impl(const uint8_t *jpeg, size_t n, const int *fmt_ids, int fmt_n, int fmt_precision, int max_scans,
+                                     int *err_out)
 {
     zz_init();
     int           err = ORC_OK;
@@ -1067,7 +1068,7 @@ static orc_spectral *decompress_impl(const uint8_t *jpeg, size_t n, const int *f
     }
     if (pend_interval != -2) ctx.interval = pend_interval == 0 ? -1 : pend_interval;
 
-    int first = 1;
+    int first = 1, nscans = 0;
     for (;;) {
         if (marker >= 0xc0 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc)
             FAIL(ORC_ERR_DECODE); /* duplicateFrameHeaderSegment */
@@ -1180,6 +1181,8 @@ static orc_spectral *decompress_impl(const uint8_t *jpeg, size_t n, const int *f
                 spectral_set_height(s, height);
                 first = 0;
             }
+            /* online decoding (examples/decode-online/main.swift:252-282): the caller looks at context.spectral after every scan */
+            if (max_scans > 0 && ++nscans == max_scans) goto done;
             continue; /* `continue scans`: marker already holds the next segment */
         }
         case 0xdd:
@@ -1210,7 +1213,7 @@ done:
 }
 API orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err_out)
 {
-    return decompress_impl(jpeg, n, NULL, 0, 8, err_out);
+    return decompress_impl(jpeg, n, NULL, 0, 8, -1, err_out);
 }
 API orc_spectral *orc_decompress_format(const uint8_t *jpeg, size_t n, const int *format_components, int n_components,
                                         int format_precision, int *err_out)
@@ -1219,7 +1222,13 @@ API orc_spectral *orc_decompress_format(const uint8_t *jpeg, size_t n, const int
         if (err_out) *err_out = ORC_ERR_PRECONDITION;
         return NULL;
     }
-    return decompress_impl(jpeg, n, format_components, n_components, format_precision, err_out);
+    return decompress_impl(jpeg, n, format_components, n_components, format_precision, -1, err_out);
+}
+/* JPEG.Context driven segment by segment (decode.swift:3565-3725), stopped after `scans` scans: the state
+ * examples/decode-online/main.swift hands to its capture closure */
+API orc_spectral *orc_decompress_scans(const uint8_t *jpeg, size_t n, int scans, int *err_out)
+{
+    return decompress_impl(jpeg, n, NULL, 0, 8, scans, err_out);
 }
 API int  orc_spectral_precision(const orc_spectral *s) { return s->precision; }
 /* a blank image of a user-defined format: component keys in plane order, sample precision */

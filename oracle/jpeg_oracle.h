@@ -77,6 +77,8 @@ orc_spectral *orc_decompress(const uint8_t *jpeg, size_t n, int *err);
  * component keys are exactly format_components and its precision is format_precision; planes in the listed order) */
 orc_spectral *orc_decompress_format(const uint8_t *jpeg, size_t n, const int *format_components, int n_components,
                                     int format_precision, int *err);
+/* JPEG.Context driven segment by segment, stopped after `scans` scans (examples/decode-online/main.swift) */
+orc_spectral *orc_decompress_scans(const uint8_t *jpeg, size_t n, int scans, int *err);
 int  orc_spectral_precision(const orc_spectral *s);
 void orc_spectral_set_format(orc_spectral *s, const int *component_ids, int precision);
 /* build an empty spectral image (Spectral.init(size:layout:...), decode.swift:2413) */

@@ -77,6 +77,8 @@ def lib():
     L.orc_decompress.argtypes = [C.c_char_p, C.c_size_t, ip]
     L.orc_decompress_format.restype = C.c_void_p
     L.orc_decompress_format.argtypes = [C.c_char_p, C.c_size_t, ip, C.c_int, C.c_int, ip]
+    L.orc_decompress_scans.restype = C.c_void_p
+    L.orc_decompress_scans.argtypes = [C.c_char_p, C.c_size_t, C.c_int, ip]
     L.orc_spectral_precision.argtypes = [C.c_void_p]
     L.orc_spectral_set_format.argtypes = [C.c_void_p, ip, C.c_int]
     L.orc_spectral_create.restype = C.c_void_p
@@ -175,6 +177,15 @@ class Spectral:
         else:
             ids, precision = format
             h = lib().orc_decompress_format(data, len(data), _ints(list(ids)), len(ids), precision, C.byref(err))
+        if not h:
+            raise OracleError(err.value)
+        return cls(h)
+
+    @classmethod
+    def decompress_scans(cls, data: bytes, scans: int):
+        """the image as JPEG.Context holds it after `scans` scans (examples/decode-online/main.swift)"""
+        err = C.c_int()
+        h = lib().orc_decompress_scans(data, len(data), scans, C.byref(err))
         if not h:
             raise OracleError(err.value)
         return cls(h)

@@ -103,6 +103,12 @@ def main():
                            "factors": [[2, 2], [2, 2], [2, 2], [1, 1]],
                            "rgb_sha256": sha(rd("examples/custom-color/output.jpg.rgb")),
                            **scans_of(rd("examples/custom-color/output.jpg"))}
+    # examples/decode-online: JPEG.Context driven segment by segment; the example dumps idct().interleaved().unpack(as: RGB)
+    # after EVERY scan of a 10-scan progressive file with DRI -- ten per-scan vectors (and the only restart-interval file
+    # of the reference with committed output)
+    rel = copy("examples/decode-online/karlie-oscars-2017.jpg", "examples")
+    man["decode_online"] = {"jpeg": rel, "rgb_sha256": [sha(rd(f"examples/decode-online/karlie-oscars-2017.jpg-{k}.rgb"))
+                                                        for k in range(10)]}
     # tests/unit/tests.swift:170-340: 162 (length, codeword) pairs of the T.81 K.3.3.2 AC-luminance table, listed in
     # the order the unit test walks the symbols (run/size 0x00, 0x01..0x0A, 0x11.., 0xF0, ...)
     import re

@@ -113,6 +113,22 @@ def test_four_planes_of_12_bit_samples(H, O):
         assert np.array_equal(back.planes[p], want[p]), p
 
 
+def test_online_decoding_through_gpu(manifest, H):
+    """examples/decode-online: the ten per-scan RGB dumps of the reference, reproduced from the image as it stands after each
+    scan (staged idct().interleaved().unpack(as: RGB) and the fused coefficients -> RGB8 call); a progressive file with DRI."""
+    v = manifest["decode_online"]
+    data = golden_bytes(v["jpeg"])
+    for gpu_lexer in (False, True):
+        got = []
+
+        def capture(s, scan):
+            got.append((sha(s.idct().interleaved().unpack_rgb().tobytes()), sha(s.to_rgb8().tobytes())))
+
+        H.Spectral.decompress(data, gpu_lexer=gpu_lexer, on_scan=capture)
+        assert [g[0] for g in got] == v["rgb_sha256"], gpu_lexer
+        assert [g[1] for g in got] == v["rgb_sha256"], gpu_lexer
+
+
 def test_custom_format_file_through_gpu(manifest, H, O):
     """N4 (host level): examples/custom-color/output.jpg -- a user-defined JPEG.Format (components 4-7, 12-bit samples, 16-bit
     DQT), ten progressive scans with two-component DC scans of unequal sampling -- decoded, inverse-transformed, forward-

@@ -71,6 +71,26 @@ def test_golden_files_parse_to_the_oracles_coefficients(manifest, host):
             assert np.array_equal(s.quanta[s.planes[p].q], ref.quanta(p)), (rel, p)
 
 
+def test_online_decoding_hook(manifest, host):
+    """examples/decode-online/main.swift:252-282: the capture closure sees the image after every scan"""
+    v = manifest["decode_online"]
+    data = golden_bytes(v["jpeg"])
+    seen = []
+
+    def capture(s, scan):
+        k = len(seen)
+        ref = O.Spectral.decompress_scans(data, k + 1)
+        assert len(s.scans) == k + 1 and s.scans[-1] is scan
+        for p in range(s.ncomp):
+            assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (k, p)
+            assert np.array_equal(s.quanta[s.planes[p].q], ref.quanta(p)), (k, p)  # not bound yet -> the default table
+        seen.append((scan.band, scan.bits, [c[0] for c in scan.comps]))
+
+    host.Spectral.decompress(data, on_scan=capture)
+    assert len(seen) == len(v["rgb_sha256"]) == 10
+    assert seen[0] == ((0, 1), (1, None), [0, 1, 2]) and seen[-1] == ((1, 64), (0, 1), [0])
+
+
 def test_custom_format_file_round_trips_byte_for_byte(manifest, host):
     """examples/custom-color/main.swift: components 4-7, 12-bit precision, 16-bit DQT, ten scans, no metadata."""
     cc = manifest["custom_color"]

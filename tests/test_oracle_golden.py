@@ -150,6 +150,21 @@ def test_decode_golden(manifest):
                 assert sha(planes[p].astype(np.uint8).tobytes()) == h
 
 
+def test_decode_online_golden(manifest):
+    """examples/decode-online/main.swift: the image after each of the ten scans of a progressive file with a restart
+    interval (DC first at bit 1, band-limited AC first scans, AC / DC refinements), as RGB -- every snapshot equals the
+    reference's committed dump.  Planes whose quanta are not bound yet dequantise with the default table (zeros)."""
+    v = manifest["decode_online"]
+    data = golden_bytes(v["jpeg"])
+    interval = [b for m, b, e in J.split(data) if m == 0xDD]
+    assert interval and int.from_bytes(interval[0], "big") > 0
+    for k, want in enumerate(v["rgb_sha256"]):
+        s = O.Spectral.decompress_scans(data, k + 1)
+        assert sha(O.unpack_rgb(s.to_rectangular()).tobytes()) == want, k
+    full = O.Spectral.decompress(data)
+    assert sha(O.unpack_rgb(full.to_rectangular()).tobytes()) == v["rgb_sha256"][-1]
+
+
 def test_decode_restart_files(manifest):
     """tests/integration/tests.swift:100-187: restart-interval files decode without error (no reference output
     exists); the row-granular interval placement is cross-checked against a DRI-less re-encode of the same
