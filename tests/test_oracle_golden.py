@@ -372,3 +372,76 @@ def test_restart_extension_roundtrip(manifest, rows):
                         act if act[0].present else empty, parts, interval=rows * width)
     for p in range(3):
         assert np.array_equal(dst.coefficients(p), src.coefficients(p))
+
+
+# ---------------------------------------------------------------- differential / fuzz (tests/fuzz, tests/compare of the reference)
+
+def test_transforms_against_an_independent_float_dct():
+    """tests/compare/main.swift compares the decoder with ImageMagick's float DCT (not available here): the same idea with
+    scipy's orthonormal DCT-II/III in float64 as the independent implementation.  The AAN networks of decode.swift:4042-4133
+    and encode.swift:123-248 must be a DCT, not merely each other's inverse: quanta 1, error below one grey level."""
+    from scipy.fft import dctn, idctn
+    rng = np.random.default_rng(7)
+    ones = np.ones(64, dtype=np.uint16)
+    zz = np.array(O.zigzag_table())
+    for precision in (8, 12):
+        top = (1 << precision) - 1
+        # forward: random sample blocks -> coefficients (zig-zag order, level shift 2^(P-1))
+        samples = rng.integers(0, top + 1, size=(8 * 6, 8 * 9)).astype(np.uint16)
+        coef = O.fdct_plane(samples, ones, precision)
+        for by in range(6):
+            for bx in range(9):
+                blk = samples[8 * by:8 * by + 8, 8 * bx:8 * bx + 8].astype(np.float64) - (1 << (precision - 1))
+                want = dctn(blk, norm="ortho")
+                got = np.empty((8, 8))
+                for h in range(8):
+                    for k in range(8):
+                        got[h, k] = coef[by, bx, zz[h][k]]
+                # zz[h][k] is indexed (vertical, horizontal) or (horizontal, vertical): accept the orientation that matches
+                err = min(np.abs(got - want).max(), np.abs(got.T - want).max())
+                assert err <= 0.5 + 1e-3, (precision, by, bx, err)
+        # inverse: smooth random coefficients -> samples
+        c = np.zeros((4, 5, 64), dtype=np.int16)
+        c[..., 0] = rng.integers(-200, 200, size=(4, 5)) * (1 << (precision - 8))
+        c[..., 1:10] = rng.integers(-30, 30, size=(4, 5, 9)) * (1 << (precision - 8))
+        out = O.idct_plane(c, ones, precision)
+        for by in range(4):
+            for bx in range(5):
+                m = np.zeros((8, 8))
+                for h in range(8):
+                    for k in range(8):
+                        m[h, k] = c[by, bx, zz[h][k]]
+                a = idctn(m, norm="ortho") + (1 << (precision - 1))
+                b = idctn(m.T, norm="ortho") + (1 << (precision - 1))
+                got = out[8 * by:8 * by + 8, 8 * bx:8 * bx + 8].astype(np.float64)
+                err = min(np.abs(got - np.clip(a, 0, top)).max(), np.abs(got - np.clip(b, 0, top)).max())
+                assert err <= 1.0 + 1e-3, (precision, by, bx, err)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_small_progressive_images_round_trip(seed):
+    """tests/fuzz/main.swift: small random progressive images, quanta all 1.  Here the property is the codec's own: random
+    coefficients -> every scan kind (with and without our restart-interval extension) -> the decoders return them exactly."""
+    rng = np.random.default_rng(100 + seed)
+    w, h = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+    factors = [[(1, 1), (1, 1), (1, 1)], [(2, 2), (1, 1), (1, 1)], [(2, 1), (1, 1), (1, 2)]][seed % 3]
+    src = O.Spectral.create((w, h), factors, progressive=True)
+    for p in range(3):
+        c = src.coefficients(p)
+        dense = rng.random(c.shape) < 0.25
+        c[...] = np.where(dense, rng.integers(-1023, 1024, size=c.shape), 0).astype(np.int16)
+        c[..., 0] = rng.integers(-1023, 1024, size=c.shape[:2])
+    scans = [((0, 1), (2, None), [0, 1, 2]), ((1, 9), (1, None), [0]), ((9, 64), (1, None), [0]), ((1, 64), (1, None), [1]),
+             ((1, 64), (1, None), [2]), ((0, 1), (1, 2), [0, 1, 2]), ((0, 1), (0, 1), [0, 1, 2]),
+             ((1, 64), (0, 1), [0]), ((1, 64), (0, 1), [1]), ((1, 64), (0, 1), [2])]
+    empty = [O.HuffSpec() for _ in range(4)]
+    for rows in (0, 1):
+        dst = O.Spectral.create((w, h), factors, progressive=True)
+        for band, bits, comps in scans:
+            width = src.blocks[0] if len(comps) > 1 else src.units(comps[0])[0]
+            ecs, dct, act = src.encode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), rows * width)
+            dst.decode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), dct if dct[0].present else empty,
+                            act if act[0].present else empty, J.unstuff_split(ecs),
+                            interval=rows * width if rows else O.INTERVAL_NONE)
+        for p in range(3):
+            assert np.array_equal(dst.coefficients(p), src.coefficients(p)), (seed, rows, p)
