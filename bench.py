@@ -65,31 +65,11 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# CompressionLevel.quanta (encode.swift:286-333), restated for the product-side benchmark driver
-_LUM = [16, 11, 10, 16, 124, 140, 151, 161, 12, 12, 14, 19, 126, 158, 160, 155, 14, 13, 16, 24, 140, 157, 169, 156,
-        14, 17, 22, 29, 151, 187, 180, 162, 18, 22, 37, 56, 168, 109, 103, 177, 24, 35, 55, 64, 181, 104, 113, 192,
-        49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 199]
-_CHR = [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99,
-        47, 66, 99, 99, 99, 99, 99, 99] + [99] * 32
-
-
-def _zigzag(k, h):
-    p = 1 if k + h < 8 else 0
-    q = (k + h) & 1
-    a, b = 72 * (p ^ 1), 2 * p - 1
-    n = b * (k + h) - 14 * p + 15
-    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1
-
-
 def quanta(level, chroma):
-    key = _CHR if chroma else _LUM
-    out = np.zeros(64, dtype=np.uint16)
-    for h in range(8):
-        for k in range(8):
-            v = 1.0 * (1 - level) + key[8 * h + k] * level
-            v = float(int(v + 0.5)) if v >= 0 else -float(int(-v + 0.5))
-            out[_zigzag(k, h)] = int(max(1.0, min(v, 255.0)))
-    return out
+    """JPEG.CompressionLevel.luminance(level).quanta / .chrominance(level).quanta (encode.swift:286-333) from the product's host
+    mirror (the reference arm takes the oracle's)"""
+    from jpeg_b200.host import CompressionLevel
+    return (CompressionLevel.chrominance(level) if chroma else CompressionLevel.luminance(level)).quanta
 
 
 class ClockSampler:

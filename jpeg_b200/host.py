@@ -67,6 +67,45 @@ def _zigzag(k, h):
 # ---------------------------------------------------------------------------------------------------------------
 # data types
 # ---------------------------------------------------------------------------------------------------------------
+class CompressionLevel:
+    """JPEG.CompressionLevel (encode.swift:260-333): quantum values for a quality parameter, 0.0 = all ones, 1.0 = the
+    keyframe table; `.quanta` is in zig-zag order.  Host-side arithmetic (Double), kept next to the types that consume it."""
+    _KEYFRAMES = {
+        "luminance": (16, 11, 10, 16, 124, 140, 151, 161, 12, 12, 14, 19, 126, 158, 160, 155,
+                      14, 13, 16, 24, 140, 157, 169, 156, 14, 17, 22, 29, 151, 187, 180, 162,
+                      18, 22, 37, 56, 168, 109, 103, 177, 24, 35, 55, 64, 181, 104, 113, 192,
+                      49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 199),
+        "chrominance": (17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                        24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99) + (99,) * 32,
+    }
+
+    def __init__(self, kind, level):
+        if kind not in self._KEYFRAMES:
+            raise ValueError(kind)
+        self.kind, self.level = kind, float(level)
+
+    @classmethod
+    def luminance(cls, level):
+        return cls("luminance", level)
+
+    @classmethod
+    def chrominance(cls, level):
+        return cls("chrominance", level)
+
+    @property
+    def quanta(self):
+        t = self.level
+        key = np.asarray(self._KEYFRAMES[self.kind], dtype=np.float64)
+        v = 1.0 * (1 - t) + key * t
+        v = np.copysign(np.floor(np.abs(v) + 0.5), v)  # Double.rounded(): to nearest, ties away from zero
+        v = np.maximum(1.0, np.minimum(v, 255.0)).astype(np.uint16)
+        out = np.zeros(64, dtype=np.uint16)
+        for h in range(8):
+            for k in range(8):
+                out[_zigzag(k, h)] = v[8 * h + k]
+        return out
+
+
 @dataclass(frozen=True)
 class Format:
     """A user-defined JPEG.Format (jpeg.swift:300-340) in the style of examples/custom-color/main.swift:41-63: recognised iff

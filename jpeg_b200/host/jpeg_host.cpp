@@ -2,6 +2,7 @@
 #include "jpeg_host.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -43,6 +44,33 @@ void Device::check(int status) const
                           : status > -20                           ? Error::Kind::decoding
                                                                    : Error::Kind::device;
     throw Error(k, what, status);
+}
+
+// JPEG.Table.Quantization.z(k:h:) decode.swift:1289-1298
+static int zigzag_of(int k, int h)
+{
+    const int p = (k + h < 8) ? 1 : 0, q = (k + h) & 1;
+    const int a = 72 * (p ^ 1), b = 2 * p - 1, n = b * (k + h) - 14 * p + 15;
+    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1;
+}
+
+Table::Quantization CompressionLevel::quanta() const
+{
+    static const uint8_t lum[64] = {16, 11, 10, 16, 124, 140, 151, 161, 12, 12, 14, 19, 126, 158, 160, 155,
+                                    14, 13, 16, 24, 140, 157, 169, 156, 14, 17, 22, 29, 151, 187, 180, 162,
+                                    18, 22, 37, 56, 168, 109, 103, 177, 24, 35, 55, 64, 181, 104, 113, 192,
+                                    49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 199};
+    static const uint8_t chr[32] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                    24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99};
+    Table::Quantization q{};
+    for (int h = 0; h < 8; ++h)
+        for (int k = 0; k < 8; ++k) {
+            const int    i = 8 * h + k;
+            const double key = kind == Kind::luminance ? lum[i] : (i < 32 ? chr[i] : 99);
+            const double v = std::round(1.0 * (1 - level) + key * level);  // Double.rounded(): ties away from zero
+            q[zigzag_of(k, h)] = (uint16_t) std::max(1.0, std::min(v, 255.0));
+        }
+    return q;
 }
 
 bool Format::recognize(std::vector<int> keys, int frame_precision) const
@@ -93,14 +121,6 @@ void Spectral::set_size(std::pair<int, int> s)
 }
 
 // ---- N3: spectral-domain operations ----------------------------------------------------------------------------------
-// JPEG.Table.Quantization.z(k:h:) decode.swift:1289-1298
-static int zigzag_of(int k, int h)
-{
-    const int p = (k + h < 8) ? 1 : 0, q = (k + h) & 1;
-    const int a = 72 * (p ^ 1), b = 2 * p - 1, n = b * (k + h) - 14 * p + 15;
-    return a + b * ((n * (n + 1)) >> 1) - q * k - (q ^ 1) * h - 1;
-}
-
 Spectral Spectral::requantized(const std::vector<Table::Quantization> &nq) const
 {
     if (nq.size() != quanta.size()) throw Error(Error::Kind::decoding, "requantized: one table per quantisation slot expected");
@@ -885,6 +905,13 @@ JPEGH_API int jpegh_recompress(const uint8_t *data, size_t n, uint64_t interval_
     } catch (const std::exception &e) {
         return fail(e, err, errcap);
     }
+}
+
+// JPEG.CompressionLevel.luminance(level).quanta / .chrominance(level).quanta (encode.swift:286-333); no device involved
+JPEGH_API void jpegh_compression_level_quanta(int32_t chrominance, double level, uint16_t quanta[64])
+{
+    const auto q = (chrominance ? jpeg::CompressionLevel::chrominance(level) : jpeg::CompressionLevel::luminance(level)).quanta();
+    std::memcpy(quanta, q.data(), 128);
 }
 
 // The same two calls for a user-defined format (examples/custom-color): components = the format's keys in plane order.

@@ -70,6 +70,16 @@ struct Scan {
     std::vector<Component> components;
 };
 
+// JPEG.CompressionLevel (encode.swift:260-333): quantum values for a quality parameter (0.0 = all ones, 1.0 = the keyframe
+// table), in zig-zag order.  Host-side Double arithmetic.
+struct CompressionLevel {
+    enum class Kind { luminance, chrominance } kind;
+    double level;
+    static CompressionLevel luminance(double level) { return {Kind::luminance, level}; }
+    static CompressionLevel chrominance(double level) { return {Kind::chrominance, level}; }
+    Table::Quantization     quanta() const;
+};
+
 // A user-defined JPEG.Format (jpeg.swift:300-340) in the style of examples/custom-color/main.swift:41-63: recognised iff the
 // frame's component keys are exactly `components` and its precision is `precision`; `components` orders the planes.
 // Where a `const Format *` is expected, nullptr means JPEG.Common (jpeg.swift:370-397).

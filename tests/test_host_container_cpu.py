@@ -132,3 +132,17 @@ def test_sixteen_bit_tables_in_an_eight_bit_image_are_rejected(manifest, host):
     host.Spectral.decompress(src)
     with pytest.raises(host.DecodingError, match="invalidScanQuantizationPrecision"):
         host.Spectral.decompress(bytes(out))
+
+
+def test_compression_level_quanta(manifest):
+    """JPEG.CompressionLevel (encode.swift:260-333) in the host mirror: equal to the oracle's for a sweep of levels, and to the
+    DQT segments of the 32 files examples/encode-basic wrote."""
+    from jpeg_b200.host import CompressionLevel
+    for level in (0.0, 0.01, 0.125, 0.25, 1 / 3, 0.5, 0.75, 1.0, 1.5, 2.0, 2.5, 4.0, 8.0, 100.0):
+        assert np.array_equal(CompressionLevel.luminance(level).quanta, O.quanta(level, 0)), level
+        assert np.array_equal(CompressionLevel.chrominance(level).quanta, O.quanta(level, 1)), level
+    for name, exp in manifest["encode_basic"]["files"].items():
+        level = float(name.rsplit("-", 1)[1])
+        assert [t[1] for t in exp["dqt"]] == [CompressionLevel.luminance(level).quanta.tolist(),
+                                              CompressionLevel.chrominance(level).quanta.tolist()], name
+

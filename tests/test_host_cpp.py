@@ -175,6 +175,20 @@ def test_format_recognition_needs_no_device(manifest, hostlib):
     assert e.value.code == DECODING and e.value.what == "unrecognizedColorFormat"
 
 
+def test_compression_level_quanta_cpp(manifest, hostlib):
+    """jpeg::CompressionLevel (encode.swift:260-333): the DQT tables of the 32 files examples/encode-basic wrote"""
+    hostlib.jpegh_compression_level_quanta.argtypes = [C.c_int32, C.c_double, C.c_void_p]
+    hostlib.jpegh_compression_level_quanta.restype = None
+    for name, exp in manifest["encode_basic"]["files"].items():
+        level = float(name.rsplit("-", 1)[1])
+        got = []
+        for chroma in (0, 1):
+            q = np.zeros(64, np.uint16)
+            hostlib.jpegh_compression_level_quanta(chroma, level, q.ctypes.data)
+            got.append(q.tolist())
+        assert [t[1] for t in exp["dqt"]] == got, name
+
+
 def test_no_cpu_fallback_without_device(hostlib):
     """Without a GPU the first hot-path stage fails loudly with the CUDA error code; nothing is computed on the CPU."""
     import torch
