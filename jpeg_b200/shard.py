@@ -35,3 +35,16 @@ def gather_in_input_order(local_results: dict, n_images: int):
     for p in parts:
         merged.update(p)
     return [merged[i] for i in range(n_images)]
+
+
+def map_sharded(items, fn):
+    """Applies `fn(index, item)` to the items this rank owns (image i -> rank i mod G) and returns the results of ALL items in
+    input order on every rank.  `fn` is the per-image work on the rank's own GPU context (e.g. host.Spectral.decompress(...)
+    .to_rgb8() digests, file writes, statistics); its result travels through all_gather_object, so keep it small -- pixel
+    data stays on the rank that produced it (there is no collective on the data path)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    local = {i: fn(i, items[i]) for i in shard_indices(len(items), rank, world)}
+    return gather_in_input_order(local, len(items))
+

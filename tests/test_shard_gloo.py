@@ -35,6 +35,13 @@ def _worker(rank, world, port, files, out):
         local[i] = hashlib.sha256(rgb.tobytes()).hexdigest()
     dist.barrier()
     ordered = shard.gather_in_input_order(local, len(files))
+    seen = []
+
+    def work(i, rel):
+        seen.append(i)
+        return (rank, local[i])
+    mapped = shard.map_sharded(files, work)
+    assert seen == mine and [m[1] for m in mapped] == ordered and [m[0] for m in mapped] == [i % world for i in range(len(files))]
     slowest = shard.max_over_ranks(1.0 + rank)
     if rank == 0:
         out.put((ordered, slowest))
