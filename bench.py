@@ -184,7 +184,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: jpeg_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = "unchanged (single rank)"
     if world > 1:
+        # one process per GPU: keep the rank's threads and pinned staging buffers on the GPU's own NUMA node (best effort)
+        if os.environ.get("JPEG_SM100_NUMA", "1") != "0":
+            from jpeg_b200 import affinity
+            placement = affinity.bind_to_gpu(local)
         os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
@@ -397,7 +402,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": n, "ecs_bytes_per_frame": inputs.ecs_bytes // n,
-                       "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective"},
+                       "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective", "cpu_affinity": placement},
             "e2e": {"value": round(px_per_step / e2e_s / 1e6, 1), "unit": "Mpixels/s",
                     "h2d_bytes_per_step": int(raw_len.sum() + raw_len.nbytes * 2), "d2h_bytes_per_step": int(rgb_bytes + 4 * n),
                     "pcie_d2h_GBps_measured": None if d2h_gbs is None else round(d2h_gbs, 1),

@@ -72,3 +72,29 @@ def test_shard_partition_properties():
             parts = [shard.shard_indices(n, r, world) for r in range(world)]
             assert sorted(i for p in parts for i in p) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_numa_placement_plan(tmp_path):
+    """jpeg_b200/affinity.py: a rank binds to the CPUs of its GPU's NUMA node, and only when that is a proper, non-empty subset
+    of what the process may use; a missing or negative numa_node means no change."""
+    from jpeg_b200 import affinity
+    assert affinity.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity.parse_cpulist("") == set()
+    assert affinity.pci_address(0, 0x1b, 0) == "0000:1b:00.0"
+    sysfs = tmp_path
+    for pci, node in (("0000:1b:00.0", "0"), ("0000:9d:00.0", "1"), ("0000:aa:00.0", "-1")):
+        d = sysfs / "bus" / "pci" / "devices" / pci
+        d.mkdir(parents=True)
+        (d / "numa_node").write_text(node + "\n")
+    for node, cpus in ((0, "0-11,24-35"), (1, "12-23,36-47")):
+        d = sysfs / "devices" / "system" / "node" / f"node{node}"
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(cpus + "\n")
+    everything = set(range(48))
+    assert affinity.plan("0000:1b:00.0", everything, str(sysfs)) == (0, set(range(12)) | set(range(24, 36)))
+    assert affinity.plan("0000:9d:00.0", everything, str(sysfs)) == (1, set(range(12, 24)) | set(range(36, 48)))
+    assert affinity.plan("0000:aa:00.0", everything, str(sysfs)) == (None, None)      # the kernel does not know
+    assert affinity.plan("0000:ff:00.0", everything, str(sysfs)) == (None, None)      # no such device
+    assert affinity.plan("0000:9d:00.0", set(range(12)), str(sysfs)) == (1, None)      # cpuset excludes the node: unchanged
+    assert affinity.plan("0000:1b:00.0", set(range(12)), str(sysfs)) == (0, None)      # already confined to it
+    assert affinity.bind_to_gpu(0, str(sysfs)).startswith("unchanged")                   # no CUDA device here: a hint never raises
