@@ -95,15 +95,16 @@ typedef struct {
 } jpeg_sm100_huff_table;
 
 /* JPEG.Scan + the geometry Spectral.decode / Spectral.encode read from `self` (decode.swift:3476, encode.swift:1559) */
+typedef struct {  /* one JPEG.Scan.Component (jpeg.swift:1135-1160), named so that bindings can address the array elements */
+    int32_t plane;               /* index into the planes array, or -1: component without a plane (decode.swift:3251) */
+    int32_t factor_x, factor_y;  /* layout.planes[c].component.factor */
+    int32_t dc, ac;              /* table slots 0..3 */
+} jpeg_sm100_scan_comp;
 typedef struct {
     int32_t band_lo, band_hi;  /* scan.band, 0 <= lo < hi <= 64 */
     int32_t bit_lo, bit_hi;    /* scan.bits; bit_hi = JPEG_SM100_BITS_MAX for an initial scan */
     int32_t n_comp;            /* 1..4, in scan-header order */
-    struct {
-        int32_t plane;               /* index into the planes array, or -1: component without a plane (decode.swift:3251) */
-        int32_t factor_x, factor_y;  /* layout.planes[c].component.factor */
-        int32_t dc, ac;              /* table slots 0..3 */
-    } comp[4];
+    jpeg_sm100_scan_comp comp[4];
     int32_t blocks_x, blocks_y;      /* Spectral.blocks: the MCU grid */
 } jpeg_sm100_scan_desc;
 

@@ -54,3 +54,17 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(base, f)).read()
                 code = "\n".join(l for l in text.splitlines() if "oracle" in l and not l.strip().startswith(("//", "#", "*", '"')))
                 assert "import oracle" not in code and "from oracle" not in code and "jpeg_oracle" not in code, f
+
+
+def test_bindings_name_only_declared_symbols():
+    """The reference-side glue (swift/JPEGSM100Shim.swift, which cannot be compiled here), INTEGRATION.md and the C++ host
+    mirror may only name entry points, types and constants the header declares."""
+    header = open(os.path.join(ROOT, "include", "jpeg_sm100.h")).read()
+    known = set(re.findall(r"\b(jpeg_sm100_[a-z0-9_]+)\b", header)) | set(re.findall(r"\b(JPEG_SM100_[A-Z0-9_]+)\b", header))
+    for rel in ("swift/JPEGSM100Shim.swift", "INTEGRATION.md", "jpeg_b200/host/jpeg_host.cpp", "jpeg_b200/host/jpeg_host.hpp"):
+        text = open(os.path.join(ROOT, rel)).read()
+        used = set(re.findall(r"\b(jpeg_sm100_[a-z0-9_]+)\b", text)) | set(re.findall(r"\b(JPEG_SM100_[A-Z0-9_]+)\b", text))
+        used -= {"jpeg_sm100_h"}
+        # prose may abbreviate a family of entry points with a trailing underscore or wildcard (jpeg_sm100_unpack_*8)
+        unknown = {u for u in used - known if not any(k.startswith(u) for k in known)}
+        assert not unknown, (rel, sorted(unknown))
