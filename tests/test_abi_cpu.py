@@ -68,3 +68,33 @@ def test_bindings_name_only_declared_symbols():
         # prose may abbreviate a family of entry points with a trailing underscore or wildcard (jpeg_sm100_unpack_*8)
         unknown = {u for u in used - known if not any(k.startswith(u) for k in known)}
         assert not unknown, (rel, sorted(unknown))
+
+
+def _calls(text):
+    """(name, number of arguments, line) of every jpeg_sm100_*( ... ) in `text`"""
+    out = []
+    for m in re.finditer(r"\b(jpeg_sm100_[a-z0-9_]+)\s*\(", text):
+        i = j = m.end()
+        depth = 1
+        while depth and j < len(text):
+            depth += {"(": 1, ")": -1}.get(text[j], 0)
+            j += 1
+        args, d, n = text[i:j - 1], 0, 0
+        for ch in args:
+            d += {"(": 1, "[": 1, "{": 1, ")": -1, "]": -1, "}": -1}.get(ch, 0)
+            n += ch == "," and d == 0
+        out.append((m.group(1), 0 if not args.strip() or args.strip() == "void" else n + 1, text[:m.start()].count("\n") + 1))
+    return out
+
+
+def test_bindings_pass_as_many_arguments_as_the_header_declares():
+    """A compile check by other means for the Swift glue (no Swift toolchain here), and a cross-check for the C++ host."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "jpeg_sm100.h")).read(), flags=re.S)
+    declared = {name: n for name, n, _ in _calls(header)}
+    assert len(declared) >= 40
+    for rel in ("swift/JPEGSM100Shim.swift", "jpeg_b200/host/jpeg_host.cpp"):
+        text = re.sub(r"//.*", "", open(os.path.join(ROOT, rel)).read())
+        used = [(name, n, line) for name, n, line in _calls(text) if name in declared]
+        assert used, rel
+        for name, n, line in used:
+            assert n == declared[name], (rel, line, name, n, declared[name])
