@@ -98,3 +98,42 @@ def test_bindings_pass_as_many_arguments_as_the_header_declares():
         assert used, rel
         for name, n, line in used:
             assert n == declared[name], (rel, line, name, n, declared[name])
+
+
+def test_ctypes_binding_matches_the_header_argument_for_argument():
+    """jpeg_b200/lib.py declares restype/argtypes by hand: the number of arguments, and integer vs pointer vs 64-bit for each
+    one, must agree with include/jpeg_sm100.h."""
+    from jpeg_b200 import lib
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "jpeg_sm100.h")).read(), flags=re.S)
+
+    def kind_of_c(decl):
+        decl = decl.strip()
+        if "*" in decl or "[" in decl:
+            return "ptr"
+        if re.search(r"\b(uint64_t|size_t|int64_t)\b", decl):
+            return "i64"
+        if re.search(r"\b(double)\b", decl):
+            return "f64"
+        return "i32"
+
+    def kind_of_ctypes(t):
+        if t in (C.c_uint64, C.c_int64, C.c_size_t):
+            return "i64"
+        if t in (C.c_int, C.c_uint32, C.c_int32):
+            return "i32"
+        if t is C.c_double:
+            return "f64"
+        return "ptr"  # c_void_p, c_char_p, POINTER(...)
+
+    checked = 0
+    for m in re.finditer(r"\b(jpeg_sm100_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        name, params = m.group(1), m.group(2)
+        if name not in lib.SYMBOLS:
+            continue
+        params = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        _, argtypes = lib.SYMBOLS[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for k, (p, t) in enumerate(zip(params, argtypes)):
+            assert kind_of_c(p) == kind_of_ctypes(t), (name, k, p.strip(), t)
+        checked += 1
+    assert checked == len(lib.SYMBOLS), (checked, len(lib.SYMBOLS))
