@@ -63,6 +63,10 @@ enum {
 #define JPEG_SM100_SCAN_FRESH    2          /* layer B only: the planes of the scan's components are newly created
                                                Spectral planes (all zero, decode.swift:2241-2256) -- the library clears
                                                them as part of the call, whatever they hold */
+#define JPEG_SM100_SCAN_T81      4          /* restart interval e starts at MCU e * interval wherever that falls in its row
+                                               (ITU-T T.81 E.1.4), instead of the reference's integer-division ROW placement
+                                               (decode.swift:3205-3207), which is only right for whole-row intervals.  Sequential
+                                               and DC scans; an extension: the Swift decoder mis-places such files */
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
 typedef struct jpeg_sm100_ctx jpeg_sm100_ctx;
@@ -123,9 +127,10 @@ typedef struct { uint8_t  *samples; int32_t units_x, units_y; int32_t factor_x, 
  * composites decode.swift:2773-2872; bitstream jpeg.swift:1873-1916).
  *   ecs_concat / ecs_offsets : the reference's ecss:[[UInt8]] (already unstuffed and split at RSTn by the lexer),
  *                              flattened; n_ecs + 1 offsets.
- *   interval                 : MCUs per restart interval, JPEG_SM100_INTERVAL_NONE if no DRI.  Must be a multiple
- *                              of the row width (blocks_x, or units_x for single-component scans) -- the only form
- *                              the reference decoder places correctly (decode.swift:3205-3207) -- else UNSUPPORTED.
+ *   interval                 : MCUs per restart interval, JPEG_SM100_INTERVAL_NONE if no DRI.  Interval e is placed as the
+ *                              reference places it: MCU rows floor(e * interval / W) ..< floor((e + 1) * interval / W), W = blocks_x
+ *                              (or units_x for single-component scans), decode.swift:3205-3207 -- exact for intervals that are
+ *                              whole rows; for other values see JPEG_SM100_SCAN_T81 above.
  *   extend                   : the reference's `extend` flag (first scan): rows stop silently at the end of data
  *                              (decode.swift:3214-3220).  Planes must already be sized for the final height
  *                              (the host handles DNL before the call); growth beyond it is not performed.

@@ -2,6 +2,8 @@
 // layer A (host buffers; what the Swift shim binds).  There is no CPU fallback anywhere in this library.
 #include <sched.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 // kernels' launchers (idct.cu, color.cu, huffman_decode.cu, fdct.cu, encode.cu)
@@ -14,6 +16,7 @@ int jpeg_color_pack_rgb(jpeg_sm100_ctx *, const uint8_t *, uint64_t, int, uint16
 int jpeg_color_decompose(jpeg_sm100_ctx *, const void *, bool, uint32_t, uint32_t, const jpeg_sm100_dev_planar *);
 int jpeg_huffman_decode_scan(jpeg_sm100_ctx *, const jpeg_sm100_scan_desc *, const uint8_t *, const uint64_t *, uint32_t,
                              uint64_t, int, const jpeg_sm100_huff_table *, int, const jpeg_sm100_dev_spectral *, int32_t *);
+int jpeg_huffman_validate_tables(const jpeg_sm100_scan_desc *, const jpeg_sm100_huff_table *);
 struct LexPlan {
     uint32_t  n_images, tiles_max;
     uint64_t  n_tiles;
@@ -76,6 +79,7 @@ JPEG_API void jpeg_sm100_destroy(jpeg_sm100_ctx *ctx)
         if (p.done) cudaEventDestroy(p.done);
     }
     for (auto &e : ctx->events) cudaEventDestroy(e);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -365,8 +369,11 @@ JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     jpeg_sm100_huff_table tables[8];
     memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
-    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off),
-                                   n_ecs, interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+    ctx->hint_interval_bytes = total / n_ecs;  // how the parallel decoders cut the intervals
+    const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off),
+                                            n_ecs, interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
+    ctx->hint_interval_bytes = 0;
+    J_TRY(k3);
     int32_t status = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)
@@ -494,9 +501,21 @@ namespace {
 
 // shared body of the two batch entry points.  raw_offsets == nullptr: `bytes` are unstuffed ECS bytes and `offsets` the
 // n_images * n_ecs + 1 ECS offsets; else `bytes` are raw scan bytes and the GPU lexer produces both.
+// On every exit path the caller's buffers must be quiescent: copies queued by earlier groups may still be writing `rgb`
+struct StreamDrain {
+    jpeg_sm100_ctx *ctx;
+    bool            armed = true;
+    ~StreamDrain()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
+    }
+};
+
 int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, uint32_t n_images, const uint8_t *bytes,
                         const uint64_t *offsets, const uint64_t *raw_offsets, const uint64_t *raw_lengths, uint32_t n_ecs,
-                        uint64_t interval, const jpeg_sm100_huff_table *tables, int tables_shared, const uint16_t *quanta,
+                        uint64_t interval, const jpeg_sm100_huff_table *tables_in, int tables_shared, const uint16_t *quanta,
                         uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb, int32_t *status)
 {
     if (scan->band_lo != 0 || scan->band_hi != 64 || scan->bit_hi >= 0) return JPEG_SM100_ERR_UNSUPPORTED;
@@ -510,6 +529,34 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
     }
     if (scx < 1 || scy < 1) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     if (!ctx->copy_out) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    // Table errors belong to their image (decode.swift:3186-3203 raises them per file): validate every set before anything is
+    // launched; an image with a missing / invalid table decodes with a stand-in set (its output is undefined) and reports its error.
+    std::vector<int32_t>               table_err(n_images, 0);
+    std::vector<jpeg_sm100_huff_table> patched;
+    const jpeg_sm100_huff_table       *tables = tables_in;
+    {
+        int good = -1, any_bad = 0;
+        const uint32_t n_sets = tables_shared ? 1u : n_images;
+        for (uint32_t i = 0; i < n_sets; ++i) {
+            const int e = jpeg_huffman_validate_tables(scan, tables_in + (size_t) 8 * i);
+            if (e == JPEG_SM100_ERR_INVALID_ARGUMENT) return e;
+            if (tables_shared) std::fill(table_err.begin(), table_err.end(), e);
+            else table_err[i] = e;
+            if (e) any_bad = 1;
+            else if (good < 0) good = (int) i;
+        }
+        if (any_bad && good < 0) {  // nothing decodable in the batch
+            if (status) for (uint32_t i = 0; i < n_images; ++i) status[i] = table_err[i];
+            return table_err[0];
+        }
+        if (any_bad) {
+            patched.assign(tables_in, tables_in + (size_t) 8 * n_sets);
+            for (uint32_t i = 0; i < n_sets; ++i)
+                if (table_err[i]) std::copy(tables_in + (size_t) 8 * good, tables_in + (size_t) 8 * good + 8, patched.begin() + (size_t) 8 * i);
+            tables = patched.data();
+        }
+    }
+    StreamDrain drain{ctx};
 
     // chunk size: ~100 MB of RGB per chunk, at least 1 image, at most the batch
     const size_t rgb_per_image = (size_t) sx * sy * 3;
@@ -626,18 +673,30 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
     }
     std::vector<int32_t> st(2 * (size_t) n_images, 0);
     CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, 2 * sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
-    // the batch call waits tens of milliseconds for PCIe.  Poll the two streams and yield the core between polls: no wake-up
-    // latency when cores are free (a blocking-sync event costs ~5 % of the call at N = 1), no core burnt when several of these
-    // calls (one per context / per GPU process) share the host.
-    for (cudaStream_t st_ : {ctx->stream, ctx->copy_out}) {
-        cudaError_t q;
-        while ((q = cudaStreamQuery(st_)) == cudaErrorNotReady) sched_yield();
-        CU_TRY(ctx, q);
+    // the batch call waits tens of milliseconds for PCIe.  Default: poll the two streams and yield the core between polls (no
+    // wake-up latency when cores are free; a blocking-sync event costs ~5 % of the call at N = 1).  JPEG_SM100_WAIT=block sleeps on
+    // blocking-sync events instead -- for hosts where many of these calls (one per context / per GPU process) share few cores.
+    {
+        const char *wm = getenv("JPEG_SM100_WAIT");
+        const bool  block = wm && strcmp(wm, "block") == 0;
+        for (cudaStream_t st_ : {ctx->stream, ctx->copy_out}) {
+            if (block) {
+                if (!ctx->wait_event) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventRecord(ctx->wait_event, st_));
+                CU_TRY(ctx, cudaEventSynchronize(ctx->wait_event));
+            } else {
+                cudaError_t q;
+                while ((q = cudaStreamQuery(st_)) == cudaErrorNotReady) sched_yield();
+                CU_TRY(ctx, q);
+            }
+        }
     }
+    drain.armed = false;  // both streams are idle
     int first = 0;
     for (uint32_t i = 0; i < n_images; ++i) {
-        // a lexer error is raised before the scan is pushed (decode.swift:3929), so it wins over a decode error
-        const int32_t v = st[n_images + i] ? st[n_images + i] : st[i];
+        // a lexer error is raised before the scan is pushed (decode.swift:3929), so it wins over a decode error; a table error
+        // is raised when the scan is pushed, before its first bit is read
+        const int32_t v = st[n_images + i] ? st[n_images + i] : (table_err[i] ? table_err[i] : st[i]);
         if (status) status[i] = v;
         if (v && !first) first = v;
     }
@@ -751,8 +810,11 @@ JPEG_API int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_sc
     jpeg_sm100_huff_table tables[8];
     memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
-    J_TRY(jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
-                                   interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status)));
+    ctx->hint_interval_bytes = raw_len / n_ecs;
+    const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
+                                            interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
+    ctx->hint_interval_bytes = 0;
+    J_TRY(k3);
     int32_t status = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)

@@ -646,6 +646,12 @@ int fill_view(const jpeg_sm100_dev_planar *pl, uint32_t sx, uint32_t sy, int cos
         V.scale_x = V.fx[p] > V.scale_x ? V.fx[p] : V.scale_x;
         V.scale_y = V.fy[p] > V.scale_y ? V.fy[p] : V.scale_y;
     }
+    // every pixel of the size_x x size_y rectangle must map into its plane (the reference indexes Planar.Plane with bounds
+    // checks and would trap, decode.swift:1586-1597): ceil(size * factor / scale) <= 8 * units
+    for (uint32_t p = 0; p < pl->n_planes; ++p) {
+        const int64_t need_x = ((int64_t) sx * V.fx[p] + V.scale_x - 1) / V.scale_x, need_y = ((int64_t) sy * V.fy[p] + V.scale_y - 1) / V.scale_y;
+        if (need_x > V.width[p] || need_y > V.height[p]) return JPEG_SM100_ERR_PRECONDITION;
+    }
     return JPEG_SM100_OK;
 }
 

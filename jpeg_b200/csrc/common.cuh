@@ -41,10 +41,12 @@ struct jpeg_sm100_ctx {
     // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> events;
+    cudaEvent_t  wait_event = nullptr;  // blocking-sync event (JPEG_SM100_WAIT=block)
     // average bytes per restart interval of the next entropy-decode call, when the caller knows it (0: unknown); consumed by K3
     uint64_t hint_interval_bytes = 0;
     int      par_smem_ac = 0;   // same for its progressive AC-first instantiation
     size_t   par_smem_set = 0;  // largest dynamic shared-memory size k_decode_par has been opted into on this device
+    bool     idct_smem_set[2] = {false, false};  // k_idct_tma<u8 / u16> opted into > 48 KB of dynamic shared memory (per device, so per ctx)
     // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda dependency)
     void *encode_tiled = nullptr;
 };

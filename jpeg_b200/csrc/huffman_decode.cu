@@ -910,6 +910,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t a)
     return v;
 }
 
+// `extend` scans (the first scan of a file, decode.swift:3214-3220, 2906-2912) test `bits[b, count: 16] != 0xffff` before every
+// MCU row.  top: the next 32 stream bits as the parallel decoders hold them (NOT 1-padded past the end of the data);
+// remaining: bits from the cursor to the end of the data (> 0).
+__device__ __forceinline__ bool row_start_all_ones(const uint32_t top, const int remaining)
+{
+    uint32_t t16 = top >> 16;
+    if (remaining < 16) t16 |= 0xffffu >> remaining;  // jpeg.swift:1881-1887: the stream is padded with 1-bits
+    return t16 == 0xffffu;
+}
+
 // Parses (FINAL = false) or decodes (FINAL = true) symbols from `st` until the bit position reaches `end_bit`.
 // Returns the number of completed blocks; `st` is the exit state.  `bad` is set when the TRUE decoder would not simply
 // carry on (truncation / rejected symbol); speculative callers ignore it.
@@ -927,7 +937,7 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
                                             bool &bad,
                                             // FINAL only:
                                             uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                            int16_t *dcdiff, int16_t *buf)
+                                            int16_t *dcdiff, int16_t *buf, const bool ext = false)
 {
     int z = st.z;
     bad = false;
@@ -966,6 +976,7 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
     int      mx = 0, my = 0;
     int16_t *bptr = nullptr, *dcp = nullptr;
     bool     inp = false, own = false;  // own: the DC symbol of the block in progress was decoded here
+    bool     rowstart = false;          // `extend` scans: the next DC symbol opens an MCU row (decode.swift:3214-3220)
     if (FINAL) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(buf)[i] = make_uint4(0, 0, 0, 0);
@@ -976,6 +987,7 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
         const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
         inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
         bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
+        rowstart = ext && z == 0 && st.b == 0 && mx == 0;
     }
     while (left > 0 || (FINAL && own)) {
         const bool in_range = left > 0;  // the symbol starts inside the subsequence (block completions are counted there)
@@ -997,6 +1009,13 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
         }
         const uint32_t top = __funnelshift_l(lo, hi, cnt);  // the next 32 bits of the stream
         const bool     isdc = z == 0;
+        if (FINAL && rowstart && isdc) {  // decode.swift:3214-3220: sixteen 1-bits at the start of a row end an `extend` scan silently
+            rowstart = false;
+            if (row_start_all_ones(top, left + slack)) {  // (never on a healthy stream: left to the sequential decoder)
+                bad = true;
+                break;
+            }
+        }
         const uint32_t tab = isdc ? dtab : atab;
         uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
         if (ent & FAST_LINK) {  // longer code: its sub-table, addressed by the bits that follow the prefix
@@ -1060,6 +1079,7 @@ __device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, con
                     mx = 0;
                     my += 1;
                 }
+                rowstart = ext && ((tabs >> 24) & 1u) != 0u && mx == 0;
                 const uint4 g = lds128(cur - 16u);
                 inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
                 bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
@@ -1082,20 +1102,20 @@ template <bool FINAL>
 __device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
                                                  const uint32_t blk0, const uint8_t *smem, const uint16_t *ref_entries, const int nblk,
                                                  bool &bad, uint32_t N, const uint32_t N_total, const int W, const int my0,
-                                                 int16_t *plane0, int16_t *dcdiff, int16_t *buf)
+                                                 int16_t *plane0, int16_t *dcdiff, int16_t *buf, const bool ext = false)
 {
     const uint32_t mask = __activemask();
     // the decoding pass may run past end_bit by the rest of one block: 63 symbols of at most 31 bits
     const uint32_t reach = end_bit + (FINAL ? 2048u : 0u);
     if (__all_sync(mask, io.stage != 0u)) {
         if (__all_sync(mask, reach + 32u <= count_bits))
-            return par_run<FINAL, true, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
-        return par_run<FINAL, true, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
+            return par_run<FINAL, true, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
+        return par_run<FINAL, true, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
     }
     const uint32_t last_word = ((uint32_t) io.lead * 8u + reach + 32u + 64u) / 32u + 2u;  // incl. the word loaded ahead
     if (__all_sync(mask, last_word < io.wlim))
-        return par_run<FINAL, false, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
-    return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf);
+        return par_run<FINAL, false, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
+    return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
 }
 
 // ---- the decoding pass, warp-synchronous: blocks leave through a warp-cooperative flush -------------------------------------------
@@ -1113,7 +1133,7 @@ __device__ __forceinline__ void sts128_zero(uint32_t a)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
 }
-template <bool SAFE>
+template <bool SAFE, bool EXT>
 __device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
                                                   const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
                                                   const uint16_t *ref_entries, const int nblk, bool &bad, uint32_t N,
@@ -1134,6 +1154,7 @@ __device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io
     int            mx = 0, my = 0;
     uint32_t       bidx = 0;  // destination of the block in progress, in 128-byte units from plane0
     bool           inp = false, own = false;
+    bool           rowstart = false;  // EXT (`extend` scans): the next DC symbol opens an MCU row (decode.swift:3214-3220)
     int16_t       *dcp = dcdiff + N;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
@@ -1152,6 +1173,7 @@ __device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io
         const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
         inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
         bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
+        if (EXT) rowstart = z == 0 && st.b == 0 && mx == 0;
     }
     __syncwarp();
     bool wait = false;  // the lane's block is complete; its block-end work is pending
@@ -1184,6 +1206,7 @@ __device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io
                         mx = 0;
                         my += 1;
                     }
+                    if (EXT) rowstart = ((tabs >> 24) & 1u) != 0u && mx == 0;
                     const uint4 g = lds128(cur - 16u);
                     inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
                     bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
@@ -1222,6 +1245,15 @@ __device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io
                 }
                 const uint32_t top = __funnelshift_l(lo, hi, cnt);
                 const bool     isdc = z == 0;
+                if (EXT) {
+                    if (rowstart & isdc) {  // sixteen 1-bits at the start of a row end an `extend` scan silently: never on a
+                        rowstart = false;   // healthy stream, so the interval just goes to the sequential decoder
+                        if (row_start_all_ones(top, left + slack)) {
+                            bad = true, run = false;
+                            break;
+                        }
+                    }
+                }
                 const uint32_t tab = isdc ? dtab : atab;
                 uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
                 if (ent & FAST_LINK) {
@@ -1277,12 +1309,16 @@ __device__ __forceinline__ uint32_t par_run_final_auto(const bool go, const ParI
                                                        const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
                                                        const uint16_t *ref_entries, const int nblk, bool &bad, const uint32_t N,
                                                        const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                                       int16_t *dcdiff, const uint32_t buf, const uint32_t fq)
+                                                       int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const bool ext)
 {
     const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 2048u + 32u + 64u) / 32u + 2u;
-    if (__all_sync(0xffffffffu, !go || last_word < io.wlim))
-        return par_run_final<true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
-    return par_run_final<false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    const bool     safe = __all_sync(0xffffffffu, !go || last_word < io.wlim);
+    if (ext) {  // (kernel-uniform)
+        if (safe) return par_run_final<true, true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+        return par_run_final<false, true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    }
+    if (safe) return par_run_final<true, false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    return par_run_final<false, false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
 }
 
 // ---- progressive AC-first scans (kind 3) on the same machinery ------------------------------------------------------------------
@@ -1375,6 +1411,102 @@ __device__ __forceinline__ uint32_t par_run_ac_auto(const ParIO &io, ParseState 
     const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 32u + 64u) / 32u + 2u;
     if (__all_sync(mask, last_word < io.wlim)) return par_run_ac<FINAL, true>(io, st, end_bit, count_bits, tab, band_lo, band_hi, al, bad, N, N_total, base);
     return par_run_ac<FINAL, false>(io, st, end_bit, count_bits, tab, band_lo, band_hi, al, bad, N, N_total, base);
+}
+
+// ---- progressive DC-first scans (kind 1) on the same machinery -------------------------------------------------------------------
+// One DC symbol per block (decode.swift:2960-3004 single component, 3295-3392 interleaved), so the parse state is (bit position,
+// block-in-MCU b) -- the tables may differ between the components of an MCU.  The decoding pass only fills the side array of DC
+// differences; the prefix sums that follow it (shared with the sequential-scan path) store `prediction << al` into coefficient 0
+// and touch nothing else of the block.  DC category 16 and invalid codewords flag the interval for the sequential kernel.
+template <bool FINAL, bool SAFE>
+__device__ __forceinline__ uint32_t par_run_dc(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                               const uint32_t blk0, bool &bad, uint32_t N, const uint32_t N_total, const uint32_t row_blocks,
+                                               int16_t *dcdiff, const bool ext)
+{
+    bad = false;
+    if (st.p >= end_bit) return 0;
+    if (FINAL && N >= N_total) return 0;
+    uint32_t  done = 0;
+    int       left = (int) (end_bit - st.p);
+    const int slack = (int) (count_bits - end_bit);
+    uint32_t  wi, cnt, hi, lo, nxt;
+    {
+        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
+        wi = ab >> 5;
+        cnt = ab & 31u;
+        hi = io.word(wi), lo = io.word(wi + 1);
+        nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));
+        wi += 3;
+    }
+    uint32_t dtab, tabs, next;
+    {
+        const uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
+        dtab = q.x, tabs = q.z, next = q.w;
+    }
+    uint32_t rowpos = (FINAL && ext) ? N % row_blocks : 1u;  // blocks since the start of the MCU row (`extend` scans only)
+    while (left > 0) {
+        if (cnt >= 32u) {
+            hi = lo;
+            asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));
+            nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
+            wi += 1;
+            cnt -= 32u;
+        }
+        const uint32_t top = __funnelshift_l(lo, hi, cnt);
+        if (FINAL && ext) {
+            if (rowpos == 0u && row_start_all_ones(top, left + slack)) {  // decode.swift:2906-2912, 3214-3220
+                bad = true;
+                break;
+            }
+            if (++rowpos == row_blocks) rowpos = 0u;
+        }
+        uint32_t ent = lds32(dtab + ((top >> (32 - FAST_BITS)) << 2));
+        if (ent & FAST_LINK) {
+            const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
+            ent = lds32(dtab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
+        }
+        if (__builtin_expect(ent == 0u, 0)) {  // invalid codeword (the reference reads it as (0, 16)) or category 16
+            bad = true;
+            break;
+        }
+        const int total = (int) (ent >> 24);
+        if (!SAFE) {
+            if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2791-2794, 2808-2811
+                bad = true;
+                break;
+            }
+        }
+        if (FINAL) {
+            const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441);
+            const uint32_t top2 = top << len;
+            const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
+            dcdiff[N] = (int16_t) ((int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail);  // T.81 EXTEND
+        }
+        cnt += (uint32_t) total;
+        left -= total;
+        done += 1;
+        N += 1;
+        {
+            const uint4 q = lds128(next);
+            dtab = q.x, tabs = q.z, next = q.w;
+        }
+        if (FINAL && N >= N_total) break;
+    }
+    st.p = end_bit - (uint32_t) left;
+    st.z = 0;
+    st.b = (uint16_t) ((tabs >> 16) & 0xffu);
+    return done;
+}
+
+template <bool FINAL>
+__device__ __forceinline__ uint32_t par_run_dc_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                                    const uint32_t blk0, bool &bad, uint32_t N, const uint32_t N_total,
+                                                    const uint32_t row_blocks, int16_t *dcdiff, const bool ext)
+{
+    const uint32_t mask = __activemask();
+    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 32u + 64u) / 32u + 2u;
+    if (__all_sync(mask, last_word < io.wlim)) return par_run_dc<FINAL, true>(io, st, end_bit, count_bits, blk0, bad, N, N_total, row_blocks, dcdiff, ext);
+    return par_run_dc<FINAL, false>(io, st, end_bit, count_bits, blk0, bad, N, N_total, row_blocks, dcdiff, ext);
 }
 
 // ---- prologue shared by the subsequence-parallel kernels ---------------------------------------------------------------------
@@ -1480,7 +1612,8 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
 // stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
 // block buffers (PAR_BUF_STRIDE bytes each)
-template <int NT, int MIN_CTAS, bool AC>
+constexpr int MODE_SEQ = 0, MODE_AC = 1, MODE_DC = 2;  // sequential scan | progressive AC-first | progressive DC-first
+template <int NT, int MIN_CTAS, int MODE>
 __global__ void __launch_bounds__(NT, MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
              uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits,
@@ -1490,7 +1623,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // The records of the synchronisation (exit / entry states, block counts, checkpoints, work list) are dead once the decoding
     // pass starts, and the threads' block buffers are unused until then: with PAR_ALIAS the records live in the buffer area
     // (4.9 KB less shared memory per CTA: 7 CTAs per SM instead of 6).  AC scans have no block buffers and keep static arrays.
-    constexpr bool ALIAS = PAR_ALIAS && !AC;
+    constexpr bool AC = MODE == MODE_AC, DC = MODE == MODE_DC;
+    constexpr bool ALIAS = PAR_ALIAS && MODE == MODE_SEQ;
     static_assert(NT * (8 + 8 + 4 + 2 + 4 * PAR_NSEG) <= NT * (int) PAR_BUF_STRIDE, "records fit in the block buffers");
     __shared__ uint64_t s_exit_st[ALIAS ? 1 : NT], s_entry_st[ALIAS ? 1 : NT];
     __shared__ uint32_t s_cnt_st[ALIAS ? 1 : NT];
@@ -1571,6 +1705,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
             if (AC) cum += par_run_ac_auto<false>(qio, st, seg_end, qcount, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
+            else if (DC) cum += par_run_dc_auto<false>(qio, st, seg_end, qcount, blk0, bad, 0, 0, 1u, nullptr, false);
             else cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
             // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
             const uint32_t over = st.p - seg_end;
@@ -1595,6 +1730,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = AC ? (uint16_t) P.band_lo : 0, st.b = 0;
         if (l > 0 && warm_bits) {
             if (AC) par_run_ac_auto<false>(io, st, start_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
+            else if (DC) par_run_dc_auto<false>(io, st, start_bit, count, blk0, bad, 0, 0, 1u, nullptr, false);
             else par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
         }
         if (l > 0 && !warm_bits) st.p = start_bit;
@@ -1658,12 +1794,12 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // ---- the one real decoding pass ---------------------------------------------------------------------------------------
     const uint32_t N_total = s_grp[g].N_total, slot = s_grp[g].slot;
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
-    if (PAR_COOP && !AC && stage_bytes == 0u) {  // every lane of every warp takes part in the cooperative flush
+    if (PAR_COOP && MODE == MODE_SEQ && stage_bytes == 0u) {  // every lane of every warp takes part in the cooperative flush
         static_assert(PAR_NSEG * 4 >= 8, "the flush queues fit in the checkpoint array");
         const bool     go = active && before < N_total;
         const uint32_t done = par_run_final_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
                                                  N_total, W, s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                                 (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u);
+                                                 (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
             atomicAdd(&s_grp[g].total, done);
@@ -1676,9 +1812,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             if (AC)  // single component, blocks in raster order: block N of the interval is N blocks after its first
                 done = par_run_ac_auto<true>(io, st, end_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, before, N_total,
                                              P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) s_grp[g].r0 * (size_t) W * 64);
+            else if (DC)
+                done = par_run_dc_auto<true>(io, st, end_bit, count, blk0, bad, before, N_total, (uint32_t) W * (uint32_t) nblk, dcdiff, P.extend != 0);
             else
                 done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff,
-                                          reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+                                          reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE), P.extend != 0);
         }
         // a subsequence that does not produce the blocks the synchronisation counted for it (or that was cut short because the
         // interval is complete while data remains) leaves the interval to the sequential decoder
@@ -1701,7 +1839,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
     // Work items (interval, component) are dealt to the warps; a lane owns a contiguous run of the component's blocks: it sums its
     // differences, the warp scans the lane sums, the lane walks its run again and stores the predictions.
-    for (uint32_t item = (uint32_t) wid; !AC && item < G * (uint32_t) P.n_comp; item += NT / 32) {
+    for (uint32_t item = (uint32_t) wid; !AC && item < G * (uint32_t) P.n_comp; item += NT / 32) {  // (sequential and DC-first scans)
         const uint32_t  gg = item / (uint32_t) P.n_comp;
         const int       c = (int) (item - gg * (uint32_t) P.n_comp);
         const ParGroup &q = s_grp[gg];
@@ -1890,7 +2028,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
         const bool     go = active && before < N_total;
         const uint32_t done = par_run_final_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
                                                  N_total, W, s_q.r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u);
+                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_bad, 1u);
             atomicAdd(&s_total, done);
@@ -1901,7 +2039,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
         bad = false;
         if (before < N_total)
             done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_q.r0, plane0, dcdiff,
-                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE));
+                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE), P.extend != 0);
         if (bad || (before < N_total && done != my_cnt)) atomicOr(&s_bad, 1u);
         atomicAdd(&s_total, done);
     }
@@ -2210,6 +2348,49 @@ finished:
     if (P.status) P.status[(size_t) img * P.n_ecs + e] = err;
 }
 
+// ---- progressive DC refinement scans (kind 2): no Huffman codes at all ---------------------------------------------------------
+// decode.swift:3007-3018 (single component), 3395-3445 (interleaved): block n of a restart interval owns bit n of its entropy-coded
+// segment and ORs it into coefficient 0 at bit `al` -- a pure gather, one thread per block.  Out-of-plane blocks of partial MCUs
+// and components without a plane consume their bit and store nothing.  An interval with fewer bits than blocks is truncated
+// (decode.swift:2775-2778).  Intervals whose row range is empty or inverted (General.Range2's quirks) are flagged for
+// k_decode_progressive, which reproduces them.
+__global__ void __launch_bounds__(256) k_decode_dc_refine(const __grid_constant__ ScanParams P, const uint32_t n_images, uint32_t *const flagged)
+{
+    const uint32_t nblk = (uint32_t) P.mcu_blocks, W = (uint32_t) P.W;
+    for (uint32_t img = blockIdx.z; img < n_images; img += gridDim.z) {
+        for (uint32_t e = blockIdx.y; e < P.n_ecs; e += gridDim.y) {
+            const size_t slot = (size_t) img * P.n_ecs + e;
+            int64_t      r0 = 0, r1 = P.H;
+            if (P.interval != UINT64_MAX) {
+                r0 = (int64_t) (((uint64_t) e * P.interval) / W);
+                r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / W);
+                if (r1 > P.H) r1 = P.H;
+            }
+            const uint64_t o0 = P.offsets[slot], o1 = P.offsets[slot + 1];
+            const uint64_t n_total = r1 > r0 ? (uint64_t) (r1 - r0) * W * nblk : 0;
+            const bool     irregular = !(r1 > r0) || n_total > 0xffffffffull || (o1 - o0) > 0x1fffffffull;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                flagged[slot] = irregular ? 1u : 0u;
+                if (!irregular) P.status[slot] = (o1 - o0) * 8 < n_total ? JPEG_SM100_ERR_TRUNCATED_ECS : 0;
+            }
+            if (irregular) continue;
+            const uint8_t *base = P.ecs + o0;
+            const uint32_t nbits = (uint32_t) ((o1 - o0) * 8), N = (uint32_t) n_total;
+            for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N && n < nbits; n += gridDim.x * blockDim.x) {
+                const uint32_t mcu = n / nblk, b = n - mcu * nblk;
+                const uint32_t row = mcu / W, mx = mcu - row * W, my = (uint32_t) r0 + row;
+                const int      c = P.blk_comp[b];
+                if (!P.plane[c]) continue;
+                const uint32_t x = mx * (uint32_t) P.fx[c] + P.blk_dx[b], y = my * (uint32_t) P.fy[c] + P.blk_dy[b];
+                if (x >= (uint32_t) P.ux[c] || y >= (uint32_t) P.uy[c]) continue;
+                const uint32_t bit = (__ldg(base + (n >> 3)) >> (7u - (n & 7u))) & 1u;
+                int16_t       *dst = P.plane[c] + (size_t) img * P.image_stride[c] + 64 * ((size_t) P.ux[c] * y + x);
+                if (bit) *dst = (int16_t) (*dst | (int16_t) (1u << P.al));
+            }
+        }
+    }
+}
+
 // per image: first non-zero status in interval order (the reference throws at the first failing interval)
 __global__ void k_reduce_status(const int32_t *__restrict__ per_ecs, uint32_t n_ecs, int32_t *__restrict__ per_image)
 {
@@ -2237,6 +2418,24 @@ int zero_plane_rows(jpeg_sm100_ctx *ctx, const ScanParams &P, int n_comp, uint32
 }
 
 }  // namespace
+
+// decode.swift:2884-2895, 3186-3203 + 310-351: the error a sequential scan raises for this table set before it reads a bit
+// (0: none).  Used by the batch entry points to give every image its own status.
+int jpeg_huffman_validate_tables(const jpeg_sm100_scan_desc *scan, const jpeg_sm100_huff_table *set8)
+{
+    for (int c = 0; c < scan->n_comp; ++c)
+        for (int k = 0; k < 2; ++k) {
+            const int sel = k == 0 ? scan->comp[c].dc : scan->comp[c].ac;
+            if (sel < 0 || sel > 3) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+            const jpeg_sm100_huff_table &t = set8[4 * k + sel];
+            if (!t.present) return k == 0 ? JPEG_SM100_ERR_UNDEFINED_DC : JPEG_SM100_ERR_UNDEFINED_AC;
+            int n, z, leaves = 0;
+            if (!huff_size(t.counts, n, z)) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+            for (int l = 0; l < 16; ++l) leaves += t.counts[l];
+            if (leaves > 256) return JPEG_SM100_ERR_INVALID_HUFFMAN;
+        }
+    return JPEG_SM100_OK;
+}
 
 // Layer-B implementation.  scratch slots 8 (LUTs) and 9 (per-ECS status) belong to this file.
 int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
@@ -2402,8 +2601,12 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
             return e && strcmp(e, "seq") == 0;  // one thread per interval only (A/B validation of the parallel decoder)
         }();
         bool par_done = false;
-        if (P.kind == 0 && !P.extend && !no_par) {
-            // subsequence-parallel decode (+ fused row clearing and DC prefix sums), then the sequential kernel for whatever it flagged
+        if (!no_par) {
+            // subsequence-parallel decode (+ fused row clearing and DC prefix sums), then the sequential kernel for whatever it flagged.
+            // `extend` (the first scan of a file, decode.swift:3214-3236): the planes are already sized, so the flag only means "rows
+            // stop silently where the data ends"; the parallel pass flags an interval that runs dry (or shows sixteen 1-bits at the
+            // start of a row) and k_decode_fast(only_flagged) reproduces the silent stop.
+            const bool     dc_first = P.kind == 1;
             const uint64_t rows_max = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W + 1;
             const uint64_t dc_per_interval = rows_max * (uint64_t) P.W * (uint64_t) volume;
             const uint64_t slots = (uint64_t) n_images * n_ecs;
@@ -2419,27 +2622,30 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 const int   env_t = env_ts ? atoi(env_ts) : 0, env_warm = env_ws ? atoi(env_ws) : 0;
                 const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
                 const uint64_t est_bits = ctx->hint_interval_bytes ? 8 * ctx->hint_interval_bytes
-                                                                   : 96 * rows_typ * (uint64_t) P.W * (uint64_t) volume;
+                                                                   : (dc_first ? 8 : 96) * rows_typ * (uint64_t) P.W * (uint64_t) volume;
                 // few, large intervals (a file without DRI is ONE interval): a 512-thread CTA per interval
-                const bool big = (est_bits >> 7) >= 16384 && slots * 128 < (uint64_t) ctx->sm_count * 1024;
+                const bool big = (est_bits >> 7) >= (dc_first ? 2048 : 16384) && slots * 128 < (uint64_t) ctx->sm_count * 1024;
                 const int  nt = big ? PAR_BIG_THREADS : PAR_THREADS, tmax = big ? 9 : 7;
                 int        tshift = tmax;
                 while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
                 while (tshift < tmax && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
                 if (env_t >= 4 && env_t <= tmax) tshift = env_t;
-                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : 1024u;
+                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? 256u : 1024u);
                 const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
                 // optional shared-memory stage for the intervals' bytes (measured slower than global reads one refill ahead: the
                 // shared memory costs occupancy; kept selectable for A/B)
                 const char    *env_ss = getenv("JPEG_SM100_PAR_STAGE");  // KB per interval, 0 = no staging
-                uint64_t       per_interval = env_ss ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
+                uint64_t       per_interval = (env_ss && !dc_first) ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
                 if (per_interval * G > 96 * 1024) per_interval = (96 * 1024 / G) & ~(uint64_t) 1023;
                 const uint32_t stage_bytes = (uint32_t) (per_interval * G);
-                const size_t   smem_total = smem_par + stage_bytes + (size_t) nt * PAR_BUF_STRIDE;
+                const size_t   smem_total = smem_par + stage_bytes + (dc_first ? 0 : (size_t) nt * PAR_BUF_STRIDE);
                 if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
-                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, MODE_DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                     ctx->par_smem_set = 200 * 1024;
                 }
                 static const bool want_stats = getenv("JPEG_SM100_PAR_STATS") != nullptr;
@@ -2450,15 +2656,27 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     d_stats = reinterpret_cast<uint32_t *>(p);
                     CU_TRY(ctx, cudaMemsetAsync(d_stats, 0, 128, ctx->stream));
                 }
-                // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
-                if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
+                if (dc_first) {
+                    // a DC-first scan defines coefficient 0 only: fresh planes are cleared as a whole, the rest of a block is not touched
+                    if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
+                } else if (fresh && interval != JPEG_SM100_INTERVAL_NONE && ((uint64_t) n_ecs * interval) / (uint64_t) P.W < (uint64_t) P.H)
+                    // rows no interval reaches (a file with too few intervals) stay as a fresh plane has them: zero
                     J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, (int) (((uint64_t) n_ecs * interval) / (uint64_t) P.W)));
                 // few, large intervals: a cluster of CTAs per interval (JPEG_SM100_PAR_CLUSTER=0: one 512-thread CTA, kept for A/B)
                 const char *env_cl = getenv("JPEG_SM100_PAR_CLUSTER");
-                uint32_t    csize = big ? (env_cl ? (uint32_t) atoi(env_cl) : 8u) : 0u;
+                uint32_t    csize = (big && !dc_first) ? (env_cl ? (uint32_t) atoi(env_cl) : 8u) : 0u;
                 while (csize > 1 && (est_bits / (CL_THREADS * csize)) < 2048) csize >>= 1;
                 if (csize > 8 || (csize & (csize - 1))) csize = 8;
-                if (big && csize >= 1 && !(env_cl && atoi(env_cl) == 0)) {
+                if (dc_first) {
+                    if (big)
+                        k_decode_par<PAR_BIG_THREADS, 1, MODE_DC><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
+                            P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
+                            d_stats, tshift, warm_bits, (uint32_t) smem_par, 0u, (uint32_t) smem_par);
+                    else
+                        k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_DC><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
+                            P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
+                            d_stats, tshift, warm_bits, (uint32_t) smem_par, 0u, (uint32_t) smem_par);
+                } else if (big && csize >= 1 && !(env_cl && atoi(env_cl) == 0)) {
                     cudaLaunchConfig_t cfg;
                     memset(&cfg, 0, sizeof cfg);
                     cfg.gridDim = dim3(csize * n_ecs, n_images);
@@ -2472,11 +2690,11 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_decode_par_cluster, P, plane0, reinterpret_cast<int16_t *>(d_dc),
                                                    (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag), warm_bits, (uint32_t) smem_par));
                 } else if (big)
-                    k_decode_par<PAR_BIG_THREADS, 1, false><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
+                    k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
                         d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
                 else
-                    k_decode_par<PAR_THREADS, PAR_MIN_CTAS, false><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
+                    k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
                         d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
                 LAUNCH_CHECK(ctx);
@@ -2493,8 +2711,10 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     fprintf(stderr, "[k_decode_par] T %d, warm %u, stage %u B, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
                             1 << tshift, warm_bits, stage_bytes, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
                 }
-                k_zero_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
-                LAUNCH_CHECK(ctx);
+                if (!dc_first) {
+                    k_zero_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+                    LAUNCH_CHECK(ctx);
+                }
                 k_decode_fast<<<grid, WARP, smem2, ctx->stream>>>(P, plane0, reinterpret_cast<const uint32_t *>(d_flag));
                 par_done = true;
             }
@@ -2526,15 +2746,29 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         const uint32_t G = (uint32_t) PAR_THREADS >> tshift;
         const size_t   smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + ((max_fast * 2 + 15) & ~size_t(15));
         if (!ctx->par_smem_ac) {
-            CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             ctx->par_smem_ac = 1;
         }
         // (the side array / block buffers of the sequential-scan variant are unused: dc_per_interval only bounds N_total)
-        k_decode_par<PAR_THREADS, PAR_MIN_CTAS, true><<<dim3((n_ecs + G - 1) / G, n_images), PAR_THREADS, smem_par, ctx->stream>>>(
+        k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_AC><<<dim3((n_ecs + G - 1) / G, n_images), PAR_THREADS, smem_par, ctx->stream>>>(
             P, plane0, nullptr, 0xffffffffu, reinterpret_cast<uint32_t *>(d_flag), nullptr, tshift, warm_bits, (uint32_t) smem_par, 0u,
             (uint32_t) smem_par);
         LAUNCH_CHECK(ctx);
         k_zero_band_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+        LAUNCH_CHECK(ctx);
+        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+    } else if (P.kind == 2 && !(getenv("JPEG_SM100_HUFF") && strcmp(getenv("JPEG_SM100_HUFF"), "seq") == 0) &&
+               (uint64_t) n_images * n_ecs * 4 <= (1ull << 30)) {
+        // progressive DC refinement: a bit gather, one thread per block; intervals with Range2 quirks go to the sequential kernel
+        if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
+        void *d_flag = nullptr;
+        J_TRY(scratch_reserve(ctx, 13, (size_t) ((uint64_t) n_images * n_ecs * 4 + 256), &d_flag));
+        const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
+        const uint64_t per = rows_typ * (uint64_t) P.W * (uint64_t) volume;
+        const dim3     g2((uint32_t) std::min<uint64_t>((per + 255) / 256 ? (per + 255) / 256 : 1, 1024), std::min<uint32_t>(n_ecs, 65535u),
+                          std::min<uint32_t>(n_images, 65535u));
+        k_decode_dc_refine<<<g2, 256, 0, ctx->stream>>>(P, n_images, reinterpret_cast<uint32_t *>(d_flag));
         LAUNCH_CHECK(ctx);
         if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
         else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));

@@ -301,10 +301,10 @@ int launch_idct(jpeg_sm100_ctx *ctx, const int16_t *d_coef, uint32_t n_images, u
         return JPEG_SM100_ERR_CUDA;
     }
     const size_t smem = (size_t) STAGES * TILE_BYTES + 1024 + 64;
-    static bool  attr_set[2] = {false, false};
-    if (!attr_set[sizeof(OutT) - 1]) {
+    // the opt-in is a per-device function attribute: remembered per ctx (one ctx = one device), never in a process-wide static
+    if (!ctx->idct_smem_set[sizeof(OutT) - 1]) {
         CU_TRY(ctx, cudaFuncSetAttribute(k_idct_tma<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_set[sizeof(OutT) - 1] = true;
+        ctx->idct_smem_set[sizeof(OutT) - 1] = true;
     }
     k_idct_tma<OutT><<<grid, TILE, smem, ctx->stream>>>(tmap, P);
     LAUNCH_CHECK(ctx);

@@ -693,8 +693,16 @@ def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None):
                     if qslot[sel] is None:
                         raise DecodingError("undefinedScanQuantizationReference")
                     s.planes[ids.index(cid)].q = qslot[sel]
-            if first and fh == 0:
-                raise DecodingError("DNL-defined height is resolved by the host before the call: unsupported here")
+            if first:
+                # decode.swift:3905-3924: the segment that follows the first scan may redefine the height (DNL); the library
+                # decodes into planes of the final size (its `extend` never grows them), so the host resolves the height
+                # BEFORE the call -- rows beyond it would be cropped by push(height:) anyway, rows short of it stay zero.
+                if m == 0xDC:
+                    if len(body) != 2:
+                        raise ParsingError("mismatched height")
+                    s.set_size((fw, (body[0] << 8) | body[1]))
+                elif fh == 0:
+                    raise DecodingError("missingHeightRedefinitionSegment")
             if gpu_lexer:
                 s.decode_scan_raw(band, bits, comps_, dc, ac, raw, ival, extend=first)
             else:
@@ -702,9 +710,6 @@ def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None):
             s.scans.append(Scan(band, bits, comps_))
             if first:
                 if m == 0xDC:
-                    if len(body) != 2:
-                        raise ParsingError("mismatched height")
-                    s.set_size((fw, (body[0] << 8) | body[1]))
                     _, m, body = lx.segment()
                 first = False
             if on_scan is not None:

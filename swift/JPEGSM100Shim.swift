@@ -42,6 +42,8 @@ extension JPEG
     enum SM100Error:Swift.Error
     {
         case cuda(Int32)
+        case usage(Int32)
+        case batch(Int32)
     }
 }
 
@@ -66,7 +68,19 @@ extension JPEG.SM100
             throw JPEG.DecodingError.undefinedScanHuffmanACReference(\.0)
         case -7:
             preconditionFailure("libjpeg_sm100: the reference implementation traps on this input")
-        default:
+        case -8:
+            throw JPEG.ParsingError.invalidHuffmanTable
+        case -9:
+            // the C-ABI reports the first offending interval only; the phases themselves stay on the device
+            throw JPEG.DecodingError.invalidRestartPhase(-1, expected: -1)
+        case -10:
+            // batch lexer only: an image whose RSTn count differs from the batch geometry has no Swift counterpart
+            throw JPEG.SM100Error.batch(status)
+        case -11:
+            throw JPEG.DecodingError.missingRestartIntervalSegment
+        case -20, -21, -22:
+            throw JPEG.SM100Error.usage(status)
+        default: // -100: device missing / launch failure
             throw JPEG.SM100Error.cuda(status)
         }
     }

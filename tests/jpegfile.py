@@ -92,3 +92,19 @@ def parse_dqt(body: bytes):
             out.append((tgt, [(body[i + 1 + 2 * k] << 8) | body[i + 2 + 2 * k] for k in range(64)]))
             i += 129
     return out
+
+
+def with_dnl(data: bytes, frame_height: int, dnl_height: int) -> bytes:
+    """The same file with the frame header's height replaced by `frame_height` (0 = "defined by DNL") and a DNL segment
+    (T.81 B.2.5; decode.swift:3905-3924) of `dnl_height` lines after the first scan."""
+    out, first = bytearray(), True
+    for m, body, ecs in split(data):
+        if 0xC0 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            body = body[:1] + frame_height.to_bytes(2, "big") + body[3:]
+        out += bytes([0xFF, m])
+        if m not in (0xD8, 0xD9):
+            out += (len(body) + 2).to_bytes(2, "big") + body + ecs
+        if m == 0xDA and first:
+            out += bytes([0xFF, 0xDC, 0, 4]) + dnl_height.to_bytes(2, "big")
+            first = False
+    return bytes(out)

@@ -137,3 +137,21 @@ def test_ctypes_binding_matches_the_header_argument_for_argument():
             assert kind_of_c(p) == kind_of_ctypes(t), (name, k, p.strip(), t)
         checked += 1
     assert checked == len(lib.SYMBOLS), (checked, len(lib.SYMBOLS))
+
+
+def test_swift_check_maps_every_status_code_of_the_header():
+    """swift/JPEGSM100Shim.swift cannot be compiled here: every status code the header defines must be named by a `case` of
+    SM100.check(), so that callers matching on the reference's error enums never see a documented code as a CUDA failure."""
+    header = open(os.path.join(ROOT, "include", "jpeg_sm100.h")).read()
+    codes = {int(v) for v in re.findall(r"JPEG_SM100_(?:OK|ERR_[A-Z_]+)\s*=\s*(-?\d+)", header)}
+    assert {0, -1, -8, -9, -11, -100} <= codes
+    swift = open(os.path.join(ROOT, "swift", "JPEGSM100Shim.swift")).read()
+    body = swift[swift.index("static func check(_ status:Int32) throws"):]
+    body = body[:body.index("// MARK:")]
+    handled = set()
+    for m in re.finditer(r"case\s+([-0-9,\s]+):", body):
+        handled |= {int(x) for x in m.group(1).replace(" ", "").split(",") if x}
+    # -100 (CUDA) is the documented meaning of `default`
+    assert codes - handled <= {-100}, sorted(codes - handled)
+    from jpeg_b200 import lib
+    assert {getattr(lib, k) for k in dir(lib) if k.startswith("ERR_") or k == "OK"} == codes

@@ -241,6 +241,14 @@ def test_config4_1080p_progressive_decode(env):
         dst.decode_scan(band, bits, comps, list(dct), list(act), J.unstuff_split(ecs), width)
     for p in range(3):
         assert np.array_equal(dst.planes[p].coef, src.planes[p].coef), p
+    # pixels: the decoded image through the fused and the staged CUDA paths against the oracle's IDCT + upsampling + colour
+    dst.quanta = [q[0].copy(), q[1].copy()]
+    dst.planes[0].q, dst.planes[1].q, dst.planes[2].q = 0, 1, 1
+    for p in range(3):
+        ref.set_quanta(p, q[p])
+    want = O.unpack_rgb(ref.to_rectangular())
+    assert np.array_equal(dst.to_rgb8(), want)
+    assert np.array_equal(dst.idct().interleaved().unpack_rgb(), want)
 
 
 def test_config5_12mpix_444_roundtrip(env):
@@ -275,6 +283,24 @@ def test_config5_12mpix_444_roundtrip(env):
     t.cuda.synchronize()
     again = out[:ln.item()].cpu().numpy()
     assert again.tobytes() == ecs[0].tobytes()
+    # the oracle on the same frame: coefficients from the stream, the re-encoded bytes and tables, and (below) the pixels
+    dct, act = _tables_to_oracle(O, tabs, 0)
+    data, lens = b.unstuff_split(ecs[0])
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    parts = [data[offs[k]:offs[k + 1]].tobytes() for k in range(len(lens))]
+    ref = O.Spectral.create((W, H), geo.factors)
+    for p in range(3):
+        ref.set_quanta(p, q[p])
+    ref.decode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], dct, act, parts, interval=500)
+    for p in range(3):
+        assert np.array_equal(ref.coefficients(p), buf.coef[p][0].cpu().numpy()), p
+    want, dct2, act2 = ref.encode_scan((0, 64), (0, None), [0, 1, 2], [0, 1, 1], [0, 1, 1], 500)
+    assert again.tobytes() == want
+    for k in range(4):
+        if dct2[k].present:
+            assert tabs2[k].as_tuple() == dct2[k].as_tuple()
+        if act2[k].present:
+            assert tabs2[4 + k].as_tuple() == act2[k].as_tuple()
     # 4:4:4 colour fast path against the generic kernel on the same planes
     ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), q.ctypes.data, 8, C.byref(buf.pl)))
     ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
@@ -284,6 +310,7 @@ def test_config5_12mpix_444_roundtrip(env):
     ctx.check(ctx.L.jpeg_sm100_dev_unpack_rgb8(ctx.h, il.data_ptr(), W * H, 3, rgb2.data_ptr()))
     t.cuda.synchronize()
     assert t.equal(buf.rgb[0], rgb2)
+    assert np.array_equal(buf.rgb[0].cpu().numpy(), O.unpack_rgb(ref.to_rectangular()))
 
 
 @pytest.mark.parametrize("size,factors", [((3840, 2160), [(2, 2), (1, 1), (1, 1)]), ((4000, 3000), [(1, 1), (1, 1), (1, 1)]),
@@ -310,6 +337,11 @@ def test_colour_kernels_agree(env, monkeypatch, size, factors):
     assert t.equal(out["tma"], out["generic"])
     assert t.equal(out["direct"], out["generic"])
     assert t.equal(out["default"], out["generic"])
+    # ... and the oracle's interleaved(cosite: false) + unpack(as: RGB) on the first image's planes
+    O = env["O"]
+    planes = [s_[0].cpu().numpy().astype(np.uint16) for s_ in buf.samples]
+    want = O.unpack_rgb(O.interleave(planes, geo.units, geo.factors, size, False))
+    assert np.array_equal(out["default"][0].cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("size,factors", [((3840, 2160), [(2, 2), (1, 1), (1, 1)]), ((4000, 3000), [(1, 1), (1, 1), (1, 1)]),
@@ -335,3 +367,56 @@ def test_forward_colour_kernels_agree(env, monkeypatch, size, factors):
         out[mode] = [s_.clone() for s_ in buf.samples]
     for p in range(3):
         assert t.equal(out["default"][p], out["generic"][p]), p
+    # ... and the oracle's pack + decomposed() on the first image
+    O = env["O"]
+    want = O.decompose(O.pack_rgb(rgb[0].cpu().numpy()), geo.factors)
+    for p in range(3):
+        assert np.array_equal(out["default"][p][0].cpu().numpy().astype(np.uint16), want[p]), p
+
+
+def test_whole_file_4k_baseline_without_dri_through_host(env):
+    """The reference's real call path for a baseline file: Spectral.decompress pushes the (only) scan with extend: true
+    (decode.swift:3892-3904), one entropy-coded segment for the whole image (its encoder never writes DRI).  The scan must run
+    through the cluster form of the subsequence-parallel decoder, and equal the oracle's decode of the same file."""
+    O = env["O"]
+    from jpeg_b200 import host
+    W, H = 3840, 2160
+    factors = [(2, 2), (1, 1), (1, 1)]
+    q = _quanta(O)
+    rgb = env["synth"].frame(21, W, H, env["dev"]).cpu().numpy()
+    sp = host.Rectangular.pack(rgb, factors).decomposed().fdct([q[0], q[1], q[2]])
+    sp.scans = [host.Scan((0, 64), (0, None), [(0, 0, 0), (1, 1, 1), (2, 1, 1)])]
+    data = sp.compress()
+    s = host.Spectral.decompress(data)
+    ref = O.Spectral.decompress(data)
+    for p in range(3):
+        assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), p
+        assert np.array_equal(s.planes[p].coef, sp.planes[p].coef), p
+    assert np.array_equal(s.to_rgb8(), O.unpack_rgb(ref.to_rectangular()))
+    # the same file cut after 60 % of its bytes: the lexer fails on the missing EOI exactly as the reference's does; the scan
+    # alone, pushed with extend, ends in truncatedEntropyCodedSegment in both
+    import sys
+    sys.path.insert(0, __file__.rsplit("/", 1)[0])
+    import jpegfile as J
+    ecs = [e for m, _, e in J.split(data) if m == 0xDA][0]
+    part = J.unstuff_split(ecs)[0]
+    part = part[:int(len(part) * 0.6)]
+    dct = [t if t.present else None for t in _scan_tables(data, 0)]
+    act = [t if t.present else None for t in _scan_tables(data, 1)]
+    cut = host.Spectral((W, H), factors)
+    with pytest.raises(env["lib"].JpegSm100Error) as ei:
+        cut.decode_scan((0, 64), (0, None), [(0, 0, 0), (1, 1, 1), (2, 1, 1)], dct, act, [part], None, extend=True)
+    assert ei.value.code == env["lib"].ERR_TRUNCATED_ECS
+
+
+def _scan_tables(data, cls):
+    """the four table slots of class `cls` (0 = DC, 1 = AC) as the file defines them"""
+    import jpegfile as J
+    from jpeg_b200 import lib
+    slots = [lib.HuffTable() for _ in range(4)]
+    for m, body, _ in J.split(data):
+        if m == 0xC4:
+            for c, tgt, counts, values in J.parse_dht(body):
+                if c == cls:
+                    slots[tgt] = lib.HuffTable.make(counts, values)
+    return slots

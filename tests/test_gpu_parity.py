@@ -75,6 +75,26 @@ def test_restart_files_through_gpu(manifest, H, O):
         assert np.array_equal(s.to_rgb8(), rgb_ref), rel
 
 
+def test_height_defined_by_dnl_through_gpu(H, O):
+    """decode.swift:3905-3924: frame height 0 + DNL, and DNL heights below / above the frame's (crop / zero extension)."""
+    for rel in ("gold/color-sequential-1.jpg", "gold/color-progressive-2.jpg", "gold/grayscale-sequential-1.jpg"):
+        data = golden_bytes(rel)
+        h = O.Spectral.decompress(data).size[1]
+        for fh, dh in ((0, h), (h, h - 21), (h, h + 40)):
+            mod = J.with_dnl(data, fh, dh)
+            if dh > h and "progressive" in rel:  # the later scans of a progressive file run out of data on the taller image
+                from jpeg_b200 import lib
+                with pytest.raises(lib.JpegSm100Error) as ei:
+                    H.Spectral.decompress(mod)
+                assert ei.value.code == lib.ERR_TRUNCATED_ECS
+                continue
+            s, ref = H.Spectral.decompress(mod), O.Spectral.decompress(mod)
+            assert s.size == ref.size
+            for p in range(s.ncomp):
+                assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (rel, fh, dh, p)
+            assert np.array_equal(s.to_rgb8(), O.unpack_rgb(ref.to_rectangular())), (rel, fh, dh)
+
+
 def test_cosited_and_generic_upsampling(H, O, manifest):
     """interleaved(cosite: true) and non-4:2:0 factors go through the generic kernel."""
     eb = manifest["encode_basic"]
@@ -400,6 +420,90 @@ def test_scan_decode_extend_flag(H, O):
     dst = H.Spectral(src.size, [(1, 1)])
     with pytest.raises(lib.JpegSm100Error):
         dst.decode_scan(band, bits, [(0, 0, 0)], _to_lib_tables(H, dct), _to_lib_tables(H, act), half, None, extend=False)
+
+
+@pytest.mark.parametrize("kind", ["baseline", "luma", "dc_first", "dc_first_luma"])
+@pytest.mark.parametrize("rows", [0, 2])
+def test_first_scan_extend_through_parallel_decoder(H, O, kind, rows):
+    """The reference pushes the first scan of every file with extend: true (decode.swift:3892-3904): rows stop silently where the
+    data ends (3214-3220, 2906-2912).  Complete scans, scans that end after 25 / 50 / 75 % of the MCU rows (silent stop) and
+    scans cut in the middle of a row (truncation error) -- same planes and same codes as the oracle, through the
+    subsequence-parallel decoders (an interval that runs dry is flagged and redone by the sequential kernel)."""
+    from jpeg_b200 import lib
+    src = O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))
+    fac = [src.factor(p) for p in range(3)]
+    band, bits = ((0, 64), (0, None)) if kind in ("baseline", "luma") else ((0, 1), (1, None))
+    comps = [0, 1, 2] if kind in ("baseline", "dc_first") else [0]
+    w, h = src.size
+    mcu_h = 8 * src.scale[1] if len(comps) > 1 else 8
+
+    def scan_of(height):
+        """the scan of the image cropped to `height` pixel rows, encoded by the oracle"""
+        part = O.Spectral.create((w, height), fac, progressive=True)
+        for p in range(3):
+            c = part.coefficients(p)
+            c[...] = src.coefficients(p)[:c.shape[0], :c.shape[1]]
+        width = part.blocks[0] if len(comps) > 1 else part.units(comps[0])[0]
+        ecs, dct, act = part.encode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), rows * width)
+        return J.unstuff_split(ecs), dct, act, (rows * width) or None
+
+    def both(parts, dct, act, ival):
+        got, want = H.Spectral(src.size, fac, process=2), O.Spectral.create(src.size, fac, progressive=True)
+        try:
+            got.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival, extend=True)
+            code = 0
+        except lib.JpegSm100Error as e:
+            code = e.code
+        try:
+            want.decode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), dct, act, parts,
+                             interval=O.INTERVAL_NONE if ival is None else ival, extend=True)
+            wcode = 0
+        except O.OracleError as e:
+            wcode = e.code
+        assert code == wcode
+        if code == 0:
+            assert want.size == src.size  # (the oracle grows planes under `extend`; it must not have had to)
+            for p in range(3):
+                assert np.array_equal(got.planes[p].coef, want.coefficients(p)), p
+        return code
+
+    total_rows = -(-h // mcu_h)
+    assert both(*scan_of(h)) == 0
+    for frac in (0.25, 0.5, 0.75):
+        k = max(1, int(total_rows * frac))
+        assert both(*scan_of(k * mcu_h)) == 0, frac      # the data ends at a row boundary: silent stop
+    parts, dct, act, ival = scan_of(h)
+    for frac in (0.25, 0.5, 0.75):                        # cut mid-row: whatever the oracle says
+        cut = list(parts)
+        j = int(len(cut) * frac)
+        cut[j] = cut[j][:max(1, int(len(cut[j]) * frac))]
+        both(cut[:j + 1] if rows == 0 else cut, dct, act, ival)
+
+
+def test_dc_refinement_scan_is_a_bit_gather(H, O):
+    """kind 2 through k_decode_dc_refine: interleaved and single-component, with and without restart intervals, odd geometry,
+    plus a scan that is one bit short (truncation, decode.swift:2775-2778)."""
+    from jpeg_b200 import lib
+    src = O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))
+    fac = [src.factor(p) for p in range(3)]
+    for comps in ([0, 1, 2], [0], [2]):
+        for rows in (0, 1, 3):
+            dst = H.Spectral(src.size, fac, process=2)
+            ref = O.Spectral.create(src.size, fac, progressive=True)
+            scans = _oracle_scans(O, src, [((0, 1), (1, None), comps), ((0, 1), (0, 1), comps)], rows)
+            for band, bits, cs, dct, act, parts, ival in scans:
+                dst.decode_scan(band, bits, [(c, 0, 0) for c in cs], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival)
+                ref.decode_scan(band, bits, cs, [0] * len(cs), [0] * len(cs), dct, act, parts, interval=O.INTERVAL_NONE if ival is None else ival)
+            for p in range(3):
+                assert np.array_equal(dst.planes[p].coef, ref.coefficients(p)), (comps, rows, p)
+                if p in comps:
+                    assert np.array_equal(dst.planes[p].coef[..., 0], src.coefficients(p)[..., 0]), (comps, rows, p)
+            band, bits, cs, dct, act, parts, ival = scans[1]
+            short = list(parts)
+            short[-1] = short[-1][:-1]
+            with pytest.raises(lib.JpegSm100Error) as ei:
+                dst.decode_scan(band, bits, [(c, 0, 0) for c in cs], _to_lib_tables(H, dct), _to_lib_tables(H, act), short, ival)
+            assert ei.value.code == lib.ERR_TRUNCATED_ECS
 
 
 # ------------------------------------------------------------------------------------------------ layer B: batches

@@ -71,6 +71,28 @@ def test_golden_files_parse_to_the_oracles_coefficients(manifest, host):
             assert np.array_equal(s.quanta[s.planes[p].q], ref.quanta(p)), (rel, p)
 
 
+def test_height_defined_by_dnl(manifest, host):
+    """decode.swift:3905-3924: a frame height of 0 is resolved by the DNL segment that follows the first scan; a DNL height
+    other than the frame's crops / extends the image.  The host resolves it before the scan is decoded."""
+    for rel in ("gold/color-sequential-1.jpg", "gold/color-progressive-2.jpg", "gold/grayscale-sequential-1.jpg"):
+        data = golden_bytes(rel)
+        h = O.Spectral.decompress(data).size[1]
+        for fh, dh in ((0, h), (h, h - 21), (h, h + 40)):
+            mod = J.with_dnl(data, fh, dh)
+            if dh > h and "progressive" in rel:  # the later scans of a progressive file run out of data on the taller image
+                with pytest.raises(O.OracleError):
+                    O.Spectral.decompress(mod)
+                with pytest.raises(host.DecodingError, match="truncatedEntropyCodedSegment"):
+                    host.Spectral.decompress(mod)
+                continue
+            s, ref = host.Spectral.decompress(mod), O.Spectral.decompress(mod)
+            assert s.size == ref.size == (ref.size[0], dh), (rel, fh, dh)
+            for p in range(s.ncomp):
+                assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (rel, fh, dh, p)
+        with pytest.raises(host.DecodingError, match="missingHeightRedefinitionSegment"):
+            host.Spectral.decompress(J.with_dnl(data, 0, h).replace(bytes([0xFF, 0xDC, 0, 4]) + h.to_bytes(2, "big"), b""))
+
+
 def test_online_decoding_hook(manifest, host):
     """examples/decode-online/main.swift:252-282: the capture closure sees the image after every scan"""
     v = manifest["decode_online"]
