@@ -74,21 +74,29 @@ struct RawSet {
     uint8_t   values[8][256];
 };
 
+constexpr uint32_t FAST_LINK = 0x80u;
+// A codeword the sequential-scan decoders cannot take in their stride (invalid; DC category 16; EOBn): byte 0 carries this flag and
+// the entry otherwise reads as a 16-bit symbol that ends its block with a zig-zag position no real symbol can reach: a SPECULATIVE
+// parse just moves on (its result is garbage either way), the decoding pass finds z > 127 when the block ends and hands the interval
+// to the sequential kernel, and k_decode_fast tests the flag and takes the careful path.
+constexpr uint32_t FAST_SPECIAL = 0x40u;
+constexpr uint32_t FAST_SPECIAL_ENTRY = FAST_SPECIAL | 16u | (200u << 16) | (16u << 24);  // 16 bits; advance 200: ends the block with z > 127
 // (symbol | length << 8) of the reference LUT -> the fast decoders' entry:
 //     byte0 = code length, byte1 = extra bits, byte2 = zig-zag advance (run + 1; 64 for EOB), byte3 = length + extra bits
-// 0 if the sequential decoders need the careful path for it (DC magnitude category > 15, or EOBn with n > 0).
+// FAST_SPECIAL_ENTRY if the sequential decoders need the careful path for it (DC magnitude category > 15, or EOBn with n > 0).
 // With z the zig-zag position before the symbol (0 for DC): the coefficient lands at z + advance - 1 (an EOB lands beyond
 // 63, i.e. nowhere) and the next position is z + advance.
-// A fast-table slot whose FAST_BITS-bit prefix is shared by longer codes holds a LINK instead: bit 7 set, bits 0..2 =
-// 16 - FAST_BITS - d, bits 8.. = byte offset (from the table base) of a 2^d-entry sub-table (same entry format) addressed
-// by the next d bits of the codeword.
+// A fast-table slot whose FAST_BITS-bit prefix is shared by longer codes holds a LINK instead: bit 7 set, bits 0..4 = 32 - d
+// (so that (top << FAST_BITS) >> entry, a wrapping shift, is the sub-table index; its low three bits are 16 - FAST_BITS - d),
+// bits 8.. = byte offset (from the table base) of a 2^d-entry sub-table (same entry format) addressed by the next d bits of the
+// codeword.
 __host__ __device__ inline uint32_t fast_entry(uint32_t ref, bool dc)
 {
     const uint32_t len = ref >> 8, sym = ref & 0xffu;
     // category 16 takes the reference's masked-shift EXTEND (decode.swift:2742-2754), which is not the textbook one
-    if (dc) return sym > 15u ? 0u : (len | (sym << 8) | (1u << 16) | ((len + sym) << 24));
+    if (dc) return sym > 15u ? FAST_SPECIAL_ENTRY : (len | (sym << 8) | (1u << 16) | ((len + sym) << 24));
     const uint32_t size = sym & 15u, run = sym >> 4;
-    if (size == 0u && run != 0u && run != 15u) return 0u;
+    if (size == 0u && run != 0u && run != 15u) return FAST_SPECIAL_ENTRY;
     const uint32_t adv = sym == 0u ? 64u : run + 1u;
     return len | (size << 8) | (adv << 16) | ((len + size) << 24);
 }
@@ -100,7 +108,6 @@ __host__ __device__ inline uint32_t fast_entry_prog(uint32_t ref)
     if (size == 0u && run != 15u) return len | (run << 8) | (0x80u << 16) | ((len + run) << 24);
     return len | (size << 8) | ((run + 1u) << 16) | ((len + size) << 24);
 }
-constexpr uint32_t FAST_LINK = 0x80u;
 constexpr uint32_t SUB_MAX = 1536;  // sub-table entries per Huffman table (6 KB); larger sets keep the reference lookup
 
 // Depth (bits beyond FAST_BITS) of the longest canonical code under every FAST_BITS-bit prefix (T.81 Annex C code
@@ -220,14 +227,16 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
         if (d == 0u) {
             bool           valid;
             const uint32_t e = ref_lookup(cw, valid);
-            fast[i] = (e >> 8) <= (uint32_t) FAST_BITS ? ((prog && ti >= 4) ? (valid ? fast_entry_prog(e) : 0u) : fast_entry(e, ti < 4)) : 0u;
+            const bool     ok = valid && (e >> 8) <= (uint32_t) FAST_BITS;
+            fast[i] = (prog && ti >= 4) ? (ok ? fast_entry_prog(e) : 0u) : (ok ? fast_entry(e, ti < 4) : FAST_SPECIAL_ENTRY);
             continue;
         }
-        fast[i] = FAST_LINK | (uint32_t) (16 - FAST_BITS - d) | ((uint32_t) s_off[i] << 10);  // shift, byte offset
+        fast[i] = FAST_LINK | (32u - d) | ((uint32_t) s_off[i] << 10);  // shift, byte offset
         for (uint32_t j = 0; j < (1u << d); ++j) {
             bool           valid;
             const uint32_t e = ref_lookup(cw | (j << (16 - FAST_BITS - d)), valid);
-            fast[s_off[i] + j] = (valid && (e >> 8) <= (uint32_t) FAST_BITS + d) ? ((prog && ti >= 4) ? fast_entry_prog(e) : fast_entry(e, ti < 4)) : 0u;
+            const bool     ok = valid && (e >> 8) <= (uint32_t) FAST_BITS + d;
+            fast[s_off[i] + j] = (prog && ti >= 4) ? (ok ? fast_entry_prog(e) : 0u) : (ok ? fast_entry(e, ti < 4) : FAST_SPECIAL_ENTRY);
         }
     }
 }
@@ -682,10 +691,10 @@ __global__ void __launch_bounds__(WARP) k_decode_fast(const __grid_constant__ Sc
             const uint32_t cw = (uint32_t) (acc >> 48);
             const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + (isdc ? cur_dfo : cur_afo));
             uint32_t        ent = fast_lookup(tab, cw);
-            if (__builtin_expect(ent == 0u, 0)) {  // invalid / rejected code (or oversized table set): the reference lookup
+            if (__builtin_expect((ent & FAST_SPECIAL) != 0u, 0)) {  // invalid / rejected code (or oversized table set): the reference lookup
                 const int ti = isdc ? (cur_tabs & 0xff) : (cur_tabs >> 8);
                 ent = fast_entry(lut_lookup(entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], cw), isdc);
-                if (ent == 0u) break;  // corrupt DC symbol or EOBn: finished (and diagnosed) by the careful phase
+                if (ent & FAST_SPECIAL) break;  // corrupt DC symbol or EOBn: finished (and diagnosed) by the careful phase
             }
             const int      len = (int) (ent & 0xffu), size = (int) __byte_perm(ent, 0, 0x4441);
             const int      adv = (int) __byte_perm(ent, 0, 0x4442), total = (int) (ent >> 24);
@@ -856,8 +865,8 @@ struct ParIO {             // where the bytes of one restart interval live
     const uint32_t *w0;    // the aligned word that holds its first byte
     uint32_t        wlim;  // words [0, wlim) need no padding
     int32_t         lead, nbytes;
-    uint32_t        stage;  // shared-memory address of the staged copy (big-endian words, 1-padded past the end); 0: not staged
-    uint32_t        wlast;  // index of the last word that holds a byte of the interval (loads are clamped to it)
+    uint32_t        clamp;  // the interval ends within 16 bytes of the end of the buffer: loads are clamped to wlast
+    uint32_t        wlast;  // index of the last word that holds a byte of the interval
     // jpeg.swift:1881-1887: bytes past the end of the interval read as 1-bits; `be` = word i, already big-endian
     __device__ __forceinline__ uint32_t pad(uint32_t be, uint32_t i) const
     {
@@ -920,405 +929,257 @@ __device__ __forceinline__ bool row_start_all_ones(const uint32_t top, const int
     return t16 == 0xffffu;
 }
 
-// Parses (FINAL = false) or decodes (FINAL = true) symbols from `st` until the bit position reaches `end_bit`.
-// Returns the number of completed blocks; `st` is the exit state.  `bad` is set when the TRUE decoder would not simply
-// carry on (truncation / rejected symbol); speculative callers ignore it.
-// SAFE: the run (plus look-ahead) stays inside the words that need no padding, so every consumed bit is a real bit and the
-// reference's truncation guards cannot fire -- no padding logic, no bit-count checks.
-// The kernel is bound by instruction issue and the lanes of a warp sit in different places of their blocks all the time, so
-// the loop is branch-free (selects + predicated memory operations) and every instruction of it counts:
-//   * the bit window is two stream words (hi:lo) plus a consumed-bit count < 32: a symbol costs one funnel shift, a refill
-//     moves lo to hi and loads one word;
-//   * tables are addressed with 32-bit shared-memory addresses held in registers and reloaded (one LDS.128, which also brings
-//     the successor's address) only when a block ends.
-template <bool FINAL, bool STAGED, bool SAFE>
-__device__ __forceinline__ uint32_t par_run(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                            const uint32_t blk0, const uint8_t *smem, const uint16_t *ref_entries, const int nblk,
-                                            bool &bad,
-                                            // FINAL only:
-                                            uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                            int16_t *dcdiff, int16_t *buf, const bool ext = false)
+// ---- generation 6: the two hot loops, rebuilt around their instruction count ---------------------------------------------------
+// The kernel is bound by instruction issue (ncu, round 1: 66 % issue-active at 32 resident warps; the synchronisation parse
+// cost 38 and the decoding pass ~105 warp instructions per symbol step).  Both loops now keep ONE absolute bit cursor
+//     a = 8 * lead + p        (a & 31: shift of the funnel shift, a >> 5: stream word; compared against `bound`, `end`, `count`)
+// instead of (cnt, left, slack); a table entry's byte 3 (code length + extra bits) is added to it with one LEA.HI; the table to
+// look a symbol up in is a state variable (DC table after a block end, AC table after any symbol) instead of a select on z == 0;
+// sub-table links carry their shift in the low five bits (consumed by a wrapping shift, no masking); codewords the sequential
+// decoders single out are ordinary entries with FAST_SPECIAL set, so the synchronisation parse never tests for them.
+// Stream words are read without padding or clamping: the bytes that follow an interval are the next interval's (readable), and a
+// symbol that reaches past `count` ends the run.  Only an interval within 16 bytes of the end of the buffer clamps (CLAMP).
+__device__ __forceinline__ uint32_t ldg_word(const uint32_t *p) { return __ldg(p); }
+// shared-memory address of the entry a symbol's first FAST_BITS bits select (top byte of `top` times four, plus the table)
+__device__ __forceinline__ uint32_t fast_slot(const uint32_t tab, const uint32_t top)
 {
-    int z = st.z;
-    bad = false;
+    uint32_t idx, addr;
+    asm volatile("shr.u32 %0, %1, %2;" : "=r"(idx) : "r"(top), "n"(32 - FAST_BITS));  // (volatile: keeps SHF + LEA, not SHF + LOP3 + IADD)
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(idx), "r"(tab));
+    return addr;
+}
+
+template <bool CLAMP>
+__device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                              const uint32_t blk0)
+{
     if (st.p >= end_bit) return 0;
-    if (FINAL && N >= N_total) return 0;
+    const uint32_t base = (uint32_t) io.lead * 8u;
+    uint32_t       a = base + st.p;
+    const uint32_t end_a = base + end_bit;
+    int            z = st.z;
     uint32_t       done = 0;
-    int            left = (int) (end_bit - st.p);            // bits up to the end of the run
-    const int      slack = (int) (count_bits - end_bit);     // bits between the end of the run and the end of the data
-    // bit window: (hi:lo) = the 64 stream bits that start at word wi - 2; cnt (< 32 at the loop top) of them are consumed
-    uint32_t wi, cnt, hi, lo, nxt = 0;  // nxt (global-memory path): the word after lo, loaded one refill ahead and still raw when SAFE
-    {
-        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
-        wi = ab >> 5;
-        cnt = ab & 31u;
-        if (STAGED) {
-            wi = io.stage + wi * 4u;  // STAGED: wi is the shared-memory address of the next word
-            hi = lds32(wi), lo = lds32(wi + 4u);
-            wi += 8u;
-        } else {
-            hi = io.word(wi), lo = io.word(wi + 1);
-            nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));  // raw: swapped (and padded) when it becomes lo
-            wi += 3;
-        }
-    }
-    uint32_t dtab, atab, tabs, next;
-    {
-        const uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
-        dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
-    }
-    // FINAL: position and destination of the current block
-    // A block is decoded by the thread in whose subsequence it STARTS: that thread runs past the end of its subsequence until the
-    // block is complete, and the thread that finds a block in progress at its entry skips to the block's end.  So every block is
-    // assembled by one thread, in that thread's 128-byte buffer in shared memory (zero-initialised, coefficient z at buf[z]), and
-    // leaves as eight 16-byte stores: whole lines, no read-modify-write of a cleared plane, an eighth of the store transactions
-    // that scattered 2-byte stores need (the pass is bound by L1TEX store transactions otherwise).
-    int      mx = 0, my = 0;
-    int16_t *bptr = nullptr, *dcp = nullptr;
-    bool     inp = false, own = false;  // own: the DC symbol of the block in progress was decoded here
-    bool     rowstart = false;          // `extend` scans: the next DC symbol opens an MCU row (decode.swift:3214-3220)
-    if (FINAL) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) reinterpret_cast<uint4 *>(buf)[i] = make_uint4(0, 0, 0, 0);
-        dcp = dcdiff + N;
-        const uint32_t mcu = N / (uint32_t) nblk;
-        my = my0 + (int) (mcu / (uint32_t) W);
-        mx = (int) (mcu - (mcu / (uint32_t) W) * (uint32_t) W);
-        const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
-        inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
-        bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
-        rowstart = ext && z == 0 && st.b == 0 && mx == 0;
-    }
-    while (left > 0 || (FINAL && own)) {
-        const bool in_range = left > 0;  // the symbol starts inside the subsequence (block completions are counted there)
-        if (cnt >= 32u) {
+    uint32_t wi = a >> 5;  // index of the stream word `nxt` holds (from here on)
+    uint32_t hi = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi)), 0, 0x0123);
+    uint32_t lo = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi + 1, io.wlast) : wi + 1)), 0, 0x0123);
+    wi += 2;
+    uint32_t nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));  // raw: swapped when it becomes lo, one refill after its load
+    uint32_t bound = (a & ~31u) + 32u;
+    // the tables of the block in progress: (DC table, AC table, selectors, link to the successor's quad), reloaded as a whole
+    uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
+    do {
+        if (a >= bound) {
             hi = lo;
-            if (STAGED) {
-                lo = lds32(wi);
-                wi += 4u;
-            } else {  // the load issued here is consumed by the NEXT refill: its latency (L2: the lanes' streams thrash L1) is hidden
-                // (the byte swap is a volatile asm so that it stays HERE, one refill after its load, instead of being hoisted to it)
-                asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));
-                // No 1-padding (jpeg.swift:1881-1887) here: a symbol that lies inside the interval is decoded from its own bits
-                // whatever follows them (prefix code), and a symbol that reaches past the end trips the check below and sends the
-                // interval to the sequential decoder, which pads.  Loads are only clamped to the interval's last word.
-                nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
-                wi += 1;
-            }
-            cnt -= 32u;
+            asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // the swap stays at the point of use (see k_decode_fast)
+            wi += 1;
+            nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
+            bound += 32u;
         }
-        const uint32_t top = __funnelshift_l(lo, hi, cnt);  // the next 32 bits of the stream
-        const bool     isdc = z == 0;
-        if (FINAL && rowstart && isdc) {  // decode.swift:3214-3220: sixteen 1-bits at the start of a row end an `extend` scan silently
-            rowstart = false;
-            if (row_start_all_ones(top, left + slack)) {  // (never on a healthy stream: left to the sequential decoder)
-                bad = true;
-                break;
-            }
-        }
-        const uint32_t tab = isdc ? dtab : atab;
-        uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
-        if (ent & FAST_LINK) {  // longer code: its sub-table, addressed by the bits that follow the prefix
-            const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
-            ent = lds32(tab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
-        }
-        if (__builtin_expect(ent == 0u, 0)) {  // invalid codeword / symbol the sequential decoders single out: reference lookup
-            const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
-            const int        ti = isdc ? (int) (tabs & 0xffu) : (int) ((tabs >> 8) & 0xffu);
-            ent = fast_entry(lut_lookup(ref_entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);  // global memory
-            if (ent == 0u) {
-                bad = true;
-                break;
-            }
-        }
-        const int total = (int) (ent >> 24), adv = (int) __byte_perm(ent, 0, 0x4442);
-        if (!SAFE) {
-            if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2808-2811, 2859-2863
-                bad = true;
-                break;
-            }
-        }
-        if (FINAL) {
-            const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441);
-            const uint32_t top2 = top << len;  // first extra bit in bit 31: it is the sign (0 = negative) of the value
-            const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
-            // T.81 EXTEND; identical to decode.swift:2742-2754 for categories 0..15 (16 never reaches this point)
-            const int v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;
-            const int zpos = z + adv - 1;
-            // DC differences go to the side array (resolved after the pass); AC values to their zig-zag slot of the block buffer
-            if (isdc) {
-                *dcp = (int16_t) v;
-                own = true;
-            } else if (own & (zpos < 64))
-                buf[zpos] = (int16_t) v;
-        }
-        cnt += (uint32_t) total;
-        left -= total;
-        z += adv;
+        const uint32_t top = __funnelshift_l(lo, hi, a);  // the next 32 bits of the stream
+        const uint32_t tab = z == 0 ? q.x : q.y;
+        uint32_t       ent = lds32(fast_slot(tab, top));
+        if (ent & FAST_LINK) ent = lds32(tab + (ent >> 8) + ((top << FAST_BITS) >> (ent & 31u)) * 4u);
+        // (no end-of-data test in the loop: see below)
+        a += ent >> 24;
+        z += (int) __byte_perm(ent, 0, 0x4442);
         if (z >= 64) {  // block complete: the successor's tables
             z = 0;
-            const uint32_t cur = next;
-            const uint4    q = lds128(cur);
-            dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
-            if (FINAL) {
-                if (own) {
-                    uint4 *src = reinterpret_cast<uint4 *>(buf), *dst = reinterpret_cast<uint4 *>(bptr);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (inp) dst[i] = src[i];
-                        src[i] = make_uint4(0, 0, 0, 0);
-                    }
-                    own = false;
-                }
-                done += in_range ? 1u : 0u;
-                N += 1;
-                dcp += 1;
-                if (N >= N_total) break;
-                mx += (int) ((tabs >> 24) & 1u);
-                if (mx == W) {
-                    mx = 0;
-                    my += 1;
-                }
-                rowstart = ext && ((tabs >> 24) & 1u) != 0u && mx == 0;
-                const uint4 g = lds128(cur - 16u);
-                inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
-                bptr = plane0 + (int64_t) (int32_t) (g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z) * 64;
-            } else {
-                done += 1;
-            }
+            done += 1;
+            q = lds128(q.w);
         }
-    }
-    st.p = end_bit - (uint32_t) left;
+    } while (a < end_a);
+    // A symbol that reaches past the data does not exist (decode.swift:2808-2811, 2859-2863).  On a healthy stream only one such
+    // "symbol" can be met: the <= 7 padding 1-bits after the interval's last block read as a DC codeword -- no real one (all-ones
+    // prefixes are never complete codes), i.e. a FAST_SPECIAL entry, 16 bits long, which ends a block that is not there.
+    if (a > base + count_bits && z == 0 && done) done -= 1;
+    st.p = a - base;
     st.z = (uint16_t) z;
-    st.b = (uint16_t) ((tabs >> 16) & 0xffu);
+    st.b = (uint16_t) ((q.z >> 16) & 0xffu);
     return done;
 }
 
-// Picks the variant, warp-uniformly (a warp whose lanes disagree would execute both one after the other):
-//   STAGED  every lane's interval has a copy in shared memory (big-endian, 1-padded): refills are shared-memory loads;
-//   SAFE    no symbol that starts inside the run can reach past the end of the data (and, reading global memory, the run, its
-//           overshoot of < 32 bits and the 64-bit look-ahead stay in unpadded words).
-template <bool FINAL>
-__device__ __forceinline__ uint32_t par_run_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                                 const uint32_t blk0, const uint8_t *smem, const uint16_t *ref_entries, const int nblk,
-                                                 bool &bad, uint32_t N, const uint32_t N_total, const int W, const int my0,
-                                                 int16_t *plane0, int16_t *dcdiff, int16_t *buf, const bool ext = false)
+// warp-uniform choice of the variant (a warp whose lanes disagree would execute both one after the other)
+__device__ __forceinline__ uint32_t par_parse_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
+                                                   const uint32_t blk0)
 {
-    const uint32_t mask = __activemask();
-    // the decoding pass may run past end_bit by the rest of one block: 63 symbols of at most 31 bits
-    const uint32_t reach = end_bit + (FINAL ? 2048u : 0u);
-    if (__all_sync(mask, io.stage != 0u)) {
-        if (__all_sync(mask, reach + 32u <= count_bits))
-            return par_run<FINAL, true, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
-        return par_run<FINAL, true, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
-    }
-    const uint32_t last_word = ((uint32_t) io.lead * 8u + reach + 32u + 64u) / 32u + 2u;  // incl. the word loaded ahead
-    if (__all_sync(mask, last_word < io.wlim))
-        return par_run<FINAL, false, true>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
-    return par_run<FINAL, false, false>(io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, ext);
+    if (__any_sync(__activemask(), io.clamp != 0u)) return par_parse<true>(io, st, end_bit, count_bits, blk0);
+    return par_parse<false>(io, st, end_bit, count_bits, blk0);
 }
 
-// ---- the decoding pass, warp-synchronous: blocks leave through a warp-cooperative flush -------------------------------------------
-// Same symbol loop as par_run<true, false, SAFE>, but every lane of the warp calls it (`go`: the lane has a subsequence to decode)
-// and the lanes stay converged, iterating until the slowest one is done (they did so anyway, as a divergent warp).  ncu of the
-// per-lane flush: at every warp iteration about two lanes complete a block, so the 8 LDS.128 + 8 STG.128 + 8 STS.128 of the
-// flush ran at 2 of 32 lanes -- 42 % of the kernel's shared-memory wavefronts and 31 % of its global requests.  Here a lane that
-// completes a block only queues (buffer address | in-plane, block index) in the warp's queue; right after the symbol step the
-// warp flushes the queued blocks together, 8 lanes x 16 bytes per block, 4 blocks per LDS.128 / STG.128 / STS.128:
-// one shared wavefront per block and direction instead of eight, one global request per four blocks instead of eight per block.
-#ifndef PAR_DEFER_DEN
-#define PAR_DEFER_DEN 4  // block-end work runs when 1 / PAR_DEFER_DEN of the warp's live lanes wait for it (32: at once)
+// ---- the decoding pass, warp-synchronous ------------------------------------------------------------------------------------------
+// Every lane of the warp calls it (`go`: the lane has a subsequence to decode) and the lanes stay converged.
+// A block is decoded by the thread in whose subsequence it STARTS: that thread runs past the end of its subsequence until the block
+// is complete, and the thread that finds a block in progress at its entry skips to the block's end.  So every block is assembled
+// by one thread, in that thread's 128-byte buffer in shared memory (zero-initialised, coefficient z at buf[z]; the DC DIFFERENCE
+// sits in slot 0 like any other coefficient), and leaves as eight 16-byte stores: whole lines.
+// Block ends are deferred: about two of 32 lanes complete a block at every step, and the ~80 instructions of block-end work
+// (successor tables, geometry, DC side array, flush) at 2 lanes cost the warp more than a symbol step.  A lane that completes a
+// block stops (z >= 64 marks it as waiting, `lim` = 0 keeps it from stepping) until the warp's next block-end section, which runs
+// after every PAR_DEFER_STEPS symbol steps: the waiting lanes do their bookkeeping together and queue (buffer | in-plane, block
+// index); the whole warp then flushes the queued blocks, 8 lanes x 16 bytes per block, 4 blocks per LDS.128 / STG.128 / STS.128.
+// The symbol step is predicated on ONE compare, a < lim  (lim = `end` while the lane skips the block in progress at its entry,
+// unbounded while it owns the block in progress, 0 while it waits or is finished), and contains no test that can wait for the
+// block end: a FAST_SPECIAL entry advances z beyond 127 and a symbol that reaches past the data leaves a > count, both seen by the
+// block-end section; the lane that skips a block stores into its own buffer like everybody else and clears it afterwards.
+#ifndef PAR_DEFER_STEPS
+#define PAR_DEFER_STEPS 4
 #endif
 __device__ __forceinline__ void sts128_zero(uint32_t a)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
 }
-template <bool SAFE, bool EXT>
-__device__ __forceinline__ uint32_t par_run_final(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
-                                                  const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
-                                                  const uint16_t *ref_entries, const int nblk, bool &bad, uint32_t N,
-                                                  const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff,
-                                                  const uint32_t buf /* shared address of the lane's block buffer */,
-                                                  const uint32_t fq /* shared address of the warp's 32-entry flush queue */)
+template <bool CLAMP, bool EXT>
+__device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
+                                               const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad_out, uint32_t N,
+                                               const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff,
+                                               const uint32_t buf /* shared address of the lane's block buffer */,
+                                               const uint32_t fq /* shared address of the warp's 32-entry flush queue */)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t base = (uint32_t) io.lead * 8u;
+    uint32_t       a = base + st.p;
+    const uint32_t end_a = base + end_bit, count_a = base + count_bits;
     int            z = st.z;
-    bad = false;
-    bool           run = go && st.p < end_bit && N < N_total;
-    uint32_t       done = 0;
-    int            left = run ? (int) (end_bit - st.p) : 0;
-    const int      slack = (int) (count_bits - end_bit);
-    uint32_t       wi = 0, cnt = 0, hi = 0, lo = 0, nxt = 0;
-    uint32_t       dtab = 0, atab = 0, tabs = 0, next = 0;
+    const bool     run = go && st.p < end_bit && N < N_total;
+    uint32_t       done = 0, lim = 0, ent = 0, bad = 0;
+    uint32_t       hi = 0, lo = 0, nxt = 0, bound = 0, wi = 0;
+    uint4          q = make_uint4(0, 0, 0, 0);
     int            mx = 0, my = 0;
-    uint32_t       bidx = 0;  // destination of the block in progress, in 128-byte units from plane0
-    bool           inp = false, own = false;
-    bool           rowstart = false;  // EXT (`extend` scans): the next DC symbol opens an MCU row (decode.swift:3214-3220)
-    int16_t       *dcp = dcdiff + N;
+    uint32_t       bidx = 0;   // destination of the block in progress, in 128-byte units from plane0
+    uint32_t       owned = 0;  // the block in progress started in this subsequence (bit 0); it lies inside its plane (bit 1)
+    bool           rowstart = false;  // EXT (`extend` scans): the next symbol is the DC symbol that opens an MCU row
 #pragma unroll
     for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
     if (run) {
-        const uint32_t ab = (uint32_t) io.lead * 8u + st.p;
-        wi = ab >> 5;
-        cnt = ab & 31u;
-        hi = io.word(wi), lo = io.word(wi + 1);
-        nxt = __ldg(io.w0 + (SAFE ? wi + 2 : min(wi + 2, io.wlast)));
-        wi += 3;
-        const uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
-        dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
+        wi = a >> 5;
+        hi = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi)), 0, 0x0123);
+        lo = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi + 1, io.wlast) : wi + 1)), 0, 0x0123);
+        wi += 2;
+        nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
+        bound = (a & ~31u) + 32u;
+        q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
         const uint32_t mcu = N / (uint32_t) nblk;
         my = my0 + (int) (mcu / (uint32_t) W);
         mx = (int) (mcu - (mcu / (uint32_t) W) * (uint32_t) W);
         const uint4 g = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk));
-        inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+        const bool  inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
         bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
+        owned = (z == 0 ? 1u : 0u) | (inp ? 2u : 0u);  // entry at a block boundary: the block that starts here is this thread's
+        lim = z == 0 ? 0xffffffffu : end_a;
         if (EXT) rowstart = z == 0 && st.b == 0 && mx == 0;
     }
     __syncwarp();
-    bool wait = false;  // the lane's block is complete; its block-end work is pending
+    const uint32_t bufm2 = buf - 2u;
     for (;;) {
-        const bool     actv = run && !wait && (left > 0 || own);
-        const uint32_t ma = __ballot_sync(FULL, actv), mw = __ballot_sync(FULL, wait);
-        if ((ma | mw) == 0u) break;
-        // Block ends are deferred: ~2 of 32 lanes complete a block at every step, and the ~80 instructions of the block-end work
-        // (successor tables, geometry, flush) at 2 lanes cost the warp more than the symbol step itself.  A lane that completes a
-        // block idles until a share of the live lanes (1 / PAR_DEFER_DEN) is waiting -- or nobody can proceed.
-        if (__popc(mw) * PAR_DEFER_DEN >= __popc(ma | mw)) {
-            bool     fin = false;
-            uint32_t fin_bidx = 0, fin_buf = 0;
-            if (wait) {
-                wait = false;
-                const uint32_t cur = next;
-                const uint4    q = lds128(cur);
-                dtab = q.x, atab = q.y, tabs = q.z, next = q.w;
-                if (own) {
-                    fin = true, fin_bidx = bidx, fin_buf = buf | (inp ? 1u : 0u);
-                    own = false;
+#pragma unroll
+        for (int step = 0; step < PAR_DEFER_STEPS; ++step) {
+            if (a < lim) {
+                if (a >= bound) {
+                    hi = lo;
+                    asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // see par_parse: swap at the point of use
+                    wi += 1;
+                    nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
+                    bound += 32u;
                 }
-                N += 1;
-                dcp += 1;
-                if (N >= N_total)
-                    run = false;
-                else {
-                    mx += (int) ((tabs >> 24) & 1u);
-                    if (mx == W) {
-                        mx = 0;
-                        my += 1;
+                const uint32_t top = __funnelshift_l(lo, hi, a);
+                if (EXT) {
+                    if (rowstart) {  // sixteen 1-bits at the start of a row end an `extend` scan silently (decode.swift:3214-3220):
+                        rowstart = false;  // never on a healthy stream, so the interval just goes to the sequential decoder
+                        if (row_start_all_ones(top, (int) (count_a - a))) bad = 1u, lim = 0u;
                     }
-                    if (EXT) rowstart = ((tabs >> 24) & 1u) != 0u && mx == 0;
-                    const uint4 g = lds128(cur - 16u);
-                    inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
-                    bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
                 }
+                const uint32_t tab = z == 0 ? q.x : q.y;
+                ent = lds32(fast_slot(tab, top));
+                if (ent & FAST_LINK) ent = lds32(tab + (ent >> 8) + ((top << FAST_BITS) >> (ent & 31u)) * 4u);
+                const uint32_t top2 = __funnelshift_l(0u, top, ent);            // top << code length (the low five bits of ent)
+                const uint32_t size = ent >> 8;                                 // (its low five bits: the number of extra bits)
+                const uint32_t tail = __funnelshift_l(top2, 0u, size);          // the extra bits: top2 >> (32 - size), 0 if none
+                const uint32_t mask = __funnelshift_l(0xffffffffu, 0u, size);   // 2^size - 1
+                const uint32_t v = (int) top2 >= 0 ? tail - mask : tail;        // T.81 EXTEND (first extra bit 0: negative)
+                a += ent >> 24;
+                z += (int) __byte_perm(ent, 0, 0x4442);
+                if (z <= 64)  // the coefficient lands at z_before + advance - 1 (an EOB lands beyond 63: nowhere)
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(bufm2 + 2u * (uint32_t) z), "h"((uint16_t) v) : "memory");
+                if (z >= 64) lim = 0u;  // block complete: the lane waits for the block-end section
             }
-            const uint32_t m = __ballot_sync(FULL, fin);
-            if (m) {
-                if (fin) {
-                    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(fq + 8u * rank), "r"(fin_buf), "r"(fin_bidx) : "memory");
-                }
-                __syncwarp();
-                const uint32_t n = __popc(m), chunk = (lane & 7u) * 16u;
-                for (uint32_t k = lane >> 3; k < n; k += 4u) {
-                    uint32_t src, dst;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(src), "=r"(dst) : "r"(fq + 8u * k) : "memory");
-                    const uint32_t a = (src & ~1u) + chunk;
-                    uint4          v;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-                    if (src & 1u)
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk) = v;
-                    sts128_zero(a);
-                }
-                __syncwarp();
-            }
+        }
+        const uint32_t mw = __ballot_sync(FULL, z >= 64);
+        if (mw == 0u) {
+            if (!__any_sync(FULL, a < lim)) break;
             continue;
         }
-        if (actv) do {
-                const bool in_range = left > 0;
-                if (cnt >= 32u) {
-                    hi = lo;
-                    asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // see par_run: swap at the point of use
-                    nxt = __ldg(io.w0 + (SAFE ? wi : min(wi, io.wlast)));
-                    wi += 1;
-                    cnt -= 32u;
+        uint32_t fin_buf = 0, fin_bidx = 0;  // fin_buf != 0: this lane hands a block to the flush
+        if (z >= 64) {
+            // a FAST_SPECIAL entry (invalid codeword / a symbol the sequential decoders single out: z > 127) or a symbol that
+            // reached past the data (decode.swift:2808-2811, 2859-2863): the interval is left to the sequential kernel
+            const bool broken = z > 127 || a > count_a;
+            done += (!broken && (a - (ent >> 24)) < end_a) ? 1u : 0u;  // counted where its last symbol STARTS (still in `ent`)
+            const uint32_t cur = q.w;
+            q = lds128(cur);
+            if (owned & 1u) {
+                fin_buf = buf | ((owned >> 1) & (broken ? 0u : 1u)) | 2u, fin_bidx = bidx;
+                uint16_t d;  // DC differences also go to the side array (resolved into predictions after the pass)
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(buf) : "memory");
+                dcdiff[N] = (int16_t) d;
+            } else {  // the block this lane skipped: its symbols were stored like any others
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
+            }
+            N += 1;
+            z = 0;
+            bad |= broken ? 1u : 0u;
+            if (N < N_total && a < end_a && bad == 0u) {  // the block that starts at `a` is this thread's
+                lim = 0xffffffffu;
+                mx += (int) ((q.z >> 24) & 1u);
+                if (mx == W) {
+                    mx = 0;
+                    my += 1;
                 }
-                const uint32_t top = __funnelshift_l(lo, hi, cnt);
-                const bool     isdc = z == 0;
-                if (EXT) {
-                    if (rowstart & isdc) {  // sixteen 1-bits at the start of a row end an `extend` scan silently: never on a
-                        rowstart = false;   // healthy stream, so the interval just goes to the sequential decoder
-                        if (row_start_all_ones(top, left + slack)) {
-                            bad = true, run = false;
-                            break;
-                        }
-                    }
-                }
-                const uint32_t tab = isdc ? dtab : atab;
-                uint32_t       ent = lds32(tab + ((top >> (32 - FAST_BITS)) << 2));
-                if (ent & FAST_LINK) {
-                    const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
-                    ent = lds32(tab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
-                }
-                if (__builtin_expect(ent == 0u, 0)) {
-                    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
-                    const int        ti = isdc ? (int) (tabs & 0xffu) : (int) ((tabs >> 8) & 0xffu);
-                    ent = fast_entry(lut_lookup(ref_entries, hdr->n[ti], hdr->zeta[ti], hdr->offset[ti], top >> 16), isdc);
-                    if (ent == 0u) {
-                        bad = true, run = false;
-                        break;
-                    }
-                }
-                const int total = (int) (ent >> 24), adv = (int) __byte_perm(ent, 0, 0x4442);
-                if (!SAFE) {
-                    if (__builtin_expect(total > left + slack, 0)) {  // decode.swift:2808-2811, 2859-2863
-                        bad = true, run = false;
-                        break;
-                    }
-                }
-                {
-                    const int      len = (int) (ent & 0x7fu), size = (int) __byte_perm(ent, 0, 0x4441);
-                    const uint32_t top2 = top << len;
-                    const uint32_t tail = __funnelshift_rc(top2, 0u, 32 - size);
-                    const int      v = (int) top2 >= 0 ? (int) (tail + (0xffffffffu << size) + 1u) : (int) tail;  // T.81 EXTEND
-                    const int      zpos = z + adv - 1;
-                    if (isdc) {
-                        *dcp = (int16_t) v;
-                        own = true;
-                    } else if (own & (zpos < 64))
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + 2u * (uint32_t) zpos), "h"((uint16_t) v) : "memory");
-                }
-                cnt += (uint32_t) total;
-                left -= total;
-                z += adv;
-                if (z >= 64) {  // block complete (counted where its last symbol starts); the rest of the block-end work is deferred
-                    z = 0;
-                    done += in_range ? 1u : 0u;
-                    wait = true;
-                }
-            } while (0);
+                if (EXT) rowstart = ((q.z >> 24) & 1u) != 0u && mx == 0;
+                const uint4 g = lds128(cur - 16u);
+                const bool  inp = ((uint32_t) mx < (g.w & 0xffffu)) & ((uint32_t) my < (g.w >> 16));
+                bidx = g.x + (uint32_t) mx * g.y + (uint32_t) my * g.z;
+                owned = 1u | (inp ? 2u : 0u);
+            }  // else: lim stays 0 -- finished
+        }
+        const uint32_t m = __ballot_sync(FULL, fin_buf != 0u);
+        if (m) {
+            if (fin_buf) {
+                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(fq + 8u * rank), "r"(fin_buf), "r"(fin_bidx) : "memory");
+            }
+            __syncwarp();
+            const uint32_t n = __popc(m), chunk = (lane & 7u) * 16u;
+            for (uint32_t k = lane >> 3; k < n; k += 4u) {
+                uint32_t src, dst;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(src), "=r"(dst) : "r"(fq + 8u * k) : "memory");
+                const uint32_t sa = (src & ~3u) + chunk;
+                uint4          v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+                if (src & 1u)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk) = v;
+                sts128_zero(sa);
+            }
+            __syncwarp();
+        }
     }
+    bad_out = bad != 0u;
     return done;
 }
 
-#ifndef PAR_COOP
-#define PAR_COOP 1  // 0: the per-lane flush of par_run<true, ...> (kept for A/B)
-#endif
-// SAFE is picked for the whole warp (see par_run_auto); lanes without work do not constrain it
-__device__ __forceinline__ uint32_t par_run_final_auto(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
-                                                       const uint32_t count_bits, const uint32_t blk0, const uint8_t *smem,
-                                                       const uint16_t *ref_entries, const int nblk, bool &bad, const uint32_t N,
-                                                       const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                                       int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const bool ext)
+__device__ __forceinline__ uint32_t par_decode_auto(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
+                                                    const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad,
+                                                    const uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
+                                                    int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const bool ext)
 {
-    const uint32_t last_word = ((uint32_t) io.lead * 8u + end_bit + 2048u + 32u + 64u) / 32u + 2u;
-    const bool     safe = __all_sync(0xffffffffu, !go || last_word < io.wlim);
+    const bool clamp = __any_sync(0xffffffffu, go && io.clamp != 0u);
     if (ext) {  // (kernel-uniform)
-        if (safe) return par_run_final<true, true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
-        return par_run_final<false, true>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+        if (clamp) return par_decode<true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+        return par_decode<false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
     }
-    if (safe) return par_run_final<true, false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
-    return par_run_final<false, false>(go, io, st, end_bit, count_bits, blk0, smem, ref_entries, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    if (clamp) return par_decode<true, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    return par_decode<false, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
 }
 
 // ---- progressive AC-first scans (kind 3) on the same machinery ------------------------------------------------------------------
@@ -1465,7 +1326,7 @@ __device__ __forceinline__ uint32_t par_run_dc(const ParIO &io, ParseState &st, 
             const uint32_t rest = (top >> 16) & ((1u << (16 - FAST_BITS)) - 1u);
             ent = lds32(dtab + (ent >> 8) + ((rest >> (ent & 7u)) << 2));
         }
-        if (__builtin_expect(ent == 0u, 0)) {  // invalid codeword (the reference reads it as (0, 16)) or category 16
+        if (__builtin_expect((ent & FAST_SPECIAL) != 0u, 0)) {  // invalid codeword (the reference reads it as (0, 16)) or category 16
             bad = true;
             break;
         }
@@ -1546,10 +1407,9 @@ __device__ __forceinline__ void par_stage_tables(const ScanParams &P, const int1
     }
 }
 
-// interval e of image img, cut into at most T subsequences; stage_addr / stage_cap: its share of the shared-memory stage (0: none)
+// interval e of image img, cut into at most T subsequences
 __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const uint32_t img, const uint32_t e, const uint32_t T,
-                                                    const uint32_t dc_per_interval, uint32_t *flagged, const uint32_t stage_addr,
-                                                    const uint32_t stage_cap)
+                                                    const uint32_t dc_per_interval, uint32_t *flagged, const uint32_t n_images)
 {
     ParGroup q;
     memset(&q, 0, sizeof q);
@@ -1593,9 +1453,9 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
         if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
         q.B = B;
         q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
-        // shared-memory copy: the words of the interval plus four words of 1-padding, if its share of the stage holds them
-        const uint32_t need = ((uint32_t) (q.io.lead + q.io.nbytes + 3) / 4u + 4u) * 4u;
-        q.io.stage = (stage_cap && need <= stage_cap) ? stage_addr : 0u;
+        // the decoders read up to four words past an interval's last byte without looking: fine wherever more data (or the
+        // buffer's slack) follows, clamped for the interval(s) at the very end of the buffer
+        q.io.clamp = (o1 + 16 > P.offsets[(size_t) n_images * P.n_ecs] + 8) ? 1u : 0u;
     }
     return q;
 }
@@ -1610,14 +1470,12 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
 #define PAR_ALIAS 1
 #endif
 // tshift: log2 of the threads per interval (4 .. 7); warm_bits: speculative warm-up before a subsequence's first bit;
-// stage_off / stage_bytes: the part of the dynamic shared memory that holds copies of the CTA's intervals; buf_off: the threads'
-// block buffers (PAR_BUF_STRIDE bytes each)
+// buf_off: the threads' block buffers (PAR_BUF_STRIDE bytes each) in the dynamic shared memory
 constexpr int MODE_SEQ = 0, MODE_AC = 1, MODE_DC = 2;  // sequential scan | progressive AC-first | progressive DC-first
 template <int NT, int MIN_CTAS, int MODE>
 __global__ void __launch_bounds__(NT, MIN_CTAS)
 k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_t *const dcdiff_all, const uint32_t dc_per_interval,
-             uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits,
-             const uint32_t stage_off, const uint32_t stage_bytes, const uint32_t buf_off)
+             uint32_t *const flagged, uint32_t *const stats, const int tshift, const uint32_t warm_bits, const uint32_t buf_off)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // The records of the synchronisation (exit / entry states, block counts, checkpoints, work list) are dead once the decoding
@@ -1665,20 +1523,9 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     par_stage_tables<NT>(P, plane0, img, tid, smem, lut_img);
     if (tid >= 32 && tid < 32 + NT / 16) {  // one thread per interval of the CTA: where its bytes are, how it is cut
         if (tid - 32 < G)
-            s_grp[tid - 32] = par_setup_group(P, img, blockIdx.x * G + (tid - 32), T, dc_per_interval, flagged,
-                                              sbase + stage_off + (tid - 32) * ((stage_bytes / G) & ~15u), (stage_bytes / G) & ~15u);
+            s_grp[tid - 32] = par_setup_group(P, img, blockIdx.x * G + (tid - 32), T, dc_per_interval, flagged, gridDim.y);
         else  // NT is not a multiple of T: the threads past the last whole interval idle (S = 0)
             memset(&s_grp[tid - 32], 0, sizeof(ParGroup));
-    }
-    __syncthreads();
-    // ---- stage the intervals in shared memory: every byte is read from global memory once (coalesced), byte-swapped and
-    // 1-padded (jpeg.swift:1881-1887) on the way; all parsing passes then refill from shared memory
-    for (uint32_t gg = 0; gg < G; ++gg) {
-        const ParIO qio = s_grp[gg].io;
-        if (qio.stage == 0u) continue;
-        const uint32_t nw = (uint32_t) (qio.lead + qio.nbytes + 3) / 4u + 4u;
-        uint32_t      *dst = reinterpret_cast<uint32_t *>(smem + (qio.stage - sbase));
-        for (uint32_t i = tid; i < nw; i += NT) dst[i] = qio.word(i);
     }
     __syncthreads();
     PAR_PHASE(0);
@@ -1706,7 +1553,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
             if (AC) cum += par_run_ac_auto<false>(qio, st, seg_end, qcount, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
             else if (DC) cum += par_run_dc_auto<false>(qio, st, seg_end, qcount, blk0, bad, 0, 0, 1u, nullptr, false);
-            else cum += par_run_auto<false>(qio, st, seg_end, qcount, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            else cum += par_parse_auto(qio, st, seg_end, qcount, blk0);
             // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
@@ -1731,7 +1578,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         if (l > 0 && warm_bits) {
             if (AC) par_run_ac_auto<false>(io, st, start_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
             else if (DC) par_run_dc_auto<false>(io, st, start_bit, count, blk0, bad, 0, 0, 1u, nullptr, false);
-            else par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            else par_parse_auto(io, st, start_bit, count, blk0);
         }
         if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
@@ -1794,15 +1641,19 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // ---- the one real decoding pass ---------------------------------------------------------------------------------------
     const uint32_t N_total = s_grp[g].N_total, slot = s_grp[g].slot;
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
-    if (PAR_COOP && MODE == MODE_SEQ && stage_bytes == 0u) {  // every lane of every warp takes part in the cooperative flush
+    if (MODE == MODE_SEQ) {  // every lane of every warp takes part in the cooperative flush
         static_assert(PAR_NSEG * 4 >= 8, "the flush queues fit in the checkpoint array");
         const bool     go = active && before < N_total;
-        const uint32_t done = par_run_final_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
-                                                 N_total, W, s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                                 (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, P.extend != 0);
+        const uint32_t done = par_decode_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, nblk, bad, before, N_total, W,
+                                              s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
+                                              (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
             atomicAdd(&s_grp[g].total, done);
+            if (stats) {  // JPEG_SM100_PAR_STATS: why intervals get flagged
+                if (bad) atomicAdd(&stats[20], 1u);
+                if (go && done != my_cnt) atomicAdd(&stats[21], 1u);
+            }
         }
     } else if (active) {
         st = unpack_state(my_entry);
@@ -1812,11 +1663,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             if (AC)  // single component, blocks in raster order: block N of the interval is N blocks after its first
                 done = par_run_ac_auto<true>(io, st, end_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, before, N_total,
                                              P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) s_grp[g].r0 * (size_t) W * 64);
-            else if (DC)
-                done = par_run_dc_auto<true>(io, st, end_bit, count, blk0, bad, before, N_total, (uint32_t) W * (uint32_t) nblk, dcdiff, P.extend != 0);
             else
-                done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_grp[g].r0, plane0, dcdiff,
-                                          reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE), P.extend != 0);
+                done = par_run_dc_auto<true>(io, st, end_bit, count, blk0, bad, before, N_total, (uint32_t) W * (uint32_t) nblk, dcdiff, P.extend != 0);
         }
         // a subsequence that does not produce the blocks the synchronisation counted for it (or that was cut short because the
         // interval is complete while data remains) leaves the interval to the sequential decoder
@@ -1829,6 +1677,10 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const bool mine = S != 0u;  // this interval was decoded here
     if (mine && l == 0) {
         const bool f = s_grp[g].bad != 0u || s_grp[g].total != N_total;
+        if (stats) {
+            if (f) atomicAdd(&stats[22], 1u);
+            if (s_grp[g].total != N_total) atomicAdd(&stats[23], 1u);
+        }
         s_grp[g].bad = f ? 1u : 0u;
         flagged[slot] = f ? 1u : 0u;
         if (!f && P.status) P.status[slot] = 0;
@@ -1932,7 +1784,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     auto remote64 = [&](uint64_t *p_, uint32_t r) -> uint64_t { return *cluster.map_shared_rank(p_, r); };
     auto remote32 = [&](uint32_t *p_, uint32_t r) -> uint32_t { return *cluster.map_shared_rank(p_, r); };
     par_stage_tables<NT>(P, plane0, img, tid, smem, lut_img);
-    if (tid == 32) s_q = par_setup_group(P, img, e, T, dc_per_interval, crank == 0 ? flagged : nullptr, 0u, 0u);
+    if (tid == 32) s_q = par_setup_group(P, img, e, T, dc_per_interval, crank == 0 ? flagged : nullptr, gridDim.y);
     if (tid == 0) s_nwork = 0, s_ctatotal = 0, s_bad = 0, s_total = 0;
     __syncthreads();
     const ParIO    io = s_q.io;
@@ -1947,7 +1799,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
-            cum += par_run_auto<false>(io, st, seg_end, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+            cum += par_parse_auto(io, st, seg_end, count, blk0);
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
             const uint32_t old = s_ck[k][sid];
@@ -1968,7 +1820,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     // ---- round 0 ----
     if (active) {
         st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
-        if (l > 0 && warm_bits) par_run_auto<false>(io, st, start_bit, count, blk0, smem, ref_entries, nblk, bad, 0, 0, W, 0, nullptr, nullptr, nullptr);
+        if (l > 0 && warm_bits) par_parse_auto(io, st, start_bit, count, blk0);
         if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
         uint64_t       x;
@@ -2023,25 +1875,16 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     for (uint32_t r = 0; r < crank; ++r) before += remote32(&s_ctatotal, r);
     // ---- the decoding pass ----
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
-    if (PAR_COOP) {
+    {
         static_assert(sizeof(s_ck) >= NT * 8, "the flush queues live in the checkpoint array");
         const bool     go = active && before < N_total;
-        const uint32_t done = par_run_final_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, smem, ref_entries, nblk, bad, before,
-                                                 N_total, W, s_q.r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                                 smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, P.extend != 0);
+        const uint32_t done = par_decode_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, nblk, bad, before, N_total, W, s_q.r0,
+                                              plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
+                                              smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_bad, 1u);
             atomicAdd(&s_total, done);
         }
-    } else if (active) {
-        st = unpack_state(s_entry[tid]);
-        uint32_t done = 0;
-        bad = false;
-        if (before < N_total)
-            done = par_run_auto<true>(io, st, end_bit, count, blk0, smem, ref_entries, nblk, bad, before, N_total, W, s_q.r0, plane0, dcdiff,
-                                      reinterpret_cast<int16_t *>(smem + buf_off + tid * PAR_BUF_STRIDE), P.extend != 0);
-        if (bad || (before < N_total && done != my_cnt)) atomicOr(&s_bad, 1u);
-        atomicAdd(&s_total, done);
     }
     cluster.sync();
     uint32_t bad_all = 0, total_all = 0;
@@ -2633,13 +2476,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? 256u : 1024u);
                 const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
-                // optional shared-memory stage for the intervals' bytes (measured slower than global reads one refill ahead: the
-                // shared memory costs occupancy; kept selectable for A/B)
-                const char    *env_ss = getenv("JPEG_SM100_PAR_STAGE");  // KB per interval, 0 = no staging
-                uint64_t       per_interval = (env_ss && !dc_first) ? (uint64_t) atoi(env_ss) * 1024 : 0;  // default: streams are read from global memory
-                if (per_interval * G > 96 * 1024) per_interval = (96 * 1024 / G) & ~(uint64_t) 1023;
-                const uint32_t stage_bytes = (uint32_t) (per_interval * G);
-                const size_t   smem_total = smem_par + stage_bytes + (dc_first ? 0 : (size_t) nt * PAR_BUF_STRIDE);
+                const size_t   smem_total = smem_par + (dc_first ? 0 : (size_t) nt * PAR_BUF_STRIDE);
                 if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2671,11 +2508,11 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     if (big)
                         k_decode_par<PAR_BIG_THREADS, 1, MODE_DC><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
                             P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
-                            d_stats, tshift, warm_bits, (uint32_t) smem_par, 0u, (uint32_t) smem_par);
+                            d_stats, tshift, warm_bits, (uint32_t) smem_par);
                     else
                         k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_DC><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
                             P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
-                            d_stats, tshift, warm_bits, (uint32_t) smem_par, 0u, (uint32_t) smem_par);
+                            d_stats, tshift, warm_bits, (uint32_t) smem_par);
                 } else if (big && csize >= 1 && !(env_cl && atoi(env_cl) == 0)) {
                     cudaLaunchConfig_t cfg;
                     memset(&cfg, 0, sizeof cfg);
@@ -2692,11 +2529,11 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 } else if (big)
                     k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ><<<grid_par, PAR_BIG_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
-                        d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
+                        d_stats, tshift, warm_bits, (uint32_t) smem_par);
                 else
                     k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ><<<grid_par, PAR_THREADS, smem_total, ctx->stream>>>(
                         P, plane0, reinterpret_cast<int16_t *>(d_dc), (uint32_t) dc_per_interval, reinterpret_cast<uint32_t *>(d_flag),
-                        d_stats, tshift, warm_bits, (uint32_t) smem_par, stage_bytes, (uint32_t) smem_par + stage_bytes);
+                        d_stats, tshift, warm_bits, (uint32_t) smem_par);
                 LAUNCH_CHECK(ctx);
                 if (want_stats) {
                     uint32_t h[32];
@@ -2708,8 +2545,9 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                         fprintf(stderr, "[k_decode_par] cycles per CTA: stage %.0f, round0 %.0f, rounds %.0f, zero+scan %.0f, final %.0f, dc %.0f\n",
                                 ph[0] / ctas, ph[1] / ctas, ph[2] / ctas, ph[3] / ctas, ph[4] / ctas, ph[5] / ctas);
                     }
-                    fprintf(stderr, "[k_decode_par] T %d, warm %u, stage %u B, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
-                            1 << tshift, warm_bits, stage_bytes, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
+                    fprintf(stderr, "[k_decode_par] flagged intervals %u (block total off: %u); subsequences: broken %u, count off %u\n", h[22], h[23], h[20], h[21]);
+                    fprintf(stderr, "[k_decode_par] T %d, warm %u, intervals %u, subsequences/interval %.1f, rounds avg %.2f max %u, re-parses per subsequence %.2f\n",
+                            1 << tshift, warm_bits, h[3], (double) h[2] / h[3], (double) h[1] / h[3], h[4], (double) h[0] / h[2]);
                 }
                 if (!dc_first) {
                     k_zero_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
@@ -2751,8 +2589,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         }
         // (the side array / block buffers of the sequential-scan variant are unused: dc_per_interval only bounds N_total)
         k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_AC><<<dim3((n_ecs + G - 1) / G, n_images), PAR_THREADS, smem_par, ctx->stream>>>(
-            P, plane0, nullptr, 0xffffffffu, reinterpret_cast<uint32_t *>(d_flag), nullptr, tshift, warm_bits, (uint32_t) smem_par, 0u,
-            (uint32_t) smem_par);
+            P, plane0, nullptr, 0xffffffffu, reinterpret_cast<uint32_t *>(d_flag), nullptr, tshift, warm_bits, (uint32_t) smem_par);
         LAUNCH_CHECK(ctx);
         k_zero_band_flagged<<<dim3(n_ecs, n_images), 128, 0, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
         LAUNCH_CHECK(ctx);
