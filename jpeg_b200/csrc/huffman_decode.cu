@@ -844,10 +844,18 @@ constexpr int PAR_THREADS = PAR_THREADS_N;  // 128: four 32-thread intervals sha
 constexpr int PAR_BIG_THREADS = 512;  // CTA size for scans with few, large intervals (no DRI: one entropy-coded segment per image)
 constexpr int PAR_MIN_BITS = 1024;
 #ifndef PAR_NSEG_N
-#define PAR_NSEG_N 4
+#define PAR_NSEG_N 8
 #endif
 constexpr int PAR_NSEG = PAR_NSEG_N;  // checkpoints per subsequence
-constexpr uint32_t PAR_BUF_STRIDE = 144;  // bytes between the threads' block buffers: 16-byte aligned, 4 banks apart
+#ifndef PAR_BUF_STRIDE_N
+#define PAR_BUF_STRIDE_N 128
+#endif
+// bytes between the threads' block buffers.  144: 16-byte aligned, 4 banks apart.  128 (2 KB less per CTA: with 56 registers a ninth
+// CTA fits on the SM): buffers are 128-byte aligned and the eight 16-byte chunks of lane L's buffer sit at chunk ^ (L & 7), so that
+// lanes writing the same zig-zag slot spread over eight bank groups instead of hitting one.
+constexpr uint32_t PAR_BUF_STRIDE = PAR_BUF_STRIDE_N;
+constexpr bool     PAR_SWIZZLE = PAR_BUF_STRIDE == 128;
+static_assert(PAR_BUF_STRIDE == 128 || PAR_BUF_STRIDE == 144, "block buffer stride");
 
 struct ParseState {
     uint32_t p;      // bit position of the next symbol
@@ -904,7 +912,8 @@ struct ParBlk {
     uint32_t dtab, atab, tabs, next;  // shared-memory addresses of the DC / AC fast tables; dc | ac << 8 | b << 16 | (b == 0) << 24;
                                       // shared-memory address of the successor block's second quad
 };
-static_assert(sizeof(ParBlk) == 32 && 12 * sizeof(ParBlk) <= 12 * sizeof(BlkInfo), "ParBlk lives in the BlkInfo area");
+static_assert(sizeof(ParBlk) == 32, "two uint4 per block of the MCU");
+constexpr uint32_t PAR_PRE = sizeof(LutHeader) + 12 * sizeof(ParBlk);  // shared-memory offset of the fast tables in the parallel kernels
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
@@ -949,9 +958,108 @@ __device__ __forceinline__ uint32_t fast_slot(const uint32_t tab, const uint32_t
     return addr;
 }
 
+// ---- a lane's window on its part of the entropy-coded segment ----------------------------------------------------------------------
+// The symbol loops run under predication: a lane refills its window when IT has consumed 32 bits (every ~6 symbols), but the warp
+// issues the (predicated) refill instructions at every step, and an instruction that names the destination register of a global
+// load in flight waits for it whether its predicate is on or not: the word loaded "one refill ahead" is really needed one STEP
+// later (ncu: a quarter of all stall samples sit on its byte swap, long scoreboard).  Two remedies, both measured:
+//   PAR_RING_N = 0 (default)  plain loads.  (PAR_L2_POLICY = 1 additionally loads the stream with an L2 evict-last policy and
+//               stores the coefficient lines with evict-first, so that the three passes over a subsequence find it in L2: no gain.)
+//   PAR_RING_N = 8, 16        the words travel global -> shared memory with cp.async (LDGSTS: no destination register, no
+//               scoreboard) into a private ring per lane, and a refill takes its word from the ring.  Removes the long-scoreboard
+//               stalls (26 % -> 5 % of samples) but costs 20 % more instructions and a CTA per SM: 2.27 ms against 1.96 ms.
+#ifndef PAR_DEFER_STEPS
+#define PAR_DEFER_STEPS 6  // measured (64 x 4K, 16 threads per interval): 4: 1.93 ms, 6: 1.89, 8: 1.94, 12: 1.99
+#endif
+#ifndef PAR_RING_N
+#define PAR_RING_N 0
+#endif
+constexpr uint32_t PAR_RING = PAR_RING_N;  // words per lane (0: no ring; else a power of two >= 2 * PAR_DEFER_STEPS, see win_refill)
+static_assert(PAR_RING == 0 || ((PAR_RING & (PAR_RING - 1)) == 0 && PAR_RING >= 2 * PAR_DEFER_STEPS), "ring depth");
+__device__ __forceinline__ void cp_async4(const uint32_t saddr, const uint32_t *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    if (PAR_RING) asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    if (PAR_RING) asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// L2 eviction policies (createpolicy): the entropy-coded bytes stay, the coefficient lines go
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#ifndef PAR_L2_POLICY
+#define PAR_L2_POLICY 0  // 1: L2 eviction policies on the stream loads / coefficient stores (measured: no gain, 2.12 vs 2.10 ms)
+#endif
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t *p, const uint64_t pol)
+{
+    if (!PAR_L2_POLICY) return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+struct Window {
+    uint32_t hi, lo;  // the 64 stream bits from word (a >> 5) on, big-endian
+    uint32_t nxt;     // the word after lo, still raw (swapped at the point of use)
+    uint32_t bound;   // bit index of the word after lo: refill when a >= bound
+    uint32_t ringp;   // ring: shared address of the slot that holds the word after nxt
+    uint32_t wnext;   // index (from io.w0) of the word the next request fetches
+    uint64_t pol;     // L2 policy of the stream loads
+};
+template <bool CLAMP>
+__device__ __forceinline__ void win_open(Window &w, const ParIO &io, const uint32_t a, const uint32_t ring)
+{
+    const uint32_t cur = a >> 5;
+    w.pol = l2_policy_evict_last();
+    if (PAR_RING) {
+#pragma unroll
+        for (uint32_t k = 0; k < PAR_RING; ++k) cp_async4(ring + 4u * k, io.w0 + (CLAMP ? min(cur + 3u + k, io.wlast) : cur + 3u + k));
+        cp_async_commit();
+    }
+    w.hi = __byte_perm(ldg_stream(io.w0 + (CLAMP ? min(cur, io.wlast) : cur), w.pol), 0, 0x0123);
+    w.lo = __byte_perm(ldg_stream(io.w0 + (CLAMP ? min(cur + 1u, io.wlast) : cur + 1u), w.pol), 0, 0x0123);
+    w.nxt = ldg_stream(io.w0 + (CLAMP ? min(cur + 2u, io.wlast) : cur + 2u), w.pol);
+    w.bound = (a & ~31u) + 32u;
+    w.ringp = ring;
+    w.wnext = cur + 3u + PAR_RING;
+    cp_async_wait<0>();
+}
+// Ring: one commit + wait_group 1 per PAR_DEFER_STEPS steps proves the slot about to be read complete -- a word is read PAR_RING
+// refills after it was requested, a step refills at most once, so with PAR_RING >= 2 * PAR_DEFER_STEPS the request lies at least
+// one whole group back.
+template <bool CLAMP>
+__device__ __forceinline__ void win_refill(Window &w, const ParIO &io)
+{
+    w.hi = w.lo;
+    asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(w.lo) : "r"(w.nxt));  // the swap stays at the point of use (see k_decode_fast)
+    if (PAR_RING) {
+        w.nxt = lds32(w.ringp);
+        cp_async4(w.ringp, io.w0 + (CLAMP ? min(w.wnext, io.wlast) : w.wnext));  // the slot just read takes the word PAR_RING further on
+        w.ringp = (w.ringp & ~(4u * PAR_RING - 1u)) | ((w.ringp + 4u) & (4u * PAR_RING - 1u));
+    } else
+        w.nxt = ldg_stream(io.w0 + (CLAMP ? min(w.wnext, io.wlast) : w.wnext), w.pol);
+    w.wnext += 1u;
+    w.bound += 32u;
+}
+
 template <bool CLAMP>
 __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                              const uint32_t blk0)
+                                              const uint32_t blk0, const uint32_t ring)
 {
     if (st.p >= end_bit) return 0;
     const uint32_t base = (uint32_t) io.lead * 8u;
@@ -959,35 +1067,33 @@ __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, c
     const uint32_t end_a = base + end_bit;
     int            z = st.z;
     uint32_t       done = 0;
-    uint32_t wi = a >> 5;  // index of the stream word `nxt` holds (from here on)
-    uint32_t hi = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi)), 0, 0x0123);
-    uint32_t lo = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi + 1, io.wlast) : wi + 1)), 0, 0x0123);
-    wi += 2;
-    uint32_t nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));  // raw: swapped when it becomes lo, one refill after its load
-    uint32_t bound = (a & ~31u) + 32u;
+    Window         w;
+    win_open<CLAMP>(w, io, a, ring);
     // the tables of the block in progress: (DC table, AC table, selectors, link to the successor's quad), reloaded as a whole
     uint4 q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
     do {
-        if (a >= bound) {
-            hi = lo;
-            asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // the swap stays at the point of use (see k_decode_fast)
-            wi += 1;
-            nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
-            bound += 32u;
+#pragma unroll
+        for (int step = 0; step < PAR_DEFER_STEPS; ++step) {
+            if (a < end_a) {
+                if (a >= w.bound) win_refill<CLAMP>(w, io);
+                const uint32_t top = __funnelshift_l(w.lo, w.hi, a);  // the next 32 bits of the stream
+                const uint32_t tab = z == 0 ? q.x : q.y;
+                uint32_t       ent = lds32(fast_slot(tab, top));
+                if (ent & FAST_LINK) ent = lds32(tab + (ent >> 8) + ((top << FAST_BITS) >> (ent & 31u)) * 4u);
+                // (no end-of-data test in the loop: see below)
+                a += ent >> 24;
+                z += (int) __byte_perm(ent, 0, 0x4442);
+                if (z >= 64) {  // block complete: the successor's tables
+                    z = 0;
+                    done += 1;
+                    q = lds128(q.w);
+                }
+            }
         }
-        const uint32_t top = __funnelshift_l(lo, hi, a);  // the next 32 bits of the stream
-        const uint32_t tab = z == 0 ? q.x : q.y;
-        uint32_t       ent = lds32(fast_slot(tab, top));
-        if (ent & FAST_LINK) ent = lds32(tab + (ent >> 8) + ((top << FAST_BITS) >> (ent & 31u)) * 4u);
-        // (no end-of-data test in the loop: see below)
-        a += ent >> 24;
-        z += (int) __byte_perm(ent, 0, 0x4442);
-        if (z >= 64) {  // block complete: the successor's tables
-            z = 0;
-            done += 1;
-            q = lds128(q.w);
-        }
+        cp_async_commit();
+        cp_async_wait<1>();
     } while (a < end_a);
+    cp_async_wait<0>();  // (the ring is reused by the next call)
     // A symbol that reaches past the data does not exist (decode.swift:2808-2811, 2859-2863).  On a healthy stream only one such
     // "symbol" can be met: the <= 7 padding 1-bits after the interval's last block read as a DC codeword -- no real one (all-ones
     // prefixes are never complete codes), i.e. a FAST_SPECIAL entry, 16 bits long, which ends a block that is not there.
@@ -1000,10 +1106,10 @@ __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, c
 
 // warp-uniform choice of the variant (a warp whose lanes disagree would execute both one after the other)
 __device__ __forceinline__ uint32_t par_parse_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                                   const uint32_t blk0)
+                                                   const uint32_t blk0, const uint32_t ring)
 {
-    if (__any_sync(__activemask(), io.clamp != 0u)) return par_parse<true>(io, st, end_bit, count_bits, blk0);
-    return par_parse<false>(io, st, end_bit, count_bits, blk0);
+    if (__any_sync(__activemask(), io.clamp != 0u)) return par_parse<true>(io, st, end_bit, count_bits, blk0, ring);
+    return par_parse<false>(io, st, end_bit, count_bits, blk0, ring);
 }
 
 // ---- the decoding pass, warp-synchronous ------------------------------------------------------------------------------------------
@@ -1021,9 +1127,6 @@ __device__ __forceinline__ uint32_t par_parse_auto(const ParIO &io, ParseState &
 // unbounded while it owns the block in progress, 0 while it waits or is finished), and contains no test that can wait for the
 // block end: a FAST_SPECIAL entry advances z beyond 127 and a symbol that reaches past the data leaves a > count, both seen by the
 // block-end section; the lane that skips a block stores into its own buffer like everybody else and clears it afterwards.
-#ifndef PAR_DEFER_STEPS
-#define PAR_DEFER_STEPS 4
-#endif
 __device__ __forceinline__ void sts128_zero(uint32_t a)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
@@ -1033,7 +1136,8 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
                                                const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad_out, uint32_t N,
                                                const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff,
                                                const uint32_t buf /* shared address of the lane's block buffer */,
-                                               const uint32_t fq /* shared address of the warp's 32-entry flush queue */)
+                                               const uint32_t fq /* shared address of the warp's 32-entry flush queue */,
+                                               const uint32_t ring /* shared address of the lane's stream ring */)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1043,7 +1147,7 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
     int            z = st.z;
     const bool     run = go && st.p < end_bit && N < N_total;
     uint32_t       done = 0, lim = 0, ent = 0, bad = 0;
-    uint32_t       hi = 0, lo = 0, nxt = 0, bound = 0, wi = 0;
+    Window         w = {0, 0, 0, 0, ring, 0, 0};
     uint4          q = make_uint4(0, 0, 0, 0);
     int            mx = 0, my = 0;
     uint32_t       bidx = 0;   // destination of the block in progress, in 128-byte units from plane0
@@ -1052,12 +1156,7 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
 #pragma unroll
     for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
     if (run) {
-        wi = a >> 5;
-        hi = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi)), 0, 0x0123);
-        lo = __byte_perm(ldg_word(io.w0 + (CLAMP ? min(wi + 1, io.wlast) : wi + 1)), 0, 0x0123);
-        wi += 2;
-        nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
-        bound = (a & ~31u) + 32u;
+        win_open<CLAMP>(w, io, a, ring);
         q = lds128(blk0 + (uint32_t) st.b * (uint32_t) sizeof(ParBlk) + 16u);
         const uint32_t mcu = N / (uint32_t) nblk;
         my = my0 + (int) (mcu / (uint32_t) W);
@@ -1070,19 +1169,15 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
         if (EXT) rowstart = z == 0 && st.b == 0 && mx == 0;
     }
     __syncwarp();
+    const uint32_t swz = PAR_SWIZZLE ? (lane & 7u) << 4 : 0u;  // chunk c of this lane's buffer sits at chunk c ^ (lane & 7)
+    const uint64_t pol_out = l2_policy_evict_first();
     const uint32_t bufm2 = buf - 2u;
     for (;;) {
 #pragma unroll
         for (int step = 0; step < PAR_DEFER_STEPS; ++step) {
             if (a < lim) {
-                if (a >= bound) {
-                    hi = lo;
-                    asm volatile("prmt.b32 %0, %1, 0, 0x0123;" : "=r"(lo) : "r"(nxt));  // see par_parse: swap at the point of use
-                    wi += 1;
-                    nxt = ldg_word(io.w0 + (CLAMP ? min(wi, io.wlast) : wi));
-                    bound += 32u;
-                }
-                const uint32_t top = __funnelshift_l(lo, hi, a);
+                if (a >= w.bound) win_refill<CLAMP>(w, io);
+                const uint32_t top = __funnelshift_l(w.lo, w.hi, a);
                 if (EXT) {
                     if (rowstart) {  // sixteen 1-bits at the start of a row end an `extend` scan silently (decode.swift:3214-3220):
                         rowstart = false;  // never on a healthy stream, so the interval just goes to the sequential decoder
@@ -1099,11 +1194,15 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
                 const uint32_t v = (int) top2 >= 0 ? tail - mask : tail;        // T.81 EXTEND (first extra bit 0: negative)
                 a += ent >> 24;
                 z += (int) __byte_perm(ent, 0, 0x4442);
-                if (z <= 64)  // the coefficient lands at z_before + advance - 1 (an EOB lands beyond 63: nowhere)
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(bufm2 + 2u * (uint32_t) z), "h"((uint16_t) v) : "memory");
+                if (z <= 64) {  // the coefficient lands at z_before + advance - 1 (an EOB lands beyond 63: nowhere)
+                    const uint32_t slot = PAR_SWIZZLE ? (((2u * (uint32_t) z - 2u) ^ swz) | buf) : bufm2 + 2u * (uint32_t) z;
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(slot), "h"((uint16_t) v) : "memory");
+                }
                 if (z >= 64) lim = 0u;  // block complete: the lane waits for the block-end section
             }
         }
+        cp_async_commit();
+        cp_async_wait<1>();
         const uint32_t mw = __ballot_sync(FULL, z >= 64);
         if (mw == 0u) {
             if (!__any_sync(FULL, a < lim)) break;
@@ -1118,9 +1217,9 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
             const uint32_t cur = q.w;
             q = lds128(cur);
             if (owned & 1u) {
-                fin_buf = buf | ((owned >> 1) & (broken ? 0u : 1u)) | 2u, fin_bidx = bidx;
+                fin_buf = buf | ((owned >> 1) & (broken ? 0u : 1u)) | 2u | (swz >> 2), fin_bidx = bidx;  // (bits 2..4: lane & 7)
                 uint16_t d;  // DC differences also go to the side array (resolved into predictions after the pass)
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(buf) : "memory");
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(buf + swz) : "memory");
                 dcdiff[N] = (int16_t) d;
             } else {  // the block this lane skipped: its symbols were stored like any others
 #pragma unroll
@@ -1154,16 +1253,21 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
             for (uint32_t k = lane >> 3; k < n; k += 4u) {
                 uint32_t src, dst;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(src), "=r"(dst) : "r"(fq + 8u * k) : "memory");
-                const uint32_t sa = (src & ~3u) + chunk;
+                const uint32_t sa = PAR_SWIZZLE ? (src & ~127u) + (chunk ^ ((src << 2) & 0x70u)) : (src & ~3u) + chunk;
                 uint4          v;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
-                if (src & 1u)
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk) = v;
+                if (!PAR_L2_POLICY) {
+                    if (src & 1u) *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk) = v;
+                } else if (src & 1u)  // (written once, read by the next kernel from DRAM: the lines should not push the stream out of L2)
+                    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(reinterpret_cast<char *>(plane0) + (int64_t) (int32_t) dst * 128 + chunk),
+                                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol_out)
+                                 : "memory");
                 sts128_zero(sa);
             }
             __syncwarp();
         }
     }
+    cp_async_wait<0>();
     bad_out = bad != 0u;
     return done;
 }
@@ -1171,15 +1275,15 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
 __device__ __forceinline__ uint32_t par_decode_auto(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
                                                     const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad,
                                                     const uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                                    int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const bool ext)
+                                                    int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const uint32_t ring, const bool ext)
 {
     const bool clamp = __any_sync(0xffffffffu, go && io.clamp != 0u);
     if (ext) {  // (kernel-uniform)
-        if (clamp) return par_decode<true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
-        return par_decode<false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+        if (clamp) return par_decode<true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
+        return par_decode<false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
     }
-    if (clamp) return par_decode<true, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
-    return par_decode<false, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq);
+    if (clamp) return par_decode<true, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
+    return par_decode<false, false>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
 }
 
 // ---- progressive AC-first scans (kind 3) on the same machinery ------------------------------------------------------------------
@@ -1377,7 +1481,7 @@ template <int NT>
 __device__ __forceinline__ void par_stage_tables(const ScanParams &P, const int16_t *plane0, const uint32_t img, const uint32_t tid,
                                                  uint8_t *smem, const uint8_t *lut_img)
 {
-    constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
+    constexpr uint32_t PRE = PAR_PRE;
     const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
     ParBlk          *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
     const int        nblk = P.mcu_blocks;
@@ -1453,9 +1557,10 @@ __device__ __forceinline__ ParGroup par_setup_group(const ScanParams &P, const u
         if (B < (uint32_t) PAR_MIN_BITS) B = PAR_MIN_BITS;
         q.B = B;
         q.S = q.count ? (q.count + B - 1) / B : 1u;  // <= T
-        // the decoders read up to four words past an interval's last byte without looking: fine wherever more data (or the
-        // buffer's slack) follows, clamped for the interval(s) at the very end of the buffer
-        q.io.clamp = (o1 + 16 > P.offsets[(size_t) n_images * P.n_ecs] + 8) ? 1u : 0u;
+        // The decoders read ahead of the cursor without looking (four words; a lane that finishes its block on a corrupt stream may
+        // run ~2 Kbit past the interval's end): fine wherever more data follows, clamped to the interval's last word for the
+        // intervals within 512 bytes of the end of the buffer.
+        q.io.clamp = (o1 + 512 > P.offsets[(size_t) n_images * P.n_ecs]) ? 1u : 0u;
     }
     return q;
 }
@@ -1492,7 +1597,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     __shared__ ParGroup s_grp[NT / 16];
     __shared__ __align__(16) uint32_t s_ck_st[ALIAS ? 1 : PAR_NSEG][ALIAS ? 4 : NT];  // checkpoints of every subsequence's recorded parse (packed, see parse_sub)
     __shared__ __align__(16) uint2 s_fq[ALIAS ? NT : 1];  // the warps' flush queues (without ALIAS they reuse the checkpoint array)
-    uint64_t *const s_exit = ALIAS ? reinterpret_cast<uint64_t *>(smem + buf_off) : s_exit_st;
+    // (the block buffers start at the first 128-byte boundary at or after buf_off when they are swizzled)
+    const uint32_t bufs_off = PAR_SWIZZLE ? ((smem_u32(smem) + buf_off + 127u) & ~127u) - smem_u32(smem) : buf_off;
+    // the lanes' stream rings follow the block buffers (sequential scans only)
+    const uint32_t ring = ((smem_u32(smem) + bufs_off + (uint32_t) NT * PAR_BUF_STRIDE + 31u) & ~31u) + threadIdx.x * 4u * PAR_RING;
+    uint64_t *const s_exit = ALIAS ? reinterpret_cast<uint64_t *>(smem + bufs_off) : s_exit_st;
     uint64_t *const s_entry = ALIAS ? s_exit + NT : s_entry_st;
     uint32_t (*const s_ck)[NT] = ALIAS ? reinterpret_cast<uint32_t (*)[NT]>(s_entry + NT) : reinterpret_cast<uint32_t (*)[NT]>(&s_ck_st[0][0]);
     uint32_t *const s_cnt = ALIAS ? &s_ck[PAR_NSEG][0] : s_cnt_st;
@@ -1516,7 +1625,6 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
     const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
     ParBlk          *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
-    constexpr uint32_t PRE = sizeof(LutHeader) + 12 * sizeof(BlkInfo);
     const uint32_t   sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
     const uint16_t  *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
     const int        W = P.W, nblk = P.mcu_blocks;
@@ -1553,7 +1661,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
             if (AC) cum += par_run_ac_auto<false>(qio, st, seg_end, qcount, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
             else if (DC) cum += par_run_dc_auto<false>(qio, st, seg_end, qcount, blk0, bad, 0, 0, 1u, nullptr, false);
-            else cum += par_parse_auto(qio, st, seg_end, qcount, blk0);
+            else cum += par_parse_auto(qio, st, seg_end, qcount, blk0, ring);
             // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
@@ -1578,7 +1686,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         if (l > 0 && warm_bits) {
             if (AC) par_run_ac_auto<false>(io, st, start_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
             else if (DC) par_run_dc_auto<false>(io, st, start_bit, count, blk0, bad, 0, 0, 1u, nullptr, false);
-            else par_parse_auto(io, st, start_bit, count, blk0);
+            else par_parse_auto(io, st, start_bit, count, blk0, ring);
         }
         if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
@@ -1645,8 +1753,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         static_assert(PAR_NSEG * 4 >= 8, "the flush queues fit in the checkpoint array");
         const bool     go = active && before < N_total;
         const uint32_t done = par_decode_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, nblk, bad, before, N_total, W,
-                                              s_grp[g].r0, plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                              (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, P.extend != 0);
+                                              s_grp[g].r0, plane0, dcdiff, sbase + bufs_off + tid * PAR_BUF_STRIDE,
+                                              (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, ring, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
             atomicAdd(&s_grp[g].total, done);
@@ -1778,8 +1886,9 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     const uint8_t  *lut_img = P.luts + (size_t) img * P.lut_stride;
     ParBlk         *s_blk = reinterpret_cast<ParBlk *>(smem + sizeof(LutHeader));
     const uint32_t  sbase = smem_u32(smem), blk0 = sbase + (uint32_t) sizeof(LutHeader);
-    const uint16_t *ref_entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
     const int       W = P.W, nblk = P.mcu_blocks;
+    const uint32_t  bufs = PAR_SWIZZLE ? (sbase + buf_off + 127u) & ~127u : sbase + buf_off;  // block buffers, then the stream rings
+    const uint32_t  ring = ((bufs + (uint32_t) NT * PAR_BUF_STRIDE + 31u) & ~31u) + tid * 4u * PAR_RING;
     // values other CTAs of the cluster hold in their shared memory
     auto remote64 = [&](uint64_t *p_, uint32_t r) -> uint64_t { return *cluster.map_shared_rank(p_, r); };
     auto remote32 = [&](uint32_t *p_, uint32_t r) -> uint32_t { return *cluster.map_shared_rank(p_, r); };
@@ -1799,7 +1908,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
-            cum += par_parse_auto(io, st, seg_end, count, blk0);
+            cum += par_parse_auto(io, st, seg_end, count, blk0, ring);
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
             const uint32_t old = s_ck[k][sid];
@@ -1820,7 +1929,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     // ---- round 0 ----
     if (active) {
         st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = 0;
-        if (l > 0 && warm_bits) par_parse_auto(io, st, start_bit, count, blk0);
+        if (l > 0 && warm_bits) par_parse_auto(io, st, start_bit, count, blk0, ring);
         if (l > 0 && !warm_bits) st.p = start_bit;
         s_entry[tid] = pack_state(st.p, st.z, st.b);
         uint64_t       x;
@@ -1879,8 +1988,8 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
         static_assert(sizeof(s_ck) >= NT * 8, "the flush queues live in the checkpoint array");
         const bool     go = active && before < N_total;
         const uint32_t done = par_decode_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, nblk, bad, before, N_total, W, s_q.r0,
-                                              plane0, dcdiff, sbase + buf_off + tid * PAR_BUF_STRIDE,
-                                              smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, P.extend != 0);
+                                              plane0, dcdiff, bufs + tid * PAR_BUF_STRIDE,
+                                              smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, ring, P.extend != 0);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_bad, 1u);
             atomicAdd(&s_total, done);
@@ -2457,7 +2566,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
             if (dc_per_interval <= 0x7fffffffull && slots * dc_per_interval * 2 <= (4ull << 30)) {
                 J_TRY(scratch_reserve(ctx, 12, (size_t) (slots * dc_per_interval * 2 + 256), &d_dc));
                 J_TRY(scratch_reserve(ctx, 13, (size_t) (slots * 4 + 256), &d_flag));
-                const size_t smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + ((max_fast * 2 + 15) & ~size_t(15));
+                const size_t smem_par = PAR_PRE + ((max_fast * 2 + 15) & ~size_t(15));
                 // Threads per interval (16 .. 128).  Every subsequence is parsed ~(2 + warm-up / length) times, so long
                 // subsequences (>= 3 Kbit) waste the least work; small batches take more threads per interval to fill the GPU.
                 // tuning / test overrides, read per call: log2(threads per interval), warm-up bits
@@ -2469,14 +2578,15 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 // few, large intervals (a file without DRI is ONE interval): a 512-thread CTA per interval
                 const bool big = (est_bits >> 7) >= (dc_first ? 2048 : 16384) && slots * 128 < (uint64_t) ctx->sm_count * 1024;
                 const int  nt = big ? PAR_BIG_THREADS : PAR_THREADS, tmax = big ? 9 : 7;
+                // (measured on 64 x 4K, 134 Kbit per interval: 16 threads 1.89 ms, 32 threads 2.00 ms; warm-up 2048 bits best)
                 int        tshift = tmax;
-                while (tshift > 4 && (est_bits >> tshift) < 4096) --tshift;
-                while (tshift < tmax && (slots << tshift) < (uint64_t) ctx->sm_count * 1024 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
+                while (tshift > 4 && (est_bits >> tshift) < 8192) --tshift;
+                while (tshift < tmax && (slots << tshift) < (uint64_t) ctx->sm_count * 512 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
                 if (env_t >= 4 && env_t <= tmax) tshift = env_t;
-                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? 256u : 1024u);
+                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? 256u : 2048u);
                 const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
-                const size_t   smem_total = smem_par + (dc_first ? 0 : (size_t) nt * PAR_BUF_STRIDE);
+                const size_t   smem_total = smem_par + (dc_first ? 0 : (size_t) nt * (PAR_BUF_STRIDE + 4 * PAR_RING) + 32 + (PAR_SWIZZLE ? 112 : 0));
                 if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2518,7 +2628,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                     memset(&cfg, 0, sizeof cfg);
                     cfg.gridDim = dim3(csize * n_ecs, n_images);
                     cfg.blockDim = dim3(CL_THREADS);
-                    cfg.dynamicSmemBytes = smem_par + (size_t) CL_THREADS * PAR_BUF_STRIDE;
+                    cfg.dynamicSmemBytes = smem_par + (size_t) CL_THREADS * (PAR_BUF_STRIDE + 4 * PAR_RING) + 32 + (PAR_SWIZZLE ? 112 : 0);
                     cfg.stream = ctx->stream;
                     cudaLaunchAttribute attr[1];
                     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2582,7 +2692,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         if (env_ts && atoi(env_ts) >= 4 && atoi(env_ts) <= 7) tshift = atoi(env_ts);
         const uint32_t warm_bits = env_ws ? (uint32_t) (atoi(env_ws) > 0 ? atoi(env_ws) : 0) : 512u;
         const uint32_t G = (uint32_t) PAR_THREADS >> tshift;
-        const size_t   smem_par = sizeof(LutHeader) + 12 * sizeof(BlkInfo) + ((max_fast * 2 + 15) & ~size_t(15));
+        const size_t   smem_par = PAR_PRE + ((max_fast * 2 + 15) & ~size_t(15));
         if (!ctx->par_smem_ac) {
             CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             ctx->par_smem_ac = 1;
