@@ -8,11 +8,14 @@
 A "step" is one pass of the hot path over one batch: scan lexing (N1: unstuff + RSTn split) -> entropy decode (K3, which also
 clears the fresh coefficient planes and resolves the DC predictions) -> dequantise + IDCT (K1) -> upsample + YCbCr->RGB +
 pack (K2).  `value` times it with every input (the raw scan bytes of the files) already resident in HBM (CUDA events on the
-launching stream, max over ranks); `e2e` times the same work through the host-buffer C-ABI call
-jpeg_sm100_decode_batch_raw_rgb8 with pinned host buffers, H2D and D2H copies inside the timed region, and reports next to
-it what the PCIe link itself sustains device -> host (the e2e bound: 3 bytes of RGB per pixel leave the device).
+launching stream, max over ranks); `e2e` -- the headline -- times the same work through the host-buffer C-ABI call
+jpeg_sm100_decode_batch_raw_rgb8 with pinned host buffers, H2D and D2H copies inside the timed region, over all K steps, and
+reports next to it what the PCIe links sustain device -> host alone AND with all ranks copying at once (the e2e bound: 3 bytes
+of RGB per pixel leave the device).
 Inputs are produced by our own GPU encoder (K4-K7) from deterministic synthetic frames, DRI = one MCU row.
 Multi-GPU: independent images are sharded across ranks, no collective on the data path ("weak": 64 frames per GPU).
+The other configurations of BASELINE.json (#3 4K encode, #4 1080p progressive decode, #5 12-Mpixel 4:4:4 decode -> re-encode,
+64 frames per GPU) and the staged whole-file API (layer A) are timed in the same run and reported under `configs` / `layer_a`.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -24,6 +27,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -37,6 +41,12 @@ FACTORS = [(2, 2), (1, 1), (1, 1)]
 LEVEL = 0.25
 WORKLOAD = "3840x2160 baseline 4:2:0 decode, batch 64 synthetic frames per GPU, DRI = 240 MCUs (1 MCU row), level 0.25"
 METRIC = "Mpixels/s decode (4K 4:2:0 baseline)"
+
+
+def base_config(frames):
+    """the `config` object, identical in both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": int(frames),
+            "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)"}
 
 
 def k1_traffic():
@@ -124,7 +134,7 @@ def run_reference(args):
     from jpeg_b200 import synth
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    sample = max(1, min(cores, 128))  # one frame per host thread
+    frames = args.batch  # the whole batch of the workload per step, one frame per task, all host threads
     q = [O.quanta(LEVEL, 0), O.quanta(LEVEL, 1), O.quanta(LEVEL, 1)]
 
     # inputs: the same synthetic frames, encoded by the oracle's reference-equivalent encoder (DRI = 240 MCUs)
@@ -142,7 +152,7 @@ def run_reference(args):
 
     torch.set_num_threads(1)
     with ThreadPoolExecutor(cores) as pool:
-        inputs = list(pool.map(make2, range(sample)))
+        inputs = list(pool.map(make2, range(frames)))
 
         def decode(inp):  # Spectral.decode(ecss:) -> idct -> interleaved -> unpack(as: RGB) on one core
             parts, dct, act = inp
@@ -158,13 +168,15 @@ def run_reference(args):
         for _ in range(args.steps):
             list(pool.map(decode, inputs))
         dt = (time.perf_counter() - t0) / args.steps
-    value = sample * W * H / dt / 1e6
+    value = frames * W * H / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "each step decodes a bounded sample of the workload on the host cores"},
+            "config": base_config(frames),
+            "details": {"note": "the reference's CPU path (C restatement of the Swift code; no Swift toolchain here): every step decodes the "
+                                "whole batch from pre-lexed entropy-coded segments (the lexer, which our arm includes, is left out), one frame per task"},
             "cpu_baseline": {"value": round(value, 2), "unit": "Mpixels/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} frames of the workload per step, one frame per thread, {cores} threads"},
+                             "sample": f"{frames} frames of the workload per step, one frame per task, {cores} threads"},
             "e2e": {"value": round(value, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -172,6 +184,24 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+def nccl_banner_to_stderr(path):
+    """NCCL's own init lines (nranks, transport) were written to NCCL_DEBUG_FILE so that stdout carries exactly one JSON line;
+    repeat the informative ones on stderr for the record"""
+    try:
+        seen = 0
+        for name in sorted(os.listdir(os.path.dirname(path))):
+            if not name.startswith(os.path.basename(path)):
+                continue
+            with open(os.path.join(os.path.dirname(path), name), errors="replace") as f:
+                for l in f:
+                    if ("nranks" in l or "Init COMPLETE" in l or "NCCL version" in l or "Connected" in l) and seen < 40:
+                        sys.stderr.write(l if l.endswith("\n") else l + "\n")
+                        seen += 1
+        sys.stderr.flush()
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -185,18 +215,32 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     placement = "unchanged (single rank)"
+    nccl_log = None
     if world > 1:
         # one process per GPU: keep the rank's threads and pinned staging buffers on the GPU's own NUMA node (best effort)
         if os.environ.get("JPEG_SM100_NUMA", "1") != "0":
             from jpeg_b200 import affinity
             placement = affinity.bind_to_gpu(local)
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL's init report goes to a file (rank 0 prints exactly one JSON line on stdout) and is repeated on stderr afterwards
+        nccl_log = os.path.join(tempfile.gettempdir(), f"jpeg_sm100_nccl_{os.environ.get('MASTER_PORT', '0')}")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log + ".%h.%p"
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     ctx = lib.Context(local, stream=stream.cuda_stream)
     geo = batch.Geometry((W, H), FACTORS)
     q = np.stack([quanta(LEVEL, 0), quanta(LEVEL, 1), quanta(LEVEL, 1)])
     n = args.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()  # (the first collective: NCCL finishes its init here)
+    if nccl_log and rank == 0:
+        nccl_banner_to_stderr(nccl_log)
 
     # ---- inputs: synthetic frames -> our GPU encoder -> (host) lexer ------------------------------------------------
     ecs_all, tables_all = [], []
@@ -248,11 +292,6 @@ def run_ours(args):
         ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
         mark()
         return e
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step(False)
@@ -313,12 +352,14 @@ def run_ours(args):
         return
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region -------------------------------------------
-    # Images are independent, so the batch is sharded over a few contexts (one stream each) driven by as many host threads:
-    # while one share is copying its RGB back over PCIe another is uploading / entropy-decoding.  (One call for the whole
-    # batch reaches ~95 % of this by itself: the entry point pipelines groups of images internally; JPEG_BENCH_STREAMS=1.)
+    # Images are independent, so the batch may be sharded over a few contexts (one stream each) driven by as many host threads:
+    # while one share is copying its RGB back over PCIe another is uploading / entropy-decoding.  One call for the whole batch
+    # reaches ~95 % of this by itself (the entry point pipelines groups of images internally), which is what ranks of a
+    # multi-GPU job use: fewer host threads per rank fighting for the host's cores (JPEG_BENCH_STREAMS overrides).
     # Every step of every share uploads its raw scan bytes from pinned memory and reads its RGB back (Bi + Bo per step).
     rgb_bytes = n * W * H * 3
-    n_streams = max(1, min(n, int(os.environ.get("JPEG_BENCH_STREAMS", "4"))))
+    default_streams = 4 if world == 1 else 1
+    n_streams = max(1, min(n, int(os.environ.get("JPEG_BENCH_STREAMS", str(default_streams)))))
     halves = []
     for k in range(n_streams):
         i0, i1 = k * n // n_streams, (k + 1) * n // n_streams
@@ -342,6 +383,8 @@ def run_ours(args):
                                                          qz.ctypes.data, W, H, 0, h["rgb"].data_ptr(), h["status"].ctypes.data))
 
     def e2e_run(steps):
+        if len(halves) == 1:
+            return e2e_worker(halves[0], steps)
         ths = [threading.Thread(target=e2e_worker, args=(h, steps)) for h in halves]
         for t_ in ths:
             t_.start()
@@ -349,7 +392,7 @@ def run_ours(args):
             t_.join()
 
     e2e_run(max(1, min(args.warmup, 2)))
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = args.steps
     barrier()
     w0 = time.perf_counter()
     e2e_run(e2e_steps)
@@ -361,27 +404,66 @@ def run_ours(args):
     assert int(got) == checksum, "e2e result differs from the device-resident result"
     e2e_launches = sum(h["ctx"].launches for h in halves)
 
-    # the e2e bound: every frame's 3 bytes per pixel cross PCIe once.  Measure what this link sustains device -> pinned host,
-    # same buffer size as a half-batch, so that e2e can be read as a fraction of ITS roofline (the kernels are ~7x faster).
-    d2h_gbs = None
-    try:
+    # The e2e bound: every frame's 3 bytes per pixel cross PCIe once.  What the link sustains device -> pinned host, same buffer
+    # as a share of the batch, (a) this rank alone while the others idle (ranks take turns), (b) all ranks at the same time --
+    # the ceiling the N-rank e2e figure has to be read against.
+    def d2h_rate(reps=3):
         src = buf.rgb.view(-1)[:halves[0]["rgb"].numel()]
-        a0, a1 = ev(), ev()
         halves[0]["rgb"].copy_(src, non_blocking=True)
         torch.cuda.synchronize()
+        a0, a1 = ev(), ev()
         a0.record(stream)
-        for _ in range(3):
+        for _ in range(reps):
             halves[0]["rgb"].copy_(src, non_blocking=True)
         a1.record(stream)
         torch.cuda.synchronize()
-        d2h_gbs = 3 * src.numel() / (a0.elapsed_time(a1) * 1e-3) / 1e9
+        return reps * src.numel() / (a0.elapsed_time(a1) * 1e-3) / 1e9
+
+    d2h_alone = d2h_conc = None
+    try:
+        for r in range(world):
+            barrier()
+            if r == rank:
+                d2h_alone = d2h_rate()
+        barrier()
+        d2h_conc = d2h_rate()
+        barrier()
     except Exception:
         pass
 
+    # ---- the other configurations of BASELINE.json + the staged whole-file API, same run (bounded: a few seconds each) ----
+    configs, layer_a = {}, None
+    del d_raw, d_ecs
+    for h in halves:
+        h["ctx"].close()
+    halves_rgb_numel = halves[0]["rgb"].numel()
+    del halves
+    torch.cuda.empty_cache()
+    if not args.no_configs:
+        import bench_configs
+        for name, fn in (("3", bench_configs.config3), ("4", bench_configs.config4), ("5", bench_configs.config5)):
+            try:
+                barrier()
+                configs[name] = fn(ctx, dev, q, rank, n)
+            except Exception as e:  # reported, never fatal: the headline numbers are already measured
+                configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                layer_a = bench_configs.layer_a(local, q)
+            except Exception as e:
+                layer_a = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    per_rank = {"placement": placement, "d2h_alone": d2h_alone, "d2h_concurrent": d2h_conc, "e2e_s": e2e_s, "ms_per_step": ms_per_step,
+                "configs": {k: {kk: vv for kk, vv in v.items() if kk in ("ms", "error", "parity_checked")} for k, v in configs.items()}}
     if world > 1:
         t = torch.tensor([ms_per_step, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step, e2e_s = t[0].item(), t[1].item()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank)
+    else:
+        gathered = [per_rank]
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -396,26 +478,54 @@ def run_ours(args):
         color_ms = statistics.mean(stage_ms["color"])
         color_bytes = (64.0 * geo.total_blocks + 3.0 * W * H) * n
         # CPU baseline on a bounded sample (single thread), same run
-        cpu = cpu_baseline_sample(ecs_all[:2], tables_all[:16], q)
+        cpu = cpu_baseline_sample(ecs_all[:3], tables_all[:24], q)
+        conc = [g["d2h_concurrent"] for g in gathered if g["d2h_concurrent"]]
+        alone = [g["d2h_alone"] for g in gathered if g["d2h_alone"]]
+        e2e_gbps_per_rank = rgb_bytes / e2e_s / 1e9
+        # configs: the job's time is the slowest rank's
+        cfg_out = {}
+        for k, v in configs.items():
+            o = dict(v)
+            ms_all = [g["configs"].get(k, {}).get("ms") for g in gathered]
+            if all(m is not None for m in ms_all) and "pixels_per_gpu" in o:
+                o["ms"] = round(max(ms_all), 3)
+                o["Mpixels_per_s"] = round(o["pixels_per_gpu"] * world / (o["ms"] * 1e-3) / 1e6, 1)
+                o["parity_checked"] = all(g["configs"][k].get("parity_checked") for g in gathered)
+                o["n_gpus"] = world
+            errs = [g["configs"].get(k, {}).get("error") for g in gathered if g["configs"].get(k, {}).get("error")]
+            if errs:
+                o["error"] = errs[0]
+            cfg_out[k] = o
         line = {
             "metric": METRIC, "value": round(px_per_step / (ms_per_step * 1e-3) / 1e6, 1), "unit": "Mpixels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": n, "ecs_bytes_per_frame": inputs.ecs_bytes // n,
-                       "l2": "inputs larger than L2 (coefficients 1.6 GB, RGB 1.6 GB per step)", "parallelism": f"images sharded over {world} GPU(s), no collective", "cpu_affinity": placement},
+            "config": base_config(n),
+            "details": {"value_is": "device-resident (inputs in HBM when the timed region starts); the headline against the reference arm is e2e",
+                        "ecs_bytes_per_frame": inputs.ecs_bytes // n, "parallelism": f"images sharded over {world} GPU(s), no collective",
+                        "cpu_affinity": [g["placement"] for g in gathered],
+                        "wait_mode": os.environ.get("JPEG_SM100_WAIT", "yield")},
             "e2e": {"value": round(px_per_step / e2e_s / 1e6, 1), "unit": "Mpixels/s",
                     "h2d_bytes_per_step": int(raw_len.sum() + raw_len.nbytes * 2), "d2h_bytes_per_step": int(rgb_bytes + 4 * n),
-                    "pcie_d2h_GBps_measured": None if d2h_gbs is None else round(d2h_gbs, 1),
-                    "pcie_d2h_GBps_achieved": round((rgb_bytes * world / max(world, 1)) / e2e_s / 1e9, 1),
-                    "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)", "steps": e2e_steps},
+                    "pcie_d2h_GBps_measured": None if not alone else round(min(alone), 1),
+                    "pcie_d2h_GBps_measured_alone_per_rank": [round(x, 1) for x in alone],
+                    "pcie_d2h_GBps_measured_concurrent": None if not conc else {"min": round(min(conc), 1), "mean": round(statistics.mean(conc), 1),
+                                                                                 "per_rank": [round(x, 1) for x in conc]},
+                    "pcie_d2h_GBps_achieved": round(e2e_gbps_per_rank, 1),
+                    "frac_of_concurrent_ceiling": None if not conc else round(e2e_gbps_per_rank / min(conc), 3),
+                    "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)",
+                    "steps": e2e_steps, "per_rank_s": [round(g["e2e_s"], 4) for g in gathered]},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "roofline": {"kernel": "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": k1_traffic() if n == BATCH else None,
                          "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5),
                          "note": "the HBM-bound kernel BASELINE.json's north_star sets the >= 70 % target on; the kernel that takes most of the step "
-                                 "(K3, bound by instruction issue / LSU, not HBM) is under roofline_dominant"},
-            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 32 threads per restart interval, 8 CTAs x 4 warps per SM, blocks assembled in shared memory and flushed by the whole warp as 128-byte lines, DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; latency-bound, then issue-bound (ncu: 66 % issue-active at 32 resident warps, profiles/), not HBM-bound",
+                                 "(K3, bound by dependent-instruction latency and instruction issue, not HBM) is under roofline_dominant"},
+            "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 16 threads per restart "
+                                            "interval, 8-9 CTAs x 4 warps per SM, blocks assembled in shared memory and flushed by the whole warp as 128-byte lines, "
+                                            "DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; latency- and issue-bound "
+                                            "(ncu: profiles/), not HBM-bound",
                                   "bound": "hbm", "achieved": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                   "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": k3_traffic() if n == BATCH else None,
                                   "bytes_per_launch": int(huff_bytes), "ms_per_launch": round(huff_ms, 4),
@@ -424,6 +534,8 @@ def run_ours(args):
                        "lexer_GBps": round(3.0 * float(raw_len.sum()) / (statistics.mean(stage_ms["lexer"]) * 1e-3) / 1e9, 1),
                        "huffman_GBps": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1),
                        "color_GBps": round(color_bytes / (color_ms * 1e-3) / 1e9, 1)},
+            "configs": cfg_out,
+            "layer_a": layer_a,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -433,7 +545,7 @@ def run_ours(args):
 
 
 def cpu_baseline_sample(ecs_list, tables, q):
-    """the oracle (CPU restatement of the reference, 'port') on a bounded sample: 2 frames, one thread"""
+    """the oracle (CPU restatement of the reference, 'port') on a bounded sample: 3 frames of the workload, one thread, ~10-20 s"""
     try:
         from jpeg_b200 import batch
         from oracle import oracle as O
@@ -447,7 +559,7 @@ def cpu_baseline_sample(ecs_list, tables, q):
             specs.append((parts, dct, act))
         t0 = time.perf_counter()
         reps = 0
-        while time.perf_counter() - t0 < 8.0 and reps < 6:
+        while time.perf_counter() - t0 < 12.0 and reps < 20:
             for parts, dct, act in specs:
                 s = O.Spectral.create((W, H), FACTORS)
                 for p in range(3):
@@ -471,6 +583,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--sweep", default="", help="with --quick: K3p settings to re-time, log2(threads per interval):warm-up bits, ...")
     ap.add_argument("--quick", action="store_true", help="device-resident stage times only (kernel A/B runs); not a bench line")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE.json's configurations #3-#5 and the layer-A timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

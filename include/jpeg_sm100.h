@@ -251,6 +251,44 @@ int jpeg_sm100_transform_blocks(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32
                                 const int32_t matrix[4], const uint8_t zmap[64], const int8_t mul[64],
                                 int16_t *out, uint32_t out_units_x, uint32_t out_units_y);
 
+/* ---- layer A with the image RESIDENT on the device ---------------------------------------------------------------------
+ * JPEG.Context holds ONE Spectral for the whole file and pushes every scan into it (decode.swift:3565-3587, 3706-3725); the
+ * stage functions then read it (Spectral.idct() decode.swift:4154 ...).  With the calls above every scan uploads and downloads
+ * all planes.  A jpeg_sm100_spectral is the same image kept in HBM: the Swift side stores the handle in its Spectral (a final
+ * class member, swift/JPEGSM100Shim.swift), pushes scans into it, runs the stages on it, and materialises host planes once,
+ * on demand.  Host buffers in, host buffers out, synchronous, like the rest of layer A; a handle belongs to the ctx that made it.
+ *   units_xy : n_planes x (units_x, units_y), the Spectral.Plane geometry (decode.swift:2456-2495).  New planes are zero
+ *              (decode.swift:2241-2256). */
+typedef struct jpeg_sm100_spectral jpeg_sm100_spectral;
+int  jpeg_sm100_spectral_create(jpeg_sm100_ctx *ctx, uint32_t n_planes, const int32_t *units_xy, jpeg_sm100_spectral **out);
+void jpeg_sm100_spectral_destroy(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s);
+/* Spectral.set(width:) / set(height:) (decode.swift:2456-2495): new geometry, the common region keeps its coefficients, the
+ * rest is zero (DNL height redefinition decode.swift:3905-3924, cropping before a rotation examples/rotate/main.swift:101-199) */
+int  jpeg_sm100_spectral_resize(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const int32_t *units_xy);
+/* host planes -> device (e.g. coefficients produced by the host) and device -> host (materialise Spectral.Plane buffers) */
+int  jpeg_sm100_spectral_upload(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_plane_i16 *planes, uint32_t n_planes);
+int  jpeg_sm100_spectral_download(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, jpeg_sm100_plane_i16 *planes, uint32_t n_planes);
+/* jpeg_sm100_decode_scan / jpeg_sm100_decode_scan_raw into the resident image: only the scan's bytes travel */
+int  jpeg_sm100_spectral_decode_scan(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                     const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs, uint64_t interval,
+                                     int extend, const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4]);
+int  jpeg_sm100_spectral_decode_scan_raw(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                         const uint8_t *raw, uint64_t raw_len, uint64_t interval, int extend,
+                                         const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4]);
+/* jpeg_sm100_encode_scan from the resident image */
+int  jpeg_sm100_spectral_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                     uint64_t interval_mcus, jpeg_sm100_huff_table dc_out[4], jpeg_sm100_huff_table ac_out[4],
+                                     uint8_t *ecs, uint64_t ecs_capacity, uint64_t *ecs_len);
+/* Spectral.idct() (decode.swift:4154): every plane, host sample planes out (planes[p].samples: 64 * units_x * units_y uint16;
+ * a NULL samples pointer skips that plane's download).  quanta: n_planes x 64 (zig-zag). */
+int  jpeg_sm100_spectral_idct(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const uint16_t *quanta_zigzag, int precision,
+                              jpeg_sm100_plane_u16 *planes, uint32_t n_planes);
+/* jpeg_sm100_spectral_to_rgb8 from the resident image: idct().interleaved(cosite:).unpack(as: RGB.self) with one download */
+int  jpeg_sm100_spectral_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const uint16_t *quanta_zigzag,
+                              const int32_t *factors_xy, uint32_t size_x, uint32_t size_y, int cosited, uint8_t *rgb);
+/* bytes this ctx has moved host -> device and device -> host so far (layer A bookkeeping for benchmarks and tests) */
+void jpeg_sm100_transfer_counts(jpeg_sm100_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+
 /* =============================================================================================================
  * LAYER B -- device pointers, asynchronous on the ctx stream, batched over images of identical geometry
  * ============================================================================================================= */

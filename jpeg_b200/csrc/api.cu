@@ -144,13 +144,13 @@ JPEG_API int jpeg_sm100_free_host(jpeg_sm100_ctx *ctx, void *p)
 JPEG_API int jpeg_sm100_upload(jpeg_sm100_ctx *ctx, void *d, const void *h, size_t n)
 {
     if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
-    if (n) CU_TRY(ctx, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CU_TRY(ctx, copy_h2d(ctx, d, h, n, ctx->stream));
     return JPEG_SM100_OK;
 }
 JPEG_API int jpeg_sm100_download(jpeg_sm100_ctx *ctx, void *h, const void *d, size_t n)
 {
     if (!ctx) return JPEG_SM100_ERR_INVALID_ARGUMENT;
-    if (n) CU_TRY(ctx, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) CU_TRY(ctx, copy_d2h(ctx, h, d, n, ctx->stream));
     return JPEG_SM100_OK;
 }
 JPEG_API int jpeg_sm100_memset(jpeg_sm100_ctx *ctx, void *d, int v, size_t n)
@@ -314,7 +314,7 @@ int upload_spectral(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_plane_i16 *p
         out.sp.plane[p].factor_y = factors ? factors[2 * p + 1] : 1;
         if (out.bytes[p]) {
             if (!planes[p].coef) return JPEG_SM100_ERR_INVALID_ARGUMENT;
-            CU_TRY(ctx, cudaMemcpyAsync(out.sp.plane[p].coef, planes[p].coef, out.bytes[p], cudaMemcpyHostToDevice, ctx->stream));
+            CU_TRY(ctx, copy_h2d(ctx, out.sp.plane[p].coef, planes[p].coef, out.bytes[p], ctx->stream));
         }
     }
     return JPEG_SM100_OK;
@@ -364,8 +364,8 @@ JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     J_TRY(scratch_reserve(ctx, 1, total + 64, &d_ecs));
     J_TRY(scratch_reserve(ctx, 2, sizeof(uint64_t) * ((size_t) n_ecs + 1), &d_off));
     J_TRY(scratch_reserve(ctx, 3, 64, &d_status));
-    if (total) CU_TRY(ctx, cudaMemcpyAsync(d_ecs, ecs_concat, total, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(d_off, ecs_offsets, sizeof(uint64_t) * ((size_t) n_ecs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (total) CU_TRY(ctx, copy_h2d(ctx, d_ecs, ecs_concat, total, ctx->stream));
+    CU_TRY(ctx, copy_h2d(ctx, d_off, ecs_offsets, sizeof(uint64_t) * ((size_t) n_ecs + 1), ctx->stream));
     jpeg_sm100_huff_table tables[8];
     memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
@@ -375,10 +375,10 @@ JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     ctx->hint_interval_bytes = 0;
     J_TRY(k3);
     int32_t status = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, &status, d_status, sizeof status, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)
         if (ps.bytes[p])
-            CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, copy_d2h(ctx, planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return status;
 }
@@ -395,7 +395,7 @@ static int idct_host(jpeg_sm100_ctx *ctx, const int16_t *coef, uint32_t ux, uint
     J_TRY(alloc_planar(ctx, 4, ps.sp, sample_bytes, pl));
     J_TRY(jpeg_sm100_dev_idct(ctx, &ps.sp, quanta, precision, &pl));
     const size_t bytes = (size_t) 64 * ux * uy * sample_bytes;
-    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(samples, pl.plane[0].samples, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) CU_TRY(ctx, copy_d2h(ctx, samples, pl.plane[0].samples, bytes, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -430,7 +430,7 @@ static int upload_planar_u16(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_pla
     if (copy)
         for (uint32_t p = 0; p < n; ++p) {
             const size_t bytes = (size_t) 128 * planes[p].units_x * planes[p].units_y;
-            if (bytes) CU_TRY(ctx, cudaMemcpyAsync(pl.plane[p].samples, planes[p].samples, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            if (bytes) CU_TRY(ctx, copy_h2d(ctx, pl.plane[p].samples, planes[p].samples, bytes, ctx->stream));
         }
     return JPEG_SM100_OK;
 }
@@ -445,7 +445,7 @@ JPEG_API int jpeg_sm100_interleave(jpeg_sm100_ctx *ctx, const jpeg_sm100_plane_u
     void        *d_out = nullptr;
     J_TRY(scratch_reserve(ctx, 5, bytes + 64, &d_out));
     J_TRY(jpeg_color_interleave(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint16_t *>(d_out)));
-    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) CU_TRY(ctx, copy_d2h(ctx, out, d_out, bytes, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -457,9 +457,9 @@ static int unpack_host(jpeg_sm100_ctx *ctx, const uint16_t *il, uint64_t n_px, i
     void *d_il = nullptr, *d_out = nullptr;
     J_TRY(scratch_reserve(ctx, 5, n_px * arity * 2 + 64, &d_il));
     J_TRY(scratch_reserve(ctx, 6, n_px * 3 + 64, &d_out));
-    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(d_il, il, n_px * arity * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_px) CU_TRY(ctx, copy_h2d(ctx, d_il, il, n_px * arity * 2, ctx->stream));
     J_TRY(jpeg_color_unpack(ctx, reinterpret_cast<uint16_t *>(d_il), n_px, arity, reinterpret_cast<uint8_t *>(d_out), to_rgb));
-    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n_px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_px) CU_TRY(ctx, copy_d2h(ctx, out, d_out, n_px * 3, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -487,7 +487,7 @@ JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_p
     void        *d_rgb = nullptr;
     J_TRY(scratch_reserve(ctx, 6, bytes + 64, &d_rgb));
     J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
-    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(rgb, d_rgb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) CU_TRY(ctx, copy_d2h(ctx, rgb, d_rgb, bytes, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -634,7 +634,7 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
         uint8_t  *g_ecs;
         uint64_t *g_off = reinterpret_cast<uint64_t *>(d_off) + (uint64_t) g0 * n_ecs + g;  // gn * n_ecs + 1 entries
         if (raw_offsets) {
-            if (b1 > b0) CU_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d_raw) + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
+            if (b1 > b0) CU_TRY(ctx, copy_h2d(ctx, reinterpret_cast<uint8_t *>(d_raw) + b0, bytes + b0, b1 - b0, ctx->stream));
             // the lexer writes the group's unstuffed bytes (never more than the raw ones) to a 16-byte aligned region of its own
             g_ecs = reinterpret_cast<uint8_t *>(d_ecs) + align_up(b0, 16) + 16 * (size_t) g;
             LexPlan plan;
@@ -642,8 +642,8 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
             J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, n_ecs, g_ecs, g_off, d_lex_status + g0));
         } else {
             g_ecs = reinterpret_cast<uint8_t *>(d_ecs);  // offsets stay absolute
-            if (b1 > b0) CU_TRY(ctx, cudaMemcpyAsync(g_ecs + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
-            CU_TRY(ctx, cudaMemcpyAsync(g_off, offsets + (uint64_t) g0 * n_ecs, ((uint64_t) gn * n_ecs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            if (b1 > b0) CU_TRY(ctx, copy_h2d(ctx, g_ecs + b0, bytes + b0, b1 - b0, ctx->stream));
+            CU_TRY(ctx, copy_h2d(ctx, g_off, offsets + (uint64_t) g0 * n_ecs, ((uint64_t) gn * n_ecs + 1) * 8, ctx->stream));
         }
         // ---- entropy decode of the group.  Spectral planes start zeroed (decode.swift:2241-2256): SCAN_FRESH
         jpeg_sm100_dev_spectral spg = sp;
@@ -667,12 +667,12 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
             J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, rgb_buf));
             CU_TRY(ctx, cudaEventRecord(ev_k[k], ctx->stream));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k[k], 0));
-            CU_TRY(ctx, cudaMemcpyAsync(rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CU_TRY(ctx, copy_d2h(ctx, rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, ctx->copy_out));
             CU_TRY(ctx, cudaEventRecord(ev_out[k], ctx->copy_out));
         }
     }
     std::vector<int32_t> st(2 * (size_t) n_images, 0);
-    CU_TRY(ctx, cudaMemcpyAsync(st.data(), d_status, 2 * sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, st.data(), d_status, 2 * sizeof(int32_t) * n_images, ctx->stream));
     // the batch call waits tens of milliseconds for PCIe.  Default: poll the two streams and yield the core between polls (no
     // wake-up latency when cores are free; a blocking-sync event costs ~5 % of the call at N = 1).  JPEG_SM100_WAIT=block sleeps on
     // blocking-sync events instead -- for hosts where many of these calls (one per context / per GPU process) share few cores.
@@ -751,20 +751,20 @@ int lex_one(jpeg_sm100_ctx *ctx, const uint8_t *raw, uint64_t raw_len, uint32_t 
     J_TRY(scratch_reserve(ctx, 5, raw_len + 64, &d_raw));
     J_TRY(scratch_reserve(ctx, 1, raw_len + 64, d_ecs));
     J_TRY(scratch_reserve(ctx, 3, 64, &d_st));
-    if (raw_len) CU_TRY(ctx, cudaMemcpyAsync(d_raw, raw, raw_len, cudaMemcpyHostToDevice, ctx->stream));
+    if (raw_len) CU_TRY(ctx, copy_h2d(ctx, d_raw, raw, raw_len, ctx->stream));
     const uint64_t off0 = 0;
     LexPlan        plan;
     J_TRY(jpeg_lex_count(ctx, reinterpret_cast<uint8_t *>(d_raw), &off0, &raw_len, 1, &plan));
     // the number of segments is data: one 4-byte read-back before the scatter pass can lay out the offsets
     J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, 0, nullptr, nullptr, nullptr));
     uint32_t splits = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&splits, plan.d_n_splits, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, &splits, plan.d_n_splits, 4, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *n_ecs = splits + 1;
     J_TRY(scratch_reserve(ctx, 2, 8 * ((size_t) *n_ecs + 1), d_off));
     J_TRY(jpeg_lex_scatter(ctx, reinterpret_cast<uint8_t *>(d_raw), &plan, *n_ecs, reinterpret_cast<uint8_t *>(*d_ecs),
                            reinterpret_cast<uint64_t *>(*d_off), reinterpret_cast<int32_t *>(d_st)));
-    CU_TRY(ctx, cudaMemcpyAsync(lex_status, d_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, lex_status, d_st, 4, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -780,11 +780,11 @@ JPEG_API int jpeg_sm100_lex_scan(jpeg_sm100_ctx *ctx, const uint8_t *raw, uint64
     J_TRY(lex_one(ctx, raw, raw_len, n_ecs, &d_ecs, &d_off, &st));
     if (st) return st;
     if (offsets_capacity < *n_ecs + 1) return JPEG_SM100_ERR_NO_MEMORY;
-    CU_TRY(ctx, cudaMemcpyAsync(ecs_offsets, d_off, 8 * ((size_t) *n_ecs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, ecs_offsets, d_off, 8 * ((size_t) *n_ecs + 1), ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const uint64_t total = ecs_offsets[*n_ecs];
     if (total > ecs_capacity || (total && !ecs)) return JPEG_SM100_ERR_NO_MEMORY;
-    if (total) CU_TRY(ctx, cudaMemcpyAsync(ecs, d_ecs, total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) CU_TRY(ctx, copy_d2h(ctx, ecs, d_ecs, total, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -816,10 +816,10 @@ JPEG_API int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_sc
     ctx->hint_interval_bytes = 0;
     J_TRY(k3);
     int32_t status = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, copy_d2h(ctx, &status, d_status, sizeof status, ctx->stream));
     for (uint32_t p = 0; p < n_planes; ++p)
         if (ps.bytes[p])
-            CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, copy_d2h(ctx, planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return status;
 }
@@ -832,9 +832,9 @@ JPEG_API int jpeg_sm100_pack_rgb8(jpeg_sm100_ctx *ctx, const uint8_t *rgb, uint6
     void *d_rgb = nullptr, *d_il = nullptr;
     J_TRY(scratch_reserve(ctx, 6, n_px * 3 + 64, &d_rgb));
     J_TRY(scratch_reserve(ctx, 5, n_px * arity * 2 + 64, &d_il));
-    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, n_px * 3, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_px) CU_TRY(ctx, copy_h2d(ctx, d_rgb, rgb, n_px * 3, ctx->stream));
     J_TRY(jpeg_color_pack_rgb(ctx, reinterpret_cast<uint8_t *>(d_rgb), n_px, arity, reinterpret_cast<uint16_t *>(d_il)));
-    if (n_px) CU_TRY(ctx, cudaMemcpyAsync(il, d_il, n_px * arity * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_px) CU_TRY(ctx, copy_d2h(ctx, il, d_il, n_px * arity * 2, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -848,11 +848,11 @@ JPEG_API int jpeg_sm100_decompose(jpeg_sm100_ctx *ctx, const uint16_t *il, uint3
     const size_t bytes = (size_t) sx * sy * n * 2;
     void        *d_il = nullptr;
     J_TRY(scratch_reserve(ctx, 5, bytes + 64, &d_il));
-    if (bytes) CU_TRY(ctx, cudaMemcpyAsync(d_il, il, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) CU_TRY(ctx, copy_h2d(ctx, d_il, il, bytes, ctx->stream));
     J_TRY(jpeg_color_decompose(ctx, d_il, false, sx, sy, &pl));
     for (uint32_t p = 0; p < n; ++p) {
         const size_t pb = (size_t) 128 * planes[p].units_x * planes[p].units_y;
-        if (pb) CU_TRY(ctx, cudaMemcpyAsync(planes[p].samples, pl.plane[p].samples, pb, cudaMemcpyDeviceToHost, ctx->stream));
+        if (pb) CU_TRY(ctx, copy_d2h(ctx, planes[p].samples, pl.plane[p].samples, pb, ctx->stream));
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
@@ -883,7 +883,7 @@ JPEG_API int jpeg_sm100_fdct(jpeg_sm100_ctx *ctx, const uint16_t *samples, uint3
         ps.sp.plane[0].factor_x = ps.sp.plane[0].factor_y = 1;
     }
     J_TRY(jpeg_sm100_dev_fdct(ctx, &pl, quanta, precision, &ps.sp));
-    if (ps.bytes[0]) CU_TRY(ctx, cudaMemcpyAsync(coef, ps.sp.plane[0].coef, ps.bytes[0], cudaMemcpyDeviceToHost, ctx->stream));
+    if (ps.bytes[0]) CU_TRY(ctx, copy_d2h(ctx, coef, ps.sp.plane[0].coef, ps.bytes[0], ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -920,11 +920,11 @@ JPEG_API int jpeg_sm100_rgb8_to_spectral(jpeg_sm100_ctx *ctx, const uint8_t *rgb
     const size_t rgb_bytes = (size_t) sx * sy * 3;
     void        *d_rgb = nullptr;
     J_TRY(scratch_reserve(ctx, 6, rgb_bytes + 64, &d_rgb));
-    if (rgb_bytes) CU_TRY(ctx, cudaMemcpyAsync(d_rgb, rgb, rgb_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (rgb_bytes) CU_TRY(ctx, copy_h2d(ctx, d_rgb, rgb, rgb_bytes, ctx->stream));
     J_TRY(jpeg_color_decompose(ctx, d_rgb, true, sx, sy, &pl));
     J_TRY(jpeg_sm100_dev_fdct(ctx, &pl, quanta, 8, &ps.sp));
     for (uint32_t p = 0; p < n; ++p)
-        if (ps.bytes[p]) CU_TRY(ctx, cudaMemcpyAsync(planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], cudaMemcpyDeviceToHost, ctx->stream));
+        if (ps.bytes[p]) CU_TRY(ctx, copy_d2h(ctx, planes[p].coef, ps.sp.plane[p].coef, ps.bytes[p], ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
 }
@@ -952,7 +952,281 @@ JPEG_API int jpeg_sm100_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     memcpy(ac_out, tables + 4, sizeof(jpeg_sm100_huff_table) * 4);
     *ecs_len = needed;
     if (needed > ecs_capacity) return JPEG_SM100_ERR_NO_MEMORY;
-    if (needed) CU_TRY(ctx, cudaMemcpyAsync(ecs, d_ecs, needed, cudaMemcpyDeviceToHost, ctx->stream));
+    if (needed) CU_TRY(ctx, copy_d2h(ctx, ecs, d_ecs, needed, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
+}
+
+// =====================================================================================================================
+// layer A with the image resident on the device (jpeg_sm100_spectral): JPEG.Context's one Spectral per file, kept in HBM
+// =====================================================================================================================
+struct jpeg_sm100_spectral {
+    uint32_t n_planes = 0;
+    int32_t  ux[4] = {0, 0, 0, 0}, uy[4] = {0, 0, 0, 0};
+    int16_t *coef[4] = {nullptr, nullptr, nullptr, nullptr};  // one allocation, plane p at coef[p]
+    void    *base = nullptr;
+    size_t   bytes = 0;
+};
+
+namespace {
+
+int spectral_layout(uint32_t n, const int32_t *units_xy, size_t off[4], size_t *total)
+{
+    if (n < 1 || n > 4 || !units_xy) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    size_t t = 0;
+    for (uint32_t p = 0; p < n; ++p) {
+        if (units_xy[2 * p] < 0 || units_xy[2 * p + 1] < 0) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        off[p] = t;
+        t += align_up((size_t) 128 * units_xy[2 * p] * units_xy[2 * p + 1], 1024);
+    }
+    *total = t + 1024;
+    return JPEG_SM100_OK;
+}
+
+void spectral_view(const jpeg_sm100_spectral *s, const int32_t *factors, jpeg_sm100_dev_spectral &sp)
+{
+    memset(&sp, 0, sizeof sp);
+    sp.n_images = 1;
+    sp.n_planes = s->n_planes;
+    for (uint32_t p = 0; p < s->n_planes; ++p) {
+        sp.plane[p].coef = s->coef[p];
+        sp.plane[p].image_stride = (uint64_t) 64 * s->ux[p] * s->uy[p];
+        sp.plane[p].units_x = s->ux[p];
+        sp.plane[p].units_y = s->uy[p];
+        sp.plane[p].factor_x = factors ? factors[2 * p] : 1;
+        sp.plane[p].factor_y = factors ? factors[2 * p + 1] : 1;
+    }
+}
+
+}  // namespace
+
+JPEG_API int jpeg_sm100_spectral_create(jpeg_sm100_ctx *ctx, uint32_t n_planes, const int32_t *units_xy, jpeg_sm100_spectral **out)
+{
+    REQUIRE_CTX(ctx);
+    if (!out) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    size_t off[4], total = 0;
+    J_TRY(spectral_layout(n_planes, units_xy, off, &total));
+    jpeg_sm100_spectral *s = new jpeg_sm100_spectral();
+    if (cudaMalloc(&s->base, total) != cudaSuccess) {
+        delete s;
+        cudaGetLastError();
+        return JPEG_SM100_ERR_NO_MEMORY;
+    }
+    s->bytes = total;
+    s->n_planes = n_planes;
+    for (uint32_t p = 0; p < n_planes; ++p) {
+        s->ux[p] = units_xy[2 * p], s->uy[p] = units_xy[2 * p + 1];
+        s->coef[p] = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->base) + off[p]);
+    }
+    const cudaError_t e = cudaMemsetAsync(s->base, 0, total, ctx->stream);  // new Spectral planes are zero (decode.swift:2241-2256)
+    if (e != cudaSuccess) {
+        cudaFree(s->base);
+        delete s;
+        return jpeg_cuda_fail(ctx, e, "cudaMemsetAsync", __FILE__, __LINE__);
+    }
+    *out = s;
+    return JPEG_SM100_OK;
+}
+
+JPEG_API void jpeg_sm100_spectral_destroy(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s)
+{
+    if (!s) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (s->base) cudaFree(s->base);
+    delete s;
+}
+
+JPEG_API int jpeg_sm100_spectral_resize(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const int32_t *units_xy)
+{
+    REQUIRE_CTX(ctx);
+    if (!s) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    size_t off[4], total = 0;
+    J_TRY(spectral_layout(s->n_planes, units_xy, off, &total));
+    void *nb = nullptr;
+    if (cudaMalloc(&nb, total) != cudaSuccess) {
+        cudaGetLastError();
+        return JPEG_SM100_ERR_NO_MEMORY;
+    }
+    CU_TRY(ctx, cudaMemsetAsync(nb, 0, total, ctx->stream));
+    for (uint32_t p = 0; p < s->n_planes; ++p) {
+        const int32_t nx = units_xy[2 * p], ny = units_xy[2 * p + 1];
+        const int32_t cx = nx < s->ux[p] ? nx : s->ux[p], cy = ny < s->uy[p] ? ny : s->uy[p];
+        if (cx > 0 && cy > 0)  // rows of 128-byte blocks: the common region keeps its coefficients (decode.swift:2456-2495)
+            CU_TRY(ctx, cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(nb) + off[p], (size_t) 128 * nx, s->coef[p], (size_t) 128 * s->ux[p],
+                                          (size_t) 128 * cx, cy, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->base);
+    s->base = nb;
+    s->bytes = total;
+    for (uint32_t p = 0; p < s->n_planes; ++p) {
+        s->ux[p] = units_xy[2 * p], s->uy[p] = units_xy[2 * p + 1];
+        s->coef[p] = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(nb) + off[p]);
+    }
+    return JPEG_SM100_OK;
+}
+
+static int spectral_check_planes(const jpeg_sm100_spectral *s, const jpeg_sm100_plane_i16 *planes, uint32_t n)
+{
+    if (!s || !planes || n != s->n_planes) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < n; ++p)
+        if (planes[p].units_x != s->ux[p] || planes[p].units_y != s->uy[p] || ((size_t) s->ux[p] * s->uy[p] && !planes[p].coef))
+            return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_spectral_upload(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_plane_i16 *planes, uint32_t n)
+{
+    REQUIRE_CTX(ctx);
+    J_TRY(spectral_check_planes(s, planes, n));
+    for (uint32_t p = 0; p < n; ++p) {
+        const size_t b = (size_t) 128 * s->ux[p] * s->uy[p];
+        if (b) CU_TRY(ctx, copy_h2d(ctx, s->coef[p], planes[p].coef, b, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_spectral_download(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, jpeg_sm100_plane_i16 *planes, uint32_t n)
+{
+    REQUIRE_CTX(ctx);
+    J_TRY(spectral_check_planes(s, planes, n));
+    for (uint32_t p = 0; p < n; ++p) {
+        const size_t b = (size_t) 128 * s->ux[p] * s->uy[p];
+        if (b) CU_TRY(ctx, copy_d2h(ctx, planes[p].coef, s->coef[p], b, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+static int spectral_decode_common(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan, void *d_ecs, void *d_off,
+                                  uint32_t n_ecs, uint64_t bytes, uint64_t interval, int extend, const jpeg_sm100_huff_table dc[4],
+                                  const jpeg_sm100_huff_table ac[4])
+{
+    void *d_status = nullptr;
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_status));
+    jpeg_sm100_huff_table tables[8];
+    memcpy(tables, dc, sizeof(jpeg_sm100_huff_table) * 4);
+    memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
+    jpeg_sm100_dev_spectral sp;
+    spectral_view(s, nullptr, sp);
+    ctx->hint_interval_bytes = n_ecs ? bytes / n_ecs : 0;
+    const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs, interval,
+                                            extend & (JPEG_SM100_SCAN_EXTEND | JPEG_SM100_SCAN_T81), tables, 1, &sp, reinterpret_cast<int32_t *>(d_status));
+    ctx->hint_interval_bytes = 0;
+    J_TRY(k3);
+    int32_t status = 0;  // the reference throws at the first failing interval: the host needs the verdict before the next scan
+    CU_TRY(ctx, copy_d2h(ctx, &status, d_status, sizeof status, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return status;
+}
+
+JPEG_API int jpeg_sm100_spectral_decode_scan(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                             const uint8_t *ecs_concat, const uint64_t *ecs_offsets, uint32_t n_ecs, uint64_t interval,
+                                             int extend, const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4])
+{
+    REQUIRE_CTX(ctx);
+    if (!s || !scan || !dc || !ac || (n_ecs && !ecs_offsets)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (n_ecs == 0) return JPEG_SM100_OK;
+    if (interval == JPEG_SM100_INTERVAL_NONE) n_ecs = 1;  // decode.swift:3500: the stride yields one element
+    const uint64_t total = ecs_offsets[n_ecs];
+    void          *d_ecs = nullptr, *d_off = nullptr;
+    J_TRY(scratch_reserve(ctx, 1, total + 64, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 2, sizeof(uint64_t) * ((size_t) n_ecs + 1), &d_off));
+    if (total) CU_TRY(ctx, copy_h2d(ctx, d_ecs, ecs_concat, total, ctx->stream));
+    CU_TRY(ctx, copy_h2d(ctx, d_off, ecs_offsets, sizeof(uint64_t) * ((size_t) n_ecs + 1), ctx->stream));
+    return spectral_decode_common(ctx, s, scan, d_ecs, d_off, n_ecs, total, interval, extend, dc, ac);
+}
+
+JPEG_API int jpeg_sm100_spectral_decode_scan_raw(jpeg_sm100_ctx *ctx, jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                                 const uint8_t *raw, uint64_t raw_len, uint64_t interval, int extend,
+                                                 const jpeg_sm100_huff_table dc[4], const jpeg_sm100_huff_table ac[4])
+{
+    REQUIRE_CTX(ctx);
+    if (!s || !scan || !dc || !ac || (!raw && raw_len)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    void    *d_ecs = nullptr, *d_off = nullptr;
+    uint32_t n_ecs = 0;
+    int32_t  st = 0;
+    J_TRY(lex_one(ctx, raw, raw_len, &n_ecs, &d_ecs, &d_off, &st));
+    if (st) return st;
+    if (interval == JPEG_SM100_INTERVAL_NONE) {
+        if (n_ecs > 1) return JPEG_SM100_ERR_MISSING_INTERVAL;  // decode.swift:3708-3720
+        n_ecs = 1;
+    }
+    return spectral_decode_common(ctx, s, scan, d_ecs, d_off, n_ecs, raw_len, interval, extend, dc, ac);
+}
+
+JPEG_API int jpeg_sm100_spectral_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const jpeg_sm100_scan_desc *scan,
+                                             uint64_t interval_mcus, jpeg_sm100_huff_table dc_out[4], jpeg_sm100_huff_table ac_out[4],
+                                             uint8_t *ecs, uint64_t ecs_capacity, uint64_t *ecs_len)
+{
+    REQUIRE_CTX(ctx);
+    if (!s || !scan || !dc_out || !ac_out || !ecs_len) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_dev_spectral sp;
+    spectral_view(s, nullptr, sp);
+    uint64_t blocks = 0;
+    for (uint32_t p = 0; p < s->n_planes; ++p) blocks += (uint64_t) (s->ux[p] + 4) * (s->uy[p] + 4);
+    const uint64_t cap = blocks * 64 * 8 + 4096;
+    void          *d_ecs = nullptr, *d_len = nullptr;
+    J_TRY(scratch_reserve(ctx, 1, cap, &d_ecs));
+    J_TRY(scratch_reserve(ctx, 3, 64, &d_len));
+    jpeg_sm100_huff_table tables[8];
+    uint64_t              needed = 0;
+    J_TRY(jpeg_huffman_encode_scan(ctx, scan, &sp, interval_mcus, tables, reinterpret_cast<uint8_t *>(d_ecs), cap,
+                                   reinterpret_cast<uint64_t *>(d_len), &needed));
+    memcpy(dc_out, tables, sizeof(jpeg_sm100_huff_table) * 4);
+    memcpy(ac_out, tables + 4, sizeof(jpeg_sm100_huff_table) * 4);
+    *ecs_len = needed;
+    if (needed > ecs_capacity) return JPEG_SM100_ERR_NO_MEMORY;
+    if (needed) CU_TRY(ctx, copy_d2h(ctx, ecs, d_ecs, needed, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_spectral_idct(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const uint16_t *quanta, int precision,
+                                      jpeg_sm100_plane_u16 *planes, uint32_t n)
+{
+    REQUIRE_CTX(ctx);
+    if (!s || !quanta || !planes || n != s->n_planes) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_dev_spectral sp;
+    spectral_view(s, nullptr, sp);
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, sp, 2, pl));
+    J_TRY(jpeg_sm100_dev_idct(ctx, &sp, quanta, precision, &pl));
+    for (uint32_t p = 0; p < n; ++p) {
+        if (planes[p].units_x != s->ux[p] || planes[p].units_y != s->uy[p]) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+        const size_t b = (size_t) 128 * s->ux[p] * s->uy[p];
+        if (b && planes[p].samples) CU_TRY(ctx, copy_d2h(ctx, planes[p].samples, pl.plane[p].samples, b, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API int jpeg_sm100_spectral_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_spectral *s, const uint16_t *quanta, const int32_t *factors,
+                                      uint32_t sx, uint32_t sy, int cosited, uint8_t *rgb)
+{
+    REQUIRE_CTX(ctx);
+    if (!s || !quanta || !factors || (s->n_planes != 1 && s->n_planes != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    jpeg_sm100_dev_spectral sp;
+    spectral_view(s, factors, sp);
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, sp, 1, pl));
+    J_TRY(jpeg_sm100_dev_idct(ctx, &sp, quanta, 8, &pl));
+    const size_t bytes = (size_t) sx * sy * 3;
+    void        *d_rgb = nullptr;
+    J_TRY(scratch_reserve(ctx, 6, bytes + 64, &d_rgb));
+    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
+    if (bytes) CU_TRY(ctx, copy_d2h(ctx, rgb, d_rgb, bytes, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return JPEG_SM100_OK;
+}
+
+JPEG_API void jpeg_sm100_transfer_counts(jpeg_sm100_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
+{
+    if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+    if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
 }

@@ -33,6 +33,7 @@ struct jpeg_sm100_ctx {
     bool         owns_stream = false;
     int          sm_count = 148;
     uint64_t     launches = 0;
+    uint64_t     h2d_bytes = 0, d2h_bytes = 0;  // layer A bookkeeping (jpeg_sm100_transfer_counts)
     std::string  last_error;
     // grow-only scratch used by layer A (host-buffer entry points)
     DeviceBuffer scratch[16];
@@ -76,6 +77,18 @@ static inline int jpeg_cuda_fail(jpeg_sm100_ctx *ctx, cudaError_t e, const char 
         (ctx)->launches += 1;                                                                                        \
         CU_TRY((ctx), cudaGetLastError());                                                                           \
     } while (0)
+
+// host <-> device copies of layer A, counted
+static inline cudaError_t copy_h2d(jpeg_sm100_ctx *ctx, void *dst, const void *src, size_t n, cudaStream_t st)
+{
+    ctx->h2d_bytes += n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+}
+static inline cudaError_t copy_d2h(jpeg_sm100_ctx *ctx, void *dst, const void *src, size_t n, cudaStream_t st)
+{
+    ctx->d2h_bytes += n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+}
 
 static inline int scratch_reserve(jpeg_sm100_ctx *ctx, int slot, size_t bytes, void **out)
 {

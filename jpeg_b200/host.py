@@ -44,6 +44,12 @@ def units(size, stride):
 _ctx = None
 
 
+def transfer_stats(s):
+    """host <-> device traffic of a device-resident Spectral's context since the Spectral was created (bytes)"""
+    a, b = s.ctx.transfers
+    return {"h2d_bytes": a - s._transfers0[0], "d2h_bytes": b - s._transfers0[1]}
+
+
 def default_context():
     global _ctx
     if _ctx is None:
@@ -118,13 +124,24 @@ class Format:
         return sorted(keys) == sorted(self.components) and precision == self.precision
 
 
-@dataclass
 class SpectralPlane:
-    units: tuple
-    factor: tuple
-    coef: np.ndarray  # int16 (uy, ux, 64)
-    q: int = 0        # index into Spectral.quanta
-    comp_id: int = 0
+    """JPEG.Data.Spectral.Plane: units, sampling factor, coefficients int16 (uy, ux, 64), index into Spectral.quanta.
+    In a device-resident Spectral the coefficients live in HBM; `coef` materialises the host copy on first use."""
+
+    def __init__(self, units, factor, coef, q=0, comp_id=0, owner=None):
+        self.units, self.factor, self._coef, self.q, self.comp_id, self._owner = units, factor, coef, q, comp_id, owner
+
+    @property
+    def coef(self):
+        if self._owner is not None:
+            self._owner._materialize()
+        return self._coef
+
+    @coef.setter
+    def coef(self, value):
+        if self._owner is not None and self._owner.resident:
+            raise ValueError("the coefficients of a device-resident Spectral are read-only on the host")
+        self._coef = value
 
 
 @dataclass
@@ -137,24 +154,66 @@ class Scan:
 class Spectral:
     """JPEG.Data.Spectral<JPEG.Common> (decode.swift:1397-1519)."""
 
-    def __init__(self, size, factors, comp_ids=None, process=0, ctx=None, precision=8):
+    def __init__(self, size, factors, comp_ids=None, process=0, ctx=None, precision=8, resident=False):
+        """resident: keep the coefficient planes in HBM (a jpeg_sm100_spectral handle) across scans and stages -- what
+        JPEG.Context does with its one Spectral per file (decode.swift:3565-3587); host planes are materialised on demand."""
         self.ctx = ctx or default_context()
         self.process = process
         self.precision = precision  # Format.precision: 8 for JPEG.Common, up to 16 for user-defined formats
         self.scale = (max(f[0] for f in factors), max(f[1] for f in factors))
         self.quanta = [np.zeros(64, dtype=np.uint16)]
+        self.resident, self._handle, self._host_valid = bool(resident), None, True
         self.planes = [SpectralPlane((0, 0), tuple(f), np.zeros((0, 0, 64), np.int16), 0,
-                                     (comp_ids[i] if comp_ids else i + 1)) for i, f in enumerate(factors)]
+                                     (comp_ids[i] if comp_ids else i + 1), self if resident else None) for i, f in enumerate(factors)]
         self.size = (0, 0)
         self.blocks = (0, 0)
         self.scans: list[Scan] = []
+        self._transfers0 = self.ctx.transfers if resident else (0, 0)
         self.set_size(size)
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                self.ctx.L.jpeg_sm100_spectral_destroy(self.ctx.h, self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _units_array(self):
+        return np.array([v for p in self.planes for v in p.units], dtype=np.int32)
+
+    def _materialize(self):
+        """device-resident: bring the coefficient planes to the host (once per change on the device)"""
+        if not self.resident or self._host_valid:
+            return
+        for p in self.planes:
+            p._coef = np.zeros((p.units[1], p.units[0], 64), dtype=np.int16)
+        arr = (L.PlaneI16 * len(self.planes))()
+        for i, p in enumerate(self.planes):
+            arr[i].coef = p._coef.ctypes.data if p._coef.size else None
+            arr[i].units_x, arr[i].units_y = p.units
+        self.ctx.check(self.ctx.L.jpeg_sm100_spectral_download(self.ctx.h, self._handle, arr, len(self.planes)))
+        for p in self.planes:
+            p._coef.setflags(write=False)
+        self._host_valid = True
 
     # decode.swift:2456-2495 set(width:) / set(height:)
     def set_size(self, size):
         w, h = size
         self.size = (w, h)
         self.blocks = (units(w, 8 * self.scale[0]), units(h, 8 * self.scale[1]))
+        if self.resident:
+            for p in self.planes:
+                p.units = (units(w * p.factor[0], 8 * self.scale[0]), units(h * p.factor[1], 8 * self.scale[1]))
+            u = self._units_array()
+            if self._handle is None:
+                h_ = C.c_void_p()
+                self.ctx.check(self.ctx.L.jpeg_sm100_spectral_create(self.ctx.h, len(self.planes), _ptr(u), C.byref(h_)))
+                self._handle = h_
+            else:
+                self.ctx.check(self.ctx.L.jpeg_sm100_spectral_resize(self.ctx.h, self._handle, _ptr(u)))
+            self._host_valid = False
+            return
         for p in self.planes:
             ux, uy = units(w * p.factor[0], 8 * self.scale[0]), units(h * p.factor[1], 8 * self.scale[1])
             new = np.zeros((uy, ux, 64), dtype=np.int16)
@@ -197,6 +256,12 @@ class Spectral:
         dcs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in dc_tables])
         acs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in ac_tables])
         desc = self.scan_desc(band, bits, comps)
+        if self.resident:
+            rc = self.ctx.L.jpeg_sm100_spectral_decode_scan(self.ctx.h, self._handle, C.byref(desc), _ptr(buf), _ptr(offs), len(ecss),
+                                                            L.INTERVAL_NONE if interval is None else interval, int(extend), dcs, acs)
+            self._host_valid = False
+            self.ctx.check(rc)
+            return
         planes = self._plane_structs()
         rc = self.ctx.L.jpeg_sm100_decode_scan(self.ctx.h, C.byref(desc), _ptr(buf), _ptr(offs), len(ecss),
                                                L.INTERVAL_NONE if interval is None else interval, int(extend),
@@ -210,6 +275,12 @@ class Spectral:
         dcs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in dc_tables])
         acs = (L.HuffTable * 4)(*[t if t is not None else L.HuffTable() for t in ac_tables])
         desc = self.scan_desc(band, bits, comps)
+        if self.resident:
+            rc = self.ctx.L.jpeg_sm100_spectral_decode_scan_raw(self.ctx.h, self._handle, C.byref(desc), _ptr(buf), len(raw),
+                                                                L.INTERVAL_NONE if interval is None else interval, int(extend), dcs, acs)
+            self._host_valid = False
+            self.ctx.check(rc)
+            return
         planes = self._plane_structs()
         rc = self.ctx.L.jpeg_sm100_decode_scan_raw(self.ctx.h, C.byref(desc), _ptr(buf), len(raw),
                                                    L.INTERVAL_NONE if interval is None else interval, int(extend),
@@ -219,20 +290,34 @@ class Spectral:
     def encode_scan(self, band, bits, comps, interval_mcus=0):
         """Spectral.encode(scan:) encode.swift:1559 -> jpeg_sm100_encode_scan.  Returns (ecs, dc[4], ac[4])."""
         desc = self.scan_desc(band, bits, comps)
-        planes = self._plane_structs()
         dcs, acs = (L.HuffTable * 4)(), (L.HuffTable * 4)()
-        cap = sum(p.coef.size for p in self.planes) * 4 + 4096
+        cap = sum(64 * p.units[0] * p.units[1] for p in self.planes) * 4 + 4096
         out = np.zeros(cap, dtype=np.uint8)
         n = C.c_uint64()
-        rc = self.ctx.L.jpeg_sm100_encode_scan(self.ctx.h, C.byref(desc), planes, len(self.planes), interval_mcus,
-                                               dcs, acs, _ptr(out), cap, C.byref(n))
+        if self.resident:
+            rc = self.ctx.L.jpeg_sm100_spectral_encode_scan(self.ctx.h, self._handle, C.byref(desc), interval_mcus, dcs, acs,
+                                                            _ptr(out), cap, C.byref(n))
+        else:
+            planes = self._plane_structs()
+            rc = self.ctx.L.jpeg_sm100_encode_scan(self.ctx.h, C.byref(desc), planes, len(self.planes), interval_mcus,
+                                                   dcs, acs, _ptr(out), cap, C.byref(n))
         self.ctx.check(rc)
         return out[:n.value].tobytes(), list(dcs), list(acs)
 
     # ---- transform stages ----------------------------------------------------------------------------------
     def idct(self):
-        """Spectral.idct() decode.swift:4154 -> jpeg_sm100_idct per plane."""
+        """Spectral.idct() decode.swift:4154 -> jpeg_sm100_idct per plane (one call on the resident image)."""
         out = []
+        if self.resident:
+            arr = (L.PlaneU16 * len(self.planes))()
+            for i, p in enumerate(self.planes):
+                out.append(np.zeros((8 * p.units[1], 8 * p.units[0]), dtype=np.uint16))
+                arr[i].samples = out[i].ctypes.data if out[i].size else None
+                arr[i].units_x, arr[i].units_y = p.units
+                arr[i].factor_x, arr[i].factor_y = p.factor
+            q = np.ascontiguousarray(np.stack([self.quanta[p.q] for p in self.planes]), dtype=np.uint16)
+            self.ctx.check(self.ctx.L.jpeg_sm100_spectral_idct(self.ctx.h, self._handle, _ptr(q), self.precision, arr, len(self.planes)))
+            return Planar(self.size, [p.units for p in self.planes], [p.factor for p in self.planes], out, self.ctx, self.precision)
         for p in self.planes:
             ux, uy = p.units
             s = np.zeros((8 * uy, 8 * ux), dtype=np.uint16)
@@ -257,11 +342,15 @@ class Spectral:
         return out
 
     def to_rgb8(self, cosited=False):
-        """Fused Spectral -> RGB8 (jpeg_sm100_spectral_to_rgb8)."""
-        planes = self._plane_structs()
+        """Fused Spectral -> RGB8 (jpeg_sm100_spectral_to_rgb8; jpeg_sm100_spectral_rgb8 on the resident image)."""
         q = np.ascontiguousarray(np.stack([self.quanta[p.q] for p in self.planes]), dtype=np.uint16)
         f = np.array([v for p in self.planes for v in p.factor], dtype=np.int32)
         rgb = np.zeros((self.size[1], self.size[0], 3), dtype=np.uint8)
+        if self.resident:
+            self.ctx.check(self.ctx.L.jpeg_sm100_spectral_rgb8(self.ctx.h, self._handle, _ptr(q), _ptr(f), self.size[0], self.size[1],
+                                                               int(cosited), _ptr(rgb)))
+            return rgb
+        planes = self._plane_structs()
         self.ctx.check(self.ctx.L.jpeg_sm100_spectral_to_rgb8(self.ctx.h, planes, len(self.planes), _ptr(q), _ptr(f),
                                                               self.size[0], self.size[1], int(cosited), _ptr(rgb)))
         return rgb
@@ -327,10 +416,11 @@ class Spectral:
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod
-    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None, on_scan=None):
+    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None, on_scan=None, resident=False):
         """on_scan(spectral, scan): called after every scan with the image as JPEG.Context holds it at that point -- the
-        capture closure of examples/decode-online/main.swift:252-282 (online / progressive display)."""
-        return _decompress(data, ctx or default_context(), gpu_lexer, format, on_scan)
+        capture closure of examples/decode-online/main.swift:252-282 (online / progressive display).
+        resident: the image stays in HBM across its scans and stages (see __init__)."""
+        return _decompress(data, ctx or default_context(), gpu_lexer, format, on_scan, resident)
 
     def compress(self, scans=None, quanta_slots=None, interval_mcus=0, jfif=True):
         return _compress(self, scans, quanta_slots, interval_mcus, jfif)
@@ -533,7 +623,7 @@ def _push_quanta(s, qslot, tables):
         qslot[tgt] = len(s.quanta) - 1
 
 
-def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None):
+def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None, resident=False):
     lx = _Lexer(bytes(data))
     _, m, body = lx.segment()
     if m != 0xD8:
@@ -594,7 +684,7 @@ def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None):
         if precision != 8 or not (len(comps) == 1 or (len(comps) == 3 and comps[1][0] == comps[0][0] + 1
                                                       and comps[2][0] == comps[0][0] + 2)):
             raise DecodingError("unrecognizedColorFormat")
-    s = Spectral((fw, fh), [(c[1], c[2]) for c in comps], [c[0] for c in comps], process, ctx, precision)
+    s = Spectral((fw, fh), [(c[1], c[2]) for c in comps], [c[0] for c in comps], process, ctx, precision, resident)
     qsel = {c[0]: c[3] for c in comps}
     _push_quanta(s, qslot, pend_q)
     approx = [[None] * 64 for _ in comps]  # Progression, jpeg.swift:1581-1634

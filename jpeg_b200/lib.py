@@ -12,6 +12,7 @@ INTERVAL_NONE = (1 << 64) - 1
 BITS_MAX = -1
 SCAN_EXTEND = 1  # bits of the `extend` argument of the decode_scan entry points
 SCAN_FRESH = 2
+SCAN_T81 = 4
 
 OK = 0
 ERR_TRUNCATED_ECS = -1
@@ -144,6 +145,17 @@ SYMBOLS = {
     "jpeg_sm100_transform_blocks": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _u32]),
     "jpeg_sm100_dev_requantize": (_i, [_vp, C.POINTER(DevSpectral), _vp, _vp, C.POINTER(DevSpectral)]),
     "jpeg_sm100_dev_transform_blocks": (_i, [_vp, C.POINTER(DevSpectral), _vp, _vp, _vp, C.POINTER(DevSpectral)]),
+    "jpeg_sm100_spectral_create": (_i, [_vp, _u32, _vp, C.POINTER(_vp)]),
+    "jpeg_sm100_spectral_destroy": (None, [_vp, _vp]),
+    "jpeg_sm100_spectral_resize": (_i, [_vp, _vp, _vp]),
+    "jpeg_sm100_spectral_upload": (_i, [_vp, _vp, C.POINTER(PlaneI16), _u32]),
+    "jpeg_sm100_spectral_download": (_i, [_vp, _vp, C.POINTER(PlaneI16), _u32]),
+    "jpeg_sm100_spectral_decode_scan": (_i, [_vp, _vp, _SD, _vp, _vp, _u32, _u64, _i, _HT, _HT]),
+    "jpeg_sm100_spectral_decode_scan_raw": (_i, [_vp, _vp, _SD, _vp, _u64, _u64, _i, _HT, _HT]),
+    "jpeg_sm100_spectral_encode_scan": (_i, [_vp, _vp, _SD, _u64, _HT, _HT, _vp, _u64, C.POINTER(_u64)]),
+    "jpeg_sm100_spectral_idct": (_i, [_vp, _vp, _vp, _i, C.POINTER(PlaneU16), _u32]),
+    "jpeg_sm100_spectral_rgb8": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _i, _vp]),
+    "jpeg_sm100_transfer_counts": (None, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
 }
 
 _lib = None
@@ -203,3 +215,10 @@ class Context:
     @property
     def launches(self):
         return int(self.L.jpeg_sm100_launch_count(self.h))
+
+    @property
+    def transfers(self):
+        """(bytes host -> device, bytes device -> host) moved by the layer-A calls of this context so far"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.L.jpeg_sm100_transfer_counts(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)

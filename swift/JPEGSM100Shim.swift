@@ -247,6 +247,129 @@ extension JPEG.RGB
     }
 }
 
+// MARK: the image resident on the device
+//
+// JPEG.Context keeps ONE Spectral for the whole file and pushes every scan into it (decode.swift:3565-3587, 3706-3725).  With the
+// per-call seams above every scan uploads and downloads all planes; with a resident image only the scan's bytes travel, the
+// stages read the planes where they are, and the host planes are materialised once, on demand.  `Spectral` gains ONE stored
+// property, `var device:JPEG.SM100.Resident?` (a final class: value-type copies of a Spectral share it, copy-on-write is
+// restored by `isKnownUniquelyReferenced` in the mutating paths), created by `Spectral.init(layout:)` when a context exists.
+extension JPEG.SM100
+{
+    final class Resident
+    {
+        let handle:OpaquePointer
+        var hostIsCurrent:Bool = true     // the Swift planes equal the device planes (true right after creation: all zero)
+        init(units:[(x:Int, y:Int)]) throws
+        {
+            var handle:OpaquePointer?
+            let flat:[Int32] = units.flatMap{ [Int32.init($0.x), Int32.init($0.y)] }
+            try JPEG.SM100.check(jpeg_sm100_spectral_create(JPEG.SM100.shared.ctx, .init(units.count), flat, &handle))
+            self.handle = handle!
+        }
+        deinit
+        {
+            jpeg_sm100_spectral_destroy(JPEG.SM100.shared.ctx, self.handle)
+        }
+    }
+}
+extension JPEG.Data.Spectral
+{
+    /// decode(ecss:interval:scan:tables:extend:) into the resident image; `descriptor`, `flat`, `offsets`, `dc`, `ac` built as in
+    /// sm100Decode above.  The Swift planes go stale (`hostIsCurrent = false`) instead of being rewritten.
+    mutating
+    func sm100DecodeResident(_ device:JPEG.SM100.Resident, descriptor:inout jpeg_sm100_scan_desc, flat:[UInt8], offsets:[UInt64],
+        interval:Int, extend:Bool, dc:[jpeg_sm100_huff_table], ac:[jpeg_sm100_huff_table]) throws
+    {
+        device.hostIsCurrent = false
+        try JPEG.SM100.check(jpeg_sm100_spectral_decode_scan(JPEG.SM100.shared.ctx, device.handle, &descriptor,
+            flat, offsets, .init(offsets.count - 1), interval == .max ? UInt64.max : .init(interval), extend ? 1 : 0, dc, ac))
+    }
+    /// Spectral.set(width:) / set(height:) (decode.swift:2456-2495), e.g. Context.push(height:) after a DNL segment
+    mutating
+    func sm100Resize(_ device:JPEG.SM100.Resident, units:[(x:Int, y:Int)]) throws
+    {
+        let flat:[Int32] = units.flatMap{ [Int32.init($0.x), Int32.init($0.y)] }
+        try JPEG.SM100.check(jpeg_sm100_spectral_resize(JPEG.SM100.shared.ctx, device.handle, flat))
+    }
+    /// called by every accessor of `Plane.buffer` (subscripts, with(ci:), serialisation) before it reads the Swift planes
+    mutating
+    func sm100Materialize(_ device:JPEG.SM100.Resident) throws
+    {
+        guard !device.hostIsCurrent
+        else
+        {
+            return
+        }
+        var buffers:[[Int16]] = self.indices.map{ .init(repeating: 0, count: 64 * self[$0].units.x * self[$0].units.y) }
+        var planes:[jpeg_sm100_plane_i16] = self.indices.map
+        {
+            .init(coef: nil, units_x: .init(self[$0].units.x), units_y: .init(self[$0].units.y))
+        }
+        try JPEG.SM100.withPointers(&buffers, &planes)
+        {
+            try JPEG.SM100.check(jpeg_sm100_spectral_download(JPEG.SM100.shared.ctx, device.handle, $0, .init(planes.count)))
+        }
+        for p:Int in self.indices
+        {
+            self[p].set(values: buffers[p], units: self[p].units)
+        }
+        device.hostIsCurrent = true
+    }
+    /// Spectral.idct() (decode.swift:4154) on the resident image: one call, the sample planes come back, the coefficients stay
+    func sm100IDCTResident(_ device:JPEG.SM100.Resident, quanta:[UInt16], precision:Int,
+        planes:inout [jpeg_sm100_plane_u16]) throws
+    {
+        try JPEG.SM100.check(jpeg_sm100_spectral_idct(JPEG.SM100.shared.ctx, device.handle, quanta, .init(precision),
+            &planes, .init(planes.count)))
+    }
+    /// idct().interleaved(cosite:).unpack(as: RGB.self) on the resident image: one download of 3 bytes per pixel
+    func sm100RGBResident(_ device:JPEG.SM100.Resident, quanta:[UInt16], factors:[Int32], cosite cosited:Bool) throws -> [JPEG.RGB]
+    {
+        let pixels:Int = self.size.x * self.size.y
+        return try .init(unsafeUninitializedCapacity: pixels)
+        {
+            (rgb:inout UnsafeMutableBufferPointer<JPEG.RGB>, initialized:inout Int) in
+            try rgb.withMemoryRebound(to: UInt8.self)
+            {
+                try JPEG.SM100.check(jpeg_sm100_spectral_rgb8(JPEG.SM100.shared.ctx, device.handle, quanta, factors,
+                    .init(self.size.x), .init(self.size.y), cosited ? 1 : 0, $0.baseAddress))
+            }
+            initialized = pixels
+        }
+    }
+    /// Spectral.encode(scan:) (encode.swift:1559) from the resident image (after sm100Upload if the Swift planes were edited)
+    func sm100EncodeResident(_ device:JPEG.SM100.Resident, descriptor:inout jpeg_sm100_scan_desc,
+        dc:inout [jpeg_sm100_huff_table], ac:inout [jpeg_sm100_huff_table], ecs:inout [UInt8]) throws -> Int
+    {
+        var length:UInt64 = 0
+        try JPEG.SM100.check(jpeg_sm100_spectral_encode_scan(JPEG.SM100.shared.ctx, device.handle, &descriptor, 0,
+            &dc, &ac, &ecs, .init(ecs.count), &length))
+        return .init(length)
+    }
+    /// Swift planes -> device, after the host edited coefficients (subscript setters mark the resident copy stale)
+    mutating
+    func sm100Upload(_ device:JPEG.SM100.Resident) throws
+    {
+        var buffers:[[Int16]] = self.indices.map{ self[$0].takeBuffer() }
+        defer
+        {
+            for p:Int in self.indices
+            {
+                self[p].set(values: buffers[p], units: self[p].units)
+            }
+        }
+        var planes:[jpeg_sm100_plane_i16] = self.indices.map
+        {
+            .init(coef: nil, units_x: .init(self[$0].units.x), units_y: .init(self[$0].units.y))
+        }
+        try JPEG.SM100.withPointers(&buffers, &planes)
+        {
+            try JPEG.SM100.check(jpeg_sm100_spectral_upload(JPEG.SM100.shared.ctx, device.handle, $0, .init(planes.count)))
+        }
+    }
+}
+
 // MARK: spectral-domain operations (N3)
 //
 // The reference has no library function for these: examples/recompress/main.swift:35-58 and examples/rotate/main.swift:164-190

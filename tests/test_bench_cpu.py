@@ -27,13 +27,13 @@ def test_bench_quanta_equal_the_oracles(level):
 
 def test_reference_arm_prints_the_contract_line():
     """bench.py --impl reference: the reference's CPU path (restated oracle) on a bounded sample; one JSON line."""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "8"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     b = _bench()
     assert d["impl"] == "reference" and d["metric"] == b.METRIC and d["unit"] == "Mpixels/s" and d["higher_is_better"] is True
-    assert d["config"]["workload"] == b.WORKLOAD and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"] == b.base_config(8) and d["value"] > 0 and d["n_gpus"] == 1  # the same object our arm prints
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -64,6 +64,56 @@ def test_golden_files_through_gpu(manifest, H, O):
         assert sha(s.to_rgb8().tobytes()) == v["rgb_sha256"], (v["jpeg"], "fused")
 
 
+def test_resident_spectral_through_gpu(manifest, H, O):
+    """The image kept in HBM across scans and stages (jpeg_sm100_spectral, what JPEG.Context does with its one Spectral per
+    file, decode.swift:3565-3587): same coefficients, planes and pixels as the oracle; only scan bytes go up, only status words
+    come down until a stage result is asked for; the host planes materialise on demand and are read-only."""
+    files = [v for v in manifest["decode"]] + [{"jpeg": r} for r in manifest["restart"]]
+    for v in files:
+        data = golden_bytes(v["jpeg"])
+        ref = O.Spectral.decompress(data)
+        for gpu_lexer in (False, True):
+            s = H.Spectral.decompress(data, resident=True, gpu_lexer=gpu_lexer)
+            t = H.transfer_stats(s)
+            assert t["h2d_bytes"] <= len(data) + 64 * 1024, (v["jpeg"], t)      # scan bytes (+ offsets, table sets)
+            assert t["d2h_bytes"] <= 64 * (len(s.scans) + 1), (v["jpeg"], t)    # one status word per scan (+ the lexer's counts)
+            rgb = s.to_rgb8()
+            assert np.array_equal(rgb, O.unpack_rgb(ref.to_rectangular())), v["jpeg"]
+            if "rgb_sha256" in v:
+                assert sha(rgb.tobytes()) == v["rgb_sha256"], v["jpeg"]
+            assert H.transfer_stats(s)["d2h_bytes"] - t["d2h_bytes"] == rgb.size                 # exactly the pixels
+            for a, b in zip(s.idct().planes, ref.idct()):
+                assert np.array_equal(a, b), v["jpeg"]
+            for p in range(s.ncomp):
+                assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (v["jpeg"], p)   # materialised here, once
+            with pytest.raises(ValueError):
+                s.planes[0].coef[0, 0, 0] = 1
+            with pytest.raises(ValueError):
+                s.planes[0].coef = np.zeros(1)
+            # the first scan re-encoded from the resident image and from host planes: the same bytes and tables
+            sc = s.scans[0]
+            host_side = H.Spectral(s.size, [p.factor for p in s.planes], process=s.process)
+            for p in range(s.ncomp):
+                host_side.planes[p].coef = np.array(s.planes[p].coef)
+            got, want = s.encode_scan(sc.band, sc.bits, sc.comps), host_side.encode_scan(sc.band, sc.bits, sc.comps)
+            assert got[0] == want[0] and [t_.as_tuple() for t_ in got[1] + got[2]] == [t_.as_tuple() for t_ in want[1] + want[2]]
+    # DNL: the resident image is resized on the device (Spectral.set(height:), decode.swift:2484-2495)
+    data = golden_bytes("gold/color-sequential-1.jpg")
+    h = O.Spectral.decompress(data).size[1]
+    for fh, dh in ((0, h), (h, h - 21), (h, h + 40)):
+        mod = J.with_dnl(data, fh, dh)
+        s, ref = H.Spectral.decompress(mod, resident=True), O.Spectral.decompress(mod)
+        assert s.size == ref.size
+        for p in range(s.ncomp):
+            assert np.array_equal(s.planes[p].coef, ref.coefficients(p)), (fh, dh, p)
+    s = H.Spectral.decompress(data, resident=True)
+    s.set_size((s.size[0], s.size[1] - 100))                       # after the scans: crop on the device, the rest intact
+    ref = O.Spectral.decompress(data)
+    for p in range(s.ncomp):
+        uy = s.planes[p].units[1]
+        assert np.array_equal(s.planes[p].coef, ref.coefficients(p)[:uy]), p
+
+
 def test_restart_files_through_gpu(manifest, H, O):
     for rel in manifest["restart"]:
         data = golden_bytes(rel)
