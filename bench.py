@@ -27,7 +27,6 @@ import os
 import statistics
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -184,22 +183,19 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
-def nccl_banner_to_stderr(path):
-    """NCCL's own init lines (nranks, transport) were written to NCCL_DEBUG_FILE so that stdout carries exactly one JSON line;
-    repeat the informative ones on stderr for the record"""
-    try:
-        seen = 0
-        for name in sorted(os.listdir(os.path.dirname(path))):
-            if not name.startswith(os.path.basename(path)):
-                continue
-            with open(os.path.join(os.path.dirname(path), name), errors="replace") as f:
-                for l in f:
-                    if ("nranks" in l or "Init COMPLETE" in l or "NCCL version" in l or "Connected" in l) and seen < 40:
-                        sys.stderr.write(l if l.endswith("\n") else l + "\n")
-                        seen += 1
-        sys.stderr.flush()
-    except Exception:
-        pass
+class StdoutGuard:
+    """Rank 0 prints exactly ONE line on stdout.  NCCL's init report (NCCL_DEBUG=INFO: nranks, transports -- the record that the
+    job really ran on N ranks) and any other library chatter go to file descriptor 1 as well, so for the duration of the run
+    fd 1 is pointed at stderr and the JSON line is written to the saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
 
 
 def run_ours(args):
@@ -215,17 +211,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     placement = "unchanged (single rank)"
-    nccl_log = None
+    out = StdoutGuard()
     if world > 1:
         # one process per GPU: keep the rank's threads and pinned staging buffers on the GPU's own NUMA node (best effort)
         if os.environ.get("JPEG_SM100_NUMA", "1") != "0":
             from jpeg_b200 import affinity
             placement = affinity.bind_to_gpu(local)
-        # NCCL's init report goes to a file (rank 0 prints exactly one JSON line on stdout) and is repeated on stderr afterwards
-        nccl_log = os.path.join(tempfile.gettempdir(), f"jpeg_sm100_nccl_{os.environ.get('MASTER_PORT', '0')}")
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")  # the init report (on stderr, see StdoutGuard)
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ["NCCL_DEBUG_FILE"] = nccl_log + ".%h.%p"
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     ctx = lib.Context(local, stream=stream.cuda_stream)
@@ -239,8 +232,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     barrier()  # (the first collective: NCCL finishes its init here)
-    if nccl_log and rank == 0:
-        nccl_banner_to_stderr(nccl_log)
 
     # ---- inputs: synthetic frames -> our GPU encoder -> (host) lexer ------------------------------------------------
     ecs_all, tables_all = [], []
@@ -324,10 +315,10 @@ def run_ours(args):
 
         def report(ms, stages):
             if rank == 0:
-                print(json.dumps({"quick": True, "tag": os.environ.get("JPEG_SM100_LIB", ""), "ms_per_step": round(ms, 4),
+                out.emit(json.dumps({"quick": True, "tag": os.environ.get("JPEG_SM100_LIB", ""), "ms_per_step": round(ms, 4),
                                   "value": round(n * W * H * world / (ms * 1e-3) / 1e6, 1),
                                   "stages_ms": {k: round(statistics.mean(v), 4) for k, v in stages.items()},
-                                  "env": {k: v for k, v in os.environ.items() if k.startswith("JPEG_SM100_")}}), flush=True)
+                                  "env": {k: v for k, v in os.environ.items() if k.startswith("JPEG_SM100_")}}))
 
         report(ms_per_step, stage_ms)
         for item in [x for x in args.sweep.split(",") if x]:
@@ -539,7 +530,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
