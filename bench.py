@@ -259,8 +259,11 @@ def run_ours(args):
     qz = np.ascontiguousarray(q, dtype=np.uint16)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"lexer": [], "huffman": [], "idct": [], "color": []}
-    STAGES = ("lexer", "huffman", "idct", "color")
+    # the back half of a step: the staged kernels K1 -> sample planes -> K2 (default: faster, see fused.cu) or K1+K2 in one kernel
+    # (JPEG_SM100_FUSE=1: 6 instead of 9 bytes of HBM traffic per pixel, but issue-bound and slower)
+    fused = os.environ.get("JPEG_SM100_FUSE", "0") not in ("", "0")
+    STAGES = ("lexer", "huffman", "idct_color") if fused else ("lexer", "huffman", "idct", "color")
+    stage_ms = {k: [] for k in STAGES}
 
     def step(record):
         e = []
@@ -278,9 +281,12 @@ def run_ours(args):
         ctx.check(ctx.L.jpeg_sm100_dev_decode_scan(ctx.h, C.byref(desc), d_ecs.data_ptr(), d_off.data_ptr(), inputs.n_ecs,
                                                    geo.blocks[0], lib.SCAN_FRESH, tables, 0, C.byref(buf.sp), d_status.data_ptr()))
         mark()
-        ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), qz.ctypes.data, 8, C.byref(buf.pl)))
-        mark()
-        ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
+        if fused:
+            ctx.check(ctx.L.jpeg_sm100_dev_spectral_to_rgb8(ctx.h, C.byref(buf.sp), qz.ctypes.data, W, H, 0, buf.rgb.data_ptr()))
+        else:
+            ctx.check(ctx.L.jpeg_sm100_dev_idct(ctx.h, C.byref(buf.sp), qz.ctypes.data, 8, C.byref(buf.pl)))
+            mark()
+            ctx.check(ctx.L.jpeg_sm100_dev_planar_to_rgb8(ctx.h, C.byref(buf.pl), W, H, 0, buf.rgb.data_ptr()))
         mark()
         return e
 
@@ -308,6 +314,32 @@ def run_ours(args):
         for k, name in enumerate(STAGES):
             stage_ms[name].append(e[k].elapsed_time(e[k + 1]))
     ms_per_step = total_ms / args.steps
+
+    # the K1+K2 fused kernel (opt-in, fused.cu) on the same coefficients, next to the staged pair of the timed step: same bytes?
+    fused_side = None
+    if not fused and not args.quick:
+        try:
+            os.environ["JPEG_SM100_FUSE"] = "1"
+            rgb2 = torch.zeros_like(buf.rgb)
+            call = lambda: ctx.check(ctx.L.jpeg_sm100_dev_spectral_to_rgb8(ctx.h, C.byref(buf.sp), qz.ctypes.data, W, H, 0, rgb2.data_ptr()))
+            call()
+            f0, f1 = ev(), ev()
+            f0.record(stream)
+            for _ in range(5):
+                call()
+            f1.record(stream)
+            torch.cuda.synchronize()
+            f_ms = f0.elapsed_time(f1) / 5
+            f_bytes = (128.0 * geo.total_blocks + 3.0 * W * H) * n
+            fused_side = {"kernel": "k_idct_rgb420", "ms": round(f_ms, 4), "algorithmic_bytes": int(f_bytes),
+                          "GBps": round(f_bytes / (f_ms * 1e-3) / 1e9, 1), "equals_staged": bool(torch.equal(rgb2, buf.rgb)),
+                          "note": "opt-in (JPEG_SM100_FUSE=1): 6 B/px of HBM traffic instead of 9, but bound by instruction issue like K1 and K2 "
+                                  "themselves; compare ms with stages.ms.idct + stages.ms.color"}
+            del rgb2
+        except Exception as e:
+            fused_side = {"error": f"{type(e).__name__}: {e}"[:200]}
+        finally:
+            os.environ.pop("JPEG_SM100_FUSE", None)
 
     if args.quick:  # kernel A/B runs: device-resident stages only; --sweep "T:WARM,T:WARM,..." re-times K3p settings
         if rank == 0:
@@ -459,14 +491,18 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         px_per_step = n * W * H * world
-        idct_ms = statistics.mean(stage_ms["idct"]) / 3.0  # three launches (Y, Cb, Cr) per step
-        idct_bytes = 192.0 * geo.total_blocks * n / 3.0    # algorithmic bytes of the average launch
+        if fused:  # one launch: 128 B of coefficients per block in, 3 B of RGB per pixel out
+            idct_ms = statistics.mean(stage_ms["idct_color"])
+            idct_bytes = (128.0 * geo.total_blocks + 3.0 * W * H) * n
+        else:
+            idct_ms = statistics.mean(stage_ms["idct"]) / 3.0  # three launches (Y, Cb, Cr) per step
+            idct_bytes = 192.0 * geo.total_blocks * n / 3.0    # algorithmic bytes of the average launch
         achieved = idct_bytes / (idct_ms * 1e-3) / 1e9
         shares = {k: round(statistics.mean(v) / (ms_per_step if world == 1 else sum(statistics.mean(x) for x in stage_ms.values())), 4)
                   for k, v in stage_ms.items()}
         huff_ms = statistics.mean(stage_ms["huffman"])
         huff_bytes = inputs.ecs_bytes + 2.0 * 64 * geo.total_blocks * n
-        color_ms = statistics.mean(stage_ms["color"])
+        color_ms = statistics.mean(stage_ms["idct_color" if fused else "color"])
         color_bytes = (64.0 * geo.total_blocks + 3.0 * W * H) * n
         # CPU baseline on a bounded sample (single thread), same run
         cpu = cpu_baseline_sample(ecs_all[:3], tables_all[:24], q)
@@ -507,9 +543,9 @@ def run_ours(args):
                     "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)",
                     "steps": e2e_steps, "per_rank_s": [round(g["e2e_s"], 4) for g in gathered]},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
-            "roofline": {"kernel": "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",
+            "roofline": {"kernel": "k_idct_rgb420 (K1+K2 in one kernel)" if fused else "k_idct_tma<u8> (fused de-zigzag+dequant+IDCT+clamp, K1)", "bound": "hbm",
                          "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": k1_traffic() if n == BATCH else None,
+                         "frac": round(achieved / peak, 4), "traffic": k1_traffic() if (n == BATCH and not fused) else None,
                          "bytes_per_launch": int(idct_bytes), "ms_per_launch": round(idct_ms, 5),
                          "note": "the HBM-bound kernel BASELINE.json's north_star sets the >= 70 % target on; the kernel that takes most of the step "
                                  "(K3, bound by dependent-instruction latency and instruction issue, not HBM) is under roofline_dominant"},
@@ -525,6 +561,7 @@ def run_ours(args):
                        "lexer_GBps": round(3.0 * float(raw_len.sum()) / (statistics.mean(stage_ms["lexer"]) * 1e-3) / 1e9, 1),
                        "huffman_GBps": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1),
                        "color_GBps": round(color_bytes / (color_ms * 1e-3) / 1e9, 1)},
+            "k1k2_fused": fused_side,
             "configs": cfg_out,
             "layer_a": layer_a,
             "cpu_baseline": cpu,

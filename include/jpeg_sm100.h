@@ -338,6 +338,13 @@ int jpeg_sm100_dev_idct(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *spec
 /* upsample + YCbCr->RGB + pack; d_rgb: n_images * size_x * size_y * 3 bytes */
 int jpeg_sm100_dev_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *planar,
                                   uint32_t size_x, uint32_t size_y, int cosited, uint8_t *d_rgb);
+/* coefficients -> RGB8 in ONE kernel where the geometry allows (three planes of 8-bit samples, 4:2:0 with centred chroma: the chain
+ * Spectral.idct() -> Planar.interleaved(cosite: false) -> unpack(as: RGB.self), decode.swift:4154 -> 4182 -> jpeg.swift:441, without
+ * the sample planes in between: 6 instead of 9 bytes of HBM traffic per pixel); any other geometry runs jpeg_sm100_dev_idct into
+ * context-owned scratch planes followed by jpeg_sm100_dev_planar_to_rgb8.  Bit-identical to the staged calls either way.
+ * The planes' factor_x / factor_y must be set.  quanta: HOST, n_planes x 64, zig-zag order. */
+int jpeg_sm100_dev_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *spectral, const uint16_t *quanta_zigzag,
+                                    uint32_t size_x, uint32_t size_y, int cosited, uint8_t *d_rgb);
 /* upsample + interleave (16-bit Rectangular.values), and the unpack kernels on device memory */
 int jpeg_sm100_dev_interleave(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_planar *planar,
                               uint32_t size_x, uint32_t size_y, int cosited, uint16_t *d_interleaved);

@@ -10,6 +10,7 @@
 int jpeg_idct_launch_u8(jpeg_sm100_ctx *, const int16_t *, uint32_t, uint32_t, uint32_t, const float[64], uint8_t *, uint64_t);
 int jpeg_idct_launch_u16(jpeg_sm100_ctx *, const int16_t *, uint32_t, uint32_t, uint32_t, const float[64], int, uint16_t *, uint64_t);
 int jpeg_color_planar_to_rgb8(jpeg_sm100_ctx *, const jpeg_sm100_dev_planar *, uint32_t, uint32_t, int, uint8_t *);
+int jpeg_fused_spectral_to_rgb8(jpeg_sm100_ctx *, const jpeg_sm100_dev_spectral *, const uint16_t *, uint32_t, uint32_t, int, uint8_t *);
 int jpeg_color_interleave(jpeg_sm100_ctx *, const jpeg_sm100_dev_planar *, uint32_t, uint32_t, int, uint16_t *);
 int jpeg_color_unpack(jpeg_sm100_ctx *, const uint16_t *, uint64_t, int, uint8_t *, bool);
 int jpeg_color_pack_rgb(jpeg_sm100_ctx *, const uint8_t *, uint64_t, int, uint16_t *);
@@ -345,7 +346,27 @@ int alloc_planar(jpeg_sm100_ctx *ctx, int slot, const jpeg_sm100_dev_spectral &s
     return JPEG_SM100_OK;
 }
 
+// coefficients -> RGB8 on the device: the fused kernel where the geometry allows, else K1 into scratch planes (slot 4) and K2
+int spectral_to_rgb8_dev(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *sp, const uint16_t *quanta, uint32_t sx, uint32_t sy,
+                         int cosited, uint8_t *d_rgb)
+{
+    const int f = jpeg_fused_spectral_to_rgb8(ctx, sp, quanta, sx, sy, cosited, d_rgb);
+    if (f <= 0) return f;
+    jpeg_sm100_dev_planar pl;
+    J_TRY(alloc_planar(ctx, 4, *sp, 1, pl));
+    J_TRY(jpeg_sm100_dev_idct(ctx, sp, quanta, 8, &pl));
+    return jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, d_rgb);
+}
+
 }  // namespace
+
+JPEG_API int jpeg_sm100_dev_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *sp, const uint16_t *quanta,
+                                             uint32_t sx, uint32_t sy, int cosited, uint8_t *d_rgb)
+{
+    REQUIRE_CTX(ctx);
+    if (!sp || !quanta || !d_rgb || (sp->n_planes != 1 && sp->n_planes != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    return spectral_to_rgb8_dev(ctx, sp, quanta, sx, sy, cosited, d_rgb);
+}
 
 JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *ecs_concat,
                                     const uint64_t *ecs_offsets, uint32_t n_ecs, uint64_t interval, int extend,
@@ -480,13 +501,10 @@ JPEG_API int jpeg_sm100_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_p
     if (!planes || !quanta || !factors || (n != 1 && n != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     PlaneSet ps;
     J_TRY(upload_spectral(ctx, 0, planes, n, factors, ps));
-    jpeg_sm100_dev_planar pl;
-    J_TRY(alloc_planar(ctx, 4, ps.sp, 1, pl));
-    J_TRY(jpeg_sm100_dev_idct(ctx, &ps.sp, quanta, 8, &pl));
     const size_t bytes = (size_t) sx * sy * 3;
     void        *d_rgb = nullptr;
     J_TRY(scratch_reserve(ctx, 6, bytes + 64, &d_rgb));
-    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
+    J_TRY(spectral_to_rgb8_dev(ctx, &ps.sp, quanta, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
     if (bytes) CU_TRY(ctx, copy_d2h(ctx, rgb, d_rgb, bytes, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;
@@ -589,10 +607,6 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
     void *d_coef = nullptr, *d_ecs = nullptr, *d_off = nullptr, *d_status = nullptr, *d_rgb = nullptr, *d_raw = nullptr;
     J_TRY(scratch_reserve(ctx, 0, coef_total + 1024, &d_coef));
     for (uint32_t p = 0; p < n_planes; ++p) sp.plane[p].coef = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(d_coef) + coef_off[p]);
-    jpeg_sm100_dev_spectral geo = sp;  // sample planes are only needed for one chunk at a time
-    geo.n_images = chunk;
-    jpeg_sm100_dev_planar pl;
-    J_TRY(alloc_planar(ctx, 4, geo, 1, pl));
     const uint64_t n_off = (uint64_t) n_images * n_ecs + 1;
     uint64_t       in_bytes = 0;
     if (raw_offsets)
@@ -660,11 +674,10 @@ int decode_batch_common(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, u
             const uint32_t i0 = g0 + c0, cnt = (c0 + chunk <= gn) ? chunk : gn - c0;
             uint8_t       *rgb_buf = reinterpret_cast<uint8_t *>(d_rgb) + (k & 1) * rgb_chunk;
             jpeg_sm100_dev_spectral spk = sp;
-            spk.n_images = pl.n_images = cnt;
+            spk.n_images = cnt;
             for (uint32_t p = 0; p < n_planes; ++p) spk.plane[p].coef = sp.plane[p].coef + (size_t) i0 * sp.plane[p].image_stride;
             if (k >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[k - 2], 0));  // RGB buffer (k & 1) is free again
-            J_TRY(jpeg_sm100_dev_idct(ctx, &spk, quanta, 8, &pl));
-            J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, rgb_buf));
+            J_TRY(spectral_to_rgb8_dev(ctx, &spk, quanta, sx, sy, cosited, rgb_buf));  // fused K1+K2, or K1 -> scratch planes -> K2
             CU_TRY(ctx, cudaEventRecord(ev_k[k], ctx->stream));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k[k], 0));
             CU_TRY(ctx, copy_d2h(ctx, rgb + (size_t) i0 * rgb_per_image, rgb_buf, rgb_per_image * cnt, ctx->copy_out));
@@ -1213,13 +1226,10 @@ JPEG_API int jpeg_sm100_spectral_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_spec
     if (!s || !quanta || !factors || (s->n_planes != 1 && s->n_planes != 3)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     jpeg_sm100_dev_spectral sp;
     spectral_view(s, factors, sp);
-    jpeg_sm100_dev_planar pl;
-    J_TRY(alloc_planar(ctx, 4, sp, 1, pl));
-    J_TRY(jpeg_sm100_dev_idct(ctx, &sp, quanta, 8, &pl));
     const size_t bytes = (size_t) sx * sy * 3;
     void        *d_rgb = nullptr;
     J_TRY(scratch_reserve(ctx, 6, bytes + 64, &d_rgb));
-    J_TRY(jpeg_color_planar_to_rgb8(ctx, &pl, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
+    J_TRY(spectral_to_rgb8_dev(ctx, &sp, quanta, sx, sy, cosited, reinterpret_cast<uint8_t *>(d_rgb)));
     if (bytes) CU_TRY(ctx, copy_d2h(ctx, rgb, d_rgb, bytes, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return JPEG_SM100_OK;

@@ -4,6 +4,7 @@
 // (jpeg.swift:441-453, 493-572), RGB.pack (jpeg.swift:463-478, 584-599) and Rectangular.decomposed()
 // (encode.swift:389-425).  All arithmetic is the reference's binary32 sequence, never contracted.
 #include "common.cuh"
+#include "pixel_core.cuh"
 
 namespace {
 
@@ -110,18 +111,7 @@ __global__ void __launch_bounds__(256) k_planar_to_rgb8(const __grid_constant__ 
     }
 }
 
-// ---- fast paths: 8-bit planes -> RGB8 --------------------------------------------------------------------------------
-// jpeg.swift:441-453 with the two zero matrix entries dropped: Y + 0 * d == Y exactly (d finite), so
-//   r = Y + 1.402 dr,   g = (Y + -0.34414 db) + -0.71414 dr,   b = Y + 1.772 db     -- same binary32 values.
-// clamp(0..255) then truncate == truncate then saturate (F2I.TRUNC + saturating byte pack, as in the IDCT kernel).
-__device__ __forceinline__ void ycc_to_rgb_fast(float Y, float db, float dr, float &r, float &g, float &b)
-{
-    r = fadd(Y, fmul(1.40200f, dr));
-    g = fadd(fadd(Y, fmul(-0.34414f, db)), fmul(-0.71414f, dr));
-    b = fadd(Y, fmul(1.77200f, db));
-}
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
-
+// ---- fast paths: 8-bit planes -> RGB8 (ycc_to_rgb_fast, byte_of: pixel_core.cuh) ----------------------------------------------
 // 8 pixels (24 bytes) of one row: Y bytes in (y0, y1), chroma as integers cb[8], cr[8]
 __device__ __forceinline__ void emit_rgb8x8(uint2 yy, const int (&cb)[8], const int (&cr)[8], uint8_t *dst, bool vec,
                                             int n_valid)
@@ -223,7 +213,6 @@ k_ycc420_to_rgb8(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb
 // (3 Pa + Pb carries 3 * 2 + 2 = 8, the rounding term of (9a + 3b + 3c + d + 8) >> 4).  The final XOR turns each chroma byte
 // into the two's-complement byte of (c - 128), so one signed byte -> float conversion yields the exact (c - 128.0f) the
 // reference computes (jpeg.swift:447) and the two subtractions per pixel disappear.
-__device__ __forceinline__ float s8_to_float(uint32_t v, int byte) { return (float) (int) (int8_t) (v >> (8 * byte)); }
 
 __global__ void __launch_bounds__(256)
 k_ycc420_to_rgb8_v2(const __grid_constant__ PlanarView V, uint8_t *__restrict__ rgb)

@@ -47,6 +47,7 @@ struct jpeg_sm100_ctx {
     uint64_t hint_interval_bytes = 0;
     int      par_smem_ac = 0;   // same for its progressive AC-first instantiation
     size_t   par_smem_set = 0;  // largest dynamic shared-memory size k_decode_par has been opted into on this device
+    bool     fused_smem_set = false;  // k_idct_rgb420 opted into its dynamic shared memory on this device
     bool     idct_smem_set[2] = {false, false};  // k_idct_tma<u8 / u16> opted into > 48 KB of dynamic shared memory (per device, so per ctx)
     // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda dependency)
     void *encode_tiled = nullptr;

@@ -24,6 +24,7 @@
 //   * The reference's two-level (8 + 8 bit) LUT is reproduced entry for entry on the GPU (k_build_luts).
 //   * Coefficients land in the Spectral.Plane layout, 64 * (units_x * y + x) + z.
 #include <cooperative_groups.h>
+#include <time.h>
 
 #include "common.cuh"
 
@@ -1681,7 +1682,36 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         exit_out = pack_state(st.p, st.z, st.b);
         return cum;
     };
-    if (active) {
+    // DC-first scans of several components (kind 1, MODE_DC): one symbol per block and nothing else in the stream, so a parse that
+    // starts with the wrong block-in-MCU index b keeps the wrong table sequence for good -- nothing ever re-synchronises b, and the
+    // rounds below degenerate into a serial walk (measured: 511 rounds for a 4K scan without DRI, 25 ms).  So round 0 parses every
+    // subsequence once per possible b at the start of its warm-up (once in all when every component uses the same DC table: then
+    // the parse does not depend on b and the exit index follows from the symbol count) and keeps (entry, exit, count) of each
+    // hypothesis; before every round one thread per interval walks the chain and adopts, subsequence by subsequence, the
+    // hypothesis whose entry is its predecessor's exit.  Only a subsequence whose warm-up did not synchronise is left to a round.
+    bool dc_uniform = true;
+    for (int c = 1; c < P.n_comp; ++c) dc_uniform = dc_uniform && P.dc[c] == P.dc[0];
+    // (short intervals of 16 or 32 subsequences converge in a few rounds anyway: there the extra parses cost more than they save)
+    const uint32_t  H = (DC && tshift >= 6) ? (dc_uniform ? 1u : (uint32_t) nblk) : 0u;
+    uint64_t *const s_hyp = reinterpret_cast<uint64_t *>(smem + ((buf_off + 15u) & ~15u));  // [NT][H]: entry over | b << 6 | exit over << 10 | b << 16 | count << 32
+    if (DC && H != 0u && active && l > 0) {
+        uint64_t first_entry = 0, first_exit = 0;
+        uint32_t first_cnt = 0;
+        for (uint32_t h = 0; h < H; ++h) {
+            st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = 0, st.b = (uint16_t) h;
+            if (warm_bits) par_run_dc_auto<false>(io, st, start_bit, count, blk0, bad, 0, 0, 1u, nullptr, false);
+            else st.p = start_bit;
+            const uint32_t e_over = st.p - start_bit, e_b = st.b;
+            const uint64_t e_state = pack_state(st.p, 0, st.b);
+            const uint32_t c = par_run_dc_auto<false>(io, st, end_bit, count, blk0, bad, 0, 0, 1u, nullptr, false);
+            const uint32_t x_over = st.p - end_bit;
+            s_hyp[(size_t) tid * H + h] = (uint64_t) (e_over < 32u ? e_over : 63u) | ((uint64_t) e_b << 6) | ((uint64_t) (x_over < 32u ? x_over : 63u) << 10) |
+                                          ((uint64_t) st.b << 16) | ((uint64_t) c << 32);
+            if (h == 0) first_entry = e_state, first_exit = pack_state(st.p, 0, st.b), first_cnt = c;
+        }
+        s_entry[tid] = first_entry, s_exit[tid] = first_exit, s_cnt[tid] = first_cnt;
+        for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) s_ck[k][tid] = 0xffffffffu;  // (no checkpoints: a re-parse never merges)
+    } else if (active) {
         st.p = start_bit > warm_bits ? start_bit - warm_bits : 0u, st.z = AC ? (uint16_t) P.band_lo : 0, st.b = 0;
         if (l > 0 && warm_bits) {
             if (AC) par_run_ac_auto<false>(io, st, start_bit, count, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
@@ -1701,6 +1731,30 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     PAR_PHASE(1);
     uint32_t n_redo = 0, n_rounds = 0;
     for (uint32_t round = 1; round <= T + 1; ++round) {
+        if (DC && H != 0u) {
+            if (active && l == 0)
+                for (uint32_t j = 1; j < S; ++j) {
+                    const uint64_t prev = s_exit[tid + j - 1];
+                    if (prev == s_entry[tid + j]) continue;
+                    const ParseState ps = unpack_state(prev);
+                    const uint32_t   over = ps.p - j * B;
+                    bool             found = false;
+                    for (uint32_t h = 0; h < H && !found && over < 32u; ++h) {
+                        const uint64_t e = s_hyp[(size_t) (tid + j) * H + h];
+                        if ((uint32_t) (e & 63u) != over || (!dc_uniform && (uint32_t) ((e >> 6) & 15u) != ps.b)) continue;
+                        const uint32_t x_over = (uint32_t) (e >> 10) & 63u, cnt = (uint32_t) (e >> 32);
+                        if (x_over == 63u && j + 1 < S) continue;  // (only the last subsequence may end without a usable exit)
+                        const uint32_t x_b = dc_uniform ? (ps.b + cnt) % (uint32_t) nblk : (uint32_t) ((e >> 16) & 15u);
+                        const uint32_t e_bit = (j + 1 == S) ? count : (j + 1) * B;
+                        s_entry[tid + j] = prev;
+                        s_exit[tid + j] = pack_state(e_bit + (x_over & 31u), 0, (int) x_b);
+                        s_cnt[tid + j] = cnt;
+                        found = true;
+                    }
+                    if (!found) break;
+                }
+            __syncthreads();
+        }
         const bool redo = active && l >= 1 && s_exit[tid - 1] != s_entry[tid];
         n_redo += redo ? 1u : 0u;
         n_rounds = round;
@@ -2343,6 +2397,415 @@ __global__ void __launch_bounds__(256) k_decode_dc_refine(const __grid_constant_
     }
 }
 
+// ---- progressive AC refinement scans (kind 4) with few, large intervals: masks -> serial parse -> parallel apply ----------------
+// decode.swift:3072-3152.  A refinement scan does not self-synchronise: how many correction bits a symbol is followed by depends on
+// which coefficients of ITS block were non-zero before the scan, so a parser that does not know its block cannot know its bit
+// position either, and the scan is serial in the bit stream.  What CAN be taken off the serial path is everything but the bit
+// count: coefficients placed by this scan are never revisited by it, so the "non-zero" test only needs the state before the scan.
+//   k_acr_masks  (one thread per block)      64-bit map of the block's non-zero coefficients inside the band;
+//   k_acr_parse  (one warp per interval)     walks the symbols with bit operations on the maps: n-th zero -> landing position,
+//                                            popcount -> correction bits to skip; inside an EOB run a block is one popcount and the
+//                                            warp takes 32 blocks per step with a prefix sum.  Leaves every block's first bit;
+//   k_acr_apply  (one thread per block)      decodes its block from that bit and updates the coefficients.
+// A file without DRI -- everything the reference's encoder writes -- is ONE interval per scan: the one-thread-per-interval kernel
+// walks it coefficient by coefficient through global memory (400 ms for a 4K luma plane).  Anything irregular flags the interval;
+// flagged intervals are left untouched here and redone by k_decode_progressive, which owns the reference's error codes.
+constexpr uint32_t ACR_EOB = 0x80000000u;
+
+struct AcrReader {  // 1-padded bit stream (jpeg.swift:1873-1916) addressed by absolute bit position; all lanes of a warp may share one
+    const uint8_t *base;
+    uint32_t       nbytes, count;  // count = 8 * nbytes
+    uint32_t       pos;
+    __device__ __forceinline__ uint32_t byte_at(uint32_t i) const { return i < nbytes ? (uint32_t) __ldg(base + i) : 0xffu; }
+    // the 32 bits at `pos` (MSB first)
+    __device__ __forceinline__ uint32_t peek32() const
+    {
+        const uint32_t b = pos >> 3, s = pos & 7u;
+        uint32_t       hi, lo;
+        if (b + 8u <= nbytes) {  // the two aligned words around byte b hold bytes b .. b + 4
+            const uintptr_t a = reinterpret_cast<uintptr_t>(base + b);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+            const uint32_t  sh = (uint32_t) (a & 3u) * 8u;
+            const uint32_t  w0 = __byte_perm(__ldg(w), 0, 0x0123), w1 = __byte_perm(__ldg(w + 1), 0, 0x0123);
+            hi = __funnelshift_l(w1, w0, sh);
+            lo = w1 << sh;  // its top byte is byte b + 4
+        } else {
+            hi = (byte_at(b) << 24) | (byte_at(b + 1) << 16) | (byte_at(b + 2) << 8) | byte_at(b + 3);
+            lo = byte_at(b + 4) << 24;
+        }
+        return __funnelshift_l(lo, hi, s);
+    }
+};
+
+// one block of the scan.  m: bit z set <=> coefficient z (band_lo <= z < band_hi) was non-zero before this scan.  APPLY = false only
+// moves the bit position; APPLY = true also updates the coefficients (blk = the block's 64 coefficients).  0 or the reference's error.
+template <bool APPLY>
+__device__ __forceinline__ int acr_block(AcrReader &br, const uint64_t m, int &skip, const int band_lo, const int band_hi, const int al,
+                                         const uint16_t *entries, const int tn, const int tz, const uint32_t toff, int16_t *blk)
+{
+    int z = band_lo;
+    while (z < band_hi) {
+        int zeroes, delta = 0;
+        if (skip > 0) {
+            zeroes = 64;
+            skip -= 1;
+        } else {
+            if (!(br.pos < br.count)) return JPEG_SM100_ERR_TRUNCATED_ECS;
+            const uint32_t w = br.peek32();
+            const uint32_t ent = lut_lookup(entries, tn, tz, toff, w >> 16);
+            const int      sym = (int) (ent & 0xffu), len = (int) (ent >> 8);
+            br.pos += (uint32_t) len;
+            const int sz = sym >> 4, binade = sym & 15;
+            // (len <= 16 and the extra bits <= 15: both inside the 32-bit window)
+            if (binade == 0) {
+                if (sz == 0) {
+                    zeroes = 64;
+                } else if (sz <= 14) {
+                    if (!(br.pos + (uint32_t) sz <= br.count)) return JPEG_SM100_ERR_TRUNCATED_ECS;
+                    const int run = (1 << sz) | (int) ((w << len) >> (32 - sz));
+                    br.pos += (uint32_t) sz;
+                    zeroes = 64;
+                    skip = run - 1;
+                } else {
+                    zeroes = 15;
+                }
+            } else {
+                if (!(br.pos + (uint32_t) binade <= br.count)) return JPEG_SM100_ERR_TRUNCATED_ECS;
+                const int v = extend16(binade, (w << len) >> (32 - binade));
+                br.pos += (uint32_t) binade;
+                if (!(v >= -1 && v <= 1)) return JPEG_SM100_ERR_INVALID_COMPOSITE_VALUE;
+                zeroes = sz;
+                delta = v;
+            }
+        }
+        // decode.swift:3118-3149: pass `zeroes` zero coefficients, refining every non-zero one on the way, and land on the next zero
+        const uint64_t from = ~0ull << z, band = from & (band_hi < 64 ? ~(~0ull << band_hi) : ~0ull);
+        uint64_t       Z = ~m & band;
+        int            target = -1;
+        if (zeroes < 64) {
+            for (int i = 0; i < zeroes; ++i) Z &= Z - 1;
+            if (Z) target = __ffsll((long long) Z) - 1;
+        }
+        const uint64_t passed = m & band & (target >= 0 ? ~(~0ull << target) : ~0ull);  // the non-zero coefficients in [z, target)
+        const uint32_t k = (uint32_t) __popcll(passed);
+        if (!(br.pos + k <= br.count)) return JPEG_SM100_ERR_TRUNCATED_ECS;
+        if (APPLY) {
+            uint64_t rest = passed;
+            uint32_t w = 0, have = 0;
+            while (rest) {
+                if (have == 0) {
+                    w = br.peek32();
+                    have = 32;
+                }
+                const int zz = __ffsll((long long) rest) - 1;
+                rest &= rest - 1;
+                if (w & 0x80000000u) {
+                    const int16_t c = blk[zz];
+                    blk[zz] = (int16_t) (c + (int16_t) ((uint32_t) (c < 0 ? -1 : 1) << al));
+                }
+                w <<= 1;
+                have -= 1;
+                br.pos += 1;
+            }
+            if (target >= 0 && delta != 0) blk[target] = (int16_t) ((uint32_t) delta << al);
+        } else {
+            br.pos += k;
+        }
+        if (target < 0) break;  // the walk ran off the band: the block is complete
+        z = target + 1;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_acr_masks(const __grid_constant__ ScanParams P, const uint32_t n_images, uint64_t *const masks)
+{
+    const uint32_t per = (uint32_t) P.ux[0] * (uint32_t) P.uy[0];
+    const uint64_t total = (uint64_t) per * n_images;
+    const uint64_t band = (~0ull << P.band_lo) & (P.band_hi < 64 ? ~(~0ull << P.band_hi) : ~0ull);
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t img = (uint32_t) (i / per), b = (uint32_t) (i - (uint64_t) img * per);
+        const uint4   *src = reinterpret_cast<const uint4 *>(P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) 64 * b);
+        uint64_t       m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4    c = __ldg(src + j);
+            const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (w[q] & 0xffffu) m |= 1ull << (8 * j + 2 * q);
+                if (w[q] >> 16) m |= 1ull << (8 * j + 2 * q + 1);
+            }
+        }
+        masks[i] = m & band;
+    }
+}
+
+// The serial parse keeps its bit window in registers (the word for the next refill is loaded one refill ahead, so no load sits on the
+// symbol-to-symbol chain) and reads symbols from the 8-bit fast tables (fast_entry_prog: one shared-memory load per symbol).
+// (kept out of line: the padded bytes around the two ends of an interval are read a handful of times per scan)
+__device__ __noinline__ uint32_t acr_edge_word(const uint32_t *w0, uint32_t i, uint32_t lead, uint32_t nbytes)
+{
+    uint32_t v = 0;
+    for (int j = 0; j < 4; ++j) {
+        const int64_t b = (int64_t) i * 4 + j - (int64_t) lead;  // byte offset inside the interval
+        v = (v << 8) | ((b >= 0 && b < (int64_t) nbytes) ? (uint32_t) __ldg(reinterpret_cast<const uint8_t *>(w0) + (size_t) i * 4 + j) : 0xffu);
+    }
+    return v;
+}
+struct AcrWindow {
+    const uint32_t *w0;  // the aligned word that holds the interval's first byte
+    uint32_t        lead, nbytes, count;
+    uint32_t        w_lo, w_n;  // words w_lo .. w_lo + w_n - 1 lie wholly inside the interval
+    uint64_t        acc;        // MSB-aligned; more than 32 valid bits whenever a symbol is read
+    int             nav;
+    uint32_t        wi, nxt, pos;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const  // big-endian word i of the 1-padded stream (jpeg.swift:1881-1887)
+    {
+        if (i - w_lo < w_n) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
+        return acr_edge_word(w0, i, lead, nbytes);
+    }
+    __device__ __forceinline__ void seek(uint32_t p)
+    {
+        pos = p;
+        const uint32_t ab = lead * 8u + p, i = ab >> 5, sh = ab & 31u;
+        acc = (((uint64_t) word(i) << 32) | word(i + 1)) << sh;
+        nav = 64 - (int) sh;
+        nxt = word(i + 2);
+        wi = i + 3;
+        refill();
+    }
+    __device__ __forceinline__ void init(const uint8_t *base, uint32_t n)
+    {
+        lead = (uint32_t) (reinterpret_cast<uintptr_t>(base) & 3u);
+        w0 = reinterpret_cast<const uint32_t *>(base - lead);
+        nbytes = n;
+        count = 8u * n;
+        w_lo = lead ? 1u : 0u;
+        const uint32_t w_hi = (lead + n) >> 2;  // first word that is not wholly inside
+        w_n = w_hi > w_lo ? w_hi - w_lo : 0u;
+        seek(0);
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nav <= 32) {
+            acc |= (uint64_t) nxt << (32 - nav);
+            nav += 32;
+            nxt = word(wi);
+            wi += 1;
+        }
+    }
+    __device__ __forceinline__ void consume(uint32_t n)  // n <= 32
+    {
+        acc <<= n;
+        nav -= (int) n;
+        pos += n;
+        refill();
+    }
+    __device__ __forceinline__ void skip(uint32_t k)
+    {
+        if (k > 32u) {
+            seek(pos + k);
+            return;
+        }
+        consume(k);
+    }
+};
+
+// One block of the parse on the fast tables; false: something the sequential kernel has to look at (truncation, an invalid code
+// or value, a code that leans on the padding) -- the interval is flagged, never guessed.
+// A symbol (run r, +-1) skips r ZERO coefficients and lands on the next one; every non-zero coefficient it passes owns one
+// correction bit.  With sel[n] = position of the block's n-th zero (band order) and rho = zeros consumed so far, the landing
+// position is sel[rho + r] and the bits to skip are (landing - z) - r: one shared-memory load and two subtractions per symbol.
+// The warp builds sel[] for the block together (lane p ranks positions p and p + 32 with a popcount), then every lane walks
+// the symbols redundantly (uniform addresses, broadcast loads).
+__device__ __forceinline__ bool acr_parse_block(AcrWindow &br, const uint64_t m, int &skip, const int band_lo, const int band_hi, const uint32_t *tab,
+                                                uint8_t *sel, const uint32_t lane)
+{
+    const uint64_t in_band = (~0ull << band_lo) & (band_hi < 64 ? ~(~0ull << band_hi) : ~0ull);
+    const uint64_t Zm = ~m & in_band;
+    {
+        const uint32_t lo = (uint32_t) Zm, hi = (uint32_t) (Zm >> 32);
+        const uint32_t below = (1u << lane) - 1u;
+        if ((lo >> lane) & 1u) sel[__popc(lo & below)] = (uint8_t) lane;
+        if ((hi >> lane) & 1u) sel[__popc(lo) + __popc(hi & below)] = (uint8_t) (lane + 32u);
+    }
+    const int nz = __popcll(Zm);
+    __syncwarp();
+    int z = band_lo, rho = 0;
+    while (z < band_hi) {
+        uint32_t ent = tab[(uint32_t) (br.acc >> (64 - FAST_BITS))];
+        if (ent & FAST_LINK) {
+            const uint32_t rest = (uint32_t) (br.acc >> 48) & ((1u << (16 - FAST_BITS)) - 1u);
+            ent = tab[(ent >> 10) + (rest >> (ent & 7u))];
+        }
+        const uint32_t len = ent & 0x7fu, size = (ent >> 8) & 0xffu, adv = (ent >> 16) & 0xffu, total = ent >> 24;
+        if (ent == 0u || !(br.pos + total <= br.count)) return false;
+        int zeroes;
+        if (adv & 0x80u) {  // EOBn: the rest of this block and of the next run - 1 blocks is correction bits
+            zeroes = 64;
+            skip = (int) ((1u << size) | (size ? (uint32_t) ((br.acc << len) >> (64 - size)) : 0u)) - 1;
+        } else if (size == 0u) {
+            zeroes = 15;  // ZRL
+        } else if (size == 1u) {
+            zeroes = (int) adv - 1;
+        } else {
+            return false;  // decode.swift:3099-3102: a refinement value must be -1, 0 or 1
+        }
+        br.consume(total);
+        const int n = rho + zeroes;
+        if (n >= nz) {  // fewer zeros left than the symbol passes: the walk runs off the band, refining what is left
+            const uint32_t k = (uint32_t) ((band_hi - z) - (nz - rho));
+            if (!(br.pos + k <= br.count)) return false;
+            br.skip(k);
+            break;
+        }
+        const int      target = (int) sel[n];
+        const uint32_t k = (uint32_t) (target - z - zeroes);
+        if (!(br.pos + k <= br.count)) return false;
+        br.skip(k);
+        z = target + 1;
+        rho = n + 1;
+    }
+    return true;
+}
+
+// one warp per (interval, image); every lane runs the same parse (uniform addresses), lane 0 writes.  rec[block] = first bit of the
+// block inside its interval | ACR_EOB when the block lies inside an end-of-band run (then it holds correction bits only)
+template <bool LUT_SMEM>
+__global__ void __launch_bounds__(WARP) k_acr_parse(const __grid_constant__ ScanParams P, const uint64_t *const masks, uint32_t *const rec,
+                                                    uint32_t *const flagged)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint8_t s_sel[2][64];  // positions of the current block's zeros (two blocks: the next build never waits for this walk)
+    const uint32_t   img = blockIdx.y, e = blockIdx.x, lane = threadIdx.x;
+    const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
+    {
+        const uint32_t  total = reinterpret_cast<const LutHeader *>(lut_img)->total_all;  // reference entries + fast tables
+        const uint32_t  words = (uint32_t) sizeof(LutHeader) / 4 + (LUT_SMEM ? (total + 1) / 2 : 0);
+        uint32_t       *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = lane; i < words; i += WARP) dst[i] = src[i];
+        __syncwarp();
+        if (LUT_SMEM) entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader));
+    }
+    const size_t slot = (size_t) img * P.n_ecs + e;
+    int64_t      r0 = 0, r1 = P.H;
+    if (P.interval != UINT64_MAX) {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r1 > P.H) r1 = P.H;
+    }
+    const uint64_t o0 = P.offsets[slot], o1 = P.offsets[slot + 1];
+    // General.Range2's quirks (empty or inverted row ranges) and streams beyond 2^31 bits belong to the sequential kernel
+    bool bad = !(r1 > r0) || (o1 - o0) > 0x0fffffffull;
+    if (!bad) {
+        const uint32_t per = (uint32_t) P.ux[0] * (uint32_t) P.uy[0];
+        const uint32_t b0 = (uint32_t) r0 * (uint32_t) P.W, b1 = (uint32_t) r1 * (uint32_t) P.W;
+        const uint64_t *mk = masks + (size_t) img * per;
+        uint32_t       *rc = rec + (size_t) img * per;
+        const int       ti = P.ac[0];
+        int             skip = 0;
+        uint32_t        b = b0;
+        if (LUT_SMEM) {
+            const uint32_t *tab = reinterpret_cast<const uint32_t *>(entries + hdr->fast[ti]);
+            AcrWindow       br;
+            br.init(P.ecs + o0, (uint32_t) (o1 - o0));
+            uint64_t m_next = b < b1 ? __ldg(mk + b) : 0ull;
+            while (b < b1 && !bad) {
+                if (skip > 0) {
+                    // inside an end-of-band run every block is its correction bits: 32 blocks per step
+                    const uint32_t n = min(min((uint32_t) skip, b1 - b), (uint32_t) WARP);
+                    const uint32_t k = lane < n ? (uint32_t) __popcll(__ldg(mk + b + lane)) : 0u;
+                    uint32_t       inc = k;
+#pragma unroll
+                    for (int d = 1; d < WARP; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                        if ((int) lane >= d) inc += t;
+                    }
+                    if (lane < n) rc[b + lane] = (br.pos + inc - k) | ACR_EOB;
+                    const uint32_t sum = __shfl_sync(0xffffffffu, inc, WARP - 1);
+                    if (!(br.pos + sum <= br.count)) bad = true;
+                    else br.skip(sum);
+                    skip -= (int) n;
+                    b += n;
+                    m_next = b < b1 ? __ldg(mk + b) : 0ull;
+                    continue;
+                }
+                if (lane == 0) rc[b] = br.pos;
+                const uint64_t m = m_next;
+                b += 1;
+                m_next = b < b1 ? __ldg(mk + b) : 0ull;  // (the next block's map is on its way while this one is parsed)
+                if (!acr_parse_block(br, m, skip, P.band_lo, P.band_hi, tab, s_sel[b & 1u], lane)) bad = true;
+            }
+        } else {
+            const int      tn = hdr->n[ti], tz = hdr->zeta[ti];
+            const uint32_t toff = hdr->offset[ti];
+            AcrReader      br;
+            br.base = P.ecs + o0;
+            br.nbytes = (uint32_t) (o1 - o0);
+            br.count = 8u * br.nbytes;
+            br.pos = 0;
+            while (b < b1 && !bad) {
+                const uint32_t r = br.pos | (skip > 0 ? ACR_EOB : 0u);
+                if (lane == 0) rc[b] = r;
+                if (acr_block<false>(br, __ldg(mk + b), skip, P.band_lo, P.band_hi, P.al, entries, tn, tz, toff, nullptr) != 0) bad = true;
+                b += 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        flagged[slot] = bad ? 1u : 0u;
+        if (!bad) P.status[slot] = 0;
+    }
+}
+
+template <bool LUT_SMEM>
+__global__ void __launch_bounds__(128) k_acr_apply(const __grid_constant__ ScanParams P, const uint64_t *const masks, const uint32_t *const rec,
+                                                   const uint32_t *const flagged)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t   img = blockIdx.z, e = blockIdx.y;
+    const uint8_t   *lut_img = P.luts + (size_t) img * P.lut_stride;
+    const LutHeader *hdr = reinterpret_cast<const LutHeader *>(smem);
+    const uint16_t  *entries = reinterpret_cast<const uint16_t *>(lut_img + sizeof(LutHeader));
+    const size_t     slot = (size_t) img * P.n_ecs + e;
+    if (flagged[slot]) return;
+    {
+        const uint32_t  total = reinterpret_cast<const LutHeader *>(lut_img)->total_entries;
+        const uint32_t  words = (uint32_t) sizeof(LutHeader) / 4 + (LUT_SMEM ? (total + 1) / 2 : 0);
+        uint32_t       *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lut_img);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (LUT_SMEM) entries = reinterpret_cast<const uint16_t *>(smem + sizeof(LutHeader));
+    }
+    int64_t r0 = 0, r1 = P.H;
+    if (P.interval != UINT64_MAX) {
+        r0 = (int64_t) (((uint64_t) e * P.interval) / (uint32_t) P.W);
+        r1 = (int64_t) (((uint64_t) (e + 1) * P.interval) / (uint32_t) P.W);
+        if (r1 > P.H) r1 = P.H;
+    }
+    const uint32_t per = (uint32_t) P.ux[0] * (uint32_t) P.uy[0];
+    const uint32_t b0 = (uint32_t) r0 * (uint32_t) P.W, b1 = (uint32_t) r1 * (uint32_t) P.W;
+    const uint64_t o0 = P.offsets[slot], o1 = P.offsets[slot + 1];
+    const int      ti = P.ac[0];
+    const int      tn = hdr->n[ti], tz = hdr->zeta[ti];
+    const uint32_t toff = hdr->offset[ti];
+    for (uint32_t b = b0 + blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += gridDim.x * blockDim.x) {
+        const uint32_t r = __ldg(rec + (size_t) img * per + b);
+        AcrReader      br;
+        br.base = P.ecs + o0;
+        br.nbytes = (uint32_t) (o1 - o0);
+        br.count = 8u * br.nbytes;
+        br.pos = r & ~ACR_EOB;
+        int skip = (r & ACR_EOB) ? 1 : 0;  // (the run's length beyond this block is the next blocks' business)
+        acr_block<true>(br, __ldg(masks + (size_t) img * per + b), skip, P.band_lo, P.band_hi, P.al, entries, tn, tz, toff,
+                        P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) 64 * b);
+    }
+}
+
 // per image: first non-zero status in interval order (the reference throws at the first failing interval)
 __global__ void k_reduce_status(const int32_t *__restrict__ per_ecs, uint32_t n_ecs, int32_t *__restrict__ per_image)
 {
@@ -2369,6 +2832,20 @@ int zero_plane_rows(jpeg_sm100_ctx *ctx, const ScanParams &P, int n_comp, uint32
     return JPEG_SM100_OK;
 }
 
+// The three-phase AC refinement path (k_acr_*) pays when intervals are few and long; with many short intervals the
+// one-thread-per-interval kernel already fills the GPU.  JPEG_SM100_ACR=0 / 1 forces it off / on (A/B validation).
+bool acr_wanted(jpeg_sm100_ctx *ctx, const ScanParams &P, uint32_t n_images, uint32_t n_ecs, uint64_t interval)
+{
+    const char *seq = getenv("JPEG_SM100_HUFF");
+    if (seq && strcmp(seq, "seq") == 0) return false;
+    if (n_ecs > 65535u || n_images > 65535u || !P.plane[0]) return false;
+    if ((uint64_t) P.ux[0] * (uint64_t) P.uy[0] > 0x7fffffffull) return false;
+    const char *e = getenv("JPEG_SM100_ACR");
+    if (e) return atoi(e) != 0;
+    const uint64_t rows = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
+    return rows * (uint64_t) P.W >= 1024 && (uint64_t) n_images * n_ecs <= (uint64_t) ctx->sm_count * 8;
+}
+
 }  // namespace
 
 // decode.swift:2884-2895, 3186-3203 + 310-351: the error a sequential scan raises for this table set before it reads a bit
@@ -2390,10 +2867,38 @@ int jpeg_huffman_validate_tables(const jpeg_sm100_scan_desc *scan, const jpeg_sm
 }
 
 // Layer-B implementation.  scratch slots 8 (LUTs) and 9 (per-ECS status) belong to this file.
+static int decode_scan_impl(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
+                            const uint64_t *d_offsets, uint32_t n_ecs, uint64_t interval, int extend,
+                            const jpeg_sm100_huff_table *tables, int tables_shared,
+                            const jpeg_sm100_dev_spectral *sp, int32_t *d_status);
+
+// JPEG_SM100_TRACE=1: every scan is bracketed by stream synchronisations and its wall time goes to stderr (a diagnostic: it
+// serialises the stream, never set it for a measurement of anything else)
 int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
                              const uint64_t *d_offsets, uint32_t n_ecs, uint64_t interval, int extend,
                              const jpeg_sm100_huff_table *tables, int tables_shared,
                              const jpeg_sm100_dev_spectral *sp, int32_t *d_status)
+{
+    static const bool trace = getenv("JPEG_SM100_TRACE") != nullptr;
+    if (!trace) return decode_scan_impl(ctx, scan, d_ecs, d_offsets, n_ecs, interval, extend, tables, tables_shared, sp, d_status);
+    cudaStreamSynchronize(ctx->stream);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const uint64_t l0 = ctx->launches;
+    const int      r = decode_scan_impl(ctx, scan, d_ecs, d_offsets, n_ecs, interval, extend, tables, tables_shared, sp, d_status);
+    cudaStreamSynchronize(ctx->stream);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    fprintf(stderr, "[jpeg_sm100] scan band %d..%d bits %d/%d comps %d images %u intervals %u extend %d: %.3f ms, %llu launches, rc %d\n",
+            scan ? scan->band_lo : -1, scan ? scan->band_hi : -1, scan ? scan->bit_hi : 0, scan ? scan->bit_lo : 0, scan ? scan->n_comp : 0,
+            sp ? sp->n_images : 0u, n_ecs, extend, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6,
+            (unsigned long long) (ctx->launches - l0), r);
+    return r;
+}
+
+static int decode_scan_impl(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const uint8_t *d_ecs,
+                            const uint64_t *d_offsets, uint32_t n_ecs, uint64_t interval, int extend,
+                            const jpeg_sm100_huff_table *tables, int tables_shared,
+                            const jpeg_sm100_dev_spectral *sp, int32_t *d_status)
 {
     if (!scan || !sp || !tables) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     if (scan->n_comp < 1 || scan->n_comp > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
@@ -2519,7 +3024,7 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     CU_TRY(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(RawSet) * (size_t) n_sets, cudaMemcpyHostToDevice, ctx->stream));
     J_TRY(pinned_release(ctx, slot));
     k_build_luts<<<dim3(8, n_sets), 128, 0, ctx->stream>>>(reinterpret_cast<const RawSet *>(d_raw),
-                                                           reinterpret_cast<uint8_t *>(d_luts), stride, P.kind == 3 ? 1 : 0);
+                                                           reinterpret_cast<uint8_t *>(d_luts), stride, (P.kind == 3 || P.kind == 4) ? 1 : 0);
     LAUNCH_CHECK(ctx);
     P.luts = reinterpret_cast<const uint8_t *>(d_luts);
     P.lut_stride = tables_shared ? 0 : stride;
@@ -2583,10 +3088,10 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                 while (tshift > 4 && (est_bits >> tshift) < 8192) --tshift;
                 while (tshift < tmax && (slots << tshift) < (uint64_t) ctx->sm_count * 512 && (est_bits >> (tshift + 1)) >= (uint64_t) PAR_MIN_BITS) ++tshift;
                 if (env_t >= 4 && env_t <= tmax) tshift = env_t;
-                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? 256u : 2048u);
+                const uint32_t warm_bits = env_ws ? (uint32_t) (env_warm > 0 ? env_warm : 0) : (dc_first ? (tshift >= 6 ? 768u : 256u) : 2048u);
                 const uint32_t G = (uint32_t) nt >> tshift;
                 const dim3     grid_par((n_ecs + G - 1) / G, n_images);
-                const size_t   smem_total = smem_par + (dc_first ? 0 : (size_t) nt * (PAR_BUF_STRIDE + 4 * PAR_RING) + 32 + (PAR_SWIZZLE ? 112 : 0));
+                const size_t   smem_total = smem_par + (dc_first ? 16 + (size_t) nt * 12 * 8 : (size_t) nt * (PAR_BUF_STRIDE + 4 * PAR_RING) + 32 + (PAR_SWIZZLE ? 112 : 0));
                 if (!ctx->par_smem_set) {  // same bound from every ctx of the process: LUTs (< 48 KB) + stage (<= 96 KB) + block buffers
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_THREADS, PAR_MIN_CTAS, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     CU_TRY(ctx, cudaFuncSetAttribute(k_decode_par<PAR_BIG_THREADS, 1, MODE_SEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2719,6 +3224,28 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         LAUNCH_CHECK(ctx);
         if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
         else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, reinterpret_cast<const uint32_t *>(d_flag));
+    } else if (P.kind == 4 && acr_wanted(ctx, P, n_images, n_ecs, interval)) {
+        // progressive AC refinement over few, large intervals: non-zero maps, a serial parse per interval (one warp), a parallel apply
+        if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
+        const uint64_t per = (uint64_t) P.ux[0] * (uint64_t) P.uy[0], blocks = per * n_images;
+        void          *d_work = nullptr, *d_flag = nullptr;
+        J_TRY(scratch_reserve(ctx, 12, (size_t) (blocks * 12 + 256), &d_work));
+        J_TRY(scratch_reserve(ctx, 13, (size_t) ((uint64_t) n_images * n_ecs * 4 + 256), &d_flag));
+        uint64_t *d_masks = reinterpret_cast<uint64_t *>(d_work);
+        uint32_t *d_rec = reinterpret_cast<uint32_t *>(d_masks + blocks);
+        uint32_t *d_fl = reinterpret_cast<uint32_t *>(d_flag);
+        k_acr_masks<<<(uint32_t) std::min<uint64_t>((blocks + 255) / 256, (uint64_t) ctx->sm_count * 16), 256, 0, ctx->stream>>>(P, n_images, d_masks);
+        LAUNCH_CHECK(ctx);
+        if (P.lut_smem) k_acr_parse<true><<<dim3(n_ecs, n_images), WARP, smem, ctx->stream>>>(P, d_masks, d_rec, d_fl);
+        else k_acr_parse<false><<<dim3(n_ecs, n_images), WARP, smem, ctx->stream>>>(P, d_masks, d_rec, d_fl);
+        LAUNCH_CHECK(ctx);
+        const uint64_t rows_typ = (interval == JPEG_SM100_INTERVAL_NONE) ? (uint64_t) P.H : (interval + P.W - 1) / P.W;
+        const dim3     ga((uint32_t) std::min<uint64_t>((rows_typ * (uint64_t) P.W + 127) / 128, 4096), n_ecs, n_images);
+        if (P.lut_smem) k_acr_apply<true><<<ga, 128, smem, ctx->stream>>>(P, d_masks, d_rec, d_fl);
+        else k_acr_apply<false><<<ga, 128, smem, ctx->stream>>>(P, d_masks, d_rec, d_fl);
+        LAUNCH_CHECK(ctx);
+        if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, d_fl);
+        else k_decode_progressive<false><<<grid, WARP, smem, ctx->stream>>>(P, d_fl);
     } else {
         if (fresh) J_TRY(zero_plane_rows(ctx, P, scan->n_comp, n_images, 0));
         if (P.lut_smem) k_decode_progressive<true><<<grid, WARP, smem, ctx->stream>>>(P, nullptr);

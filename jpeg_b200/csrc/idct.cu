@@ -18,6 +18,7 @@
 //   * Arithmetic is the reference's binary32 AAN network, op for op, never contracted (-fmad=false +
 //     __f*_rn) => results are bit-identical to the Swift path, not just within +-1.
 #include "common.cuh"
+#include "pixel_core.cuh"
 
 namespace {
 
@@ -37,64 +38,6 @@ struct IdctParams {
     const int16_t *coef;        // only used by the non-TMA variant
     void    *out;
 };
-
-// decode.swift:4042-4093  idct8 -- one lane of the reference's SIMD8 network
-__device__ __forceinline__ void idct8(float &h0, float &h1, float &h2, float &h3, float &h4, float &h5, float &h6,
-                                      float &h7, const float shift)
-{
-    const float sh0 = fadd(shift, h0);
-    const float a0 = fadd(sh0, h4);
-    const float a1 = fsub(sh0, h4);
-    const float b = fadd(h2, h6);
-    const float c = fsub(fmul(1.414213562f, fsub(h2, h6)), b);
-    const float r0 = fadd(a0, b), r1 = fadd(a1, c), r2 = fsub(a1, c), r3 = fsub(a0, b);
-    const float d0 = fsub(h5, h3), d1 = fadd(h1, h7), d2 = fsub(h1, h7), d3 = fadd(h5, h3);
-    const float f = fmul(1.414213562f, fsub(d1, d3));
-    const float l = fmul(1.847759065f, fadd(d0, d2));
-    const float m0 = fsub(l, fmul(d2, 1.082392200f));
-    const float m1 = fsub(l, fmul(d0, 2.613125930f));
-    const float s0 = fadd(d1, d3);
-    const float s1 = fsub(m1, s0);
-    const float s2 = fsub(f, s1);
-    const float s3 = fsub(m0, s2);
-    h0 = fadd(r0, s0);
-    h1 = fadd(r1, s1);
-    h2 = fadd(r2, s2);
-    h3 = fadd(r3, s3);
-    h4 = fsub(r3, s3);
-    h5 = fsub(r2, s2);
-    h6 = fsub(r1, s1);
-    h7 = fsub(r0, s0);
-}
-
-// idct8 without the level shift (first pass: shift = 0 in the reference, `0 + h0` is exact)
-__device__ __forceinline__ void idct8_noshift(float &h0, float &h1, float &h2, float &h3, float &h4, float &h5,
-                                              float &h6, float &h7)
-{
-    // (0 + h0) == h0 for every h0 except -0.0 -> +0.0, which cannot change any later sum's value
-    const float a0 = fadd(h0, h4);
-    const float a1 = fsub(h0, h4);
-    const float b = fadd(h2, h6);
-    const float c = fsub(fmul(1.414213562f, fsub(h2, h6)), b);
-    const float r0 = fadd(a0, b), r1 = fadd(a1, c), r2 = fsub(a1, c), r3 = fsub(a0, b);
-    const float d0 = fsub(h5, h3), d1 = fadd(h1, h7), d2 = fsub(h1, h7), d3 = fadd(h5, h3);
-    const float f = fmul(1.414213562f, fsub(d1, d3));
-    const float l = fmul(1.847759065f, fadd(d0, d2));
-    const float m0 = fsub(l, fmul(d2, 1.082392200f));
-    const float m1 = fsub(l, fmul(d0, 2.613125930f));
-    const float s0 = fadd(d1, d3);
-    const float s1 = fsub(m1, s0);
-    const float s2 = fsub(f, s1);
-    const float s3 = fsub(m0, s2);
-    h0 = fadd(r0, s0);
-    h1 = fadd(r1, s1);
-    h2 = fadd(r2, s2);
-    h3 = fadd(r3, s3);
-    h4 = fsub(r3, s3);
-    h5 = fsub(r2, s2);
-    h6 = fsub(r1, s1);
-    h7 = fsub(r0, s0);
-}
 
 // w[32]: the block's 64 int16 coefficients in zig-zag order, two per word.
 template <typename OutT>
@@ -243,6 +186,9 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+}  // namespace
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (also used by fused.cu)
 int resolve_encode_tiled(jpeg_sm100_ctx *ctx)
 {
     if (ctx->encode_tiled) return JPEG_SM100_OK;
@@ -256,6 +202,8 @@ int resolve_encode_tiled(jpeg_sm100_ctx *ctx)
     ctx->encode_tiled = fn;
     return JPEG_SM100_OK;
 }
+
+namespace {
 
 template <typename OutT>
 int launch_idct(jpeg_sm100_ctx *ctx, const int16_t *d_coef, uint32_t n_images, uint32_t ux, uint32_t uy,

@@ -133,6 +133,7 @@ SYMBOLS = {
     "jpeg_sm100_dev_decode_scan": (_i, [_vp, _SD, _vp, _vp, _u32, _u64, _i, _HT, _i, C.POINTER(DevSpectral), _vp]),
     "jpeg_sm100_dev_idct": (_i, [_vp, C.POINTER(DevSpectral), _vp, _i, C.POINTER(DevPlanar)]),
     "jpeg_sm100_dev_planar_to_rgb8": (_i, [_vp, C.POINTER(DevPlanar), _u32, _u32, _i, _vp]),
+    "jpeg_sm100_dev_spectral_to_rgb8": (_i, [_vp, C.POINTER(DevSpectral), _vp, _u32, _u32, _i, _vp]),
     "jpeg_sm100_dev_interleave": (_i, [_vp, C.POINTER(DevPlanar), _u32, _u32, _i, _vp]),
     "jpeg_sm100_dev_unpack_rgb8": (_i, [_vp, _vp, _u64, _i, _vp]),
     "jpeg_sm100_dev_unpack_ycc8": (_i, [_vp, _vp, _u64, _i, _vp]),

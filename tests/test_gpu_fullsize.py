@@ -420,3 +420,38 @@ def _scan_tables(data, cls):
                 if c == cls:
                     slots[tgt] = lib.HuffTable.make(counts, values)
     return slots
+
+
+@pytest.mark.parametrize("size,n,band", [((3840, 2160), 2, 0), ((1936, 1081), 3, 0), ((48, 33), 2, 0), ((16, 16), 1, 0), ((8, 8), 1, 0),
+                                         ((400, 300), 2, 8), ((1000, 250), 2, 8), ((391, 517), 1, 10), ((776, 129), 1, 9)])
+def test_fused_idct_colour_equals_staged_kernels(env, monkeypatch, size, n, band):
+    """K1+K2 fused (k_idct_rgb420 behind jpeg_sm100_dev_spectral_to_rgb8): the same bytes as jpeg_sm100_dev_idct followed by
+    jpeg_sm100_dev_planar_to_rgb8 (JPEG_SM100_FUSE=0), on random sparse coefficients -- strips of 24 MCUs with partial last
+    strips, bands of MCU rows (forced short so that several bands and their re-transformed halo rows are exercised), odd sizes
+    whose luma plane is one block short of the MCU grid -- and the oracle's idct + interleaved + unpack on the first image."""
+    t, b, ctx, dev, O = env["torch"], env["batch"], env["ctx"], env["dev"], env["O"]
+    W, H = size
+    factors = [(2, 2), (1, 1), (1, 1)]
+    geo = b.Geometry(size, factors)
+    buf = b.DeviceBuffers(geo, n, dev)
+    g = t.Generator(device=dev)
+    g.manual_seed(W * 31 + H)
+    for c in buf.coef:
+        dense = t.rand(c.shape, generator=g, device=dev) < 0.15
+        c.copy_(t.where(dense, t.randint(-40, 41, c.shape, generator=g, device=dev), t.zeros((), dtype=t.int64, device=dev)).to(t.int16))
+        c[..., 0] = t.randint(-200, 201, c.shape[:-1], generator=g, device=dev).to(t.int16)
+    q = _quanta(O)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("JPEG_SM100_FUSE", mode)
+        if band:
+            monkeypatch.setenv("JPEG_SM100_FUSE_BAND", str(band))
+        rgb = t.full((n, H, W, 3), 7, dtype=t.uint8, device=dev)
+        ctx.check(ctx.L.jpeg_sm100_dev_spectral_to_rgb8(ctx.h, C.byref(buf.sp), q.ctypes.data, W, H, 0, rgb.data_ptr()))
+        t.cuda.synchronize()
+        out[mode] = rgb
+    assert t.equal(out["1"], out["0"])
+    if W * H <= 1936 * 1081:
+        planes = [O.idct_plane(c[0].cpu().numpy(), q[p]) for p, c in enumerate(buf.coef)]
+        want = O.unpack_rgb(O.interleave(planes, geo.units, geo.factors, size, False))
+        assert np.array_equal(out["1"][0].cpu().numpy(), want)

@@ -361,6 +361,21 @@ def test_scan_decode_parallel_variants(H, O, monkeypatch, tshift, warm):
                 dst.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival)
             for p in range(3):
                 assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (rows, p)
+    # DC-first scans (kind 1): from 64 subsequences per interval up, every subsequence is parsed once per block-in-MCU hypothesis
+    # and the chain of exits picks the right one; Y and the chroma planes use different DC tables here, and the same one below
+    for tables in ([0, 1, 1], [0, 0, 0]):
+        for comps in ([0, 1, 2], [0], [1, 2]):
+            for rows in (0, 2):
+                width = src.blocks[0] if len(comps) > 1 else src.units(comps[0])[0]
+                ecs, dct, act = src.encode_scan((0, 1), (1, None), comps, [tables[c] for c in comps], [0] * len(comps), rows * width)
+                dst = H.Spectral(src.size, fac, process=2)
+                ref = O.Spectral.create(src.size, fac, progressive=True)
+                dst.decode_scan((0, 1), (1, None), [(c, tables[c], 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act),
+                                J.unstuff_split(ecs), (rows * width) or None)
+                ref.decode_scan((0, 1), (1, None), comps, [tables[c] for c in comps], [0] * len(comps), dct, act, J.unstuff_split(ecs),
+                                interval=(rows * width) or O.INTERVAL_NONE)
+                for p in range(3):
+                    assert np.array_equal(dst.planes[p].coef, ref.coefficients(p)), (tables, comps, rows, p)
     # corrupt intervals: flagged by the parallel decoder, diagnosed by the sequential one
     (band, bits, comps, dct, act, parts, ival), = _oracle_scans(O, src, BASELINE, 1)
     rng = np.random.default_rng(11)
@@ -554,6 +569,78 @@ def test_dc_refinement_scan_is_a_bit_gather(H, O):
             with pytest.raises(lib.JpegSm100Error) as ei:
                 dst.decode_scan(band, bits, [(c, 0, 0) for c in cs], _to_lib_tables(H, dct), _to_lib_tables(H, act), short, ival)
             assert ei.value.code == lib.ERR_TRUNCATED_ECS
+
+
+DEEP_REFINEMENT = [((0, 1), (0, None), [0, 1, 2]), ((1, 64), (2, None), [0]), ((1, 20), (1, None), [1]), ((20, 64), (1, None), [1]),
+                   ((1, 64), (1, None), [2]), ((1, 64), (1, 2), [0]), ((1, 9), (0, 1), [0]), ((9, 64), (0, 1), [0]),
+                   ((1, 64), (0, 1), [1]), ((1, 64), (0, 1), [2])]
+
+
+@pytest.mark.parametrize("forced", ["1", "0"])
+@pytest.mark.parametrize("rows", [0, 1, 3])
+def test_ac_refinement_three_phase(H, O, monkeypatch, forced, rows):
+    """kind 4 through k_acr_masks / k_acr_parse / k_acr_apply (forced on, and the one-thread-per-interval kernel forced for the same
+    inputs): two refinement passes over split bands, with and without restart intervals, on a golden image and on sparse random
+    planes whose end-of-band runs span hundreds of blocks; then truncated and garbage refinement data -- same planes and same
+    error codes as the oracle (a flagged interval is left untouched and redone by the sequential kernel)."""
+    from jpeg_b200 import lib
+    monkeypatch.setenv("JPEG_SM100_ACR", forced)
+    rng = np.random.default_rng(5)
+    sources = [O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))]
+    sparse = O.Spectral.create((1000, 72), [(1, 1), (1, 1), (1, 1)], progressive=True)
+    for p in range(3):
+        c = sparse.coefficients(p)
+        c[...] = np.where(rng.random(c.shape) < 0.02, rng.integers(-9, 10, c.shape), 0).astype(np.int16)
+        c[rng.random(c.shape[:2]) < 0.9, 1:] = 0      # long runs of blocks without AC coefficients
+        c[0, :40, 1:] = rng.integers(-3, 4, (40, 63))  # and a dense stretch: many correction bits per symbol
+    sources.append(sparse)
+    for src in sources:
+        fac = [src.factor(p) for p in range(3)]
+        for progression in (PROGRESSIVE, DEEP_REFINEMENT):
+            dst = H.Spectral(src.size, fac, process=2)
+            ref = O.Spectral.create(src.size, fac, progressive=True)
+            scans = _oracle_scans(O, src, progression, rows)
+            for band, bits, comps, dct, act, parts, ival in scans:
+                dst.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival)
+                ref.decode_scan(band, bits, comps, [0] * len(comps), [0] * len(comps), dct, act, parts,
+                                interval=O.INTERVAL_NONE if ival is None else ival)
+            for p in range(3):
+                assert np.array_equal(dst.planes[p].coef, ref.coefficients(p)), (rows, p)
+                assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (rows, p)
+        # damaged refinement scans: the last scan of the progression decoded from a good state, with bad data
+        scans = _oracle_scans(O, src, PROGRESSIVE, rows)
+        band, bits, comps, dct, act, parts, ival = scans[6]  # luma AC refinement
+        cases = []
+        cut = list(parts)
+        cut[-1] = cut[-1][:len(cut[-1]) // 2]
+        cases.append(cut)
+        short = list(parts)
+        short[0] = short[0][:-1]
+        cases.append(short)
+        for k in range(3):
+            junk = list(parts)
+            j = k % len(junk)
+            junk[j] = bytes(rng.integers(0, 256, len(parts[j]), dtype=np.uint8))
+            cases.append(junk)
+        for ci, bad in enumerate(cases):
+            got, want = H.Spectral(src.size, fac, process=2), O.Spectral.create(src.size, fac, progressive=True)
+            for b_, bi_, cs_, d_, a_, pa_, iv_ in scans[:6]:
+                got.decode_scan(b_, bi_, [(c, 0, 0) for c in cs_], _to_lib_tables(H, d_), _to_lib_tables(H, a_), pa_, iv_)
+                want.decode_scan(b_, bi_, cs_, [0] * len(cs_), [0] * len(cs_), d_, a_, pa_, interval=O.INTERVAL_NONE if iv_ is None else iv_)
+            try:
+                got.decode_scan(band, bits, [(c, 0, 0) for c in comps], _to_lib_tables(H, dct), _to_lib_tables(H, act), bad, ival)
+                code = 0
+            except lib.JpegSm100Error as e:
+                code = e.code
+            try:
+                want.decode_scan(band, bits, comps, [0], [0], dct, act, bad, interval=O.INTERVAL_NONE if ival is None else ival)
+                wcode = 0
+            except O.OracleError as e:
+                wcode = e.code
+            assert code == wcode, (ci, code, wcode)
+            if code == 0:
+                for p in range(3):
+                    assert np.array_equal(got.planes[p].coef, want.coefficients(p)), (ci, p)
 
 
 # ------------------------------------------------------------------------------------------------ layer B: batches
