@@ -392,7 +392,7 @@ JPEG_API int jpeg_sm100_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_d
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
     ctx->hint_interval_bytes = total / n_ecs;  // how the parallel decoders cut the intervals
     const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off),
-                                            n_ecs, interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
+                                            n_ecs, interval, extend & (JPEG_SM100_SCAN_EXTEND | JPEG_SM100_SCAN_T81), tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
     ctx->hint_interval_bytes = 0;
     J_TRY(k3);
     int32_t status = 0;
@@ -825,7 +825,7 @@ JPEG_API int jpeg_sm100_decode_scan_raw(jpeg_sm100_ctx *ctx, const jpeg_sm100_sc
     memcpy(tables + 4, ac, sizeof(jpeg_sm100_huff_table) * 4);
     ctx->hint_interval_bytes = raw_len / n_ecs;
     const int k3 = jpeg_huffman_decode_scan(ctx, scan, reinterpret_cast<uint8_t *>(d_ecs), reinterpret_cast<uint64_t *>(d_off), n_ecs,
-                                            interval, extend & JPEG_SM100_SCAN_EXTEND, tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
+                                            interval, extend & (JPEG_SM100_SCAN_EXTEND | JPEG_SM100_SCAN_T81), tables, 1, &ps.sp, reinterpret_cast<int32_t *>(d_status));
     ctx->hint_interval_bytes = 0;
     J_TRY(k3);
     int32_t status = 0;

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -135,6 +136,17 @@ static inline int pinned_release(jpeg_sm100_ctx *ctx, int slot)
     ctx->pinned[slot].in_flight = true;
     return JPEG_SM100_OK;
 }
+
+// ---- restart intervals that are not whole MCU rows: the scan on a virtual MCU grid (remap.cu) ---------------------------------
+struct JpegVirtualScan {
+    jpeg_sm100_scan_desc    scan;  // the scan on the virtual grid (blocks_x = gcd(interval, MCUs), planes in scan order)
+    jpeg_sm100_dev_spectral sp;    // virtual planes (context scratch)
+    alignas(8) unsigned char params[320];
+};
+bool jpeg_virtual_scan_needed(const jpeg_sm100_scan_desc *scan, const jpeg_sm100_dev_spectral *sp, uint64_t interval);
+int  jpeg_virtual_scan_setup(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const jpeg_sm100_dev_spectral *sp, uint64_t interval,
+                             JpegVirtualScan *v);
+int  jpeg_virtual_scan_copy(jpeg_sm100_ctx *ctx, const JpegVirtualScan *v, bool to_virtual);
 
 // ---- geometry helpers (decode.swift:1364-1369) -----------------------------------------------------------------
 static inline int units_of(int size, int stride) { return size / stride + (size % stride != 0 ? 1 : 0); }

@@ -14,9 +14,13 @@
 //     blocks that share a word never race.
 //   * Huffman table construction stays on the host (<= 257 symbols; must reproduce the reference's heap tie-breaking
 //     bit for bit) between the statistics pass and the emit pass.
-//   * progressive AC scans (EOB runs and refinement bits carry state across blocks) run one thread per restart
-//     interval -- a correctness path, not yet a fast one.
+//   * progressive AC scans: end-of-band runs tie blocks together, but who heads a run follows from one flag per block and two
+//     scans (k_enc_acp_flags / k_enc_acp_chain), after which they too run one thread per block through the same three passes.
+#include <time.h>
+
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "common.cuh"
 
@@ -173,6 +177,7 @@ struct EncParams {
     uint32_t *hist;                 // n_images x 8 x 256
     const uint32_t *codes;          // n_images x 8 x 256  (code | len << 16)
     uint32_t *blk_bits;             // n_images x S: bits per block, then exclusive offset within its interval
+    uint32_t *ac_info;              // n_images x S (progressive AC scans): flags, then run | absorbed (see k_enc_acp_chain)
     uint64_t *ivl;                  // n_images x (n_intervals + 1): bits per interval, then byte offset; [n] = total bytes
     uint32_t *raw;                  // unstuffed stream, big-endian words, zeroed
     uint64_t  raw_stride;           // bytes per image
@@ -277,6 +282,32 @@ struct EmitSink {
     }
 };
 
+// progressive AC scans read their block from a transposed copy in shared memory (AcView, below)
+struct AcView {
+    const uint32_t *col;  // this thread's column: word w of the block at col[32 * w]
+    __device__ __forceinline__ int operator[](int z) const { return (int) (short) (col[32 * (z >> 1)] >> (16 * (z & 1))); }
+};
+template <class Sink>
+__device__ __forceinline__ uint32_t encode_block_ac(const EncParams &P, const AcView pl, uint32_t info, Sink &sink);  // (below)
+// A thread's block is 128 contiguous bytes, so the lanes of a warp read 32 different lines whenever they read "coefficient z":
+// 63 two-byte loads per block and pass cost 63 x 32 L1 wavefronts per warp (ncu-less arithmetic: 1.9 ms per pass over 8.3 M
+// blocks).  Instead every lane fetches its block with eight 16-byte loads and parks it as a column of a word-transposed tile in
+// shared memory (conflict-free to write and to read): 63 single-wavefront shared loads per pass.
+__device__ __forceinline__ AcView stage_block_ac(const EncParams &P, uint32_t img, uint32_t blk, bool valid, uint32_t *tile /* [32][blockDim.x] */)
+{
+    uint32_t *col = tile + (threadIdx.x & ~31u) * 32u + (threadIdx.x & 31u);
+    if (valid) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.plane[0] + (size_t) img * P.image_stride[0] + (size_t) blk * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 v = __ldg(src + j);
+            col[32 * (4 * j + 0)] = v.x, col[32 * (4 * j + 1)] = v.y, col[32 * (4 * j + 2)] = v.z, col[32 * (4 * j + 3)] = v.w;
+        }
+    }
+    __syncwarp();
+    return AcView{col};
+}
+
 // encode.swift:919-959 (sequential) / 1013-1044, 1386-1510 (DC first) / 1046-1058, 1513-1557 (DC refine)
 template <class Sink>
 __device__ __forceinline__ void encode_block(const EncParams &P, uint32_t img, uint32_t s, Sink &sink)
@@ -336,11 +367,22 @@ __device__ __forceinline__ void encode_block(const EncParams &P, uint32_t img, u
 __global__ void __launch_bounds__(256) k_enc_hist(const __grid_constant__ EncParams P)
 {
     __shared__ uint32_t h[8 * 256];
+    extern __shared__ uint32_t ac_tile[];  // [32][256] for progressive AC scans (dynamic: the other kinds do not pay for it)
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) h[i] = 0;
     __syncthreads();
     const uint32_t img = blockIdx.y;
     HistSink       sink{h};
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.S; s += gridDim.x * blockDim.x) encode_block(P, img, s, sink);
+    if (P.kind >= 3) {
+        uint32_t *tile = ac_tile;
+        for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < P.S; s0 += gridDim.x * blockDim.x) {
+            const uint32_t s = s0 + threadIdx.x;
+            const AcView   v = stage_block_ac(P, img, s, s < P.S, tile);
+            if (s < P.S) encode_block_ac(P, v, P.ac_info[(size_t) img * P.S + s], sink);
+            __syncwarp();
+        }
+    } else {
+        for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.S; s += gridDim.x * blockDim.x) encode_block(P, img, s, sink);
+    }
     __syncthreads();
     uint32_t *g = P.hist + (size_t) img * 8 * 256;
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x)
@@ -349,7 +391,21 @@ __global__ void __launch_bounds__(256) k_enc_hist(const __grid_constant__ EncPar
 
 __global__ void __launch_bounds__(256) k_enc_len(const __grid_constant__ EncParams P)
 {
+    extern __shared__ uint32_t ac_tile[];
     const uint32_t img = blockIdx.y;
+    if (P.kind >= 3) {
+        for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < P.S; s0 += gridDim.x * blockDim.x) {
+            const uint32_t s = s0 + threadIdx.x;
+            const AcView   v = stage_block_ac(P, img, s, s < P.S, ac_tile);
+            if (s < P.S) {
+                LenSink sink{P.codes + (size_t) img * 8 * 256, 0u};
+                encode_block_ac(P, v, P.ac_info[(size_t) img * P.S + s], sink);
+                P.blk_bits[(size_t) img * P.S + s] = sink.bits;
+            }
+            __syncwarp();
+        }
+        return;
+    }
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.S; s += gridDim.x * blockDim.x) {
         LenSink sink{P.codes + (size_t) img * 8 * 256, 0u};
         encode_block(P, img, s, sink);
@@ -415,18 +471,26 @@ __global__ void __launch_bounds__(1024) k_enc_scan_bits(const __grid_constant__ 
 
 __global__ void __launch_bounds__(256) k_enc_emit(const __grid_constant__ EncParams P)
 {
+    extern __shared__ uint32_t ac_tile[];
     const uint32_t  img = blockIdx.y;
     const uint64_t *ivl = P.ivl + (size_t) img * (P.n_intervals + 1);
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < P.S; s += gridDim.x * blockDim.x) {
-        const uint32_t e = s / P.blocks_per_interval;
-        EmitSink       sink;
-        sink.codes = P.codes + (size_t) img * 8 * 256;
-        sink.words = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(P.raw) + (size_t) img * P.raw_stride);
-        sink.begin(ivl[e] * 8 + P.blk_bits[(size_t) img * P.S + s]);
-        encode_block(P, img, s, sink);
-        const bool last = (s + 1 == P.S) || ((s + 1) % P.blocks_per_interval == 0);
-        if (last) sink.pad_to_byte();
-        sink.finish();
+    for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < P.S; s0 += gridDim.x * blockDim.x) {
+        const uint32_t s = s0 + threadIdx.x;
+        AcView         v{nullptr};
+        if (P.kind >= 3) v = stage_block_ac(P, img, s, s < P.S, ac_tile);
+        if (s < P.S) {
+            const uint32_t e = s / P.blocks_per_interval;
+            EmitSink       sink;
+            sink.codes = P.codes + (size_t) img * 8 * 256;
+            sink.words = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(P.raw) + (size_t) img * P.raw_stride);
+            sink.begin(ivl[e] * 8 + P.blk_bits[(size_t) img * P.S + s]);
+            if (P.kind >= 3) encode_block_ac(P, v, P.ac_info[(size_t) img * P.S + s], sink);
+            else encode_block(P, img, s, sink);
+            const bool last = (s + 1 == P.S) || ((s + 1) % P.blocks_per_interval == 0);
+            if (last) sink.pad_to_byte();
+            sink.finish();
+        }
+        if (P.kind >= 3) __syncwarp();
     }
 }
 
@@ -775,6 +839,209 @@ __device__ void encode_interval_ac(const EncParams &P, uint32_t img, uint32_t e,
     }
 }
 
+// ---- progressive AC scans, one thread per block -----------------------------------------------------------------------------------
+// What ties the blocks of an interval together is only the end-of-band run: a block whose symbols leave trailing zeros (or, in a
+// refinement scan, trailing correction bits) opens a run that absorbs the following `pure` blocks, 4096 blocks at most
+// (encode.swift:1101-1117, 1166-1198).  Whether a block is pure, and whether it opens a run, depends on the block alone; who heads
+// a run and how long it is follows from the positions of the non-pure blocks around it -- two scans over one flag per block:
+//   k_enc_acp_flags   thread per block: PURE (emits nothing but its share of a run), OPENS (ends with something for an EOB);
+//   k_enc_acp_chain   CTA per image: last non-pure block at or before i, next non-pure block after i  ->  info[i] = run length
+//                     if block i heads a run (its offset in the chain of pure blocks is a multiple of 4096) | ABSORBED;
+//   then the histogram / length / emit passes of the sequential scans run one thread per block (encode_block_ac): its own symbols
+//   unless absorbed, the EOBn symbol if it heads a run, its (tail) correction bits -- in exactly the order the serial walk emits.
+constexpr uint32_t ACF_PURE = 1u, ACF_OPENS = 2u, ACI_ABSORBED = 0x80000000u;
+
+struct NullSink {
+    __device__ __forceinline__ void symbol(int, int, uint32_t, int) {}
+    __device__ __forceinline__ void raw(uint32_t, int) {}
+};
+
+// info: 0 while the flags are being computed.  Returns the block's flags.
+template <class Sink>
+__device__ __forceinline__ uint32_t encode_block_ac(const EncParams &P, const AcView pl, uint32_t info, Sink &sink)
+{
+    const int      ac = P.ac[0], al = P.al, lo = P.band_lo, hi = P.band_hi;
+    const bool     refine = P.kind == 4;
+    const int      mask = (int) (short) (uint16_t) (0xffffu << (al + 1));
+    const bool     absorbed = (info & ACI_ABSORBED) != 0u;
+    const int      run = (int) (info & 0xffffu);
+    int            zeroes = 0, tail_from = lo;
+    bool           pure = true;
+    if (!absorbed) {
+        for (int z = lo; z < hi; ++z) {
+            const int c = pl[z], mag = c < 0 ? -c : c, sign = c < 0 ? -1 : 1;
+            if (!refine) {  // encode.swift:1076-1099
+                const int high = sign * (mag >> al);
+                if (high == 0) {
+                    ++zeroes;
+                    continue;
+                }
+                pure = false;
+                for (int i = 0; i < zeroes / 16; ++i) sink.symbol(ac, 0xf0, 0, 0);
+                int      binade;
+                uint32_t tail;
+                compact16(high, binade, tail);
+                sink.symbol(ac, ((zeroes % 16) << 4) | binade, tail, binade);
+                zeroes = 0;
+            } else {  // encode.swift:1130-1164
+                const int product = mag & mask, low = sign * ((mag & ~mask) >> al);
+                if (product != 0) continue;
+                if (low == 0) {
+                    ++zeroes;
+                    continue;
+                }
+                pure = false;
+                // newly significant: ZRLs (each followed by the correction bits staged during its 16 zeros), then (zeroes % 16, low)
+                // followed by the remaining staged bits
+                int zseen = 0, zz = tail_from;
+                for (int i = 0; i < zeroes / 16; ++i) {
+                    sink.symbol(ac, 0xf0, 0, 0);
+                    for (; zz < z; ++zz) {
+                        const int c2 = pl[zz], m2 = c2 < 0 ? -c2 : c2;
+                        if ((m2 & mask) != 0) sink.raw((uint32_t) (((m2 & ~mask) >> al) & 1), 1);
+                        else if (++zseen % 16 == 0) {
+                            ++zz;
+                            break;
+                        }
+                    }
+                }
+                int      binade;
+                uint32_t tail;
+                compact16(low, binade, tail);
+                sink.symbol(ac, ((zeroes % 16) << 4) | binade, tail, binade);
+                for (; zz < z; ++zz) {
+                    const int c2 = pl[zz], m2 = c2 < 0 ? -c2 : c2;
+                    if ((m2 & mask) != 0) sink.raw((uint32_t) (((m2 & ~mask) >> al) & 1), 1);
+                }
+                zeroes = 0;
+                tail_from = z + 1;
+            }
+        }
+    }
+    if (run > 0) {
+        const int binade = 31 - __clz(run);
+        sink.symbol(ac, binade << 4, (uint32_t) (run & ~(1 << binade)), binade);
+    }
+    bool tail_bits = false;
+    if (refine)  // the correction bits after the block's last symbol (all of them for an absorbed block)
+        for (int z = tail_from; z < hi; ++z) {
+            const int c = pl[z], mag = c < 0 ? -c : c;
+            if ((mag & mask) != 0) {
+                tail_bits = true;
+                sink.raw((uint32_t) (((mag & ~mask) >> al) & 1), 1);
+            }
+        }
+    return (pure ? ACF_PURE : 0u) | ((zeroes > 0 || tail_bits) ? ACF_OPENS : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_enc_acp_flags(const __grid_constant__ EncParams P)
+{
+    __shared__ uint32_t tile[32 * 256];
+    const uint32_t img = blockIdx.y;
+    NullSink       sink;
+    for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < P.S; s0 += gridDim.x * blockDim.x) {  // (whole warps stay in the loop: stage_block_ac syncs them)
+        const uint32_t s = s0 + threadIdx.x;
+        const AcView   v = stage_block_ac(P, img, s, s < P.S, tile);
+        if (s < P.S) P.ac_info[(size_t) img * P.S + s] = encode_block_ac(P, v, 0u, sink);
+        __syncwarp();
+    }
+}
+
+// one CTA per image; interval by interval, tiles of 1024 blocks forwards (last non-pure block at or before i) and then backwards
+// (next non-pure block after i), carries in shared memory.  blk_bits serves as scratch for the forward result.
+__global__ void __launch_bounds__(1024) k_enc_acp_chain(const __grid_constant__ EncParams P)
+{
+    __shared__ int32_t warp_v[32];
+    __shared__ int32_t carry;
+    const uint32_t img = blockIdx.x;
+    uint32_t      *info = P.ac_info + (size_t) img * P.S;
+    int32_t       *last_np = reinterpret_cast<int32_t *>(P.blk_bits + (size_t) img * P.S);
+    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t e = 0; e < P.n_intervals; ++e) {
+        const int32_t lo = (int32_t) (e * P.blocks_per_interval), hi = (int32_t) min(P.S, (uint32_t) lo + P.blocks_per_interval);
+        // ---- forwards: inclusive max-scan of (i if block i is not pure else lo - 1)
+        if (threadIdx.x == 0) carry = lo - 1;
+        __syncthreads();
+        for (int32_t base = lo; base < hi; base += 1024) {
+            const int32_t i = base + (int32_t) threadIdx.x;
+            int32_t       x = (i < hi && !(info[i] & ACF_PURE)) ? i : lo - 1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x = max(x, y);
+            }
+            if (lane == 31) warp_v[wid] = x;
+            __syncthreads();
+            if (wid == 0) {
+                int32_t w = warp_v[lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                    if (lane >= d) w = max(w, y);
+                }
+                warp_v[lane] = w;
+            }
+            __syncthreads();
+            const int32_t c = carry;
+            const int32_t v = max(max(x, wid ? warp_v[wid - 1] : lo - 1), c);
+            if (i < hi) last_np[i] = v;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = max(c, warp_v[31]);
+            __syncthreads();
+        }
+        // ---- backwards: exclusive min-scan of (i if block i is not pure else hi) from the right, then the verdict per block
+        if (threadIdx.x == 0) carry = hi;
+        __syncthreads();
+        const int32_t n_tiles = (hi - lo + 1023) / 1024;
+        for (int32_t t = n_tiles - 1; t >= 0; --t) {
+            const int32_t i = lo + t * 1024 + 1023 - (int32_t) threadIdx.x;  // thread 0 takes the tile's last block
+            const uint32_t f = i < hi ? info[i] : ACF_PURE;
+            const int32_t  own = (i < hi && !(f & ACF_PURE)) ? i : hi;
+            int32_t        x = own;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x = min(x, y);
+            }
+            if (lane == 31) warp_v[wid] = x;
+            __syncthreads();
+            if (wid == 0) {
+                int32_t w = warp_v[lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                    if (lane >= d) w = min(w, y);
+                }
+                warp_v[lane] = w;
+            }
+            __syncthreads();
+            const int32_t c = carry;
+            // exclusive: the blocks strictly after i = the threads before this one in the reversed tile, and the tiles to the right
+            int32_t after = __shfl_up_sync(0xffffffffu, x, 1);
+            if (lane == 0) after = hi;
+            const int32_t next_np = min(min(after, wid ? warp_v[wid - 1] : hi), c);
+            if (i < hi) {
+                uint32_t out;
+                if (!(f & ACF_PURE)) {
+                    out = (f & ACF_OPENS) ? (uint32_t) min(4096, next_np - i) : 0u;  // heads a run iff it ends with something for an EOB
+                } else {
+                    const int32_t j = last_np[i];  // last non-pure block before i (lo - 1: none)
+                    const int32_t head = (j >= lo && (info[j] & ACF_OPENS)) ? j : j + 1;
+                    const int32_t off = i - head;
+                    out = (off % 4096 == 0) ? (uint32_t) min(4096, next_np - i) : ACI_ABSORBED;
+                }
+                // (the flags of block i are read by the pure blocks after it: info[] is rewritten only after the whole interval is judged)
+                last_np[i] = (int32_t) out;
+            }
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = min(c, warp_v[31]);
+            __syncthreads();
+        }
+        for (int32_t i = lo + (int32_t) threadIdx.x; i < hi; i += 1024) info[i] = (uint32_t) last_np[i];
+        __syncthreads();
+    }
+}
+
 struct GlobalHistSink {
     uint32_t *h;
     __device__ __forceinline__ void symbol(int table, int sym, uint32_t, int) { atomicAdd(&h[table * 256 + sym], 1u); }
@@ -829,6 +1096,13 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
 {
     if (!scan || !sp || !tables_out || !d_ecs || !d_ecs_len) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     if (scan->n_comp < 1 || scan->n_comp > 4) return JPEG_SM100_ERR_INVALID_ARGUMENT;
+    if (interval_mcus && jpeg_virtual_scan_needed(scan, sp, interval_mcus)) {
+        // an interval that is not whole MCU rows (ITU-T T.81 E.1.4): the same MCUs in the same order on a virtual grid (remap.cu)
+        JpegVirtualScan v;
+        J_TRY(jpeg_virtual_scan_setup(ctx, scan, sp, interval_mcus, &v));
+        J_TRY(jpeg_virtual_scan_copy(ctx, &v, true));
+        return jpeg_huffman_encode_scan(ctx, &v.scan, &v.sp, interval_mcus, tables_out, d_ecs, ecs_image_stride, d_ecs_len, h_needed);
+    }
     if (!(scan->band_lo >= 0 && scan->band_lo < scan->band_hi && scan->band_hi <= 64)) return JPEG_SM100_ERR_INVALID_ARGUMENT;
     const uint32_t n_images = sp->n_images;
     if (n_images == 0) return JPEG_SM100_OK;
@@ -892,7 +1166,7 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     if (P.blocks_per_interval == 0) P.blocks_per_interval = 1;
     P.n_intervals = P.S ? (P.S + P.blocks_per_interval - 1) / P.blocks_per_interval : 1;
     // worst case per block: 64 x (16 + 16) bits; intervals must stay below 2^32 bits for the 32-bit in-interval offsets
-    if ((uint64_t) P.blocks_per_interval * 64 * 32 > 0xffffffffull && P.kind <= 2) {
+    if ((uint64_t) P.blocks_per_interval * 64 * 32 > 0xffffffffull) {
         // tighter, still safe bound is not available before the length pass; cap the interval size instead
         if ((uint64_t) P.blocks_per_interval > (1ull << 21)) return JPEG_SM100_ERR_UNSUPPORTED;
     }
@@ -902,13 +1176,17 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     const size_t code_bytes = hist_bytes;
     const size_t bits_bytes = align_up((size_t) n_images * std::max<uint32_t>(P.S, 1) * 4, 256);
     const size_t ivl_bytes = align_up((size_t) n_images * (P.n_intervals + 1) * 8, 256);
+    // progressive AC scans: one thread per block (k_enc_acp_*); JPEG_SM100_ENC_AC=seq keeps the one-thread-per-interval kernels (A/B)
+    const char *ac_env = getenv("JPEG_SM100_ENC_AC");
+    const bool  ac_blocks = P.kind >= 3 && !(ac_env && strcmp(ac_env, "seq") == 0);
     void        *work = nullptr;
-    J_TRY(scratch_reserve(ctx, 10, hist_bytes + code_bytes + bits_bytes + ivl_bytes + 1024, &work));
+    J_TRY(scratch_reserve(ctx, 10, hist_bytes + code_bytes + bits_bytes * (ac_blocks ? 2 : 1) + ivl_bytes + 1024, &work));
     uint8_t *wp = reinterpret_cast<uint8_t *>(work);
     P.hist = reinterpret_cast<uint32_t *>(wp);
     P.codes = reinterpret_cast<uint32_t *>(wp + hist_bytes);
     P.blk_bits = reinterpret_cast<uint32_t *>(wp + hist_bytes + code_bytes);
     P.ivl = reinterpret_cast<uint64_t *>(wp + hist_bytes + code_bytes + bits_bytes);
+    P.ac_info = ac_blocks ? reinterpret_cast<uint32_t *>(wp + hist_bytes + code_bytes + bits_bytes + ivl_bytes) : nullptr;
     P.out = d_ecs;
     P.out_stride = ecs_image_stride;
     P.out_len = d_ecs_len;
@@ -917,43 +1195,81 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
 
     const dim3 grid_blocks(std::max<uint32_t>(1, std::min<uint32_t>((P.S + 255) / 256, (uint32_t) ctx->sm_count * 8)), n_images);
     const dim3 grid_ivl((P.n_intervals + 31) / 32, n_images);
+    const size_t ac_smem = ac_blocks ? (size_t) 32 * 256 * 4 : 0;  // the transposed block tile of stage_block_ac
 
+    // JPEG_SM100_TRACE: wall-clock split of the call (a diagnostic: adds stream synchronisations)
+    static const bool trace = getenv("JPEG_SM100_TRACE") != nullptr;
+    timespec          tr_t[6];
+    int               tr_n = 0;
+    auto              tick = [&](bool sync) {
+        if (!trace) return;
+        if (sync) cudaStreamSynchronize(ctx->stream);
+        clock_gettime(CLOCK_MONOTONIC, &tr_t[tr_n++]);
+    };
+    tick(true);
     // ---- pass 1: statistics -> optimal tables (host) ----------------------------------------------------------
     std::vector<uint32_t> h_hist((size_t) n_images * 8 * 256, 0u), h_codes((size_t) n_images * 8 * 256, 0u);
     const bool need_dc = P.kind == 0 || P.kind == 1, need_ac = P.kind == 0 || P.kind == 3 || P.kind == 4;
     if (P.kind != 2) {
         if (P.S) {
-            if (P.kind <= 1) k_enc_hist<<<grid_blocks, 256, 0, ctx->stream>>>(P);
+            if (ac_blocks) {
+                k_enc_acp_flags<<<grid_blocks, 256, 0, ctx->stream>>>(P);
+                LAUNCH_CHECK(ctx);
+                k_enc_acp_chain<<<n_images, 1024, 0, ctx->stream>>>(P);
+                LAUNCH_CHECK(ctx);
+            }
+            if (P.kind <= 1 || ac_blocks) k_enc_hist<<<grid_blocks, 256, ac_smem, ctx->stream>>>(P);
             else k_enc_ac<0><<<grid_ivl, 32, 0, ctx->stream>>>(P);
             LAUNCH_CHECK(ctx);
         }
         CU_TRY(ctx, cudaMemcpyAsync(h_hist.data(), P.hist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    for (uint32_t i = 0; i < n_images; ++i) {
-        jpeg_sm100_huff_table *t = tables_out + (size_t) i * 8;
-        memset(t, 0, sizeof(jpeg_sm100_huff_table) * 8);
+    tick(false);  // [1] statistics on the device, read back
+    // one optimal table per (image, slot): independent heaps of <= 257 leaves (~40 us each) -- a batch spreads them over host threads
+    {
         bool used[8] = {false, false, false, false, false, false, false, false};
         for (int c = 0; c < scan->n_comp; ++c) {
             if (need_dc) used[P.dc[c]] = true;
             if (need_ac) used[P.ac[c]] = true;
         }
-        for (int k = 0; k < 8; ++k) {
-            if (!used[k]) continue;
-            const uint32_t *f = h_hist.data() + ((size_t) i * 8 + k) * 256;
-            bool any = false;
-            for (int v = 0; v < 256; ++v) any |= f[v] != 0;
-            if (!any) return JPEG_SM100_ERR_PRECONDITION;  // encode.swift:705: all-zero frequencies trap
-            huffman_from_frequencies(f, t[k]);
-            canonical_codes(t[k], h_codes.data() + ((size_t) i * 8 + k) * 256);
+        std::atomic<int> failed{0};
+        auto build = [&](uint32_t i0, uint32_t i1) {
+            for (uint32_t i = i0; i < i1; ++i) {
+                jpeg_sm100_huff_table *t = tables_out + (size_t) i * 8;
+                memset(t, 0, sizeof(jpeg_sm100_huff_table) * 8);
+                for (int k = 0; k < 8; ++k) {
+                    if (!used[k]) continue;
+                    const uint32_t *f = h_hist.data() + ((size_t) i * 8 + k) * 256;
+                    bool any = false;
+                    for (int v = 0; v < 256; ++v) any |= f[v] != 0;
+                    if (!any) {  // encode.swift:705: all-zero frequencies trap
+                        failed.store(1);
+                        continue;
+                    }
+                    huffman_from_frequencies(f, t[k]);
+                    canonical_codes(t[k], h_codes.data() + ((size_t) i * 8 + k) * 256);
+                }
+            }
+        };
+        const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+        const uint32_t n_thr = std::min<uint32_t>(std::min<uint32_t>(hw, 16u), n_images / 8u);
+        if (n_thr <= 1) build(0, n_images);
+        else {
+            std::vector<std::thread> pool;
+            const uint32_t           per = (n_images + n_thr - 1) / n_thr;
+            for (uint32_t t0 = 0; t0 < n_images; t0 += per) pool.emplace_back(build, t0, std::min(n_images, t0 + per));
+            for (auto &th : pool) th.join();
         }
+        if (failed.load()) return JPEG_SM100_ERR_PRECONDITION;
     }
+    tick(false);  // [2] tables on the host
     CU_TRY(ctx, cudaMemcpyAsync(const_cast<uint32_t *>(P.codes), h_codes.data(), code_bytes, cudaMemcpyHostToDevice, ctx->stream));
 
     // ---- pass 2: lengths and offsets ----------------------------------------------------------------------------
     if (P.S) {
-        if (P.kind <= 2) {
-            k_enc_len<<<grid_blocks, 256, 0, ctx->stream>>>(P);
+        if (P.kind <= 2 || ac_blocks) {
+            k_enc_len<<<grid_blocks, 256, ac_smem, ctx->stream>>>(P);
             LAUNCH_CHECK(ctx);
             k_enc_scan_bits<<<n_images, 1024, 0, ctx->stream>>>(P);
             LAUNCH_CHECK(ctx);
@@ -969,6 +1285,7 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
     CU_TRY(ctx, cudaMemcpyAsync(h_ivl.data(), P.ivl, h_ivl.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     uint64_t max_raw = 0;
+    tick(false);  // [3] lengths + offsets on the device, read back
     for (uint32_t i = 0; i < n_images; ++i) max_raw = std::max(max_raw, h_ivl[(size_t) i * (P.n_intervals + 1) + P.n_intervals]);
     P.raw_stride = align_up(max_raw + 8, 256);
     void *raw = nullptr;
@@ -978,7 +1295,7 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
 
     // ---- pass 3: emit, stuff --------------------------------------------------------------------------------------
     if (P.S) {
-        if (P.kind <= 2) k_enc_emit<<<grid_blocks, 256, 0, ctx->stream>>>(P);
+        if (P.kind <= 2 || ac_blocks) k_enc_emit<<<grid_blocks, 256, ac_smem, ctx->stream>>>(P);
         else k_enc_ac<2><<<grid_ivl, 32, 0, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
@@ -995,6 +1312,12 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         LAUNCH_CHECK(ctx);
         k_enc_stuff_scatter<<<grid_t, STUFF_THREADS, 0, ctx->stream>>>(P, tiles_max, reinterpret_cast<const uint32_t *>(tf));
         LAUNCH_CHECK(ctx);
+    }
+    if (trace) {
+        tick(true);  // [4] emit + stuffing
+        auto ms = [&](int a, int b) { return (tr_t[b].tv_sec - tr_t[a].tv_sec) * 1e3 + (tr_t[b].tv_nsec - tr_t[a].tv_nsec) * 1e-6; };
+        fprintf(stderr, "[jpeg_sm100] encode scan band %d..%d bits %d/%d comps %d images %u: statistics %.3f ms, host tables %.3f, lengths %.3f, emit %.3f\n",
+                scan->band_lo, scan->band_hi, scan->bit_hi, scan->bit_lo, scan->n_comp, n_images, ms(0, 1), ms(1, 2), ms(2, 3), ms(3, 4));
     }
     if (h_needed) {
         std::vector<uint64_t> lens(n_images);

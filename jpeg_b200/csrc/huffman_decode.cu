@@ -2552,62 +2552,47 @@ __device__ __noinline__ uint32_t acr_edge_word(const uint32_t *w0, uint32_t i, u
     }
     return v;
 }
-struct AcrWindow {
+struct AcrWindow {  // absolute bit cursor + the three stream words around it; the 32 bits at the cursor are one funnel shift away
     const uint32_t *w0;  // the aligned word that holds the interval's first byte
-    uint32_t        lead, nbytes, count;
+    uint32_t        lead, nbytes;
     uint32_t        w_lo, w_n;  // words w_lo .. w_lo + w_n - 1 lie wholly inside the interval
-    uint64_t        acc;        // MSB-aligned; more than 32 valid bits whenever a symbol is read
-    int             nav;
-    uint32_t        wi, nxt, pos;
+    uint32_t        a, end;     // cursor and end of data, in bits from w0
+    uint32_t        wi, hi, lo, nxt;  // words wi, wi + 1, wi + 2 (big-endian); wi == a >> 5
     __device__ __forceinline__ uint32_t word(uint32_t i) const  // big-endian word i of the 1-padded stream (jpeg.swift:1881-1887)
     {
         if (i - w_lo < w_n) return __byte_perm(__ldg(w0 + i), 0, 0x0123);
         return acr_edge_word(w0, i, lead, nbytes);
     }
-    __device__ __forceinline__ void seek(uint32_t p)
+    __device__ __forceinline__ void seek(uint32_t abs_bit)
     {
-        pos = p;
-        const uint32_t ab = lead * 8u + p, i = ab >> 5, sh = ab & 31u;
-        acc = (((uint64_t) word(i) << 32) | word(i + 1)) << sh;
-        nav = 64 - (int) sh;
-        nxt = word(i + 2);
-        wi = i + 3;
-        refill();
+        a = abs_bit;
+        wi = a >> 5;
+        hi = word(wi), lo = word(wi + 1), nxt = word(wi + 2);
     }
     __device__ __forceinline__ void init(const uint8_t *base, uint32_t n)
     {
         lead = (uint32_t) (reinterpret_cast<uintptr_t>(base) & 3u);
         w0 = reinterpret_cast<const uint32_t *>(base - lead);
         nbytes = n;
-        count = 8u * n;
+        end = 8u * (lead + n);
         w_lo = lead ? 1u : 0u;
         const uint32_t w_hi = (lead + n) >> 2;  // first word that is not wholly inside
         w_n = w_hi > w_lo ? w_hi - w_lo : 0u;
-        seek(0);
+        seek(8u * lead);
     }
-    __device__ __forceinline__ void refill()
+    __device__ __forceinline__ uint32_t pos() const { return a - 8u * lead; }
+    __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(lo, hi, a); }
+    __device__ __forceinline__ void advance(uint32_t n)
     {
-        if (nav <= 32) {
-            acc |= (uint64_t) nxt << (32 - nav);
-            nav += 32;
-            nxt = word(wi);
-            wi += 1;
-        }
-    }
-    __device__ __forceinline__ void consume(uint32_t n)  // n <= 32
-    {
-        acc <<= n;
-        nav -= (int) n;
-        pos += n;
-        refill();
-    }
-    __device__ __forceinline__ void skip(uint32_t k)
-    {
-        if (k > 32u) {
-            seek(pos + k);
+        a += n;
+        const uint32_t d = (a >> 5) - wi;
+        if (d == 0u) return;
+        if (d == 1u) {
+            hi = lo, lo = nxt, wi += 1u;
+            nxt = word(wi + 2u);  // (needed two words from now: the load is off the symbol-to-symbol chain)
             return;
         }
-        consume(k);
+        seek(a);
     }
 };
 
@@ -2633,17 +2618,15 @@ __device__ __forceinline__ bool acr_parse_block(AcrWindow &br, const uint64_t m,
     __syncwarp();
     int z = band_lo, rho = 0;
     while (z < band_hi) {
-        uint32_t ent = tab[(uint32_t) (br.acc >> (64 - FAST_BITS))];
-        if (ent & FAST_LINK) {
-            const uint32_t rest = (uint32_t) (br.acc >> 48) & ((1u << (16 - FAST_BITS)) - 1u);
-            ent = tab[(ent >> 10) + (rest >> (ent & 7u))];
-        }
+        const uint32_t top = br.top();
+        uint32_t       ent = tab[top >> (32 - FAST_BITS)];
+        if (ent & FAST_LINK) ent = tab[(ent >> 10) + (((top >> 16) & ((1u << (16 - FAST_BITS)) - 1u)) >> (ent & 7u))];
         const uint32_t len = ent & 0x7fu, size = (ent >> 8) & 0xffu, adv = (ent >> 16) & 0xffu, total = ent >> 24;
-        if (ent == 0u || !(br.pos + total <= br.count)) return false;
+        if (ent == 0u) return false;
         int zeroes;
         if (adv & 0x80u) {  // EOBn: the rest of this block and of the next run - 1 blocks is correction bits
             zeroes = 64;
-            skip = (int) ((1u << size) | (size ? (uint32_t) ((br.acc << len) >> (64 - size)) : 0u)) - 1;
+            skip = (int) ((1u << size) | (size ? (top << len) >> (32 - size) : 0u)) - 1;
         } else if (size == 0u) {
             zeroes = 15;  // ZRL
         } else if (size == 1u) {
@@ -2651,18 +2634,17 @@ __device__ __forceinline__ bool acr_parse_block(AcrWindow &br, const uint64_t m,
         } else {
             return false;  // decode.swift:3099-3102: a refinement value must be -1, 0 or 1
         }
-        br.consume(total);
         const int n = rho + zeroes;
         if (n >= nz) {  // fewer zeros left than the symbol passes: the walk runs off the band, refining what is left
-            const uint32_t k = (uint32_t) ((band_hi - z) - (nz - rho));
-            if (!(br.pos + k <= br.count)) return false;
-            br.skip(k);
+            const uint32_t k = total + (uint32_t) ((band_hi - z) - (nz - rho));
+            if (!(br.a + k <= br.end)) return false;
+            br.advance(k);
             break;
         }
         const int      target = (int) sel[n];
-        const uint32_t k = (uint32_t) (target - z - zeroes);
-        if (!(br.pos + k <= br.count)) return false;
-        br.skip(k);
+        const uint32_t k = total + (uint32_t) (target - z - zeroes);  // the symbol, then one correction bit per non-zero coefficient passed
+        if (!(br.a + k <= br.end)) return false;
+        br.advance(k);
         z = target + 1;
         rho = n + 1;
     }
@@ -2724,16 +2706,16 @@ __global__ void __launch_bounds__(WARP) k_acr_parse(const __grid_constant__ Scan
                         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
                         if ((int) lane >= d) inc += t;
                     }
-                    if (lane < n) rc[b + lane] = (br.pos + inc - k) | ACR_EOB;
+                    if (lane < n) rc[b + lane] = (br.pos() + inc - k) | ACR_EOB;
                     const uint32_t sum = __shfl_sync(0xffffffffu, inc, WARP - 1);
-                    if (!(br.pos + sum <= br.count)) bad = true;
-                    else br.skip(sum);
+                    if (!(br.a + sum <= br.end)) bad = true;
+                    else br.advance(sum);
                     skip -= (int) n;
                     b += n;
                     m_next = b < b1 ? __ldg(mk + b) : 0ull;
                     continue;
                 }
-                if (lane == 0) rc[b] = br.pos;
+                if (lane == 0) rc[b] = br.pos();
                 const uint64_t m = m_next;
                 b += 1;
                 m_next = b < b1 ? __ldg(mk + b) : 0ull;  // (the next block's map is on its way while this one is parsed)
@@ -2880,6 +2862,15 @@ int jpeg_huffman_decode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
                              const jpeg_sm100_dev_spectral *sp, int32_t *d_status)
 {
     static const bool trace = getenv("JPEG_SM100_TRACE") != nullptr;
+    if ((extend & JPEG_SM100_SCAN_T81) && jpeg_virtual_scan_needed(scan, sp, interval)) {
+        // ITU-T T.81 placement of an interval that is not whole MCU rows: the same scan on a virtual MCU grid (remap.cu)
+        JpegVirtualScan v;
+        J_TRY(jpeg_virtual_scan_setup(ctx, scan, sp, interval, &v));
+        if (!(extend & JPEG_SM100_SCAN_FRESH)) J_TRY(jpeg_virtual_scan_copy(ctx, &v, true));
+        J_TRY(decode_scan_impl(ctx, &v.scan, d_ecs, d_offsets, n_ecs, interval, extend & ~JPEG_SM100_SCAN_T81, tables, tables_shared, &v.sp, d_status));
+        return jpeg_virtual_scan_copy(ctx, &v, false);
+    }
+    extend &= ~JPEG_SM100_SCAN_T81;
     if (!trace) return decode_scan_impl(ctx, scan, d_ecs, d_offsets, n_ecs, interval, extend, tables, tables_shared, sp, d_status);
     cudaStreamSynchronize(ctx->stream);
     timespec t0, t1;

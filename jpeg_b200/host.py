@@ -416,11 +416,14 @@ class Spectral:
 
     # ---- container: JPEG.Context.decompress (decode.swift:3728-3960) ----------------------------------------
     @classmethod
-    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None, on_scan=None, resident=False):
+    def decompress(cls, data: bytes, ctx=None, gpu_lexer=False, format=None, on_scan=None, resident=False, t81_intervals=False):
         """on_scan(spectral, scan): called after every scan with the image as JPEG.Context holds it at that point -- the
         capture closure of examples/decode-online/main.swift:252-282 (online / progressive display).
-        resident: the image stays in HBM across its scans and stages (see __init__)."""
-        return _decompress(data, ctx or default_context(), gpu_lexer, format, on_scan, resident)
+        resident: the image stays in HBM across its scans and stages (see __init__).
+        t81_intervals: restart intervals are placed as ITU-T T.81 defines them (interval e starts at MCU e * Ri; JPEG_SM100_SCAN_T81)
+        instead of the reference's placement by rows (decode.swift:3205-3207), which mis-decodes files whose DRI is not a whole
+        number of MCU rows.  An extension; the default is the reference's behaviour."""
+        return _decompress(data, ctx or default_context(), gpu_lexer, format, on_scan, resident, t81_intervals)
 
     def compress(self, scans=None, quanta_slots=None, interval_mcus=0, jfif=True):
         return _compress(self, scans, quanta_slots, interval_mcus, jfif)
@@ -623,7 +626,7 @@ def _push_quanta(s, qslot, tables):
         qslot[tgt] = len(s.quanta) - 1
 
 
-def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None, resident=False):
+def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None, resident=False, t81_intervals=False):
     lx = _Lexer(bytes(data))
     _, m, body = lx.segment()
     if m != 0xD8:
@@ -793,10 +796,11 @@ def _decompress(data, ctx, gpu_lexer=False, format=None, on_scan=None, resident=
                     s.set_size((fw, (body[0] << 8) | body[1]))
                 elif fh == 0:
                     raise DecodingError("missingHeightRedefinitionSegment")
+            flags = (L.SCAN_EXTEND if first else 0) | (L.SCAN_T81 if t81_intervals else 0)
             if gpu_lexer:
-                s.decode_scan_raw(band, bits, comps_, dc, ac, raw, ival, extend=first)
+                s.decode_scan_raw(band, bits, comps_, dc, ac, raw, ival, extend=flags)
             else:
-                s.decode_scan(band, bits, comps_, dc, ac, ecss, ival, extend=first)
+                s.decode_scan(band, bits, comps_, dc, ac, ecss, ival, extend=flags)
             s.scans.append(Scan(band, bits, comps_))
             if first:
                 if m == 0xDC:

@@ -643,6 +643,95 @@ def test_ac_refinement_three_phase(H, O, monkeypatch, forced, rows):
                     assert np.array_equal(got.planes[p].coef, want.coefficients(p)), (ci, p)
 
 
+def _oracle_on_virtual_grid(O, src, comps, interval):
+    """The oracle extended to ITU-T T.81 interval placement the same way the library is (remap.cu): the scan's MCUs, in order, on
+    a grid of gcd(interval, MCUs) columns, where every interval is whole rows.  Returns the virtual Spectral (scan components only)."""
+    import math
+    inter = len(comps) > 1
+    W, Hh = src.blocks if inter else src.units(comps[0])
+    fac = [src.factor(c) for c in comps] if inter else [(1, 1)]
+    sx, sy = (max(f[0] for f in fac), max(f[1] for f in fac))
+    M = W * Hh
+    g = math.gcd(interval, M)
+    v = O.Spectral.create((g * 8 * sx, (M // g) * 8 * sy), fac, progressive=True)
+    m = np.arange(M)
+    for i, c in enumerate(comps):
+        fx, fy = fac[i]
+        real, virt = src.coefficients(c), v.coefficients(i)
+        assert virt.shape[:2] == ((M // g) * fy, g * fx)
+        for dy in range(fy):
+            for dx in range(fx):
+                ry, rx = (m // W) * fy + dy, (m % W) * fx + dx
+                vy, vx = (m // g) * fy + dy, (m % g) * fx + dx
+                ok = (ry < real.shape[0]) & (rx < real.shape[1])
+                virt[vy[ok], vx[ok]] = real[ry[ok], rx[ok]]
+    return v
+
+
+@pytest.mark.parametrize("name,progression", [("baseline", BASELINE), ("split", BASELINE_SPLIT), ("progressive", PROGRESSIVE)])
+def test_restart_intervals_that_are_not_whole_rows(H, O, name, progression):
+    """N2: interval e starts at MCU e * Ri wherever that falls in its row (ITU-T T.81 E.1.4; JPEG_SM100_SCAN_T81 on decode, any
+    interval_mcus on encode).  The reference cannot be the oracle here (it places intervals by rows, decode.swift:3205-3207, and
+    never writes DRI), so: the GPU encoder's bytes and tables equal the oracle's on the virtual grid of the same MCUs, and the
+    GPU decoder returns the coefficients the scans were made from -- all five scan kinds, partial MCUs, intervals of 1 MCU,
+    primes, just over a row, and longer than the scan."""
+    from jpeg_b200 import lib
+    rng = np.random.default_rng(23)
+    odd = O.Spectral.create((131, 77), [(2, 2), (1, 1), (1, 1)], progressive=True)  # 17 x 10 luma blocks on a 9 x 5 MCU grid
+    for p in range(3):
+        c = odd.coefficients(p)
+        c[...] = np.where(rng.random(c.shape) < 0.2, rng.integers(-30, 31, c.shape), 0).astype(np.int16)
+        c[..., 0] = rng.integers(-300, 301, c.shape[:2])
+    for src in (O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg")), odd):
+        _t81_roundtrip(H, O, lib, src, progression)
+
+
+def test_whole_file_with_odd_restart_interval(H, O):
+    """compress(interval_mcus = 7 and 33) -> DRI + RSTn every 7 / 33 MCUs -> decompress(t81_intervals=True), host lexer and GPU
+    lexer, host planes and resident image: the coefficients and the pixels of the file without restart intervals."""
+    data = golden_bytes("gold/color-sequential-1.jpg")
+    plain = H.Spectral.decompress(data)
+    rgb = plain.to_rgb8()
+    for ival in (7, 33):
+        assert ival % (-(-plain.size[0] // 16)) != 0
+        again = plain.compress(interval_mcus=ival)
+        assert sum(again.count(bytes([0xff, 0xd0 + k])) for k in range(8)) > 10
+        for kw in (dict(), dict(gpu_lexer=True), dict(resident=True), dict(resident=True, gpu_lexer=True)):
+            back = H.Spectral.decompress(again, t81_intervals=True, **kw)
+            for p in range(plain.ncomp):
+                assert np.array_equal(back.planes[p].coef, plain.planes[p].coef), (ival, kw, p)
+            assert np.array_equal(back.to_rgb8(), rgb), (ival, kw)
+
+
+def _t81_roundtrip(H, O, lib, src, progression):
+    fac = [src.factor(p) for p in range(3)]
+    dev = H.Spectral(src.size, fac, process=2)
+    for p in range(3):
+        dev.planes[p].coef = np.array(src.coefficients(p))
+    for k, ival_of in enumerate((lambda W, M: 7, lambda W, M: W + 3, lambda W, M: 1 if M < 700 else 101, lambda W, M: M + 5)):
+        dst = H.Spectral(src.size, fac, process=2)
+        for band, bits, comps in progression:
+            W, Hh = src.blocks if len(comps) > 1 else src.units(comps[0])
+            ival = ival_of(W, W * Hh)
+            assert ival % W != 0
+            sel = [0, 1, 1][:len(comps)] if len(comps) > 1 else [0]
+            v = _oracle_on_virtual_grid(O, src, comps, ival)
+            want, dct, act = v.encode_scan(band, bits, list(range(len(comps))), sel, sel, ival)
+            got, gdc, gac = dev.encode_scan(band, bits, [(c, d, d) for c, d in zip(comps, sel)], ival)
+            for t in range(4):
+                if dct[t].present:
+                    assert gdc[t].as_tuple() == dct[t].as_tuple(), (k, band, bits, comps)
+                if act[t].present:
+                    assert gac[t].as_tuple() == act[t].as_tuple(), (k, band, bits, comps)
+            assert got == want, (k, band, bits, comps, ival, len(got), len(want))
+            parts = J.unstuff_split(got)
+            assert len(parts) == -(-W * Hh // ival)
+            dst.decode_scan(band, bits, [(c, d, d) for c, d in zip(comps, sel)], _to_lib_tables(H, dct), _to_lib_tables(H, act), parts, ival,
+                            extend=lib.SCAN_T81)
+        for p in range(3):
+            assert np.array_equal(dst.planes[p].coef, src.coefficients(p)), (k, p)
+
+
 # ------------------------------------------------------------------------------------------------ layer B: batches
 def test_batched_device_pipeline(H, O, manifest):
     """Layer B on a small batch of different images with identical geometry and per-image tables:
@@ -744,6 +833,37 @@ def test_scan_encode_all_kinds(H, O, name, progression, rows):
             if act[k].present:
                 assert gac[k].as_tuple() == act[k].as_tuple(), (name, band, bits, "ac", k)
         assert got == want, (name, rows, band, bits, comps, len(got), len(want))
+
+
+@pytest.mark.parametrize("mode", ["blocks", "seq"])
+@pytest.mark.parametrize("rows", [0, 2, 40])
+def test_progressive_ac_encoders_block_parallel(H, O, monkeypatch, mode, rows):
+    """kinds 3 and 4 through k_enc_acp_flags / k_enc_acp_chain + the per-block passes (and the one-thread-per-interval kernels
+    forced on the same input): two refinement passes over split bands on a plane of 16384 blocks that is mostly empty, so that
+    end-of-band runs exceed the 4096-block limit several times over, with dense stretches, blocks whose last coefficient is
+    non-zero (no EOB) and blocks that only hold correction bits -- bytes and tables identical to the oracle's."""
+    if mode == "seq":
+        monkeypatch.setenv("JPEG_SM100_ENC_AC", "seq")
+    rng = np.random.default_rng(17)
+    size, fac = (2048, 512), [(1, 1), (1, 1), (1, 1)]
+    src = O.Spectral.create(size, fac, progressive=True)
+    for p in range(3):
+        c = src.coefficients(p)
+        c[...] = np.where(rng.random(c.shape) < 0.03, rng.integers(-12, 13, c.shape), 0).astype(np.int16)
+        c[rng.random(c.shape[:2]) < (0.97 if p == 0 else 0.6), 1:] = 0   # plane 0: runs of thousands of empty blocks
+        c[3, 10:60, 1:] = rng.integers(-5, 6, (50, 63))                    # a dense stretch
+        c[5, 7, 63] = 9                                                    # last coefficient set: the block needs no EOB
+        c[7, :, 1:] = 0
+        c[7, ::3, 5] = 6                                                   # significant since the first pass: correction bits only
+    dev = H.Spectral(size, fac, process=2)
+    for p in range(3):
+        dev.planes[p].coef = np.array(src.coefficients(p))
+    for band, bits, comps in DEEP_REFINEMENT[1:]:
+        width = src.units(comps[0])[0]
+        want, dct, act = src.encode_scan(band, bits, comps, [0], [0], rows * width)
+        got, gdc, gac = dev.encode_scan(band, bits, [(comps[0], 0, 0)], rows * width)
+        assert gac[0].as_tuple() == act[0].as_tuple(), (band, bits, comps)
+        assert got == want, (mode, rows, band, bits, comps, len(got), len(want))
 
 
 def test_encode_basic_golden_through_gpu(manifest, H):
