@@ -539,6 +539,7 @@ def run_ours(args):
                     "pcie_d2h_GBps_measured_concurrent": None if not conc else {"min": round(min(conc), 1), "mean": round(statistics.mean(conc), 1),
                                                                                  "per_rank": [round(x, 1) for x in conc]},
                     "pcie_d2h_GBps_achieved": round(e2e_gbps_per_rank, 1),
+                    "pcie_both_directions_GBps_achieved": round((rgb_bytes + float(raw_len.sum())) / e2e_s / 1e9, 1),
                     "frac_of_concurrent_ceiling": None if not conc else round(e2e_gbps_per_rank / min(conc), 3),
                     "streams": n_streams, "call": "jpeg_sm100_decode_batch_raw_rgb8 (raw scan bytes in pinned host memory -> GPU lexer -> RGB8 in pinned host memory)",
                     "steps": e2e_steps, "per_rank_s": [round(g["e2e_s"], 4) for g in gathered]},

@@ -1,7 +1,8 @@
 #!/bin/bash
 # one gpurun call: the ncu launch list of a short bench run and one --set full capture of every hot kernel of one step
+# usage: tools/gpu_profile.sh [out dir under gpurun_out/]
 set -u
-OUT=gpurun_out/prof
+OUT=gpurun_out/${1:-prof}
 mkdir -p $OUT
 # per step: 4 lexer kernels, k_build_luts, k_decode_par, k_zero_flagged, k_decode_fast, k_reduce_status, 3 x k_idct_tma, colour = 13
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_lex|k_build|k_decode|k_zero|k_reduce|k_idct|k_ycc" -s 13 -c 26 \
