@@ -342,6 +342,7 @@ int jpeg_sm100_dev_planar_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_plan
  * Spectral.idct() -> Planar.interleaved(cosite: false) -> unpack(as: RGB.self), decode.swift:4154 -> 4182 -> jpeg.swift:441, without
  * the sample planes in between: 6 instead of 9 bytes of HBM traffic per pixel); any other geometry runs jpeg_sm100_dev_idct into
  * context-owned scratch planes followed by jpeg_sm100_dev_planar_to_rgb8.  Bit-identical to the staged calls either way.
+ * The one-kernel path is opt-in (environment JPEG_SM100_FUSE=1, read per call): measured slower than the staged pair on B200.
  * The planes' factor_x / factor_y must be set.  quanta: HOST, n_planes x 64, zig-zag order. */
 int jpeg_sm100_dev_spectral_to_rgb8(jpeg_sm100_ctx *ctx, const jpeg_sm100_dev_spectral *spectral, const uint16_t *quanta_zigzag,
                                     uint32_t size_x, uint32_t size_y, int cosited, uint8_t *d_rgb);
