@@ -37,7 +37,7 @@ struct jpeg_sm100_ctx {
     uint64_t     h2d_bytes = 0, d2h_bytes = 0;  // layer A bookkeeping (jpeg_sm100_transfer_counts)
     std::string  last_error;
     // grow-only scratch used by layer A (host-buffer entry points)
-    DeviceBuffer scratch[16];
+    DeviceBuffer scratch[20];
     PinnedSlot   pinned[4];
     int          pinned_next = 0;
     // copy streams + events of the chunked host-buffer pipeline (jpeg_sm100_decode_batch_rgb8)

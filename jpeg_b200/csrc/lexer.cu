@@ -30,17 +30,22 @@ struct LexImage {
 };
 
 struct Chunk {
-    uint32_t emit[4];   // per byte 0xFF / 0x00
-    uint32_t split[4];
+    uint32_t emit[4];   // bit 7 of every byte that is emitted
+    uint32_t split[4];  // bit 7 of every byte that ends an entropy-coded segment (the n of an RSTn)
     uint32_t out[4];    // output byte values
     uint32_t cur[4];    // raw bytes (masked to the image)
     uint32_t foreign;   // any foreign marker
+    bool     plain;     // no FF in or right before the chunk, all 16 bytes inside the image: everything is emitted as it is
 };
 
 __device__ __forceinline__ uint32_t bytes_below(int n)  // 0xFF in bytes j < n
 {
     return n <= 0 ? 0u : (n >= 4 ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u));
 }
+// SIMD-in-a-register byte compare, exact: bit 7 of every byte of v that is zero (three integer instructions; the SIMD video
+// instructions the first generation used -- __vcmpeq4 -- are emulated on sm_100: the count pass spent 236 and the scatter pass
+// 518 instructions per 16 bytes on them, which made both passes issue-bound at a quarter of the HBM rate)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); }
 
 // classify the 16 bytes at raw[base .. base+16); only bytes in [lo, hi) belong to the image
 __device__ __forceinline__ Chunk classify(const uint8_t *__restrict__ raw, uint64_t base, uint64_t lo, uint64_t hi)
@@ -48,33 +53,41 @@ __device__ __forceinline__ Chunk classify(const uint8_t *__restrict__ raw, uint6
     Chunk c;
     uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + base));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t prev = (base > lo) ? (uint32_t) __ldg(raw + base - 1) : 0u;
+    const uint32_t before = (base > lo) ? (uint32_t) __ldg(raw + base - 1) : 0u;
     const int s = lo > base ? (int) (lo - base) : 0;
     const int e = hi - base >= 16 ? 16 : (int) (hi - base);
+    const bool full = s == 0 && e == 16;
     c.foreign = 0;
+    // entropy-coded data holds an FF every few hundred bytes: most chunks have none, and then every byte is emitted as it is
+    // ((~w - 0x01..01) & w & 0x80..80 is non-zero iff some byte of w is FF)
+    const uint32_t any_ff = (((~w[0] - 0x01010101u) & w[0]) | ((~w[1] - 0x01010101u) & w[1]) | ((~w[2] - 0x01010101u) & w[2]) |
+                             ((~w[3] - 0x01010101u) & w[3])) & 0x80808080u;
+    c.plain = full && any_ff == 0u && before != 0xFFu;
+    if (c.plain) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.emit[i] = 0x80808080u, c.split[i] = 0u, c.out[i] = c.cur[i] = w[i];
+        return c;
+    }
+    uint32_t carry = before == 0xFFu ? 0x80u : 0u;  // "the previous byte was FF", as bit 7 of the byte before byte 0
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint32_t valid = (s == 0 && e == 16) ? 0xFFFFFFFFu : (bytes_below(e - 4 * i) & ~bytes_below(s - 4 * i));
-        const uint32_t cur = w[i] & valid;
-        const uint32_t pw = (cur << 8) | prev;  // little endian: the byte before byte j sits 8 bits lower
-        prev = cur >> 24;
-        const uint32_t cur_ff = __vcmpeq4(cur, 0xFFFFFFFFu);
-        const uint32_t prev_ff = __vcmpeq4(pw, 0xFFFFFFFFu);
-        const uint32_t cur_00 = __vcmpeq4(cur, 0u);
-        const uint32_t cur_rst = __vcmpeq4(cur & 0xF8F8F8F8u, 0xD0D0D0D0u);
-        c.emit[i] = ((~prev_ff & ~cur_ff) | (prev_ff & cur_00)) & valid;
-        c.split[i] = prev_ff & cur_rst & valid;
-        c.out[i] = cur | prev_ff;
+        const uint32_t valid = full ? 0xFFFFFFFFu : (bytes_below(e - 4 * i) & ~bytes_below(s - 4 * i));
+        const uint32_t cur = w[i] & valid, v80 = valid & 0x80808080u;
+        const uint32_t cur_ff = zero_bytes(~cur);  // (bytes outside the image are 0 here: never FF)
+        const uint32_t prev_ff = (cur_ff << 8) | carry;  // little endian: the byte before byte j sits 8 bits lower
+        carry = cur_ff >> 24;
+        const uint32_t cur_00 = zero_bytes(cur);
+        const uint32_t cur_rst = zero_bytes((cur & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+        c.emit[i] = ((~prev_ff & ~cur_ff) | (prev_ff & cur_00)) & v80;
+        c.split[i] = prev_ff & cur_rst & v80;
+        c.out[i] = cur | ((prev_ff >> 7) * 0xFFu);
         c.cur[i] = cur;
-        c.foreign |= prev_ff & ~cur_00 & ~cur_ff & ~cur_rst & valid;
+        c.foreign |= prev_ff & ~cur_00 & ~cur_ff & ~cur_rst & v80;
     }
     return c;
 }
 
-__device__ __forceinline__ uint32_t count_bytes(const uint32_t m[4])
-{
-    return __popc(m[0] & 0x01010101u) + __popc(m[1] & 0x01010101u) + __popc(m[2] & 0x01010101u) + __popc(m[3] & 0x01010101u);
-}
+__device__ __forceinline__ uint32_t count_bytes(const uint32_t m[4]) { return __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]); }
 
 // block-wide exclusive scan of a packed (emit | split << 16) value; returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_count(const uint8_t *__rest
     uint32_t       v = 0, bad = 0;
     if (base < hi) {
         const Chunk c = classify(raw, base, lo, hi);
-        v = count_bytes(c.emit) | (count_bytes(c.split) << 16);
+        v = c.plain ? 16u : (count_bytes(c.emit) | (count_bytes(c.split) << 16));
         bad = c.foreign;
     }
     uint32_t total;
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_scatter(const uint8_t *__re
     uint32_t       v = 0;
     if (base < hi) {
         c = classify(raw, base, lo, hi);
-        v = count_bytes(c.emit) | (count_bytes(c.split) << 16);
+        v = c.plain ? 16u : (count_bytes(c.emit) | (count_bytes(c.split) << 16));
     }
     uint32_t       total;
     const uint32_t ex = block_exclusive_scan(v, &total);
@@ -222,8 +235,8 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_scatter(const uint8_t *__re
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if ((c.emit[i] >> (8 * j)) & 1u) s_out[pos++] = (uint8_t) (c.out[i] >> (8 * j));
-                    if ((c.split[i] >> (8 * j)) & 1u) {
+                    if ((c.emit[i] >> (8 * j + 7)) & 1u) s_out[pos++] = (uint8_t) (c.out[i] >> (8 * j));
+                    if ((c.split[i] >> (8 * j + 7)) & 1u) {
                         // the ECS that ends here has index k; the marker's phase must be k mod 8 (decode.swift:3929)
                         const uint32_t phase = ((c.cur[i] >> (8 * j)) & 7u);
                         if (phase != (k & 7u)) atomicMin(&bad_phase[img], k);

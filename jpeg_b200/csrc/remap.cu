@@ -69,7 +69,7 @@ bool jpeg_virtual_scan_needed(const jpeg_sm100_scan_desc *scan, const jpeg_sm100
     return W > 0 && interval % (uint64_t) W != 0;
 }
 
-// scratch slot 15 belongs to this file.  Fills `v` (virtual planes, scan description on the virtual grid, copy parameters).
+// scratch slot 16 belongs to this file.  Fills `v` (virtual planes, scan description on the virtual grid, copy parameters).
 int jpeg_virtual_scan_setup(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *scan, const jpeg_sm100_dev_spectral *sp, uint64_t interval,
                             JpegVirtualScan *v)
 {
@@ -122,7 +122,7 @@ int jpeg_virtual_scan_setup(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sca
     }
     R.mcu_blocks = volume;
     void *base = nullptr;
-    J_TRY(scratch_reserve(ctx, 15, total + 1024, &base));
+    J_TRY(scratch_reserve(ctx, 16, total + 1024, &base));
     for (int c = 0; c < scan->n_comp; ++c)
         if (R.real[c]) {
             R.virt[c] = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(base) + off[c]);
