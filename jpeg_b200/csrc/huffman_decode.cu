@@ -2608,6 +2608,7 @@ __device__ __forceinline__ bool acr_parse_block(AcrWindow &br, const uint64_t m,
 {
     const uint64_t in_band = (~0ull << band_lo) & (band_hi < 64 ? ~(~0ull << band_hi) : ~0ull);
     const uint64_t Zm = ~m & in_band;
+    __syncwarp();  // every lane is done with the table of two blocks ago (racecheck: blocks inside end-of-band runs do not come here)
     {
         const uint32_t lo = (uint32_t) Zm, hi = (uint32_t) (Zm >> 32);
         const uint32_t below = (1u << lane) - 1u;

@@ -84,6 +84,7 @@ int jpeg_virtual_scan_setup(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sca
     }
     if (W <= 0 || H <= 0 || (uint64_t) W * (uint64_t) H > 0x7fffffffull) return JPEG_SM100_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t) W * (uint64_t) H, g = gcd64(interval, M);
+    if (M / g > 0xffffull) return JPEG_SM100_ERR_UNSUPPORTED;  // the decoders count MCU rows in 16 bits (more than 65535 virtual rows: a huge image with an interval coprime to its MCU count)
     RemapParams    R;
     memset(&R, 0, sizeof R);
     R.W = (int32_t) W, R.g = (int32_t) g, R.M = (uint32_t) M;
