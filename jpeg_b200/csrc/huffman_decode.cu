@@ -154,12 +154,10 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
     // leaf j of level l starts at  sum_{l' < l} counts[l'] * clones(l')  +  j * clones(l)
     uint32_t level_start = 0, leaf_base = 0;
     for (int l = 0; l < 16; ++l) {
-        const uint32_t clones = (0x8080u >> l) & 0xffu;
-        for (uint32_t j = threadIdx.x; j < counts[l]; j += blockDim.x) {
-            const uint16_t e = (uint16_t) (values[leaf_base + j] | ((l + 1) << 8));
-            uint16_t      *o = entries + level_start + j * clones;
-            for (uint32_t c = 0; c < clones; ++c) o[c] = e;
-        }
+        const uint32_t clones = (0x8080u >> l) & 0xffu, shift = 7u - ((uint32_t) l & 7u);  // clones == 1 << shift
+        // one thread per ENTRY, not per leaf (a 1-bit code alone is 128 clones)
+        for (uint32_t k = threadIdx.x; k < (uint32_t) counts[l] * clones; k += blockDim.x)
+            entries[level_start + k] = (uint16_t) (values[leaf_base + (k >> shift)] | ((l + 1) << 8));
         level_start += counts[l] * clones;
         leaf_base += counts[l];
     }
@@ -233,7 +231,13 @@ __global__ void __launch_bounds__(128) k_build_luts(const RawSet *__restrict__ r
             continue;
         }
         fast[i] = FAST_LINK | (32u - d) | ((uint32_t) s_off[i] << 10);  // shift, byte offset
-        for (uint32_t j = 0; j < (1u << d); ++j) {
+    }
+    // the sub-tables (up to 256 entries under one prefix): a warp per prefix, its lanes over the entries
+    for (uint32_t i = threadIdx.x >> 5; i < (uint32_t) FAST_ENTRIES; i += blockDim.x >> 5) {
+        const uint32_t d = s_depth[i];
+        if (d == 0u) continue;
+        const uint32_t cw = i << (16 - FAST_BITS);
+        for (uint32_t j = threadIdx.x & 31u; j < (1u << d); j += 32u) {
             bool           valid;
             const uint32_t e = ref_lookup(cw | (j << (16 - FAST_BITS - d)), valid);
             const bool     ok = valid && (e >> 8) <= (uint32_t) FAST_BITS + d;
