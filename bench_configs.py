@@ -138,10 +138,11 @@ def config4(ctx, dev, q, rank, n_frames=64):
         lens = torch.zeros(N, dtype=torch.int64, device=dev)
         tables = (lib.HuffTable * (8 * N))()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        ctx.check(ctx.L.jpeg_sm100_dev_encode_scan(ctx.h, C.byref(d), C.byref(src.sp), width, tables, out.data_ptr(), stride, lens.data_ptr()))
-        e1.record(stream)
-        torch.cuda.synchronize()
+        for rep in range(2):  # (the first call grows the context's scratch buffers: cudaMalloc / cudaFree; the second is timed)
+            e0.record(stream)
+            ctx.check(ctx.L.jpeg_sm100_dev_encode_scan(ctx.h, C.byref(d), C.byref(src.sp), width, tables, out.data_ptr(), stride, lens.data_ptr()))
+            e1.record(stream)
+            torch.cuda.synchronize()
         enc_ms.append(e0.elapsed_time(e1))
         lh = lens.cpu().tolist()
         host = out.cpu().numpy()

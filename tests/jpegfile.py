@@ -1,6 +1,8 @@
 """Minimal JPEG container splitter for the tests (markers + raw entropy-coded bytes; nothing is decoded)."""
 from __future__ import annotations
 
+import numpy as np
+
 
 def split(data: bytes):
     """Returns a list of (marker, body, ecs) where ecs is the raw (still stuffed, incl. RSTn) bytes that follow
@@ -108,3 +110,28 @@ def with_dnl(data: bytes, frame_height: int, dnl_height: int) -> bytes:
             out += bytes([0xFF, 0xDC, 0, 4]) + dnl_height.to_bytes(2, "big")
             first = False
     return bytes(out)
+
+
+def oracle_on_virtual_grid(O, src, comps, interval):
+    """The oracle extended to ITU-T T.81 interval placement the same way the library is (remap.cu): the scan's MCUs, in order, on
+    a grid of gcd(interval, MCUs) columns, where every interval is whole rows.  Returns the virtual Spectral (scan components only)."""
+    import math
+    inter = len(comps) > 1
+    W, Hh = src.blocks if inter else src.units(comps[0])
+    fac = [src.factor(c) for c in comps] if inter else [(1, 1)]
+    sx, sy = (max(f[0] for f in fac), max(f[1] for f in fac))
+    M = W * Hh
+    g = math.gcd(interval, M)
+    v = O.Spectral.create((g * 8 * sx, (M // g) * 8 * sy), fac, progressive=True)
+    m = np.arange(M)
+    for i, c in enumerate(comps):
+        fx, fy = fac[i]
+        real, virt = src.coefficients(c), v.coefficients(i)
+        assert virt.shape[:2] == ((M // g) * fy, g * fx)
+        for dy in range(fy):
+            for dx in range(fx):
+                ry, rx = (m // W) * fy + dy, (m % W) * fx + dx
+                vy, vx = (m // g) * fy + dy, (m % g) * fx + dx
+                ok = (ry < real.shape[0]) & (rx < real.shape[1])
+                virt[vy[ok], vx[ok]] = real[ry[ok], rx[ok]]
+    return v
