@@ -266,9 +266,16 @@ struct EmitSink {
     }
     __device__ __forceinline__ void symbol(int table, int sym, uint32_t extra, int nextra)
     {
+        // code and extra bits leave as ONE bit string (ncu: the two shift-mask-merge sequences of put() were a third of the emit
+        // pass's instructions at 9 of 32 lanes); only a 16-bit code followed by 16 extra bits (DC category 16) needs two
         const uint32_t c = codes[table * 256 + sym];
-        put(c & 0xffffu, (int) (c >> 16));
-        put(extra, nextra);
+        const int      len = (int) (c >> 16);
+        if (len + nextra <= 32 && nextra < 32) {
+            put(((c & 0xffffu) << nextra) | (extra & ((1u << nextra) - 1u)), len + nextra);
+        } else {
+            put(c & 0xffffu, len);
+            put(extra, nextra);
+        }
     }
     __device__ __forceinline__ void raw(uint32_t v, int n) { put(v, n); }
     __device__ __forceinline__ void pad_to_byte()
