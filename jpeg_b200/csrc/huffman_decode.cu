@@ -3054,7 +3054,13 @@ static int decode_scan_impl(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sca
             return e && strcmp(e, "seq") == 0;  // one thread per interval only (A/B validation of the parallel decoder)
         }();
         bool par_done = false;
-        if (!no_par) {
+        // DC-first scans cut into many SHORT intervals (config #4: 5.7 Kbit each): one thread per interval is faster than sixteen
+        // (measured 1.04 vs 1.19 ms for 256 x 1080p) -- the block-in-MCU index never re-synchronises, so the sixteen subsequences of
+        // an interval are repaired one round at a time anyway.  (JPEG_SM100_PAR_T set: tests force the parallel decoder.)
+        const bool dc_short = P.kind == 1 && interval != JPEG_SM100_INTERVAL_NONE && !getenv("JPEG_SM100_PAR_T") &&
+                              (ctx->hint_interval_bytes ? 8 * ctx->hint_interval_bytes
+                                                        : 8 * ((interval + P.W - 1) / P.W) * (uint64_t) P.W * (uint64_t) volume) < 16384;
+        if (!no_par && !dc_short) {
             // subsequence-parallel decode (+ fused row clearing and DC prefix sums), then the sequential kernel for whatever it flagged.
             // `extend` (the first scan of a file, decode.swift:3214-3236): the planes are already sized, so the flag only means "rows
             // stop silently where the data ends"; the parallel pass flags an interval that runs dry (or shows sixteen 1-bits at the

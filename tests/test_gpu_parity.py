@@ -489,12 +489,13 @@ def test_scan_decode_extend_flag(H, O):
 
 @pytest.mark.parametrize("kind", ["baseline", "luma", "dc_first", "dc_first_luma"])
 @pytest.mark.parametrize("rows", [0, 2])
-def test_first_scan_extend_through_parallel_decoder(H, O, kind, rows):
+def test_first_scan_extend_through_parallel_decoder(H, O, monkeypatch, kind, rows):
     """The reference pushes the first scan of every file with extend: true (decode.swift:3892-3904): rows stop silently where the
     data ends (3214-3220, 2906-2912).  Complete scans, scans that end after 25 / 50 / 75 % of the MCU rows (silent stop) and
     scans cut in the middle of a row (truncation error) -- same planes and same codes as the oracle, through the
     subsequence-parallel decoders (an interval that runs dry is flagged and redone by the sequential kernel)."""
     from jpeg_b200 import lib
+    monkeypatch.setenv("JPEG_SM100_PAR_T", "4")  # (short DC-first intervals would otherwise take the one-thread-per-interval kernel)
     src = O.Spectral.decompress(golden_bytes("gold/color-progressive-1.jpg"))
     fac = [src.factor(p) for p in range(3)]
     band, bits = ((0, 64), (0, None)) if kind in ("baseline", "luma") else ((0, 1), (1, None))
