@@ -1301,7 +1301,12 @@ int jpeg_huffman_encode_scan(jpeg_sm100_ctx *ctx, const jpeg_sm100_scan_desc *sc
         else {
             std::vector<std::thread> pool;
             const uint32_t           per = (n_images + n_thr - 1) / n_thr;
-            for (uint32_t t0 = 0; t0 < n_images; t0 += per) pool.emplace_back(build, t0, std::min(n_images, t0 + per));
+            uint32_t                 next = 0;
+            try {
+                for (; next < n_images; next += per) pool.emplace_back(build, next, std::min(n_images, next + per));
+            } catch (...) {  // no more threads to be had (std::system_error must not cross the C ABI): the rest on this one
+            }
+            if (next < n_images) build(next, n_images);
             for (auto &th : pool) th.join();
         }
         if (failed.load()) return JPEG_SM100_ERR_PRECONDITION;
