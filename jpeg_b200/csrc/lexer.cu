@@ -23,7 +23,8 @@ namespace {
 
 constexpr int LEX_THREADS = 256;
 constexpr int LEX_CHUNK = 16;                        // raw bytes per thread
-constexpr int LEX_TILE = LEX_THREADS * LEX_CHUNK;    // 4 KB of raw bytes per CTA
+constexpr int LEX_TILE = LEX_THREADS * LEX_CHUNK;    // 4 KB of raw bytes per tile
+constexpr int LEX_COUNT_TILES = 4;                   // tiles per CTA of the count pass
 
 struct LexImage {
     uint64_t raw_off, raw_len;
@@ -120,26 +121,35 @@ __global__ void __launch_bounds__(LEX_THREADS) k_lex_count(const uint8_t *__rest
                                                             uint32_t *__restrict__ foreign, unsigned long long *__restrict__ img_emit,
                                                             uint32_t *__restrict__ img_split)
 {
-    const uint32_t img = blockIdx.y, tile = blockIdx.x;
+    // a CTA takes LEX_COUNT_TILES consecutive tiles: their 16-byte loads are independent and all in flight together (with one
+    // tile per CTA the pass was bound by the latency of its short dependent chain image table -> bytes, not by bandwidth)
+    const uint32_t img = blockIdx.y, tile0 = blockIdx.x * LEX_COUNT_TILES;
     const LexImage im = images[img];
     const uint64_t lo = im.raw_off, hi = im.raw_off + im.raw_len;
-    const uint64_t base = (lo & ~15ull) + (uint64_t) tile * LEX_TILE + threadIdx.x * LEX_CHUNK;
-    uint32_t       v = 0, bad = 0;
-    if (base < hi) {
-        const Chunk c = classify(raw, base, lo, hi);
-        v = c.plain ? 16u : (count_bytes(c.emit) | (count_bytes(c.split) << 16));
-        bad = c.foreign;
+    __shared__ uint32_t s_total[LEX_COUNT_TILES];
+    if (threadIdx.x < LEX_COUNT_TILES) s_total[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t bad = 0, v[LEX_COUNT_TILES];
+#pragma unroll
+    for (int t = 0; t < LEX_COUNT_TILES; ++t) {
+        const uint64_t base = (lo & ~15ull) + (uint64_t) (tile0 + t) * LEX_TILE + threadIdx.x * LEX_CHUNK;
+        v[t] = 0;
+        if (base < hi) {
+            const Chunk c = classify(raw, base, lo, hi);
+            v[t] = c.plain ? 16u : (count_bytes(c.emit) | (count_bytes(c.split) << 16));
+            bad |= c.foreign;
+        }
     }
-    // only the tile total is needed here: a warp reduction and one shared-memory atomic per warp (not a block scan)
-    __shared__ uint32_t s_total;
-    if (threadIdx.x == 0) s_total = 0;
+    // only the tile totals are needed here: a warp reduction and one shared-memory atomic per warp and tile (not a block scan)
+#pragma unroll
+    for (int t = 0; t < LEX_COUNT_TILES; ++t) {
+        const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, v[t]);
+        if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_total[t], wsum);
+    }
     __syncthreads();
-    const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_total, wsum);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = s_total;
-        tile_counts[(size_t) img * tiles_max + tile] = total;
+    if (threadIdx.x < LEX_COUNT_TILES && tile0 + threadIdx.x < tiles_max) {
+        const uint32_t total = s_total[threadIdx.x];
+        tile_counts[(size_t) img * tiles_max + tile0 + threadIdx.x] = total;
         if (total) {  // per-image totals: the second level of the scan
             atomicAdd(&img_emit[img], (unsigned long long) (total & 0xFFFFu));
             if (total >> 16) atomicAdd(&img_split[img], total >> 16);
@@ -365,7 +375,7 @@ int jpeg_lex_count(jpeg_sm100_ctx *ctx, const uint8_t *d_raw, const uint64_t *ra
     unsigned long long *d_img_emit = reinterpret_cast<unsigned long long *>(b + o_totals);
     uint32_t           *d_img_split = reinterpret_cast<uint32_t *>(b + o_totals + 8 * (size_t) n_images);
     CU_TRY(ctx, cudaMemsetAsync(d_img_emit, 0, 12 * (size_t) n_images, ctx->stream));
-    const dim3 grid(plan->tiles_max, n_images);
+    const dim3 grid((plan->tiles_max + LEX_COUNT_TILES - 1) / LEX_COUNT_TILES, n_images);
     k_lex_count<<<grid, LEX_THREADS, 0, ctx->stream>>>(d_raw, reinterpret_cast<const LexImage *>(plan->d_images), plan->tiles_max, plan->d_counts,
                                                        plan->d_foreign, d_img_emit, d_img_split);
     LAUNCH_CHECK(ctx);
