@@ -1,4 +1,4 @@
-// fused.cu -- K1+K2 in one kernel: coefficients -> RGB8 for 4:2:0 (centred) and 4:4:4 images of 8-bit samples.
+// fused.cu -- K1+K2 in one kernel: coefficients -> RGB8 for 4:2:0 (centred chroma) images of 8-bit samples.
 //
 // Replaces the chain Spectral.idct() -> Planar.interleaved(cosite: false) -> unpack(as: RGB.self) (reference
 // decode.swift:4154 -> 4182-4276 -> jpeg.swift:441-453) without the sample planes in between: 128 B of coefficients per block in,
