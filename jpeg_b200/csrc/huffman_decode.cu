@@ -1007,6 +1007,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+#ifndef PAR_DC_INLINE
+#define PAR_DC_INLINE 1  // 1: DC predictions resolved BEFORE the flush (per-subsequence DC sums from the synchronisation parse, scanned
+                         // with the block counts): no side array, no fix-up pass over the flushed lines -- see k_decode_par
+#endif
 #ifndef PAR_L2_POLICY
 #define PAR_L2_POLICY 0  // 1: L2 eviction policies on the stream loads / coefficient stores (measured: no gain, 2.12 vs 2.10 ms)
 #endif
@@ -1062,9 +1066,21 @@ __device__ __forceinline__ void win_refill(Window &w, const ParIO &io)
     w.bound += 32u;
 }
 
-template <bool CLAMP>
+// four wrapping 16-bit sums (one per component of the scan) in two registers
+__device__ __forceinline__ uint32_t add16x2(uint32_t a, uint32_t b) { return ((a & 0x7fff7fffu) + (b & 0x7fff7fffu)) ^ ((a ^ b) & 0x80008000u); }
+__device__ __forceinline__ uint32_t sub16x2(uint32_t a, uint32_t b) { return add16x2(a, add16x2(~b, 0x00010001u)); }
+__device__ __forceinline__ void     acc16(uint2 &s, const uint32_t comp, const uint32_t v)  // s[comp] += v (mod 2^16)
+{
+    const uint32_t add = (comp & 1u) ? v << 16 : v & 0xffffu;
+    if (comp & 2u) s.y = add16x2(s.y, add);
+    else s.x = add16x2(s.x, add);
+}
+__device__ __forceinline__ uint32_t get16(const uint2 s, const uint32_t comp) { return ((comp & 2u) ? s.y : s.x) >> (16u * (comp & 1u)) & 0xffffu; }
+
+// DCS: also accumulate the DC differences of the blocks that START in [st.p, end_bit), per component, into dcs (PAR_DC_INLINE)
+template <bool CLAMP, bool DCS = false>
 __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                              const uint32_t blk0, const uint32_t ring)
+                                              const uint32_t blk0, const uint32_t ring, uint2 *dcs = nullptr)
 {
     if (st.p >= end_bit) return 0;
     const uint32_t base = (uint32_t) io.lead * 8u;
@@ -1085,6 +1101,13 @@ __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, c
                 const uint32_t tab = z == 0 ? q.x : q.y;
                 uint32_t       ent = lds32(fast_slot(tab, top));
                 if (ent & FAST_LINK) ent = lds32(tab + (ent >> 8) + ((top << FAST_BITS) >> (ent & 31u)) * 4u);
+                if (DCS) {
+                    if (z == 0) {  // the DC symbol of a block that starts in this subsequence: its difference, T.81 EXTEND as in par_decode
+                        const uint32_t top2 = __funnelshift_l(0u, top, ent), size = ent >> 8;
+                        const uint32_t tail = __funnelshift_l(top2, 0u, size), mask = __funnelshift_l(0xffffffffu, 0u, size);
+                        acc16(*dcs, (q.z >> 25) & 3u, (int) top2 >= 0 ? tail - mask : tail);
+                    }
+                }
                 // (no end-of-data test in the loop: see below)
                 a += ent >> 24;
                 z += (int) __byte_perm(ent, 0, 0x4442);
@@ -1110,11 +1133,12 @@ __device__ __forceinline__ uint32_t par_parse(const ParIO &io, ParseState &st, c
 }
 
 // warp-uniform choice of the variant (a warp whose lanes disagree would execute both one after the other)
+template <bool DCS = false>
 __device__ __forceinline__ uint32_t par_parse_auto(const ParIO &io, ParseState &st, const uint32_t end_bit, const uint32_t count_bits,
-                                                   const uint32_t blk0, const uint32_t ring)
+                                                   const uint32_t blk0, const uint32_t ring, uint2 *dcs = nullptr)
 {
-    if (__any_sync(__activemask(), io.clamp != 0u)) return par_parse<true>(io, st, end_bit, count_bits, blk0, ring);
-    return par_parse<false>(io, st, end_bit, count_bits, blk0, ring);
+    if (__any_sync(__activemask(), io.clamp != 0u)) return par_parse<true, DCS>(io, st, end_bit, count_bits, blk0, ring, dcs);
+    return par_parse<false, DCS>(io, st, end_bit, count_bits, blk0, ring, dcs);
 }
 
 // ---- the decoding pass, warp-synchronous ------------------------------------------------------------------------------------------
@@ -1136,13 +1160,15 @@ __device__ __forceinline__ void sts128_zero(uint32_t a)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
 }
-template <bool CLAMP, bool EXT>
+// DCI (PAR_DC_INLINE): `pred` holds, per component, the DC prediction at the lane's first own block (the sum of the differences of
+// all blocks that start before its subsequence); every own block's difference is turned into its DC value before the flush.
+template <bool CLAMP, bool EXT, bool DCI = false>
 __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
                                                const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad_out, uint32_t N,
                                                const uint32_t N_total, const int W, const int my0, int16_t *plane0, int16_t *dcdiff,
                                                const uint32_t buf /* shared address of the lane's block buffer */,
                                                const uint32_t fq /* shared address of the warp's 32-entry flush queue */,
-                                               const uint32_t ring /* shared address of the lane's stream ring */)
+                                               const uint32_t ring /* shared address of the lane's stream ring */, uint2 pred = make_uint2(0u, 0u))
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1219,13 +1245,17 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
             // reached past the data (decode.swift:2808-2811, 2859-2863): the interval is left to the sequential kernel
             const bool broken = z > 127 || a > count_a;
             done += (!broken && (a - (ent >> 24)) < end_a) ? 1u : 0u;  // counted where its last symbol STARTS (still in `ent`)
-            const uint32_t cur = q.w;
+            const uint32_t cur = q.w, comp_done = (q.z >> 25) & 3u;
             q = lds128(cur);
             if (owned & 1u) {
                 fin_buf = buf | ((owned >> 1) & (broken ? 0u : 1u)) | 2u | (swz >> 2), fin_bidx = bidx;  // (bits 2..4: lane & 7)
-                uint16_t d;  // DC differences also go to the side array (resolved into predictions after the pass)
+                uint16_t d;
                 asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(buf + swz) : "memory");
-                dcdiff[N] = (int16_t) d;
+                if (DCI) {  // difference -> DC value, in the buffer, before the block leaves (decode.swift:3248-3254: wrapping Int16)
+                    acc16(pred, comp_done, (uint32_t) d);
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + swz), "h"((uint16_t) get16(pred, comp_done)) : "memory");
+                } else
+                    dcdiff[N] = (int16_t) d;  // DC differences also go to the side array (resolved into predictions after the pass)
             } else {  // the block this lane skipped: its symbols were stored like any others
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sts128_zero(buf + 16u * (uint32_t) i);
@@ -1280,9 +1310,20 @@ __device__ __forceinline__ uint32_t par_decode(const bool go, const ParIO &io, c
 __device__ __forceinline__ uint32_t par_decode_auto(const bool go, const ParIO &io, const ParseState st, const uint32_t end_bit,
                                                     const uint32_t count_bits, const uint32_t blk0, const int nblk, bool &bad,
                                                     const uint32_t N, const uint32_t N_total, const int W, const int my0, int16_t *plane0,
-                                                    int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const uint32_t ring, const bool ext)
+                                                    int16_t *dcdiff, const uint32_t buf, const uint32_t fq, const uint32_t ring, const bool ext,
+                                                    const bool dci = false, const uint2 pred = make_uint2(0u, 0u))
 {
     const bool clamp = __any_sync(0xffffffffu, go && io.clamp != 0u);
+#if PAR_DC_INLINE
+    if (dci) {  // (kernel-uniform)
+        if (ext) {
+            if (clamp) return par_decode<true, true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring, pred);
+            return par_decode<false, true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring, pred);
+        }
+        if (clamp) return par_decode<true, false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring, pred);
+        return par_decode<false, false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring, pred);
+    }
+#endif
     if (ext) {  // (kernel-uniform)
         if (clamp) return par_decode<true, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
         return par_decode<false, true>(go, io, st, end_bit, count_bits, blk0, nblk, bad, N, N_total, W, my0, plane0, dcdiff, buf, fq, ring);
@@ -1510,7 +1551,7 @@ __device__ __forceinline__ void par_stage_tables(const ScanParams &P, const int1
         const uint32_t LY = (has && uy > dy) ? min((uy - dy + fy - 1u) / fy, 0xffffu) : 0u;
         pb.lim = LX | (LY << 16);
         pb.dtab = sbase + PRE + 2u * (gh->fast[P.dc[c]] - ref_total), pb.atab = sbase + PRE + 2u * (gh->fast[P.ac[c]] - ref_total);
-        pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u);
+        pb.tabs = (uint32_t) P.dc[c] | ((uint32_t) P.ac[c] << 8) | ((uint32_t) b << 16) | (b == 0 ? 1u << 24 : 0u) | ((uint32_t) c << 25);
         pb.next = blk0 + (uint32_t) ((b + 1 == nblk) ? 0 : b + 1) * (uint32_t) sizeof(ParBlk) + 16u;
         s_blk[b] = pb;
     }
@@ -1611,6 +1652,11 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     uint32_t (*const s_ck)[NT] = ALIAS ? reinterpret_cast<uint32_t (*)[NT]>(s_entry + NT) : reinterpret_cast<uint32_t (*)[NT]>(&s_ck_st[0][0]);
     uint32_t *const s_cnt = ALIAS ? &s_ck[PAR_NSEG][0] : s_cnt_st;
     uint16_t *const s_work = ALIAS ? reinterpret_cast<uint16_t *>(s_cnt + NT) : s_work_st;
+    // PAR_DC_INLINE: cumulative DC sums (four 16-bit sums in a uint2) at every checkpoint of every subsequence's recorded parse, in the
+    // same dead buffer area (54 + 64 of its 128 bytes per thread); short intervals only (the scan of the sums stays inside a warp)
+    constexpr bool DCI_OK = PAR_DC_INLINE && ALIAS && (22 + 12 * PAR_NSEG) <= (int) PAR_BUF_STRIDE && (NT % 4) == 0;
+    const bool     dci = DCI_OK && tshift <= 5;
+    uint2 (*const s_dcs)[NT] = reinterpret_cast<uint2 (*)[NT]>(reinterpret_cast<uint8_t *>(s_work) + 2 * NT);
     const uint32_t   img = blockIdx.y, tid = threadIdx.x;
     const uint32_t   T = 1u << tshift, G = NT >> tshift;
 #ifdef PAR_INSTRUMENT  // -DPAR_INSTRUMENT builds: with JPEG_SM100_PAR_STATS, cycles per phase (thread 0 of the CTA)
@@ -1661,11 +1707,13 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
                          const bool first_time, uint64_t &exit_out) -> uint32_t {
         const uint32_t seglen = (e_bit - s_bit) / PAR_NSEG;
         uint32_t       cum = 0;
+        uint2          dcs = make_uint2(0u, 0u);  // (PAR_DC_INLINE) DC differences of the blocks that start in the subsequence so far
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
             if (AC) cum += par_run_ac_auto<false>(qio, st, seg_end, qcount, s_blk[0].atab, P.band_lo, P.band_hi, P.al, bad, 0, 0, nullptr);
             else if (DC) cum += par_run_dc_auto<false>(qio, st, seg_end, qcount, blk0, bad, 0, 0, 1u, nullptr, false);
+            else if (DCI_OK && dci) cum += par_parse_auto<true>(qio, st, seg_end, qcount, blk0, ring, &dcs);
             else cum += par_parse_auto(qio, st, seg_end, qcount, blk0, ring);
             // checkpoint = (overshoot past seg_end (< 32), z, b) in 16 bits + blocks so far in 16 bits; 0xffff....: unusable
             const uint32_t over = st.p - seg_end;
@@ -1678,10 +1726,19 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
                     const uint32_t o = s_ck[kk][sid], c2 = (o >> 16) + delta;
                     s_ck[kk][sid] = (o == 0xffffffffu || c2 >= 0xffffu) ? 0xffffffffu : ((o & 0xffffu) | (c2 << 16));
                 }
+                if (DCI_OK && dci) {  // the recorded sums of the tail shift by what this parse found differently up to here
+                    const uint2 od = s_dcs[k][sid];
+                    const uint2 dd = make_uint2(sub16x2(dcs.x, od.x), sub16x2(dcs.y, od.y));
+                    for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) {
+                        const uint2 o2 = s_dcs[kk][sid];
+                        s_dcs[kk][sid] = make_uint2(add16x2(o2.x, dd.x), add16x2(o2.y, dd.y));
+                    }
+                }
                 exit_out = s_exit[sid];
                 return s_cnt[sid] + delta;
             }
             s_ck[k][sid] = code;
+            if (DCI_OK && dci) s_dcs[k][sid] = dcs;
         }
         exit_out = pack_state(st.p, st.z, st.b);
         return cum;
@@ -1789,6 +1846,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     PAR_PHASE(2);
     const uint32_t my_cnt = s_cnt[tid];
     const uint64_t my_entry = s_entry[tid];
+    const uint2    my_dcs = (DCI_OK && dci && active) ? s_dcs[PAR_NSEG - 1][tid] : make_uint2(0u, 0u);
     // ---- first block of every subsequence: exclusive scan of the block counts within the interval -------------------------
     uint32_t incl = my_cnt;
     const int      lane = tid & 31, wid = tid >> 5;
@@ -1797,6 +1855,16 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
         if ((lane & seg) >= (uint32_t) d) incl += y;
+    }
+    // (PAR_DC_INLINE) the same exclusive scan over the per-subsequence DC sums: the prediction at every thread's first own block
+    uint2 pred = my_dcs;
+    if (DCI_OK && dci) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yx = __shfl_up_sync(0xffffffffu, pred.x, d), yy = __shfl_up_sync(0xffffffffu, pred.y, d);
+            if ((lane & seg) >= (uint32_t) d) pred.x = add16x2(pred.x, yx), pred.y = add16x2(pred.y, yy);
+        }
+        pred.x = sub16x2(pred.x, my_dcs.x), pred.y = sub16x2(pred.y, my_dcs.y);
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
@@ -1812,7 +1880,8 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
         const bool     go = active && before < N_total;
         const uint32_t done = par_decode_auto(go, io, unpack_state(my_entry), end_bit, count, blk0, nblk, bad, before, N_total, W,
                                               s_grp[g].r0, plane0, dcdiff, sbase + bufs_off + tid * PAR_BUF_STRIDE,
-                                              (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, ring, P.extend != 0);
+                                              (ALIAS ? smem_u32(&s_fq[0]) : smem_u32(&s_ck_st[0][0])) + (tid & ~31u) * 8u, ring, P.extend != 0,
+                                              DCI_OK && dci, pred);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_grp[g].bad, 1u);
             atomicAdd(&s_grp[g].total, done);
@@ -1857,7 +1926,7 @@ k_decode_par(const __grid_constant__ ScanParams P, int16_t *const plane0, int16_
     // Out-of-plane blocks take part in the prediction but are not stored (decode.swift:1470-1475).
     // Work items (interval, component) are dealt to the warps; a lane owns a contiguous run of the component's blocks: it sums its
     // differences, the warp scans the lane sums, the lane walks its run again and stores the predictions.
-    for (uint32_t item = (uint32_t) wid; !AC && item < G * (uint32_t) P.n_comp; item += NT / 32) {  // (sequential and DC-first scans)
+    for (uint32_t item = (uint32_t) wid; !AC && !(DCI_OK && dci) && item < G * (uint32_t) P.n_comp; item += NT / 32) {  // (sequential and DC-first scans)
         const uint32_t  gg = item / (uint32_t) P.n_comp;
         const int       c = (int) (item - gg * (uint32_t) P.n_comp);
         const ParGroup &q = s_grp[gg];
