@@ -552,7 +552,7 @@ def run_ours(args):
                                  "(K3, bound by dependent-instruction latency and instruction issue, not HBM) is under roofline_dominant"},
             "roofline_dominant": {"kernel": "K3 stage = k_build_luts + k_decode_par (self-synchronising subsequence-parallel Huffman decode: 16 threads per restart "
                                             "interval, 8-9 CTAs x 4 warps per SM, blocks assembled in shared memory and flushed by the whole warp as 128-byte lines, "
-                                            "DC prefix sums fused) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; latency- and issue-bound "
+                                            "DC predictions resolved before the flush) + k_zero_flagged + k_decode_fast(flagged only) + k_reduce_status; latency- and issue-bound "
                                             "(ncu: profiles/), not HBM-bound",
                                   "bound": "hbm", "achieved": round(huff_bytes / (huff_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                   "frac": round(huff_bytes / (huff_ms * 1e-3) / 1e9 / peak, 4), "traffic": k3_traffic() if n == BATCH else None,
