@@ -2007,6 +2007,10 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     __shared__ int      s_dcw[4][NT / 32];
     __shared__ ParGroup s_q;
     __shared__ __align__(16) uint32_t s_ck[PAR_NSEG][NT];
+    // PAR_DC_INLINE (see k_decode_par): cumulative DC sums per checkpoint, warp / CTA totals of the per-subsequence sums
+    constexpr bool CL_DCI = PAR_DC_INLINE != 0;
+    __shared__ uint2    s_dcs[CL_DCI ? PAR_NSEG : 1][CL_DCI ? NT : 1];
+    __shared__ uint64_t s_warpd[NT / 32], s_ctad;
     const uint32_t  img = blockIdx.y, tid = threadIdx.x, e = blockIdx.x / csize;
     const uint32_t  T = NT * csize, l = crank * NT + tid;
     const int       lane = tid & 31, wid = tid >> 5;
@@ -2032,10 +2036,12 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     auto parse_sub = [&](const uint32_t s_bit, const uint32_t e_bit, const uint32_t sid, const bool first_time, uint64_t &exit_out) -> uint32_t {
         const uint32_t seglen = (e_bit - s_bit) / PAR_NSEG;
         uint32_t       cum = 0;
+        uint2          dcs = make_uint2(0u, 0u);
 #pragma unroll 1
         for (uint32_t k = 0; k < (uint32_t) PAR_NSEG; ++k) {
             const uint32_t seg_end = (k + 1 == (uint32_t) PAR_NSEG) ? e_bit : s_bit + (k + 1) * seglen;
-            cum += par_parse_auto(io, st, seg_end, count, blk0, ring);
+            if (CL_DCI) cum += par_parse_auto<true>(io, st, seg_end, count, blk0, ring, &dcs);
+            else cum += par_parse_auto(io, st, seg_end, count, blk0, ring);
             const uint32_t over = st.p - seg_end;
             const uint32_t code = (over < 32u && cum < 0xffffu) ? (over | ((uint32_t) st.z << 5) | ((uint32_t) st.b << 11) | (cum << 16)) : 0xffffffffu;
             const uint32_t old = s_ck[k][sid];
@@ -2045,10 +2051,19 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
                     const uint32_t o = s_ck[kk][sid], c2 = (o >> 16) + delta;
                     s_ck[kk][sid] = (o == 0xffffffffu || c2 >= 0xffffu) ? 0xffffffffu : ((o & 0xffffu) | (c2 << 16));
                 }
+                if (CL_DCI) {
+                    const uint2 od = s_dcs[k][sid];
+                    const uint2 dd = make_uint2(sub16x2(dcs.x, od.x), sub16x2(dcs.y, od.y));
+                    for (uint32_t kk = k; kk < (uint32_t) PAR_NSEG; ++kk) {
+                        const uint2 o2 = s_dcs[kk][sid];
+                        s_dcs[kk][sid] = make_uint2(add16x2(o2.x, dd.x), add16x2(o2.y, dd.y));
+                    }
+                }
                 exit_out = s_exit[sid];
                 return s_cnt[sid] + delta;
             }
             s_ck[k][sid] = code;
+            if (CL_DCI) s_dcs[k][sid] = dcs;
         }
         exit_out = pack_state(st.p, st.z, st.b);
         return cum;
@@ -2107,8 +2122,34 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     uint32_t before = incl - my_cnt;
     for (int w = 0; w < wid; ++w) before += s_warp[w];
     if (tid == NT - 1) s_ctatotal = before + my_cnt;
+    // (PAR_DC_INLINE) the same two-level exclusive scan over the per-subsequence DC sums: warp, CTA, the CTAs before this one
+    uint2 pred = make_uint2(0u, 0u);
+    if (CL_DCI) {
+        const uint2 my_dcs = active ? s_dcs[PAR_NSEG - 1][tid] : make_uint2(0u, 0u);
+        uint2       inc = my_dcs;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yx = __shfl_up_sync(0xffffffffu, inc.x, d), yy = __shfl_up_sync(0xffffffffu, inc.y, d);
+            if (lane >= d) inc.x = add16x2(inc.x, yx), inc.y = add16x2(inc.y, yy);
+        }
+        if (lane == 31) s_warpd[wid] = (uint64_t) inc.x | ((uint64_t) inc.y << 32);
+        __syncthreads();
+        pred = make_uint2(sub16x2(inc.x, my_dcs.x), sub16x2(inc.y, my_dcs.y));
+        uint2 cta = make_uint2(0u, 0u);
+        for (int w = 0; w < NT / 32; ++w) {
+            const uint64_t t = s_warpd[w];
+            if (w < wid) pred.x = add16x2(pred.x, (uint32_t) t), pred.y = add16x2(pred.y, (uint32_t) (t >> 32));
+            cta.x = add16x2(cta.x, (uint32_t) t), cta.y = add16x2(cta.y, (uint32_t) (t >> 32));
+        }
+        if (tid == 0) s_ctad = (uint64_t) cta.x | ((uint64_t) cta.y << 32);
+    }
     cluster.sync();
     for (uint32_t r = 0; r < crank; ++r) before += remote32(&s_ctatotal, r);
+    if (CL_DCI)
+        for (uint32_t r = 0; r < crank; ++r) {
+            const uint64_t t = remote64(&s_ctad, r);
+            pred.x = add16x2(pred.x, (uint32_t) t), pred.y = add16x2(pred.y, (uint32_t) (t >> 32));
+        }
     // ---- the decoding pass ----
     int16_t *const dcdiff = dcdiff_all + (size_t) slot * dc_per_interval;
     {
@@ -2116,7 +2157,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
         const bool     go = active && before < N_total;
         const uint32_t done = par_decode_auto(go, io, unpack_state(s_entry[tid]), end_bit, count, blk0, nblk, bad, before, N_total, W, s_q.r0,
                                               plane0, dcdiff, bufs + tid * PAR_BUF_STRIDE,
-                                              smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, ring, P.extend != 0);
+                                              smem_u32(&s_ck[0][0]) + (tid & ~31u) * 8u, ring, P.extend != 0, CL_DCI, pred);
         if (active) {
             if (bad || (go && done != my_cnt)) atomicOr(&s_bad, 1u);
             atomicAdd(&s_total, done);
@@ -2133,7 +2174,7 @@ k_decode_par_cluster(const __grid_constant__ ScanParams P, int16_t *const plane0
     // ---- DC differences -> DC coefficients.  Every warp of the cluster takes a contiguous range of each component's blocks:
     // lane runs are summed, warps publish their totals, everybody adds up the totals before its own (DSMEM), second walk stores.
     // The side array was written by other SMs: L2 loads (ld.global.cg), ordered by the cluster barrier above.
-    const bool     do_dc = mine && !f;
+    const bool     do_dc = mine && !f && !CL_DCI;  // (PAR_DC_INLINE: the DC values left with their blocks)
     const uint32_t warps_cta = NT / 32, gw = crank * warps_cta + (uint32_t) wid, n_gw = csize * warps_cta;
     int            lane_ex[4] = {0, 0, 0, 0};
     uint32_t       rk0[4] = {0, 0, 0, 0}, rk1[4] = {0, 0, 0, 0};
